@@ -1,0 +1,1610 @@
+// bito_b200/csrc/gp_engine.cu — host engine: HBM-resident state, op-list compiler
+// (fusion + dependency levels), level-by-level / CUDA-graph execution, NCCL scalars.
+#include "gp_engine.h"
+
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <sstream>
+
+#include "gp_kernels.h"
+
+namespace bito_gp {
+
+namespace {
+thread_local std::string g_last_error;
+
+#define GP_CUDA(expr)                                                                  \
+  do {                                                                                 \
+    cudaError_t err__ = (expr);                                                        \
+    if (err__ != cudaSuccess) {                                                        \
+      std::ostringstream os__;                                                         \
+      os__ << "CUDA error: " << cudaGetErrorString(err__) << " at " << __FILE__ << ":" \
+           << __LINE__ << " (" #expr ")";                                              \
+      throw GpError(os__.str());                                                       \
+    }                                                                                  \
+  } while (0)
+
+[[noreturn]] void Fail(const std::string& msg) { throw GpError(msg); }
+
+inline int64_t RoundUp(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// dag_branch_handler.hpp:266-295
+constexpr double kDefaultBranchLength = 0.1;
+constexpr double kMinLogBranchLength = -13.9;
+constexpr double kMaxLogBranchLength = 1.1;
+constexpr double kDenominatorToleranceForNewton = 1e-10;
+constexpr double kStepSizeForOptimization = 5e-4;
+constexpr double kStepSizeForLogSpaceOptimization = 1.0005;
+constexpr int64_t kMaxIterForOptimization = 1000;
+constexpr double kBranchLengthDifferenceThreshold = 1e-15;
+
+uint64_t HashOps(const bito_gp_op* ops, int64_t n, const int64_t* vec, int64_t vec_len) {
+  uint64_t h = 1469598103934665603ull;
+  auto mix = [&h](const void* data, size_t bytes) {
+    const unsigned char* p = static_cast<const unsigned char*>(data);
+    // FNV-1a over 8-byte words (inputs are int64 tables).
+    for (size_t i = 0; i + 8 <= bytes; i += 8) {
+      uint64_t w;
+      std::memcpy(&w, p + i, 8);
+      h = (h ^ w) * 1099511628211ull;
+      h ^= h >> 29;
+    }
+  };
+  mix(&n, sizeof n);
+  mix(ops, static_cast<size_t>(n) * sizeof(bito_gp_op));
+  mix(&vec_len, sizeof vec_len);
+  if (vec_len > 0) mix(vec, static_cast<size_t>(vec_len) * sizeof(int64_t));
+  return h;
+}
+
+// ---- NCCL through dlopen: the library loads and runs single-GPU without NCCL ----------
+struct NcclUniqueId {
+  char internal[128];
+};
+using NcclComm = void*;
+struct NcclApi {
+  int (*GetUniqueId)(NcclUniqueId*) = nullptr;
+  int (*CommInitRank)(NcclComm*, int, NcclUniqueId, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+  int (*CommDestroy)(NcclComm) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool loaded = false;
+};
+NcclApi& Nccl() {
+  static NcclApi api;
+  if (api.loaded) return api;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+  if (h == nullptr) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (h == nullptr) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (h == nullptr) Fail(std::string("cannot load NCCL (libnccl.so.2): ") + dlerror());
+  api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+  api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+  api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(h, "ncclAllReduce"));
+  api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+  api.GetErrorString =
+      reinterpret_cast<decltype(api.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+  if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy)
+    Fail("libnccl.so.2 lacks the expected symbols");
+  api.loaded = true;
+  return api;
+}
+void NcclCheck(int rc, const char* what) {
+  if (rc != 0) {
+    auto& api = Nccl();
+    Fail(std::string("NCCL error in ") + what + ": " +
+         (api.GetErrorString ? api.GetErrorString(rc) : "?"));
+  }
+}
+constexpr int kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2;
+
+}  // namespace
+
+void SetLastError(const std::string& msg) { g_last_error = msg; }
+const char* LastError() { return g_last_error.c_str(); }
+
+void MakeNcclUniqueId(uint8_t id[128]) {
+  NcclUniqueId uid;
+  NcclCheck(Nccl().GetUniqueId(&uid), "ncclGetUniqueId");
+  std::memcpy(id, uid.internal, 128);
+}
+
+// ---- SlabPool / DeviceArray -----------------------------------------------------------
+void SlabPool::Init(size_t slot_bytes, size_t target_chunk_bytes) {
+  slot_bytes_ = RoundUp(static_cast<int64_t>(slot_bytes), 256);
+  slots_per_chunk_ = std::max<size_t>(1, target_chunk_bytes / slot_bytes_);
+  next_in_chunk_ = slots_per_chunk_;
+}
+void* SlabPool::Alloc() {
+  handed_out_++;
+  if (!free_.empty()) {
+    void* p = free_.back();
+    free_.pop_back();
+    return p;
+  }
+  if (next_in_chunk_ == slots_per_chunk_) {
+    char* c = nullptr;
+    GP_CUDA(cudaMalloc(&c, slots_per_chunk_ * slot_bytes_));
+    chunks_.push_back(c);
+    next_in_chunk_ = 0;
+  }
+  return chunks_.back() + (next_in_chunk_++) * slot_bytes_;
+}
+void SlabPool::Release() {
+  for (char* c : chunks_) cudaFree(c);
+  chunks_.clear();
+  free_.clear();
+  next_in_chunk_ = slots_per_chunk_;
+  handed_out_ = 0;
+}
+
+template <typename T>
+void DeviceArray<T>::Resize(size_t count, bool keep, cudaStream_t stream) {
+  if (count <= n) return;
+  T* fresh = nullptr;
+  GP_CUDA(cudaMalloc(&fresh, count * sizeof(T)));
+  if (keep && ptr != nullptr && n > 0) {
+    GP_CUDA(cudaMemcpyAsync(fresh, ptr, n * sizeof(T), cudaMemcpyDeviceToDevice, stream));
+    GP_CUDA(cudaStreamSynchronize(stream));
+  }
+  if (ptr != nullptr) cudaFree(ptr);
+  ptr = fresh;
+  n = count;
+}
+template <typename T>
+void DeviceArray<T>::Release() {
+  if (ptr != nullptr) cudaFree(ptr);
+  ptr = nullptr;
+  n = 0;
+}
+
+// ---- construction: GPEngine::GPEngine, gp_engine.cpp:9-43 ------------------------------
+Engine::Engine(const bito_gp_config& cfg) : cfg_(cfg) {
+  if (cfg.abi_version != BITO_GP_ABI_VERSION) Fail("bito_gp_config.abi_version mismatch");
+  if (cfg.taxon_count <= 0 || cfg.pattern_count <= 0 || cfg.node_count <= 0 ||
+      cfg.gpcsp_count <= 0)
+    Fail("bito_gp_create: taxon, pattern, node and gpcsp counts must be positive");
+  if (!(cfg.rescaling_threshold > 0.) || !(cfg.rescaling_threshold < 1.))
+    Fail("bito_gp_create: rescaling_threshold must lie in (0, 1)");
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
+    Fail("bito_gp_create: no CUDA device is visible; this engine has no CPU fallback");
+  if (cfg.device < 0 || cfg.device >= n_dev) Fail("bito_gp_create: bad device ordinal");
+  device_ = cfg.device;
+  GP_CUDA(cudaSetDevice(device_));
+  cudaDeviceProp prop;
+  GP_CUDA(cudaGetDeviceProperties(&prop, device_));
+  if (prop.major < 10)
+    Fail("bito_gp_create: kernels are built for sm_100a (B200) only; found sm_" +
+         std::to_string(prop.major) + std::to_string(prop.minor));
+  GP_CUDA(cudaStreamCreateWithFlags(&own_stream_, cudaStreamNonBlocking));
+  stream_ = own_stream_;
+  GP_CUDA(cudaEventCreate(&ev_begin_));
+  GP_CUDA(cudaEventCreate(&ev_end_));
+  GP_CUDA(cudaMallocHost(&pinned_, 4096));
+
+  taxon_count_ = cfg.taxon_count;
+  P_ = cfg.pattern_count;
+  P_stride_ = RoundUp(P_, 8);
+  site_count_ = cfg.site_count;
+  node_count_ = cfg.node_count;
+  gpcsp_count_ = cfg.gpcsp_count;
+  spare_nodes_ = cfg.spare_node_count > 0 ? cfg.spare_node_count : 16;
+  spare_gpcsps_ = cfg.spare_gpcsp_count > 0 ? cfg.spare_gpcsp_count : 3;
+  thr_ = cfg.rescaling_threshold;
+  method_ = cfg.use_gradients ? BITO_GP_BRENT_OPTIMIZATION_WITH_GRADIENTS
+                              : BITO_GP_BRENT_OPTIMIZATION;  // gp_engine.cpp:660-665
+  if (taxon_count_ > node_count_) Fail("bito_gp_create: taxon_count exceeds node_count");
+
+  size_t free_b = 0, total_b = 0;
+  GP_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  max_device_bytes_ = cfg.max_device_bytes > 0 ? cfg.max_device_bytes
+                                               : static_cast<int64_t>(free_b * 0.9);
+
+  // JC69 eigensystem, substitution_model.cpp:20-26.
+  ModelConst m{};
+  const double V[16] = {1.0, 2.0, 0.0, 0.5, 1.0, -2.0, 0.5, 0.0,
+                        1.0, 2.0, 0.0, -0.5, 1.0, -2.0, -0.5, 0.0};
+  const double Vinv[16] = {0.25, 0.25, 0.25, 0.25, 0.125, -0.125, 0.125, -0.125,
+                           0.0, 1.0, 0.0, -1.0, 1.0, 0.0, -1.0, 0.0};
+  const double lambda[4] = {0.0, -1.3333333333333333, -1.3333333333333333,
+                            -1.3333333333333333};
+  std::memcpy(m.V, V, sizeof V);
+  std::memcpy(m.Vinv, Vinv, sizeof Vinv);
+  std::memcpy(m.lambda, lambda, sizeof lambda);
+  for (int i = 0; i < 4; ++i) m.pi[i] = 0.25;
+  m.n_groups = 0;
+  for (int k = 0; k < 4; ++k) {
+    int g = -1;
+    for (int j = 0; j < m.n_groups; ++j)
+      if (m.group_lambda[j] == lambda[k]) g = j;
+    if (g < 0) {
+      g = m.n_groups++;
+      m.group_lambda[g] = lambda[k];
+    }
+    m.group[k] = g;
+  }
+  n_eigen_groups_ = m.n_groups;
+  GP_CUDA(UploadModel(m));
+
+  // PLV slabs: ~256 MiB chunks (or one PLV, whichever is larger).
+  plv_pool_.Init(static_cast<size_t>(32 * P_stride_), size_t(256) << 20);
+  row_pool_.Init(static_cast<size_t>(8 * P_stride_), size_t(64) << 20);
+  plvs_.assign(static_cast<size_t>(padded_plv_count()), PlvSlot{});
+  rows_.assign(static_cast<size_t>(padded_gpcsp_count()), nullptr);
+
+  d_symbols_.Resize(static_cast<size_t>(taxon_count_ * P_stride_), false, stream_);
+  d_weights_.Resize(static_cast<size_t>(P_stride_), false, stream_);
+  d_log_marg_.Resize(static_cast<size_t>(P_stride_), false, stream_);
+  d_counts_.Resize(static_cast<size_t>(padded_plv_count()), false, stream_);
+  GP_CUDA(cudaMemsetAsync(d_counts_.ptr, 0, d_counts_.n * sizeof(int32_t), stream_));
+  GP_CUDA(cudaMemsetAsync(d_weights_.ptr, 0, d_weights_.n * sizeof(double), stream_));
+  LaunchFill(stream_, d_log_marg_.ptr, P_stride_, -std::numeric_limits<double>::infinity());
+  d_status_.Resize(1, false, stream_);
+  GP_CUDA(cudaMemsetAsync(d_status_.ptr, 0, sizeof(uint32_t), stream_));
+  d_feval_total_.Resize(1, false, stream_);
+  GP_CUDA(cudaMemsetAsync(d_feval_total_.ptr, 0, sizeof(unsigned long long), stream_));
+  d_active_.Resize(1, false, stream_);
+  AllocEdgeArrays(padded_gpcsp_count());
+  GP_CUDA(cudaStreamSynchronize(stream_));
+}
+
+Engine::~Engine() {
+  cudaSetDevice(device_);
+  cudaStreamSynchronize(stream_);
+  for (auto& kv : programs_) FreeProgram(*kv.second);
+  if (nccl_comm_ != nullptr) Nccl().CommDestroy(nccl_comm_);
+  plv_pool_.Release();
+  row_pool_.Release();
+  d_symbols_.Release(); d_weights_.Release(); d_log_marg_.Release(); d_counts_.Release();
+  d_q_.Release(); d_bl_.Release(); d_diff_.Release(); d_hybrid_.Release(); d_ll_sum_.Release();
+  d_inverted_.Release(); d_uncond_.Release(); d_status_.Release(); d_feval_total_.Release();
+  d_partials_.Release(); d_packed_.Release(); d_level_max_.Release(); d_coef_.Release();
+  d_dense_tmp_.Release(); d_opt_states_.Release(); d_active_.Release(); d_single_opt_.Release();
+  if (pinned_ != nullptr) cudaFreeHost(pinned_);
+  if (ev_begin_) cudaEventDestroy(ev_begin_);
+  if (ev_end_) cudaEventDestroy(ev_end_);
+  if (own_stream_) cudaStreamDestroy(own_stream_);
+}
+
+void Engine::Activate() const { GP_CUDA(cudaSetDevice(device_)); }
+
+// Per-edge arrays; new entries get the reference defaults (gp_engine.cpp:112-162,
+// dag_branch_handler.cpp:8-18): q = 1, inverted prior = 1, branch length 0.1, diff 0,
+// hybrid marginal -inf.
+void Engine::AllocEdgeArrays(int64_t padded) {
+  const size_t old_n = d_bl_.n;
+  const size_t want = static_cast<size_t>(padded);
+  if (want <= old_n) return;
+  d_q_.Resize(want, true, stream_);
+  d_inverted_.Resize(want, true, stream_);
+  d_bl_.Resize(want, true, stream_);
+  d_diff_.Resize(want, true, stream_);
+  d_hybrid_.Resize(want, true, stream_);
+  // ll_sum has one extra trailing slot: the weighted total log marginal (marg_sum).
+  d_ll_sum_.Resize(want + 1, true, stream_);
+  const int64_t fresh = static_cast<int64_t>(want - old_n);
+  LaunchFill(stream_, d_q_.ptr + old_n, fresh, 1.0);
+  LaunchFill(stream_, d_inverted_.ptr + old_n, fresh, 1.0);
+  LaunchFill(stream_, d_bl_.ptr + old_n, fresh, kDefaultBranchLength);
+  LaunchFill(stream_, d_diff_.ptr + old_n, fresh, 0.0);
+  LaunchFill(stream_, d_hybrid_.ptr + old_n, fresh, -std::numeric_limits<double>::infinity());
+  LaunchFill(stream_, d_ll_sum_.ptr + old_n, fresh + 1, 0.0);
+  d_uncond_.Resize(static_cast<size_t>(node_count_ + spare_nodes_), true, stream_);
+}
+
+DeviceState Engine::State() const {
+  DeviceState st{};
+  st.P = P_;
+  st.P_stride = P_stride_;
+  st.counts = d_counts_.ptr;
+  st.q = d_q_.ptr;
+  st.bl = d_bl_.ptr;
+  st.diff = d_diff_.ptr;
+  st.hybrid = d_hybrid_.ptr;
+  st.ll_sum = d_ll_sum_.ptr;
+  st.weights = d_weights_.ptr;
+  st.log_marg = d_log_marg_.ptr;
+  st.marg_sum = d_ll_sum_.ptr + (d_ll_sum_.n - 1);
+  st.status = d_status_.ptr;
+  st.thr = thr_;
+  st.log_thr = std::log(thr_);
+  st.total_weight = total_weight_;
+  st.feval_total = d_feval_total_.ptr;
+  return st;
+}
+
+void Engine::CheckPlv(int64_t id, const char* what) const {
+  if (id < 0 || id >= padded_plv_count())
+    Fail(std::string(what) + ": PLV index " + std::to_string(id) + " out of range [0, " +
+         std::to_string(padded_plv_count()) + ")");
+}
+void Engine::CheckEdge(int64_t id, const char* what) const {
+  if (id < 0 || id >= padded_gpcsp_count())
+    Fail(std::string(what) + ": GPCSP index " + std::to_string(id) + " out of range [0, " +
+         std::to_string(padded_gpcsp_count()) + ")");
+}
+
+void Engine::InvalidatePrograms() { alloc_version_++; }
+
+// ---- site patterns: gp_engine.cpp:22-26, 544-562 -----------------------------------------
+void Engine::SetSitePatterns(const uint8_t* symbols, const double* weights, bool on_device) {
+  Activate();
+  const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  if (!on_device) {
+    for (int64_t i = 0; i < taxon_count_ * P_; ++i)
+      if (symbols[i] > 4) Fail("bito_gp_set_site_patterns: symbol outside 0..4");
+  }
+  GP_CUDA(cudaMemcpy2DAsync(d_symbols_.ptr, static_cast<size_t>(P_stride_), symbols,
+                            static_cast<size_t>(P_), static_cast<size_t>(P_),
+                            static_cast<size_t>(taxon_count_), kind, stream_));
+  GP_CUDA(cudaMemcpyAsync(d_weights_.ptr, weights, static_cast<size_t>(P_) * sizeof(double), kind,
+                          stream_));
+  // Leaf P-PLVs (ids [0, taxa)) stay symbolic: 1 byte per pattern instead of 32.
+  for (int64_t t = 0; t < taxon_count_; ++t) {
+    PlvSlot& s = plvs_[static_cast<size_t>(t)];
+    if (s.kind == kPlvDense) plv_pool_.Free(s.ptr);
+    s.ptr = d_symbols_.ptr + t * P_stride_;
+    s.kind = kPlvSymbols;
+  }
+  // Total weight (all ranks) for the rescaling term of the branch-length objective.
+  const int64_t tiles = TilesFor(P_);
+  EnsureScratch(tiles, 2);
+  LaunchFill(stream_, d_dense_tmp_.ptr, P_stride_, 1.0);
+  LaunchWeightedSum(stream_, State(), d_dense_tmp_.ptr, d_partials_.ptr);
+  LaunchReducePartials(stream_, d_partials_.ptr, 1, tiles, d_packed_.ptr, nullptr, nullptr);
+  AllReduce(d_packed_.ptr, 1, false);
+  GP_CUDA(cudaMemcpyAsync(pinned_, d_packed_.ptr, sizeof(double), cudaMemcpyDeviceToHost, stream_));
+  GP_CUDA(cudaStreamSynchronize(stream_));
+  total_weight_ = *static_cast<double*>(pinned_);
+  have_patterns_ = true;
+  InvalidatePrograms();
+}
+
+void Engine::InitializePriors(const double* sbn_prior, const double* unconditional,
+                              const double* inverted) {
+  Activate();
+  GP_CUDA(cudaMemcpyAsync(d_q_.ptr, sbn_prior, gpcsp_count_ * sizeof(double),
+                          cudaMemcpyHostToDevice, stream_));
+  GP_CUDA(cudaMemcpyAsync(d_inverted_.ptr, inverted, gpcsp_count_ * sizeof(double),
+                          cudaMemcpyHostToDevice, stream_));
+  GP_CUDA(cudaMemcpyAsync(d_uncond_.ptr, unconditional, node_count_ * sizeof(double),
+                          cudaMemcpyHostToDevice, stream_));
+  GP_CUDA(cudaStreamSynchronize(stream_));
+}
+
+void Engine::SetNullPrior() {
+  Activate();
+  LaunchFill(stream_, d_q_.ptr, static_cast<int64_t>(d_q_.n), 1.0);
+}
+
+// ---- PLV / row residency -----------------------------------------------------------------
+void Engine::EnsureDense(int64_t id) {
+  PlvSlot& s = plvs_[static_cast<size_t>(id)];
+  if (s.kind == kPlvDense) return;
+  if (plv_pool_.NeedsChunk()) {
+    const int64_t reserved =
+        static_cast<int64_t>(plv_pool_.BytesReserved() + row_pool_.BytesReserved());
+    if (reserved + static_cast<int64_t>(plv_pool_.ChunkBytes()) > max_device_bytes_)
+      Fail("PLV storage would exceed the device memory budget (" +
+           std::to_string(max_device_bytes_ >> 20) + " MiB): " +
+           std::to_string(plv_pool_.SlotsInUse()) + " PLVs of " +
+           std::to_string(plv_pool_.slot_bytes()) + " bytes are resident");
+  }
+  double* fresh = static_cast<double*>(plv_pool_.Alloc());
+  if (s.kind == kPlvSymbols) {
+    PlvRef src{s.ptr, kPlvSymbols, static_cast<int32_t>(id)};
+    LaunchExportPlv(stream_, State(), src, fresh);
+  } else {
+    GP_CUDA(cudaMemsetAsync(fresh, 0, static_cast<size_t>(32 * P_stride_), stream_));
+  }
+  s.ptr = fresh;
+  s.kind = kPlvDense;
+  InvalidatePrograms();
+}
+
+double* Engine::EnsureRow(int64_t edge) {
+  double*& r = rows_[static_cast<size_t>(edge)];
+  if (r == nullptr) {
+    if (cfg_.flags & BITO_GP_FLAG_NO_LOGLIK_MATRIX) return nullptr;
+    r = static_cast<double*>(row_pool_.Alloc());
+    GP_CUDA(cudaMemsetAsync(r, 0, static_cast<size_t>(8 * P_stride_), stream_));
+    InvalidatePrograms();
+  }
+  return r;
+}
+
+PlvRef Engine::Ref(int64_t id) const {
+  const PlvSlot& s = plvs_[static_cast<size_t>(id)];
+  return PlvRef{s.ptr, s.kind, static_cast<int32_t>(id)};
+}
+
+void Engine::EnsureScratch(int64_t partial_doubles, int64_t packed_doubles) {
+  bool grew = false;
+  auto grow = [&](DeviceArray<double>& a, int64_t want) {
+    if (static_cast<size_t>(want) > a.n) {
+      // Round up generously so repeated growth (and graph invalidation) is rare.
+      GP_CUDA(cudaStreamSynchronize(stream_));
+      a.Resize(static_cast<size_t>(want + want / 2 + 64), false, stream_);
+      grew = true;
+    }
+  };
+  grow(d_partials_, partial_doubles);
+  grow(d_packed_, packed_doubles);
+  grow(d_dense_tmp_, 4 * P_stride_);
+  if (grew) {
+    // Captured graphs hold the old scratch addresses.
+    for (auto& kv : programs_) {
+      if (kv.second->graph != nullptr) {
+        cudaGraphExecDestroy(kv.second->graph);
+        kv.second->graph = nullptr;
+      }
+      kv.second->graph_tried = false;
+    }
+  }
+}
+
+void Engine::AllReduce(double* buf, int64_t n, bool max_op) {
+  if (n_ranks_ <= 1 || n <= 0) return;
+  NcclCheck(Nccl().AllReduce(buf, buf, static_cast<size_t>(n), kNcclFloat64,
+                             max_op ? kNcclMax : kNcclSum, nccl_comm_, stream_),
+            "ncclAllReduce");
+  stats_.collective_calls++;
+}
+
+void Engine::CommInit(int n_ranks, int rank, const uint8_t id[128]) {
+  Activate();
+  if (n_ranks < 1 || rank < 0 || rank >= n_ranks) Fail("bito_gp_comm_init: bad rank / n_ranks");
+  if (nccl_comm_ != nullptr) Fail("bito_gp_comm_init: communicator already initialised");
+  n_ranks_ = n_ranks;
+  rank_ = rank;
+  if (n_ranks == 1) return;
+  NcclUniqueId uid;
+  std::memcpy(uid.internal, id, 128);
+  NcclComm comm = nullptr;
+  NcclCheck(Nccl().CommInitRank(&comm, n_ranks, uid, rank), "ncclCommInitRank");
+  nccl_comm_ = comm;
+  if (have_patterns_) {  // total weight must now be global
+    GP_CUDA(cudaMemcpyAsync(d_packed_.ptr, &total_weight_, sizeof(double), cudaMemcpyHostToDevice,
+                            stream_));
+    AllReduce(d_packed_.ptr, 1, false);
+    GP_CUDA(cudaMemcpyAsync(pinned_, d_packed_.ptr, sizeof(double), cudaMemcpyDeviceToHost,
+                            stream_));
+    GP_CUDA(cudaStreamSynchronize(stream_));
+    total_weight_ = *static_cast<double*>(pinned_);
+  }
+  InvalidatePrograms();
+}
+
+void Engine::SetStream(cudaStream_t s) {
+  Activate();
+  GP_CUDA(cudaStreamSynchronize(stream_));
+  stream_ = s != nullptr ? s : own_stream_;
+  for (auto& kv : programs_) {  // graphs are stream-agnostic, but be conservative
+    kv.second->graph_tried = false;
+  }
+}
+
+void Engine::Synchronize() {
+  Activate();
+  GP_CUDA(cudaStreamSynchronize(stream_));
+  CheckStatus();
+}
+
+// Surface device-side asserts with the reference's messages (gp_engine.cpp:237-238, 256-257,
+// 283, 325, 585-586).
+void Engine::CheckStatus() {
+  uint32_t* h = static_cast<uint32_t*>(pinned_);
+  GP_CUDA(cudaMemcpyAsync(h, d_status_.ptr, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream_));
+  GP_CUDA(cudaStreamSynchronize(stream_));
+  const uint32_t bits = *h;
+  if (bits == 0) return;
+  GP_CUDA(cudaMemsetAsync(d_status_.ptr, 0, sizeof(uint32_t), stream_));
+  stats_.device_status_bits |= bits;
+  if (!(cfg_.flags & BITO_GP_FLAG_STRICT_ASSERTS)) return;  // Release-build semantics
+  std::string msg;
+  if (bits & kErrRescalingDifference)
+    msg += "dest_ rescaling too large in IncrementWithWeightedEvolvedPLV; ";
+  if (bits & kErrMultiplyNotFinite) msg += "Multiply dest_ is not finite; ";
+  if (bits & kErrNegativePLV) msg += "PLV with negative entry passed to RescalePLVIfNeeded; ";
+  if (bits & kErrRescaledStationary)
+    msg += "Surprise! Rescaled stationary distribution in IncrementMarginalLikelihood; ";
+  if (bits & kErrEmptyPrep) msg += "Empty src_vector in PrepForMarginalization; ";
+  msg += "(bito_gp device status " + std::to_string(bits) + ")";
+  Fail(msg);
+}
+
+// ---- the op-list compiler -----------------------------------------------------------------
+namespace {
+enum MacroKind { kMkZero, kMkScalar, kMkStat, kMkAccum, kMkMult, kMkLik, kMkMarg, kMkOpt };
+struct Macro {
+  MacroKind kind;
+  int idx;  // into the per-kind host vector
+  int level = 0;
+  std::vector<int64_t> reads, writes;
+};
+struct MargGroupHost {
+  int item_off, n_items, reset;
+};
+}  // namespace
+
+Program* Engine::Compile(const bito_gp_op* ops, int64_t n, const int64_t* vec, int64_t vec_len) {
+  const bool fuse = !(cfg_.flags & BITO_GP_FLAG_NO_FUSION);
+  const int64_t n_plv = padded_plv_count();
+  const int64_t n_edge = padded_gpcsp_count();
+
+  // -- pass 0: validate and make every written PLV / row resident ------------------------
+  for (int64_t i = 0; i < n; ++i) {
+    const bito_gp_op& op = ops[i];
+    switch (op.kind) {
+      case BITO_GP_ZERO_PLV:
+        CheckPlv(op.a, "ZeroPLV");
+        if (plvs_[op.a].kind == kPlvSymbols) EnsureDense(op.a);
+        break;
+      case BITO_GP_SET_TO_STATIONARY_DISTRIBUTION:
+        CheckPlv(op.a, "SetToStationaryDistribution");
+        CheckEdge(op.b, "SetToStationaryDistribution");
+        EnsureDense(op.a);
+        break;
+      case BITO_GP_INCREMENT_WITH_WEIGHTED_EVOLVED_PLV:
+        CheckPlv(op.a, "IncrementWithWeightedEvolvedPLV");
+        CheckEdge(op.b, "IncrementWithWeightedEvolvedPLV");
+        CheckPlv(op.c, "IncrementWithWeightedEvolvedPLV");
+        EnsureDense(op.a);
+        break;
+      case BITO_GP_MULTIPLY:
+        CheckPlv(op.a, "Multiply");
+        CheckPlv(op.b, "Multiply");
+        CheckPlv(op.c, "Multiply");
+        EnsureDense(op.a);
+        break;
+      case BITO_GP_LIKELIHOOD:
+        CheckEdge(op.a, "Likelihood");
+        CheckPlv(op.b, "Likelihood");
+        CheckPlv(op.c, "Likelihood");
+        EnsureRow(op.a);
+        break;
+      case BITO_GP_OPTIMIZE_BRANCH_LENGTH:
+        CheckPlv(op.a, "OptimizeBranchLength");
+        CheckPlv(op.b, "OptimizeBranchLength");
+        CheckEdge(op.c, "OptimizeBranchLength");
+        break;
+      case BITO_GP_UPDATE_SBN_PROBABILITIES:
+        CheckEdge(op.a, "UpdateSBNProbabilities");
+        if (op.b <= op.a) Fail("UpdateSBNProbabilities: empty range");
+        CheckEdge(op.b - 1, "UpdateSBNProbabilities");
+        break;
+      case BITO_GP_RESET_MARGINAL_LIKELIHOOD:
+        break;
+      case BITO_GP_INCREMENT_MARGINAL_LIKELIHOOD:
+        CheckPlv(op.a, "IncrementMarginalLikelihood");
+        CheckEdge(op.b, "IncrementMarginalLikelihood");
+        CheckPlv(op.c, "IncrementMarginalLikelihood");
+        EnsureRow(op.b);
+        break;
+      case BITO_GP_PREP_FOR_MARGINALIZATION:
+        CheckPlv(op.a, "PrepForMarginalization");
+        if (op.vec_off < 0 || op.vec_len < 0 || op.vec_off + op.vec_len > vec_len)
+          Fail("PrepForMarginalization: src_vector outside the vec pool");
+        for (int64_t k = 0; k < op.vec_len; ++k)
+          CheckPlv(vec[op.vec_off + k], "PrepForMarginalization");
+        break;
+      default:
+        Fail("unknown GPOperation kind " + std::to_string(op.kind));
+    }
+  }
+
+  // -- pass 1: fuse into macro-ops, in program order -----------------------------------------
+  std::vector<ZeroOp> h_zero;
+  std::vector<ScalarOp> h_scalar;
+  std::vector<StatOp> h_stat;
+  std::vector<AccumGroup> h_accum;
+  std::vector<AccumItem> h_items;
+  std::vector<int32_t> h_pool;
+  std::vector<MultOp> h_mult;
+  std::vector<LikOp> h_lik;
+  std::vector<MargGroupHost> h_marg_groups;
+  std::vector<MargItem> h_marg_items;
+  std::vector<OptOp> h_opt;
+  std::vector<Macro> macros;
+  double alg_bytes = 0.;
+
+  const int64_t res_bl = n_plv, res_q = n_plv + n_edge, res_row = n_plv + 2 * n_edge,
+                res_marg = n_plv + 3 * n_edge;
+  std::vector<char> pending_zero(static_cast<size_t>(n_plv), 0);
+
+  auto emit_zero = [&](int64_t id) {
+    Macro m;
+    if (plvs_[id].kind == kPlvDense) {
+      m.kind = kMkZero;
+      m.idx = static_cast<int>(h_zero.size());
+      h_zero.push_back(ZeroOp{static_cast<double*>(plvs_[id].ptr), static_cast<int32_t>(id), 0});
+    } else {  // owns no memory: already reads as zero, only the count is reset
+      m.kind = kMkScalar;
+      m.idx = static_cast<int>(h_scalar.size());
+      h_scalar.push_back(ScalarOp{kScalarCountZero, static_cast<int32_t>(id), 0, 0, 0, 0});
+    }
+    m.writes.push_back(id);
+    macros.push_back(std::move(m));
+  };
+  auto before_read = [&](int64_t id) {
+    if (pending_zero[id]) {
+      pending_zero[id] = 0;
+      emit_zero(id);
+    }
+  };
+  auto add_pool = [&](const int64_t* src, int64_t len) {
+    const int off = static_cast<int>(h_pool.size());
+    for (int64_t k = 0; k < len; ++k) h_pool.push_back(static_cast<int32_t>(src[k]));
+    return off;
+  };
+
+  int64_t i = 0;
+  while (i < n) {
+    const bito_gp_op& op = ops[i];
+    switch (op.kind) {
+      case BITO_GP_ZERO_PLV: {
+        if (fuse) {
+          pending_zero[op.a] = 1;  // a second ZeroPLV simply supersedes the first
+        } else {
+          emit_zero(op.a);
+        }
+        ++i;
+        break;
+      }
+      case BITO_GP_SET_TO_STATIONARY_DISTRIBUTION: {
+        pending_zero[op.a] = 0;  // fully overwritten
+        Macro m;
+        m.kind = kMkStat;
+        m.idx = static_cast<int>(h_stat.size());
+        h_stat.push_back(StatOp{static_cast<double*>(plvs_[op.a].ptr), static_cast<int32_t>(op.a),
+                                static_cast<int32_t>(op.b)});
+        m.writes.push_back(op.a);
+        m.reads.push_back(res_q + op.b);
+        macros.push_back(std::move(m));
+        alg_bytes += 32;
+        ++i;
+        break;
+      }
+      case BITO_GP_PREP_FOR_MARGINALIZATION:
+      case BITO_GP_INCREMENT_WITH_WEIGHTED_EVOLVED_PLV: {
+        // [Prep(dest)] Increment(dest, ..)+  -> one accumulate group.
+        const int64_t dest = op.a;
+        bool has_prep = false;
+        int64_t j = i;
+        if (op.kind == BITO_GP_PREP_FOR_MARGINALIZATION) {
+          bool dest_in_src = false;
+          for (int64_t k = 0; k < op.vec_len; ++k) dest_in_src |= (vec[op.vec_off + k] == dest);
+          const bool followed = fuse && op.vec_len > 0 && !dest_in_src && i + 1 < n &&
+                                ops[i + 1].kind == BITO_GP_INCREMENT_WITH_WEIGHTED_EVOLVED_PLV &&
+                                ops[i + 1].a == dest;
+          if (!followed) {  // stand-alone Prep: scalar op
+            before_read(dest);
+            for (int64_t k = 0; k < op.vec_len; ++k) before_read(vec[op.vec_off + k]);
+            Macro m;
+            m.kind = kMkScalar;
+            m.idx = static_cast<int>(h_scalar.size());
+            h_scalar.push_back(ScalarOp{kScalarPrep, static_cast<int32_t>(dest), 0,
+                                        add_pool(vec + op.vec_off, op.vec_len),
+                                        static_cast<int32_t>(op.vec_len), 0});
+            m.writes.push_back(dest);
+            for (int64_t k = 0; k < op.vec_len; ++k) m.reads.push_back(vec[op.vec_off + k]);
+            macros.push_back(std::move(m));
+            ++i;
+            break;
+          }
+          has_prep = true;
+          j = i + 1;
+        }
+        AccumGroup g{};
+        g.dest = static_cast<double*>(plvs_[dest].ptr);
+        g.dest_id = static_cast<int32_t>(dest);
+        g.item_off = static_cast<int>(h_items.size());
+        Macro m;
+        m.kind = kMkAccum;
+        // Sources first: a pending ZeroPLV on a source must be materialised before us.
+        int64_t end = j;
+        while (end < n && ops[end].kind == BITO_GP_INCREMENT_WITH_WEIGHTED_EVOLVED_PLV &&
+               ops[end].a == dest && (fuse || end == j)) {
+          if (ops[end].c == dest && end != j) break;  // reads its own partial sum: new group
+          ++end;
+          if (ops[end - 1].c == dest) break;
+        }
+        for (int64_t k = j; k < end; ++k)
+          if (ops[k].c != dest) before_read(ops[k].c);
+        if (has_prep)
+          for (int64_t k = 0; k < op.vec_len; ++k) before_read(vec[op.vec_off + k]);
+        // Destination: fold a pending ZeroPLV.
+        if (pending_zero[dest]) {
+          pending_zero[dest] = 0;
+          g.init_zero = 1;
+          g.count_mode = kCountZero;
+        }
+        if (has_prep) {
+          g.count_mode = kCountPrep;
+          g.prep_off = add_pool(vec + op.vec_off, op.vec_len);
+          g.prep_len = static_cast<int32_t>(op.vec_len);
+          for (int64_t k = 0; k < op.vec_len; ++k) m.reads.push_back(vec[op.vec_off + k]);
+        }
+        for (int64_t k = j; k < end; ++k) {
+          AccumItem it{};
+          it.src = Ref(ops[k].c);
+          it.edge = static_cast<int32_t>(ops[k].b);
+          h_items.push_back(it);
+          m.reads.push_back(ops[k].c);
+          m.reads.push_back(res_bl + ops[k].b);
+          m.reads.push_back(res_q + ops[k].b);
+        }
+        g.n_items = static_cast<int32_t>(end - j);
+        m.idx = static_cast<int>(h_accum.size());
+        h_accum.push_back(g);
+        m.writes.push_back(dest);
+        macros.push_back(std::move(m));
+        alg_bytes += 32. * g.n_items + 32.;
+        i = end;
+        break;
+      }
+      case BITO_GP_MULTIPLY: {
+        if (op.b != op.a) before_read(op.b);
+        if (op.c != op.a) before_read(op.c);
+        if (op.b == op.a || op.c == op.a) before_read(op.a);
+        pending_zero[op.a] = 0;
+        Macro m;
+        m.kind = kMkMult;
+        m.idx = static_cast<int>(h_mult.size());
+        MultOp mo{};
+        mo.dest = static_cast<double*>(plvs_[op.a].ptr);
+        mo.s1 = Ref(op.b);
+        mo.s2 = Ref(op.c);
+        mo.dest_id = static_cast<int32_t>(op.a);
+        mo.max_slot = static_cast<int32_t>(h_mult.size());
+        h_mult.push_back(mo);
+        m.writes.push_back(op.a);
+        m.reads.push_back(op.b);
+        m.reads.push_back(op.c);
+        macros.push_back(std::move(m));
+        alg_bytes += 96;
+        ++i;
+        break;
+      }
+      case BITO_GP_LIKELIHOOD: {
+        before_read(op.b);
+        before_read(op.c);
+        Macro m;
+        m.kind = kMkLik;
+        m.idx = static_cast<int>(h_lik.size());
+        LikOp lo{};
+        lo.parent = Ref(op.c);
+        lo.child = Ref(op.b);
+        lo.row = rows_[op.a];
+        lo.edge = static_cast<int32_t>(op.a);
+        h_lik.push_back(lo);
+        m.writes.push_back(res_row + op.a);
+        m.reads.push_back(op.b);
+        m.reads.push_back(op.c);
+        m.reads.push_back(res_bl + op.a);
+        macros.push_back(std::move(m));
+        alg_bytes += 72;
+        ++i;
+        break;
+      }
+      case BITO_GP_OPTIMIZE_BRANCH_LENGTH: {
+        before_read(op.a);
+        before_read(op.b);
+        Macro m;
+        m.kind = kMkOpt;
+        m.idx = static_cast<int>(h_opt.size());
+        OptOp oo{};
+        oo.parent = Ref(op.b);
+        oo.child = Ref(op.a);
+        oo.edge = static_cast<int32_t>(op.c);
+        h_opt.push_back(oo);
+        m.reads.push_back(op.a);
+        m.reads.push_back(op.b);
+        m.writes.push_back(res_bl + op.c);
+        macros.push_back(std::move(m));
+        alg_bytes += 64;
+        ++i;
+        break;
+      }
+      case BITO_GP_UPDATE_SBN_PROBABILITIES: {
+        Macro m;
+        m.kind = kMkScalar;
+        m.idx = static_cast<int>(h_scalar.size());
+        h_scalar.push_back(ScalarOp{kScalarSbn, static_cast<int32_t>(op.a),
+                                    static_cast<int32_t>(op.b), 0, 0, 0});
+        for (int64_t e = op.a; e < op.b; ++e) {
+          m.reads.push_back(res_row + e);
+          m.writes.push_back(res_q + e);
+        }
+        macros.push_back(std::move(m));
+        alg_bytes += 8. * static_cast<double>(op.b - op.a);
+        ++i;
+        break;
+      }
+      case BITO_GP_RESET_MARGINAL_LIKELIHOOD:
+      case BITO_GP_INCREMENT_MARGINAL_LIKELIHOOD: {
+        MargGroupHost g{static_cast<int>(h_marg_items.size()), 0, 0};
+        Macro m;
+        m.kind = kMkMarg;
+        int64_t j = i;
+        if (op.kind == BITO_GP_RESET_MARGINAL_LIKELIHOOD) {
+          g.reset = 1;
+          ++j;
+        }
+        while (j < n && ops[j].kind == BITO_GP_INCREMENT_MARGINAL_LIKELIHOOD) {
+          const bito_gp_op& mo = ops[j];
+          before_read(mo.a);
+          before_read(mo.c);
+          MargItem it{};
+          it.stationary = Ref(mo.a);
+          it.p = Ref(mo.c);
+          it.row = rows_[mo.b];
+          it.edge = static_cast<int32_t>(mo.b);
+          h_marg_items.push_back(it);
+          m.reads.push_back(mo.a);
+          m.reads.push_back(mo.c);
+          m.reads.push_back(res_q + mo.b);
+          m.writes.push_back(res_row + mo.b);
+          g.n_items++;
+          alg_bytes += 88;
+          ++j;
+          if (!fuse) break;
+        }
+        m.writes.push_back(res_marg);
+        m.idx = static_cast<int>(h_marg_groups.size());
+        h_marg_groups.push_back(g);
+        macros.push_back(std::move(m));
+        i = j;
+        break;
+      }
+      default:
+        Fail("unknown GPOperation kind");
+    }
+  }
+  // ZeroPLVs never followed by another access in this list.
+  for (int64_t k = 0; k < n; ++k)
+    if (ops[k].kind == BITO_GP_ZERO_PLV && pending_zero[ops[k].a]) {
+      pending_zero[ops[k].a] = 0;
+      emit_zero(ops[k].a);
+    }
+
+  // -- pass 2: dependency levels (RAW, WAW, WAR on PLVs, edge scalars, rows, marginal) ------
+  const int64_t n_res = res_marg + 1;
+  std::vector<int> last_write(static_cast<size_t>(n_res), -1), last_read(static_cast<size_t>(n_res), -1);
+  int n_levels = 0;
+  for (Macro& m : macros) {
+    int lv = 0;
+    for (int64_t r : m.reads) lv = std::max(lv, last_write[r] + 1);
+    for (int64_t w : m.writes) lv = std::max(lv, std::max(last_write[w], last_read[w]) + 1);
+    m.level = lv;
+    for (int64_t r : m.reads) last_read[r] = std::max(last_read[r], lv);
+    for (int64_t w : m.writes) last_write[w] = lv;
+    n_levels = std::max(n_levels, lv + 1);
+  }
+
+  // -- pass 3: per-level contiguous tables ---------------------------------------------------
+  std::vector<std::vector<int>> by_level(static_cast<size_t>(n_levels));
+  for (size_t k = 0; k < macros.size(); ++k) by_level[macros[k].level].push_back(static_cast<int>(k));
+
+  auto prog = std::make_unique<Program>();
+  prog->levels.resize(static_cast<size_t>(n_levels));
+  std::vector<ZeroOp> f_zero;
+  std::vector<ScalarOp> f_scalar;
+  std::vector<StatOp> f_stat;
+  std::vector<AccumGroup> f_accum;
+  std::vector<MultOp> f_mult;
+  std::vector<LikOp> f_lik;
+  std::vector<MargItem> f_marg;
+  std::vector<OptOp> f_opt;
+  std::vector<int32_t> f_lik_scatter, f_marg_scatter;
+  const int64_t tiles = TilesFor(P_);
+  const int32_t marg_slot = static_cast<int32_t>(d_ll_sum_.n - 1);
+  for (int lv = 0; lv < n_levels; ++lv) {
+    Level& L = prog->levels[lv];
+    L.zero_off = static_cast<int>(f_zero.size());
+    L.scalar_off = static_cast<int>(f_scalar.size());
+    L.stat_off = static_cast<int>(f_stat.size());
+    L.accum_off = static_cast<int>(f_accum.size());
+    L.mult_off = static_cast<int>(f_mult.size());
+    L.lik_off = static_cast<int>(f_lik.size());
+    L.marg_off = static_cast<int>(f_marg.size());
+    L.marg_scatter_off = static_cast<int>(f_marg_scatter.size());
+    L.opt_off = static_cast<int>(f_opt.size());
+    for (int k : by_level[lv]) {
+      const Macro& m = macros[k];
+      switch (m.kind) {
+        case kMkZero: f_zero.push_back(h_zero[m.idx]); L.n_zero++; break;
+        case kMkScalar: f_scalar.push_back(h_scalar[m.idx]); L.n_scalar++; break;
+        case kMkStat: f_stat.push_back(h_stat[m.idx]); L.n_stat++; break;
+        case kMkAccum: f_accum.push_back(h_accum[m.idx]); L.n_accum++; break;
+        case kMkMult: {
+          MultOp mo = h_mult[m.idx];
+          mo.max_slot = static_cast<int32_t>(f_mult.size());
+          f_mult.push_back(mo);
+          L.n_mult++;
+          break;
+        }
+        case kMkLik:
+          f_lik.push_back(h_lik[m.idx]);
+          f_lik_scatter.push_back(h_lik[m.idx].edge);
+          L.n_lik++;
+          break;
+        case kMkMarg: {
+          const MargGroupHost& g = h_marg_groups[m.idx];
+          if (L.has_marg) Fail("internal: two marginal groups in one level");
+          L.has_marg = 1;
+          L.marg_reset = g.reset;
+          for (int t = 0; t < g.n_items; ++t) {
+            f_marg.push_back(h_marg_items[g.item_off + t]);
+            f_marg_scatter.push_back(h_marg_items[g.item_off + t].edge);
+            L.n_marg++;
+          }
+          f_marg_scatter.push_back(marg_slot);
+          break;
+        }
+        case kMkOpt: f_opt.push_back(h_opt[m.idx]); L.n_opt++; break;
+      }
+    }
+    prog->max_partials = std::max<int64_t>(
+        prog->max_partials, std::max<int64_t>(L.n_lik, L.has_marg ? L.n_marg + 1 : 0) * tiles);
+    prog->max_packed = std::max<int64_t>(prog->max_packed,
+                                         std::max<int64_t>(L.n_lik, L.n_marg + 1));
+    prog->launches += (L.n_zero > 0) + (L.n_scalar > 0) + (L.n_stat > 0) + (L.n_accum > 0) +
+                      2 * (L.n_mult > 0) + 2 * (L.n_lik > 0) + 2 * L.has_marg;
+  }
+  prog->n_mult_total = static_cast<int>(f_mult.size());
+  prog->n_opt_total = static_cast<int>(f_opt.size());
+  prog->n_macro = static_cast<int64_t>(macros.size());
+  prog->alg_bytes_per_pattern = alg_bytes;
+  prog->alloc_version = alloc_version_;
+
+  // -- pass 4: one device arena for all tables -------------------------------------------------
+  size_t off = 0;
+  auto reserve = [&off](size_t bytes) {
+    const size_t at = off;
+    off += RoundUp(static_cast<int64_t>(std::max<size_t>(bytes, 8)), 256);
+    return at;
+  };
+  const size_t o_zero = reserve(f_zero.size() * sizeof(ZeroOp));
+  const size_t o_scalar = reserve(f_scalar.size() * sizeof(ScalarOp));
+  const size_t o_stat = reserve(f_stat.size() * sizeof(StatOp));
+  const size_t o_accum = reserve(f_accum.size() * sizeof(AccumGroup));
+  const size_t o_items = reserve(h_items.size() * sizeof(AccumItem));
+  const size_t o_mult = reserve(f_mult.size() * sizeof(MultOp));
+  const size_t o_lik = reserve(f_lik.size() * sizeof(LikOp));
+  const size_t o_marg = reserve(f_marg.size() * sizeof(MargItem));
+  const size_t o_opt = reserve(f_opt.size() * sizeof(OptOp));
+  const size_t o_pool = reserve(h_pool.size() * sizeof(int32_t));
+  const size_t o_ls = reserve(f_lik_scatter.size() * sizeof(int32_t));
+  const size_t o_ms = reserve(f_marg_scatter.size() * sizeof(int32_t));
+  prog->arena_bytes = off;
+  std::vector<char> host(off, 0);
+  auto put = [&host](size_t at, const void* src, size_t bytes) {
+    if (bytes > 0) std::memcpy(host.data() + at, src, bytes);
+  };
+  put(o_zero, f_zero.data(), f_zero.size() * sizeof(ZeroOp));
+  put(o_scalar, f_scalar.data(), f_scalar.size() * sizeof(ScalarOp));
+  put(o_stat, f_stat.data(), f_stat.size() * sizeof(StatOp));
+  put(o_accum, f_accum.data(), f_accum.size() * sizeof(AccumGroup));
+  put(o_items, h_items.data(), h_items.size() * sizeof(AccumItem));
+  put(o_mult, f_mult.data(), f_mult.size() * sizeof(MultOp));
+  put(o_lik, f_lik.data(), f_lik.size() * sizeof(LikOp));
+  put(o_marg, f_marg.data(), f_marg.size() * sizeof(MargItem));
+  put(o_opt, f_opt.data(), f_opt.size() * sizeof(OptOp));
+  put(o_pool, h_pool.data(), h_pool.size() * sizeof(int32_t));
+  put(o_ls, f_lik_scatter.data(), f_lik_scatter.size() * sizeof(int32_t));
+  put(o_ms, f_marg_scatter.data(), f_marg_scatter.size() * sizeof(int32_t));
+  GP_CUDA(cudaMalloc(&prog->arena, off));
+  GP_CUDA(cudaMemcpyAsync(prog->arena, host.data(), off, cudaMemcpyHostToDevice, stream_));
+  GP_CUDA(cudaStreamSynchronize(stream_));  // `host` dies at scope exit
+  char* a = prog->arena;
+  prog->d_zero = reinterpret_cast<ZeroOp*>(a + o_zero);
+  prog->d_scalar = reinterpret_cast<ScalarOp*>(a + o_scalar);
+  prog->d_stat = reinterpret_cast<StatOp*>(a + o_stat);
+  prog->d_accum = reinterpret_cast<AccumGroup*>(a + o_accum);
+  prog->d_items = reinterpret_cast<AccumItem*>(a + o_items);
+  prog->d_mult = reinterpret_cast<MultOp*>(a + o_mult);
+  prog->d_lik = reinterpret_cast<LikOp*>(a + o_lik);
+  prog->d_marg = reinterpret_cast<MargItem*>(a + o_marg);
+  prog->d_opt = reinterpret_cast<OptOp*>(a + o_opt);
+  prog->d_pool = reinterpret_cast<int32_t*>(a + o_pool);
+  prog->d_lik_scatter = reinterpret_cast<int32_t*>(a + o_ls);
+  prog->d_marg_scatter = reinterpret_cast<int32_t*>(a + o_ms);
+
+  stats_.programs_compiled++;
+  Program* raw = prog.get();
+  const uint64_t key = HashOps(ops, n, vec, vec_len);
+  auto it = programs_.find(key);
+  if (it != programs_.end()) FreeProgram(*it->second);
+  programs_[key] = std::move(prog);
+  return raw;
+}
+
+void Engine::FreeProgram(Program& p) {
+  if (p.graph != nullptr) cudaGraphExecDestroy(p.graph);
+  p.graph = nullptr;
+  if (p.arena != nullptr) cudaFree(p.arena);
+  p.arena = nullptr;
+}
+
+// ---- execution --------------------------------------------------------------------------------
+void Engine::ExecuteLevels(Program& prog, size_t first, size_t last) {
+  const DeviceState st = State();
+  const int64_t tiles = TilesFor(P_);
+  for (size_t li = first; li < last; ++li) {
+    const Level& L = prog.levels[li];
+    LaunchZero(stream_, st, prog.d_zero + L.zero_off, L.n_zero);
+    LaunchScalar(stream_, st, prog.d_scalar + L.scalar_off, prog.d_pool, L.n_scalar);
+    LaunchStationary(stream_, st, prog.d_stat + L.stat_off, L.n_stat);
+    LaunchAccum(stream_, st, prog.d_accum + L.accum_off, prog.d_items, prog.d_pool, L.n_accum);
+    if (L.n_mult > 0) {
+      LaunchMultiply(stream_, st, prog.d_mult + L.mult_off, L.n_mult, d_level_max_.ptr);
+      // The rescale decision needs the max over ALL patterns of the PLV (gp_engine.cpp:583-597).
+      AllReduce(d_level_max_.ptr + L.mult_off, L.n_mult, true);
+      LaunchRescale(stream_, st, prog.d_mult + L.mult_off, L.n_mult, d_level_max_.ptr);
+    }
+    if (L.n_lik > 0) {
+      LaunchLikelihood(stream_, st, prog.d_lik + L.lik_off, L.n_lik, d_partials_.ptr);
+      if (n_ranks_ == 1) {
+        LaunchReducePartials(stream_, d_partials_.ptr, L.n_lik, tiles, d_packed_.ptr,
+                             prog.d_lik_scatter + L.lik_off, st.ll_sum);
+      } else {
+        LaunchReducePartials(stream_, d_partials_.ptr, L.n_lik, tiles, d_packed_.ptr, nullptr,
+                             nullptr);
+        AllReduce(d_packed_.ptr, L.n_lik, false);
+        LaunchScatter(stream_, d_packed_.ptr, L.n_lik, prog.d_lik_scatter + L.lik_off, st.ll_sum);
+      }
+    }
+    if (L.has_marg) {
+      LaunchMarginal(stream_, st, prog.d_marg + L.marg_off, L.n_marg, L.marg_reset,
+                     d_partials_.ptr);
+      const int n_out = L.n_marg + 1;
+      if (n_ranks_ == 1) {
+        LaunchReducePartials(stream_, d_partials_.ptr, n_out, tiles, d_packed_.ptr,
+                             prog.d_marg_scatter + L.marg_scatter_off, st.ll_sum);
+      } else {
+        LaunchReducePartials(stream_, d_partials_.ptr, n_out, tiles, d_packed_.ptr, nullptr,
+                             nullptr);
+        AllReduce(d_packed_.ptr, n_out, false);
+        LaunchScatter(stream_, d_packed_.ptr, n_out, prog.d_marg_scatter + L.marg_scatter_off,
+                      st.ll_sum);
+      }
+    }
+    if (L.n_opt > 0) RunOptimizeLevel(prog, L);
+  }
+}
+
+void Engine::RunOptimizeLevel(Program& prog, const Level& L) {
+  RunOptimizer(prog.d_opt + L.opt_off, L.n_opt, method_, optimization_count_ != 0);
+}
+
+// Device-resident 1-D optimisers stepping every edge of the batch in lockstep: one
+// objective evaluation per round (eval -> reduce -> [all-reduce] -> step).
+void Engine::RunOptimizer(const OptOp* d_ops, int n_ops, int method, bool check_convergence) {
+  const DeviceState st = State();
+  const int64_t tiles = TilesFor(P_);
+  const int G = n_eigen_groups_;
+  const int64_t coef_per_op = P_stride_ * G;
+  const int64_t budget_doubles = (int64_t(256) << 20) / 8;
+  const int chunk = static_cast<int>(
+      std::max<int64_t>(1, std::min<int64_t>(n_ops, budget_doubles / coef_per_op)));
+  d_coef_.Resize(static_cast<size_t>(chunk * coef_per_op), false, stream_);
+  d_opt_states_.Resize(static_cast<size_t>(chunk), false, stream_);
+  EnsureScratch(static_cast<int64_t>(chunk) * 3 * tiles, static_cast<int64_t>(chunk) * 3);
+
+  OptParams prm{};
+  prm.significant_digits = significant_digits_;
+  prm.check_convergence = check_convergence ? 1 : 0;
+  prm.max_iter = kMaxIterForOptimization;
+  prm.min_log_bl = kMinLogBranchLength;
+  prm.max_log_bl = kMaxLogBranchLength;
+  prm.denominator_tolerance = kDenominatorToleranceForNewton;
+  prm.step_size = kStepSizeForOptimization;
+  prm.log_step_size = kStepSizeForLogSpaceOptimization;
+  prm.diff_threshold = kBranchLengthDifferenceThreshold;
+  const int nd = method == BITO_GP_BRENT_OPTIMIZATION ? 0
+                 : method == BITO_GP_NEWTON_OPTIMIZATION ? 2 : 1;
+  const int64_t max_rounds = 3 * kMaxIterForOptimization + 8;
+  int32_t* h_active = static_cast<int32_t*>(pinned_);
+
+  for (int c0 = 0; c0 < n_ops; c0 += chunk) {
+    const int m = std::min(chunk, n_ops - c0);
+    LaunchOptPrepare(stream_, st, d_ops + c0, m, d_opt_states_.ptr, prm, method, d_coef_.ptr, 1);
+    stats_.kernel_launches++;
+    int64_t rounds = 0;
+    int batch = method <= BITO_GP_BRENT_OPTIMIZATION_WITH_GRADIENTS ? 12 : 6;
+    for (;;) {
+      for (int r = 0; r < batch; ++r) {
+        const bool last = (r == batch - 1);
+        LaunchOptEval(stream_, st, m, d_opt_states_.ptr, d_coef_.ptr, nd, d_partials_.ptr, G);
+        LaunchReducePartials(stream_, d_partials_.ptr, 3 * m, tiles, d_packed_.ptr, nullptr,
+                             nullptr);
+        AllReduce(d_packed_.ptr, 3 * m, false);
+        if (last) GP_CUDA(cudaMemsetAsync(d_active_.ptr, 0, sizeof(int32_t), stream_));
+        LaunchOptStep(stream_, st, m, d_opt_states_.ptr, prm, d_packed_.ptr,
+                      last ? d_active_.ptr : nullptr);
+        stats_.kernel_launches += 3;
+      }
+      rounds += batch;
+      GP_CUDA(cudaMemcpyAsync(h_active, d_active_.ptr, sizeof(int32_t), cudaMemcpyDeviceToHost,
+                              stream_));
+      GP_CUDA(cudaStreamSynchronize(stream_));
+      if (*h_active == 0) break;
+      if (rounds > max_rounds) Fail("OptimizeBranchLength: optimiser did not terminate");
+      batch = 4;
+    }
+  }
+}
+
+void Engine::Execute(Program& prog) {
+  EnsureScratch(prog.max_partials, prog.max_packed);
+  if (static_cast<size_t>(prog.n_mult_total) > d_level_max_.n) {
+    GP_CUDA(cudaStreamSynchronize(stream_));
+    d_level_max_.Resize(static_cast<size_t>(prog.n_mult_total) + 64, false, stream_);
+    for (auto& kv : programs_) {
+      if (kv.second->graph != nullptr) cudaGraphExecDestroy(kv.second->graph);
+      kv.second->graph = nullptr;
+      kv.second->graph_tried = false;
+    }
+  }
+  const bool want_graph = !(cfg_.flags & BITO_GP_FLAG_NO_CUDA_GRAPHS) && prog.n_opt_total == 0;
+  auto body = [&]() {
+    if (prog.n_mult_total > 0)
+      GP_CUDA(cudaMemsetAsync(d_level_max_.ptr, 0, prog.n_mult_total * sizeof(double), stream_));
+    ExecuteLevels(prog, 0, prog.levels.size());
+  };
+  if (want_graph) {
+    if (prog.graph == nullptr && !prog.graph_tried) {
+      prog.graph_tried = true;
+      cudaGraph_t graph = nullptr;
+      GP_CUDA(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+      try {
+        body();
+      } catch (...) {
+        cudaStreamEndCapture(stream_, &graph);
+        if (graph != nullptr) cudaGraphDestroy(graph);
+        throw;
+      }
+      GP_CUDA(cudaStreamEndCapture(stream_, &graph));
+      cudaError_t err = cudaGraphInstantiate(&prog.graph, graph, 0);
+      cudaGraphDestroy(graph);
+      if (err != cudaSuccess) {
+        prog.graph = nullptr;
+        cudaGetLastError();
+      }
+    }
+    if (prog.graph != nullptr) {
+      GP_CUDA(cudaGraphLaunch(prog.graph, stream_));
+      stats_.graph_launches++;
+      stats_.kernel_launches += prog.launches;
+      return;
+    }
+  }
+  body();
+  stats_.kernel_launches += prog.launches;
+}
+
+void Engine::ProcessOperations(const bito_gp_op* ops, int64_t n, const int64_t* vec,
+                               int64_t vec_len) {
+  Activate();
+  if (!have_patterns_) Fail("ProcessOperations: call bito_gp_set_site_patterns first");
+  stats_.process_calls++;
+  if (n == 0) return;
+  const uint64_t key = HashOps(ops, n, vec, vec_len);
+  Program* prog = nullptr;
+  auto it = programs_.find(key);
+  if (it != programs_.end() && it->second->alloc_version == alloc_version_) {
+    prog = it->second.get();
+  } else {
+    prog = Compile(ops, n, vec, vec_len);
+    // Compile may itself have made PLVs resident (bumping the version) before building the
+    // tables, so the tables are current: stamp them with the final version.
+    prog->alloc_version = alloc_version_;
+  }
+  stats_.levels_last = static_cast<int64_t>(prog->levels.size());
+  stats_.fused_ops_last = prog->n_macro;
+  stats_.algorithmic_bytes_last = prog->alg_bytes_per_pattern * static_cast<double>(P_);
+  GP_CUDA(cudaEventRecord(ev_begin_, stream_));
+  Execute(*prog);
+  GP_CUDA(cudaEventRecord(ev_end_, stream_));
+  timing_pending_ = true;
+  CheckStatus();
+}
+
+// ---- branch lengths / optimiser settings ---------------------------------------------------------
+void Engine::SetBranchLengths(const double* bl) {
+  Activate();
+  GP_CUDA(cudaMemcpyAsync(d_bl_.ptr, bl, gpcsp_count_ * sizeof(double), cudaMemcpyHostToDevice,
+                          stream_));
+  GP_CUDA(cudaStreamSynchronize(stream_));
+}
+void Engine::SetBranchLengthsToConstant(double v) {
+  Activate();
+  LaunchFill(stream_, d_bl_.ptr, static_cast<int64_t>(d_bl_.n), v);
+}
+void Engine::GetBranchLengths(int64_t start, int64_t length, double* out) {
+  Activate();
+  if (start < 0 || length < 0 || start + length > padded_gpcsp_count())
+    Fail("Requested range of BranchLengths is out-of-range.");
+  GP_CUDA(cudaMemcpyAsync(out, d_bl_.ptr + start, length * sizeof(double), cudaMemcpyDeviceToHost,
+                          stream_));
+  GP_CUDA(cudaStreamSynchronize(stream_));
+}
+void Engine::GetBranchLengthDifferences(double* out) {
+  Activate();
+  GP_CUDA(cudaMemcpyAsync(out, d_diff_.ptr, gpcsp_count_ * sizeof(double), cudaMemcpyDeviceToHost,
+                          stream_));
+  GP_CUDA(cudaStreamSynchronize(stream_));
+}
+void Engine::SetOptimizationMethod(int m) {
+  if (m < 0 || m > 4) Fail("DAGBranchHandler::Optimization(): Invalid OptimizationMethod given.");
+  method_ = m;
+}
+void Engine::ResetOptimizationCount() {  // dag_branch_handler.hpp:49-52
+  Activate();
+  optimization_count_ = 0;
+  LaunchFill(stream_, d_diff_.ptr, static_cast<int64_t>(d_diff_.n), 0.0);
+}
+
+void Engine::LogLikelihoodAndDerivatives(int64_t gpcsp, int64_t rootward, int64_t leafward,
+                                         double out[3]) {
+  Activate();
+  CheckEdge(gpcsp, "LogLikelihoodAndDerivative");
+  CheckPlv(rootward, "LogLikelihoodAndDerivative");
+  CheckPlv(leafward, "LogLikelihoodAndDerivative");
+  const DeviceState st = State();
+  const int64_t tiles = TilesFor(P_);
+  const int G = n_eigen_groups_;
+  d_coef_.Resize(static_cast<size_t>(P_stride_ * G), false, stream_);
+  d_opt_states_.Resize(1, false, stream_);
+  d_single_opt_.Resize(1, false, stream_);
+  EnsureScratch(3 * tiles, 3);
+  double bl = 0.;
+  int32_t counts[2];
+  GP_CUDA(cudaMemcpyAsync(&bl, d_bl_.ptr + gpcsp, sizeof(double), cudaMemcpyDeviceToHost, stream_));
+  GP_CUDA(cudaMemcpyAsync(&counts[0], d_counts_.ptr + rootward, sizeof(int32_t),
+                          cudaMemcpyDeviceToHost, stream_));
+  GP_CUDA(cudaMemcpyAsync(&counts[1], d_counts_.ptr + leafward, sizeof(int32_t),
+                          cudaMemcpyDeviceToHost, stream_));
+  GP_CUDA(cudaStreamSynchronize(stream_));
+  OptOp op{};
+  op.parent = Ref(rootward);
+  op.child = Ref(leafward);
+  op.edge = static_cast<int32_t>(gpcsp);
+  OptState s{};
+  s.t_eval = bl;
+  s.done = 0;
+  GP_CUDA(cudaMemcpyAsync(d_single_opt_.ptr, &op, sizeof op, cudaMemcpyHostToDevice, stream_));
+  GP_CUDA(cudaMemcpyAsync(d_opt_states_.ptr, &s, sizeof s, cudaMemcpyHostToDevice, stream_));
+  OptParams prm{};
+  LaunchOptPrepare(stream_, st, d_single_opt_.ptr, 1, d_opt_states_.ptr, prm, 0, d_coef_.ptr, 0);
+  LaunchOptEval(stream_, st, 1, d_opt_states_.ptr, d_coef_.ptr, 2, d_partials_.ptr, G);
+  LaunchReducePartials(stream_, d_partials_.ptr, 3, tiles, d_packed_.ptr, nullptr, nullptr);
+  AllReduce(d_packed_.ptr, 3, false);
+  GP_CUDA(cudaMemcpyAsync(out, d_packed_.ptr, 3 * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+  GP_CUDA(cudaStreamSynchronize(stream_));
+  stats_.kernel_launches += 3;
+  out[0] += (static_cast<double>(counts[0]) * st.log_thr + static_cast<double>(counts[1]) * st.log_thr) *
+            total_weight_;
+}
+
+void Engine::GetTransitionMatrix(double t, double out[16]) {
+  Activate();
+  EnsureScratch(16, 16);
+  LaunchTransitionMatrix(stream_, t, d_packed_.ptr);
+  GP_CUDA(cudaMemcpyAsync(out, d_packed_.ptr, 16 * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+  GP_CUDA(cudaStreamSynchronize(stream_));
+}
+
+// ---- read-back: gp_engine.cpp:413-468 ---------------------------------------------------------------
+double Engine::GetLogMarginalLikelihood() {
+  Activate();
+  double v = 0.;
+  GP_CUDA(cudaMemcpyAsync(&v, d_ll_sum_.ptr + (d_ll_sum_.n - 1), sizeof(double),
+                          cudaMemcpyDeviceToHost, stream_));
+  GP_CUDA(cudaStreamSynchronize(stream_));
+  return v;
+}
+void Engine::GetPerGpcspLogLikelihoods(int64_t start, int64_t length, double* out) {
+  Activate();
+  if (start < 0 || length < 0 || start + length > padded_gpcsp_count())
+    Fail("Requested range of PerGPCSPLogLikelihoods is out-of-range.");
+  GP_CUDA(cudaMemcpyAsync(out, d_ll_sum_.ptr + start, length * sizeof(double),
+                          cudaMemcpyDeviceToHost, stream_));
+  GP_CUDA(cudaStreamSynchronize(stream_));
+}
+void Engine::GetPerGpcspComponentsOfFullLogMarginal(double* out) {
+  std::vector<double> q(static_cast<size_t>(gpcsp_count_));
+  GetPerGpcspLogLikelihoods(0, gpcsp_count_, out);
+  GetSbnParameters(q.data());
+  for (int64_t e = 0; e < gpcsp_count_; ++e)
+    out[e] += static_cast<double>(site_count_) * std::log(q[e]);
+}
+void Engine::GetLogLikelihoodMatrix(double* out) {
+  Activate();
+  if (cfg_.flags & BITO_GP_FLAG_NO_LOGLIK_MATRIX)
+    Fail("GetLogLikelihoodMatrix: engine was created with BITO_GP_FLAG_NO_LOGLIK_MATRIX");
+  for (int64_t e = 0; e < gpcsp_count_; ++e) {
+    if (rows_[e] == nullptr) {
+      std::memset(out + e * P_, 0, static_cast<size_t>(P_) * sizeof(double));
+    } else {
+      GP_CUDA(cudaMemcpyAsync(out + e * P_, rows_[e], static_cast<size_t>(P_) * sizeof(double),
+                              cudaMemcpyDeviceToHost, stream_));
+    }
+  }
+  GP_CUDA(cudaStreamSynchronize(stream_));
+}
+void Engine::GetPerPatternLogMarginal(double* out) {
+  Activate();
+  GP_CUDA(cudaMemcpyAsync(out, d_log_marg_.ptr, static_cast<size_t>(P_) * sizeof(double),
+                          cudaMemcpyDeviceToHost, stream_));
+  GP_CUDA(cudaStreamSynchronize(stream_));
+}
+void Engine::GetSbnParameters(double* out) {
+  Activate();
+  GP_CUDA(cudaMemcpyAsync(out, d_q_.ptr, gpcsp_count_ * sizeof(double), cudaMemcpyDeviceToHost,
+                          stream_));
+  GP_CUDA(cudaStreamSynchronize(stream_));
+}
+void Engine::SetSbnParameters(const double* q) {
+  Activate();
+  GP_CUDA(cudaMemcpyAsync(d_q_.ptr, q, gpcsp_count_ * sizeof(double), cudaMemcpyHostToDevice,
+                          stream_));
+  GP_CUDA(cudaStreamSynchronize(stream_));
+}
+void Engine::GetPlv(int64_t id, double* out) {
+  Activate();
+  CheckPlv(id, "GetPLV");
+  const PlvSlot& s = plvs_[id];
+  if (s.kind == kPlvZero) {
+    std::memset(out, 0, static_cast<size_t>(4 * P_) * sizeof(double));
+    return;
+  }
+  const double* src = static_cast<const double*>(s.ptr);
+  if (s.kind == kPlvSymbols) {
+    EnsureScratch(0, 0);
+    LaunchExportPlv(stream_, State(), Ref(id), d_dense_tmp_.ptr);
+    src = d_dense_tmp_.ptr;
+  }
+  GP_CUDA(cudaMemcpyAsync(out, src, static_cast<size_t>(4 * P_) * sizeof(double),
+                          cudaMemcpyDeviceToHost, stream_));
+  GP_CUDA(cudaStreamSynchronize(stream_));
+}
+void Engine::SetPlv(int64_t id, const double* in, int32_t count) {
+  Activate();
+  CheckPlv(id, "SetPLV");
+  if (plvs_[id].kind != kPlvDense) {
+    // Content is about to be replaced: allocate without expanding.
+    plvs_[id].kind = kPlvZero;
+    EnsureDense(id);
+  }
+  GP_CUDA(cudaMemcpyAsync(plvs_[id].ptr, in, static_cast<size_t>(4 * P_) * sizeof(double),
+                          cudaMemcpyHostToDevice, stream_));
+  GP_CUDA(cudaMemcpyAsync(d_counts_.ptr + id, &count, sizeof(int32_t), cudaMemcpyHostToDevice,
+                          stream_));
+  GP_CUDA(cudaStreamSynchronize(stream_));
+}
+void Engine::GetRescalingCounts(int32_t* out) {
+  Activate();
+  GP_CUDA(cudaMemcpyAsync(out, d_counts_.ptr, static_cast<size_t>(padded_plv_count()) * sizeof(int32_t),
+                          cudaMemcpyDeviceToHost, stream_));
+  GP_CUDA(cudaStreamSynchronize(stream_));
+}
+
+// ---- resize / copy: gp_engine.cpp:64-209, 386-409 ------------------------------------------------------
+// PLV id = type * node_count + node, so a change of node_count moves every id. With PLVs
+// behind a slot table this is a table permutation; no PLV data moves in HBM.
+void Engine::GrowPlvs(int64_t new_node_count, const int64_t* reindexer, int64_t explicit_alloc) {
+  Activate();
+  (void)explicit_alloc;  // capacity is on-demand here; there is nothing to pre-allocate
+  if (new_node_count < taxon_count_) Fail("GrowPLVs: node_count below taxon_count");
+  const int64_t old_n = node_count_;
+  const int64_t old_padded = padded_plv_count();
+  std::vector<int32_t> old_counts(static_cast<size_t>(old_padded));
+  GetRescalingCounts(old_counts.data());
+  std::vector<PlvSlot> old_slots = plvs_;
+  node_count_ = new_node_count;
+  const int64_t new_padded = padded_plv_count();
+  std::vector<PlvSlot> slots(static_cast<size_t>(new_padded));
+  std::vector<int32_t> counts(static_cast<size_t>(new_padded), 0);
+  std::vector<char> moved(static_cast<size_t>(old_padded), 0);
+  const int64_t old_stride = old_n, new_stride = new_node_count;
+  // Reindexer semantics (reindexer.hpp): new_index = reindexer[old_index]; nodes that did
+  // not exist before keep fresh (zero) PLVs. Spare PLVs keep their offsets past 6N.
+  for (int type = 0; type < 6; ++type) {
+    for (int64_t node = 0; node < std::min(old_n, new_node_count); ++node) {
+      const int64_t to = reindexer != nullptr ? reindexer[node] : node;
+      if (to < 0 || to >= new_node_count) Fail("Node Reindexer is not valid.");
+      const int64_t src = type * old_stride + node, dst = type * new_stride + to;
+      slots[dst] = old_slots[src];
+      counts[dst] = old_counts[src];
+      moved[src] = 1;
+    }
+  }
+  for (int64_t j = 0; j < 6 * spare_nodes_; ++j) {
+    const int64_t src = 6 * old_stride + j, dst = 6 * new_stride + j;
+    slots[dst] = old_slots[src];
+    counts[dst] = old_counts[src];
+    moved[src] = 1;
+  }
+  for (int64_t k = 0; k < old_padded; ++k)
+    if (!moved[k] && old_slots[k].kind == kPlvDense) plv_pool_.Free(old_slots[k].ptr);
+  plvs_ = std::move(slots);
+  GP_CUDA(cudaStreamSynchronize(stream_));
+  d_counts_.Resize(static_cast<size_t>(new_padded), false, stream_);
+  GP_CUDA(cudaMemcpyAsync(d_counts_.ptr, counts.data(), counts.size() * sizeof(int32_t),
+                          cudaMemcpyHostToDevice, stream_));
+  d_uncond_.Resize(static_cast<size_t>(node_count_ + spare_nodes_), true, stream_);
+  GP_CUDA(cudaStreamSynchronize(stream_));
+  InvalidatePrograms();
+}
+
+void Engine::GrowGpcsps(int64_t new_count, const int64_t* reindexer, int64_t explicit_alloc) {
+  Activate();
+  (void)explicit_alloc;
+  const int64_t old_count = gpcsp_count_;
+  const int64_t old_padded = padded_gpcsp_count();
+  auto pull = [&](DeviceArray<double>& a, int64_t n) {
+    std::vector<double> v(static_cast<size_t>(n));
+    GP_CUDA(cudaMemcpyAsync(v.data(), a.ptr, n * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+    GP_CUDA(cudaStreamSynchronize(stream_));
+    return v;
+  };
+  std::vector<double> q = pull(d_q_, old_padded), inv = pull(d_inverted_, old_padded),
+                      bl = pull(d_bl_, old_padded), diff = pull(d_diff_, old_padded),
+                      hyb = pull(d_hybrid_, old_padded), lls = pull(d_ll_sum_, old_padded);
+  const double marg = GetLogMarginalLikelihood();
+  gpcsp_count_ = new_count;
+  const int64_t new_padded = padded_gpcsp_count();
+  const double ninf = -std::numeric_limits<double>::infinity();
+  std::vector<double> nq(new_padded, 1.), ninv(new_padded, 1.), nbl(new_padded, kDefaultBranchLength),
+      ndiff(new_padded, 0.), nhyb(new_padded, ninf), nlls(new_padded + 1, 0.);
+  std::vector<double*> nrows(static_cast<size_t>(new_padded), nullptr);
+  std::vector<char> moved(static_cast<size_t>(old_padded), 0);
+  for (int64_t e = 0; e < std::min(old_count, new_count); ++e) {
+    const int64_t to = reindexer != nullptr ? reindexer[e] : e;
+    if (to < 0 || to >= new_count) Fail("GPCSP Reindexer is not valid for GPEngine size.");
+    nq[to] = q[e]; ninv[to] = inv[e]; nbl[to] = bl[e]; ndiff[to] = diff[e]; nhyb[to] = hyb[e];
+    nlls[to] = lls[e];
+    nrows[to] = rows_[e];
+    moved[e] = 1;
+  }
+  for (int64_t j = 0; j < spare_gpcsps_; ++j) {
+    const int64_t src = old_count + j, dst = new_count + j;
+    nq[dst] = q[src]; ninv[dst] = inv[src]; nbl[dst] = bl[src]; ndiff[dst] = diff[src];
+    nlls[dst] = lls[src];
+    nrows[dst] = rows_[src];
+    moved[src] = 1;
+  }
+  for (int64_t e = 0; e < old_padded; ++e)
+    if (!moved[e] && rows_[e] != nullptr) row_pool_.Free(rows_[e]);
+  nlls[new_padded] = marg;
+  rows_ = std::move(nrows);
+  auto push = [&](DeviceArray<double>& a, const std::vector<double>& v) {
+    a.Resize(v.size(), false, stream_);
+    GP_CUDA(cudaMemcpyAsync(a.ptr, v.data(), v.size() * sizeof(double), cudaMemcpyHostToDevice,
+                            stream_));
+  };
+  // The marginal slot is the LAST element of d_ll_sum_: keep n exact.
+  if (d_ll_sum_.n != static_cast<size_t>(new_padded + 1)) {
+    d_ll_sum_.Release(); d_q_.Release(); d_inverted_.Release(); d_bl_.Release(); d_diff_.Release();
+    d_hybrid_.Release();
+  }
+  push(d_q_, nq); push(d_inverted_, ninv); push(d_bl_, nbl); push(d_diff_, ndiff);
+  push(d_hybrid_, nhyb); push(d_ll_sum_, nlls);
+  GP_CUDA(cudaStreamSynchronize(stream_));
+  InvalidatePrograms();
+}
+
+void Engine::GrowSparePlvs(int64_t new_spare) {
+  if (new_spare <= spare_nodes_) return;
+  Activate();
+  const int64_t old_padded = padded_plv_count();
+  spare_nodes_ = new_spare;
+  plvs_.resize(static_cast<size_t>(padded_plv_count()));
+  GP_CUDA(cudaStreamSynchronize(stream_));
+  d_counts_.Resize(static_cast<size_t>(padded_plv_count()), true, stream_);
+  GP_CUDA(cudaMemsetAsync(d_counts_.ptr + old_padded, 0,
+                          static_cast<size_t>(padded_plv_count() - old_padded) * sizeof(int32_t),
+                          stream_));
+  d_uncond_.Resize(static_cast<size_t>(node_count_ + spare_nodes_), true, stream_);
+  InvalidatePrograms();
+}
+
+void Engine::GrowSpareGpcsps(int64_t new_spare) {
+  if (new_spare <= spare_gpcsps_) return;
+  // Pull, extend with the reference defaults, push (values of existing edges kept).
+  const int64_t keep = gpcsp_count_;
+  const int64_t old_spare = spare_gpcsps_;
+  Activate();
+  auto extend = [&](DeviceArray<double>& a, int64_t old_n, int64_t new_n, double fill, bool tail_slot) {
+    std::vector<double> v(static_cast<size_t>(old_n + (tail_slot ? 1 : 0)));
+    GP_CUDA(cudaMemcpyAsync(v.data(), a.ptr, v.size() * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+    GP_CUDA(cudaStreamSynchronize(stream_));
+    std::vector<double> w(static_cast<size_t>(new_n + (tail_slot ? 1 : 0)), fill);
+    std::copy(v.begin(), v.begin() + old_n, w.begin());
+    if (tail_slot) w[new_n] = v[old_n];
+    a.Release();
+    a.Resize(w.size(), false, stream_);
+    GP_CUDA(cudaMemcpyAsync(a.ptr, w.data(), w.size() * sizeof(double), cudaMemcpyHostToDevice, stream_));
+    GP_CUDA(cudaStreamSynchronize(stream_));
+  };
+  const int64_t old_padded = keep + old_spare, new_padded = keep + new_spare;
+  extend(d_q_, old_padded, new_padded, 1., false);
+  extend(d_inverted_, old_padded, new_padded, 1., false);
+  extend(d_bl_, old_padded, new_padded, kDefaultBranchLength, false);
+  extend(d_diff_, old_padded, new_padded, 0., false);
+  extend(d_hybrid_, old_padded, new_padded, -std::numeric_limits<double>::infinity(), false);
+  extend(d_ll_sum_, old_padded, new_padded, 0., true);
+  spare_gpcsps_ = new_spare;
+  rows_.resize(static_cast<size_t>(new_padded), nullptr);
+  InvalidatePrograms();
+}
+
+void Engine::CopyPlvData(int64_t src, int64_t dest) {  // gp_engine.cpp:394-399
+  Activate();
+  if (src < 0 || dest < 0 || src >= padded_plv_count() || dest >= padded_plv_count())
+    Fail("Cannot copy PLV data with src or dest index out-of-range.");
+  if (src == dest) return;
+  const PlvSlot s = plvs_[src];
+  if (s.kind == kPlvZero) {
+    if (plvs_[dest].kind == kPlvDense)
+      GP_CUDA(cudaMemsetAsync(plvs_[dest].ptr, 0, static_cast<size_t>(32 * P_stride_), stream_));
+    else if (plvs_[dest].kind == kPlvSymbols) {
+      plvs_[dest].kind = kPlvZero;
+      plvs_[dest].ptr = nullptr;
+      InvalidatePrograms();
+    }
+  } else {
+    if (plvs_[dest].kind != kPlvDense) {
+      plvs_[dest].kind = kPlvZero;
+      EnsureDense(dest);
+    }
+    if (s.kind == kPlvDense) {
+      GP_CUDA(cudaMemcpyAsync(plvs_[dest].ptr, s.ptr, static_cast<size_t>(32 * P_stride_),
+                              cudaMemcpyDeviceToDevice, stream_));
+    } else {
+      LaunchExportPlv(stream_, State(), Ref(src), static_cast<double*>(plvs_[dest].ptr));
+    }
+  }
+  GP_CUDA(cudaMemcpyAsync(d_counts_.ptr + dest, d_counts_.ptr + src, sizeof(int32_t),
+                          cudaMemcpyDeviceToDevice, stream_));
+}
+
+void Engine::CopyGpcspData(int64_t src, int64_t dest) {  // gp_engine.cpp:401-409
+  Activate();
+  if (src < 0 || dest < 0 || src >= padded_gpcsp_count() || dest >= padded_gpcsp_count())
+    Fail("Cannot copy PLV data with src or dest index out-of-range.");
+  auto cp = [&](DeviceArray<double>& a) {
+    GP_CUDA(cudaMemcpyAsync(a.ptr + dest, a.ptr + src, sizeof(double), cudaMemcpyDeviceToDevice,
+                            stream_));
+  };
+  cp(d_bl_);
+  cp(d_q_);
+  cp(d_inverted_);
+}
+
+void Engine::GetStats(bito_gp_stats* out) {
+  Activate();
+  GP_CUDA(cudaStreamSynchronize(stream_));
+  if (timing_pending_) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ev_begin_, ev_end_) == cudaSuccess) stats_.last_process_ms = ms;
+    timing_pending_ = false;
+  }
+  unsigned long long fevals = 0;
+  GP_CUDA(cudaMemcpy(&fevals, d_feval_total_.ptr, sizeof fevals, cudaMemcpyDeviceToHost));
+  stats_.objective_evaluations = static_cast<int64_t>(fevals);
+  stats_.device_bytes_in_use =
+      static_cast<int64_t>(plv_pool_.BytesReserved() + row_pool_.BytesReserved());
+  int64_t resident = 0;
+  for (const PlvSlot& s : plvs_) resident += (s.kind == kPlvDense);
+  stats_.plvs_resident = resident;
+  *out = stats_;
+}
+
+}  // namespace bito_gp

@@ -1,0 +1,231 @@
+// bito_b200/csrc/gp_engine.h — host side of the B200 GP engine.
+//
+// Owns every piece of numeric state the reference GPEngine owns
+// (/root/reference/src/gp_engine.hpp:287-377) but in HBM, compiles each GPOperationVector
+// into a level-scheduled program of fused macro-ops (the role of the serial visitor loop
+// GPEngine::ProcessOperations, gp_engine.cpp:335-339) and launches the kernels of
+// gp_kernels.cu. The C-ABI in gp_c_api.cu is a thin wrapper over this class.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/bito_gp.h"
+#include "gp_types.h"
+
+namespace bito_gp {
+
+struct GpError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+// Fixed-size slot allocator over a few large cudaMalloc chunks. PLVs (32*P_stride bytes)
+// and log-likelihood rows (8*P_stride bytes) are handed out on first write, so a DAG only
+// pays HBM for the vectors its op lists actually produce.
+class SlabPool {
+ public:
+  SlabPool() = default;
+  void Init(size_t slot_bytes, size_t target_chunk_bytes);
+  void* Alloc();
+  void Free(void* p) { free_.push_back(p); }
+  void Release();
+  size_t BytesReserved() const { return chunks_.size() * slots_per_chunk_ * slot_bytes_; }
+  size_t SlotsInUse() const { return handed_out_ - free_.size(); }
+  size_t slot_bytes() const { return slot_bytes_; }
+  bool NeedsChunk() const { return free_.empty() && next_in_chunk_ == slots_per_chunk_; }
+  size_t ChunkBytes() const { return slots_per_chunk_ * slot_bytes_; }
+
+ private:
+  size_t slot_bytes_ = 0, slots_per_chunk_ = 0, next_in_chunk_ = 0, handed_out_ = 0;
+  std::vector<char*> chunks_;
+  std::vector<void*> free_;
+};
+
+template <typename T>
+struct DeviceArray {
+  T* ptr = nullptr;
+  size_t n = 0;
+  void Resize(size_t count, bool keep, cudaStream_t stream);
+  void Release();
+};
+
+struct PlvSlot {
+  void* ptr = nullptr;
+  int32_t kind = kPlvZero;
+};
+
+struct Level {
+  int zero_off = 0, n_zero = 0;
+  int scalar_off = 0, n_scalar = 0;
+  int stat_off = 0, n_stat = 0;
+  int accum_off = 0, n_accum = 0;
+  int mult_off = 0, n_mult = 0;
+  int lik_off = 0, n_lik = 0;
+  int marg_off = 0, n_marg = 0, marg_reset = 0, has_marg = 0, marg_scatter_off = 0;
+  int opt_off = 0, n_opt = 0;
+};
+
+struct Program {
+  uint64_t alloc_version = 0;
+  std::vector<Level> levels;
+  // device tables (one arena)
+  char* arena = nullptr;
+  size_t arena_bytes = 0;
+  ZeroOp* d_zero = nullptr;
+  ScalarOp* d_scalar = nullptr;
+  StatOp* d_stat = nullptr;
+  AccumGroup* d_accum = nullptr;
+  AccumItem* d_items = nullptr;
+  MultOp* d_mult = nullptr;
+  LikOp* d_lik = nullptr;
+  MargItem* d_marg = nullptr;
+  OptOp* d_opt = nullptr;
+  int32_t* d_pool = nullptr;
+  int32_t* d_lik_scatter = nullptr;   // per LikOp: edge
+  int32_t* d_marg_scatter = nullptr;  // per marginal level: n_marg edges + marginal slot
+  int n_mult_total = 0;
+  int n_opt_total = 0;
+  int64_t max_partials = 0;  // doubles of tile partials needed by any level
+  int64_t max_packed = 0;    // reduced scalars needed by any level
+  int64_t n_macro = 0;
+  int64_t launches = 0;      // kernels per execution (without optimiser rounds)
+  double alg_bytes_per_pattern = 0.;
+  cudaGraphExec_t graph = nullptr;
+  bool graph_tried = false;
+};
+
+class Engine {
+ public:
+  explicit Engine(const bito_gp_config& cfg);
+  ~Engine();
+  Engine(const Engine&) = delete;
+  Engine& operator=(const Engine&) = delete;
+
+  void SetSitePatterns(const uint8_t* symbols, const double* weights, bool on_device);
+  void InitializePriors(const double* sbn_prior, const double* unconditional,
+                        const double* inverted);
+  void SetNullPrior();
+  void ProcessOperations(const bito_gp_op* ops, int64_t n, const int64_t* vec, int64_t vec_len);
+
+  void SetBranchLengths(const double* bl);
+  void SetBranchLengthsToConstant(double v);
+  void GetBranchLengths(int64_t start, int64_t length, double* out);
+  void GetBranchLengthDifferences(double* out);
+  void SetOptimizationMethod(int m);
+  void SetSignificantDigits(int d) { significant_digits_ = d; }
+  int64_t optimization_count() const { return optimization_count_; }
+  void ResetOptimizationCount();
+  void IncrementOptimizationCount() { optimization_count_++; }
+  void LogLikelihoodAndDerivatives(int64_t gpcsp, int64_t rootward, int64_t leafward,
+                                   double out[3]);
+  void GetTransitionMatrix(double t, double out[16]);
+
+  double GetLogMarginalLikelihood();
+  void GetPerGpcspLogLikelihoods(int64_t start, int64_t length, double* out);
+  void GetPerGpcspComponentsOfFullLogMarginal(double* out);
+  void GetLogLikelihoodMatrix(double* out);
+  void GetPerPatternLogMarginal(double* out);
+  void GetSbnParameters(double* out);
+  void SetSbnParameters(const double* q);
+  void GetPlv(int64_t id, double* out);
+  void SetPlv(int64_t id, const double* in, int32_t count);
+  void GetRescalingCounts(int32_t* out);
+
+  int64_t node_count() const { return node_count_; }
+  int64_t plv_count() const { return 6 * node_count_; }
+  int64_t padded_plv_count() const { return 6 * (node_count_ + spare_nodes_); }
+  int64_t gpcsp_count() const { return gpcsp_count_; }
+  int64_t padded_gpcsp_count() const { return gpcsp_count_ + spare_gpcsps_; }
+  int64_t pattern_count() const { return P_; }
+
+  void GrowPlvs(int64_t new_node_count, const int64_t* reindexer, int64_t explicit_alloc);
+  void GrowGpcsps(int64_t new_count, const int64_t* reindexer, int64_t explicit_alloc);
+  void GrowSparePlvs(int64_t new_spare);
+  void GrowSpareGpcsps(int64_t new_spare);
+  void CopyPlvData(int64_t src, int64_t dest);
+  void CopyGpcspData(int64_t src, int64_t dest);
+
+  void CommInit(int n_ranks, int rank, const uint8_t id[128]);
+  void SetStream(cudaStream_t s);
+  void Synchronize();
+  void GetStats(bito_gp_stats* out);
+
+ private:
+  // state helpers
+  void Activate() const;
+  DeviceState State() const;
+  void AllocEdgeArrays(int64_t padded);
+  void EnsureDense(int64_t plv_id);  // allocate (zero-filled / expanded) HBM for a PLV
+  double* EnsureRow(int64_t edge);
+  PlvRef Ref(int64_t plv_id) const;
+  void CheckPlv(int64_t id, const char* what) const;
+  void CheckEdge(int64_t id, const char* what) const;
+  void CheckStatus();
+  void InvalidatePrograms();
+
+  // scheduling
+  Program* Compile(const bito_gp_op* ops, int64_t n, const int64_t* vec, int64_t vec_len);
+  void Execute(Program& prog);
+  void ExecuteLevels(Program& prog, size_t first, size_t last);
+  void RunOptimizeLevel(Program& prog, const Level& lv);
+  void RunOptimizer(const OptOp* d_ops, int n_ops, int method, bool check_convergence);
+  void FreeProgram(Program& p);
+  void EnsureScratch(int64_t partial_doubles, int64_t packed_doubles);
+  void AllReduce(double* buf, int64_t n, bool max_op);
+
+  bito_gp_config cfg_;
+  int device_ = 0;
+  cudaStream_t stream_ = nullptr;
+  cudaStream_t own_stream_ = nullptr;
+  cudaEvent_t ev_begin_ = nullptr, ev_end_ = nullptr;
+
+  int64_t taxon_count_ = 0, P_ = 0, P_stride_ = 0, site_count_ = 0;
+  int64_t node_count_ = 0, gpcsp_count_ = 0, spare_nodes_ = 16, spare_gpcsps_ = 3;
+  double thr_ = 1e-40, total_weight_ = 0.;
+  int method_ = 0, significant_digits_ = 10;
+  int64_t optimization_count_ = 0;
+  bool have_patterns_ = false;
+  bool timing_pending_ = false;
+  int n_eigen_groups_ = 2;
+
+  SlabPool plv_pool_, row_pool_;
+  std::vector<PlvSlot> plvs_;      // by logical PLV id (padded count)
+  std::vector<double*> rows_;      // by edge id (padded count)
+  uint64_t alloc_version_ = 1;
+  int64_t max_device_bytes_ = 0;
+
+  DeviceArray<uint8_t> d_symbols_;
+  DeviceArray<double> d_weights_, d_log_marg_;
+  DeviceArray<int32_t> d_counts_;
+  DeviceArray<double> d_q_, d_bl_, d_diff_, d_hybrid_, d_ll_sum_, d_inverted_, d_uncond_;
+  DeviceArray<uint32_t> d_status_;
+  DeviceArray<unsigned long long> d_feval_total_;
+  // scratch
+  DeviceArray<double> d_partials_, d_packed_, d_level_max_, d_coef_, d_dense_tmp_;
+  DeviceArray<OptState> d_opt_states_;
+  DeviceArray<int32_t> d_active_;
+  DeviceArray<OptOp> d_single_opt_;
+  void* pinned_ = nullptr;  // small pinned staging block
+
+  std::unordered_map<uint64_t, std::unique_ptr<Program>> programs_;
+
+  // NCCL (dlopen'ed)
+  void* nccl_comm_ = nullptr;
+  int n_ranks_ = 1, rank_ = 0;
+
+  bito_gp_stats stats_{};
+};
+
+void MakeNcclUniqueId(uint8_t id[128]);
+
+// Thread-local error text for the C-ABI.
+void SetLastError(const std::string& msg);
+const char* LastError();
+
+}  // namespace bito_gp

@@ -1,0 +1,884 @@
+// bito_b200/csrc/gp_kernels.cu — hand-written sm_100a kernels of the GP likelihood engine.
+//
+// Every kernel is a streaming pass over pattern-contiguous FP64 PLVs: one thread owns one
+// site pattern (4 states = one 32-byte LDG.E.256 / STG.E.256), a thread block owns a tile
+// of kTile patterns of ONE macro-op, and a launch covers every macro-op of a dependency
+// level. The 4x4 transition matrices are built on the device from the edge's branch
+// length into shared memory. HBM-bound by construction (~0.6 flop/B):
+// tensor cores are deliberately not used.
+#include "gp_kernels.h"
+
+#include <cfloat>
+#include <cmath>
+
+namespace bito_gp {
+
+__constant__ ModelConst c_model;
+
+cudaError_t UploadModel(const ModelConst& model) {
+  return cudaMemcpyToSymbol(c_model, &model, sizeof(ModelConst));
+}
+
+namespace {
+
+struct V4 {
+  double a, b, c, d;
+};
+
+// 256-bit global accesses (PTX ISA 8.8, sm_100+): one request per pattern.
+__device__ __forceinline__ V4 ld256(const double* p) {
+  V4 v;
+  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+               : "=d"(v.a), "=d"(v.b), "=d"(v.c), "=d"(v.d)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st256(double* p, const V4& v) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.a), "d"(v.b), "d"(v.c),
+               "d"(v.d)
+               : "memory");
+}
+
+__device__ __forceinline__ V4 load_plv(const PlvRef& r, int64_t p) {
+  if (r.kind == kPlvDense) return ld256(static_cast<const double*>(r.ptr) + 4 * p);
+  V4 v = {0., 0., 0., 0.};
+  if (r.kind == kPlvSymbols) {
+    // InitializePLVsWithSitePatterns, gp_engine.cpp:544-562
+    const int s = static_cast<const uint8_t*>(r.ptr)[p];
+    const bool gap = (s == 4);
+    v.a = (gap || s == 0) ? 1. : 0.;
+    v.b = (gap || s == 1) ? 1. : 0.;
+    v.c = (gap || s == 2) ? 1. : 0.;
+    v.d = (gap || s == 3) ? 1. : 0.;
+  }
+  return v;
+}
+
+// M = scale * ((V * diag(f_k)) * V^-1), f_k = lambda_k^deriv * exp(lambda_k t)
+// (gp_engine.cpp:341-358; evaluation order (V*D)*V^-1 as in Eigen).
+__device__ void build_matrix(double t, int deriv, double scale, double* out16) {
+  double d[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const double l = c_model.lambda[k];
+    const double e = exp(t * l);
+    d[k] = deriv == 0 ? e : (deriv == 1 ? l * e : l * l * e);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      double s = 0.;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s += (c_model.V[4 * i + k] * d[k]) * c_model.Vinv[4 * k + j];
+      out16[4 * i + j] = scale * s;
+    }
+}
+
+__device__ __forceinline__ V4 matvec(const double* M, const V4& x) {
+  V4 y;
+  y.a = M[0] * x.a + M[1] * x.b + M[2] * x.c + M[3] * x.d;
+  y.b = M[4] * x.a + M[5] * x.b + M[6] * x.c + M[7] * x.d;
+  y.c = M[8] * x.a + M[9] * x.b + M[10] * x.c + M[11] * x.d;
+  y.d = M[12] * x.a + M[13] * x.b + M[14] * x.c + M[15] * x.d;
+  return y;
+}
+
+// r^T M p
+__device__ __forceinline__ double quad(const V4& r, const double* M, const V4& p) {
+  const double c0 = r.a * M[0] + r.b * M[4] + r.c * M[8] + r.d * M[12];
+  const double c1 = r.a * M[1] + r.b * M[5] + r.c * M[9] + r.d * M[13];
+  const double c2 = r.a * M[2] + r.b * M[6] + r.c * M[10] + r.d * M[14];
+  const double c3 = r.a * M[3] + r.b * M[7] + r.c * M[11] + r.d * M[15];
+  return c0 * p.a + c1 * p.b + c2 * p.c + c3 * p.d;
+}
+
+// NumericalUtils::LogAdd, numerical_utils.hpp:35-52
+__device__ __forceinline__ double log_add(double x, double y) {
+  if (y > x) {
+    const double t = x;
+    x = y;
+    y = t;
+  }
+  if (x == -INFINITY) return x;
+  const double neg_diff = y - x;
+  if (neg_diff < -36.04365338911715 /* log(DBL_EPSILON) */) return x;
+  return x + log(1.0 + exp(neg_diff));
+}
+
+// Deterministic block reductions (shuffle tree, then warp 0 over the warp leaders).
+template <typename Op>
+__device__ __forceinline__ double block_reduce(double v, Op op, double identity) {
+  __shared__ double s_part[kTile / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_down_sync(0xffffffffu, v, o));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();  // protect s_part across back-to-back calls
+  if (lane == 0) s_part[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    v = lane < (blockDim.x >> 5) ? s_part[lane] : identity;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_down_sync(0xffffffffu, v, o));
+  }
+  return v;  // valid in thread 0
+}
+struct SumOp {
+  __device__ double operator()(double a, double b) const { return a + b; }
+};
+struct MaxOp {
+  __device__ double operator()(double a, double b) const { return a > b ? a : b; }
+};
+
+// ---- IncrementWithWeightedEvolvedPLV groups -------------------------------------------
+// dest (+)= sum_i (thr^(count[src_i]-count[dest]) * q[e_i]) * M(t_{e_i}) * src_i, applied in
+// op-list order (gp_engine.cpp:229-249), with the preceding ZeroPLV /
+// PrepForMarginalization folded in (:213-216, :323-333).
+__global__ void __launch_bounds__(kTile)
+    k_accum(DeviceState st, const AccumGroup* __restrict__ groups,
+            const AccumItem* __restrict__ items, const int32_t* __restrict__ pool, int tiles) {
+  const int g = blockIdx.x / tiles;
+  const int tile = blockIdx.x - g * tiles;
+  const AccumGroup grp = groups[g];
+  __shared__ double sM[kItemChunk][16];
+  __shared__ int s_dest_count;
+
+  if (threadIdx.x == 0) {
+    int c;
+    if (grp.count_mode == kCountPrep) {
+      c = INT_MAX;
+      for (int i = 0; i < grp.prep_len; ++i) c = min(c, st.counts[pool[grp.prep_off + i]]);
+    } else if (grp.count_mode == kCountZero) {
+      c = 0;
+    } else {
+      c = st.counts[grp.dest_id];
+    }
+    s_dest_count = c;
+    if (tile == 0 && grp.count_mode != kCountKeep) st.counts[grp.dest_id] = c;
+  }
+  __syncthreads();
+  const int dest_count = s_dest_count;
+
+  const int64_t p = static_cast<int64_t>(tile) * kTile + threadIdx.x;
+  const bool live = p < st.P;
+  V4 acc = {0., 0., 0., 0.};
+  if (live && !grp.init_zero) acc = ld256(grp.dest + 4 * p);
+
+  for (int base = 0; base < grp.n_items; base += kItemChunk) {
+    const int n = min(kItemChunk, grp.n_items - base);
+    if (threadIdx.x < n) {
+      const AccumItem it = items[grp.item_off + base + threadIdx.x];
+      const int diff = st.counts[it.src.id] - dest_count;
+      if (diff < 0) atomicOr(st.status, kErrRescalingDifference);
+      const double factor = diff == 0 ? 1. : pow(st.thr, static_cast<double>(diff));
+      build_matrix(st.bl[it.edge], 0, factor * st.q[it.edge], sM[threadIdx.x]);
+    }
+    __syncthreads();
+    if (live) {
+      int i = 0;
+      // Two independent 32-byte loads in flight per iteration.
+      for (; i + 1 < n; i += 2) {
+        const V4 x0 = load_plv(items[grp.item_off + base + i].src, p);
+        const V4 x1 = load_plv(items[grp.item_off + base + i + 1].src, p);
+        const V4 y0 = matvec(sM[i], x0);
+        acc.a += y0.a; acc.b += y0.b; acc.c += y0.c; acc.d += y0.d;
+        const V4 y1 = matvec(sM[i + 1], x1);
+        acc.a += y1.a; acc.b += y1.b; acc.c += y1.c; acc.d += y1.d;
+      }
+      if (i < n) {
+        const V4 x0 = load_plv(items[grp.item_off + base + i].src, p);
+        const V4 y0 = matvec(sM[i], x0);
+        acc.a += y0.a; acc.b += y0.b; acc.c += y0.c; acc.d += y0.d;
+      }
+    }
+    __syncthreads();
+  }
+  if (live) st256(grp.dest + 4 * p, acc);
+}
+
+// ---- Multiply: dest = s1 o s2, count = c1 + c2, per-PLV max for the rescale decision ----
+__global__ void __launch_bounds__(kTile)
+    k_multiply(DeviceState st, const MultOp* __restrict__ ops, int tiles,
+               unsigned long long* __restrict__ level_max) {
+  const int o = blockIdx.x / tiles;
+  const int tile = blockIdx.x - o * tiles;
+  const MultOp op = ops[o];
+  const int64_t p = static_cast<int64_t>(tile) * kTile + threadIdx.x;
+  double mx = 0.;
+  if (p < st.P) {
+    const V4 x = load_plv(op.s1, p);
+    const V4 y = load_plv(op.s2, p);
+    V4 v = {x.a * y.a, x.b * y.b, x.c * y.c, x.d * y.d};
+    st256(op.dest + 4 * p, v);
+    const double hi = fmax(fmax(v.a, v.b), fmax(v.c, v.d));
+    const double lo = fmin(fmin(v.a, v.b), fmin(v.c, v.d));
+    // AssertPLVIsFinite (:575-577), non-negativity (:585-586). fmax/fmin drop NaNs, so
+    // test the sum as well.
+    if (!isfinite(v.a + v.b + v.c + v.d)) atomicOr(st.status, kErrMultiplyNotFinite);
+    else if (lo < 0.) atomicOr(st.status, kErrNegativePLV);
+    mx = hi > 0. ? hi : 0.;
+  }
+  mx = block_reduce(mx, MaxOp(), 0.);
+  if (threadIdx.x == 0) {
+    // Non-negative doubles order like their bit patterns.
+    if (mx > 0.) atomicMax(level_max + op.max_slot, static_cast<unsigned long long>(__double_as_longlong(mx)));
+    if (tile == 0) st.counts[op.dest_id] = st.counts[op.s1.id] + st.counts[op.s2.id];
+  }
+}
+
+// RescalePLVIfNeeded + RescalePLV (gp_engine.cpp:564-573, 583-597). The maximum is over
+// the whole PLV (all patterns, all ranks); almost always a no-op.
+__global__ void __launch_bounds__(kTile)
+    k_rescale(DeviceState st, const MultOp* __restrict__ ops, int tiles,
+              const double* __restrict__ level_max) {
+  const int o = blockIdx.x / tiles;
+  const int tile = blockIdx.x - o * tiles;
+  const MultOp op = ops[o];
+  double max_entry = level_max[op.max_slot];
+  if (max_entry == 0.) return;
+  int rescaling_count = 0;
+  while (max_entry < st.thr) {
+    max_entry /= st.thr;
+    rescaling_count++;
+  }
+  if (rescaling_count == 0) return;
+  const double divisor = pow(st.thr, static_cast<double>(rescaling_count));
+  const int64_t p = static_cast<int64_t>(tile) * kTile + threadIdx.x;
+  if (p < st.P) {
+    V4 v = ld256(op.dest + 4 * p);
+    v.a /= divisor; v.b /= divisor; v.c /= divisor; v.d /= divisor;
+    st256(op.dest + 4 * p, v);
+  }
+  // Every block of this op has read level_max before any could reach here only through
+  // its own copy; counts[dest] is written by one thread and read by none in this launch.
+  if (tile == 0 && threadIdx.x == 0) st.counts[op.dest_id] += rescaling_count;
+}
+
+// ---- Likelihood: row[p] = log(parent^T M(t_e) child) + (count_p + count_c) log thr -------
+// (gp_engine.cpp:287-291, gp_engine.hpp:273-282); also the weighted tile partial of the row.
+__global__ void __launch_bounds__(kTile)
+    k_likelihood(DeviceState st, const LikOp* __restrict__ ops, int tiles,
+                 double* __restrict__ partials) {
+  const int o = blockIdx.x / tiles;
+  const int tile = blockIdx.x - o * tiles;
+  const LikOp op = ops[o];
+  __shared__ double sM[16];
+  if (threadIdx.x == 0) build_matrix(st.bl[op.edge], 0, 1., sM);
+  __syncthreads();
+  const double resc =
+      static_cast<double>(st.counts[op.parent.id]) * st.log_thr +
+      static_cast<double>(st.counts[op.child.id]) * st.log_thr;
+  const int64_t p = static_cast<int64_t>(tile) * kTile + threadIdx.x;
+  double wsum = 0.;
+  if (p < st.P) {
+    const V4 r = load_plv(op.parent, p);
+    const V4 c = load_plv(op.child, p);
+    const double ll = log(quad(r, sM, c)) + resc;
+    if (op.row != nullptr) op.row[p] = ll;
+    wsum = ll * st.weights[p];
+  }
+  wsum = block_reduce(wsum, SumOp(), 0.);
+  if (threadIdx.x == 0) partials[static_cast<int64_t>(o) * tiles + tile] = wsum;
+}
+
+// ---- [ResetMarginalLikelihood] IncrementMarginalLikelihood x n (gp_engine.cpp:251-276) ----
+// One launch handles the whole group in op order, so the per-pattern LogAdd chain is the
+// reference's. partials: rows 0..n-1 = per-rootsplit conditional rows, row n = marginal.
+__global__ void __launch_bounds__(kTile)
+    k_marginal(DeviceState st, const MargItem* __restrict__ items, int n_items, int reset,
+               int tiles, double* __restrict__ partials) {
+  const int tile = blockIdx.x;
+  const int64_t p = static_cast<int64_t>(tile) * kTile + threadIdx.x;
+  const bool live = p < st.P;
+  double lm = -INFINITY;
+  double w = 0.;
+  if (live) {
+    w = st.weights[p];
+    if (!reset) lm = st.log_marg[p];
+  }
+  for (int i = 0; i < n_items; ++i) {
+    const MargItem it = items[i];
+    if (threadIdx.x == 0 && tile == 0 && st.counts[it.stationary.id] != 0)
+      atomicOr(st.status, kErrRescaledStationary);
+    const double resc = static_cast<double>(st.counts[it.p.id]) * st.log_thr;
+    const double log_q = log(st.q[it.edge]);
+    double wsum = 0.;
+    if (live) {
+      const V4 s = load_plv(it.stationary, p);
+      const V4 x = load_plv(it.p, p);
+      double row = log(s.a * x.a + s.b * x.b + s.c * x.c + s.d * x.d) + resc;
+      lm = log_add(lm, row);
+      row -= log_q;
+      if (it.row != nullptr) it.row[p] = row;
+      wsum = row * w;
+    }
+    wsum = block_reduce(wsum, SumOp(), 0.);
+    if (threadIdx.x == 0) partials[static_cast<int64_t>(i) * tiles + tile] = wsum;
+  }
+  double msum = 0.;
+  if (live) {
+    st.log_marg[p] = lm;
+    msum = lm * w;
+  }
+  msum = block_reduce(msum, SumOp(), 0.);
+  if (threadIdx.x == 0) partials[static_cast<int64_t>(n_items) * tiles + tile] = msum;
+}
+
+// ---- SetToStationaryDistribution (gp_engine.cpp:218-227) ---------------------------------
+__global__ void __launch_bounds__(kTile)
+    k_stationary(DeviceState st, const StatOp* __restrict__ ops, int tiles) {
+  const int o = blockIdx.x / tiles;
+  const int tile = blockIdx.x - o * tiles;
+  const StatOp op = ops[o];
+  const double qv = st.q[op.edge];
+  const int64_t p = static_cast<int64_t>(tile) * kTile + threadIdx.x;
+  if (p < st.P) {
+    V4 v = {qv * c_model.pi[0], qv * c_model.pi[1], qv * c_model.pi[2], qv * c_model.pi[3]};
+    st256(op.dest + 4 * p, v);
+  }
+  if (tile == 0 && threadIdx.x == 0) st.counts[op.dest_id] = 0;
+}
+
+// ---- ZeroPLV that could not be folded (gp_engine.cpp:213-216) -----------------------------
+__global__ void __launch_bounds__(kTile)
+    k_zero(DeviceState st, const ZeroOp* __restrict__ ops, int tiles) {
+  const int o = blockIdx.x / tiles;
+  const int tile = blockIdx.x - o * tiles;
+  const ZeroOp op = ops[o];
+  const int64_t p = static_cast<int64_t>(tile) * kTile + threadIdx.x;
+  if (p < st.P) {
+    V4 v = {0., 0., 0., 0.};
+    st256(op.dest + 4 * p, v);
+  }
+  if (tile == 0 && threadIdx.x == 0) st.counts[op.dest_id] = 0;
+}
+
+// ---- scalar-only ops: count resets, stand-alone Prep, UpdateSBNProbabilities -------------
+__global__ void k_scalar(DeviceState st, const ScalarOp* __restrict__ ops,
+                         const int32_t* __restrict__ pool, int n_ops) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n_ops) return;
+  const ScalarOp op = ops[o];
+  if (op.kind == kScalarCountZero) {
+    st.counts[op.a] = 0;
+  } else if (op.kind == kScalarPrep) {  // gp_engine.cpp:323-333
+    if (op.vec_len <= 0) {
+      atomicOr(st.status, kErrEmptyPrep);
+      return;
+    }
+    int c = INT_MAX;
+    for (int i = 0; i < op.vec_len; ++i) c = min(c, st.counts[pool[op.vec_off + i]]);
+    st.counts[op.a] = c;
+  } else if (op.kind == kScalarSbn) {  // gp_engine.cpp:297-321
+    const int start = op.a, stop = op.b;
+    if (stop - start == 1) {
+      st.q[start] = 1.;
+      return;
+    }
+    double hybrid_min = INFINITY;
+    for (int e = start; e < stop; ++e) hybrid_min = fmin(hybrid_min, st.hybrid[e]);
+    const double* ll = hybrid_min > -INFINITY ? st.hybrid : st.ll_sum;
+    // NumericalUtils::LogSum is a left fold of LogAdd (numerical_utils.cpp:8).
+    double norm = ll[start] + log(st.q[start]);
+    for (int e = start + 1; e < stop; ++e) norm = log_add(norm, ll[e] + log(st.q[e]));
+    for (int e = start; e < stop; ++e) st.q[e] = exp((ll[e] + log(st.q[e])) - norm);
+  }
+}
+
+// ---- deterministic second stage of every reduction ------------------------------------------
+__global__ void k_reduce_partials(const double* __restrict__ partials, int n_out, int64_t tiles,
+                                  double* __restrict__ out, const int32_t* __restrict__ scatter_idx,
+                                  double* __restrict__ scatter_dst) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= n_out) return;
+  const double* row = partials + static_cast<int64_t>(warp) * tiles;
+  double v = 0.;
+  for (int64_t t = lane; t < tiles; t += 32) v += row[t];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if (lane == 0) {
+    out[warp] = v;
+    if (scatter_idx != nullptr && scatter_idx[warp] >= 0) scatter_dst[scatter_idx[warp]] = v;
+  }
+}
+
+__global__ void k_scatter(const double* __restrict__ packed, int n,
+                          const int32_t* __restrict__ scatter_idx, double* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && scatter_idx[i] >= 0) dst[scatter_idx[i]] = packed[i];
+}
+
+// ---- OptimizeBranchLength ----------------------------------------------------------------------
+// The objective of one edge is l(t) = sum_p w_p log(r_p^T V diag(e^{lambda t}) V^-1 p_p) + const.
+// Its PLVs do not change during the 1-D search, so the pass below reads them ONCE (64 B per
+// pattern) and keeps, per pattern, one coefficient per distinct eigenvalue:
+//   coef[p][g] = sum_{k in g} (V^T r_p)_k (V^-1 p_p)_k,   L_p(t) = sum_g coef[p][g] e^{lambda_g t}
+// (2 doubles per pattern for JC69). Every later evaluation of l, l', l'' streams only those.
+
+enum OptPhase : int32_t {
+  kPhBrentInit = 0,
+  kPhBrentU = 1,
+  kPhBrentGradGx = 2,
+  kPhBrentGradU2 = 3,
+  kPhGradientAscent = 4,
+  kPhLogSpaceGradientAscent = 5,
+  kPhNewton = 6
+};
+
+__device__ void opt_request(OptState& s, double x, bool log_space) {
+  s.x_eval = x;
+  s.t_eval = log_space ? exp(x) : x;
+  s.evals++;
+}
+
+// dag_branch_handler.cpp:123-146 (+ the first objective request of :150-280).
+__device__ void opt_init(OptState& s, const DeviceState& st, const OptParams& prm, int method,
+                         const OptOp& op) {
+  s.method = method;
+  s.edge = op.edge;
+  s.done = 0;
+  s.evals = 0;
+  s.iter = 0;
+  s.ll_offset = (static_cast<double>(st.counts[op.parent.id]) * st.log_thr +
+                 static_cast<double>(st.counts[op.child.id]) * st.log_thr) *
+                st.total_weight;
+  if (prm.check_convergence && st.diff[op.edge] < prm.diff_threshold) {
+    s.done = 1;
+    return;
+  }
+  const double bl = st.bl[op.edge];
+  switch (method) {
+    case 0:  // BrentOptimization
+    case 1:  // BrentOptimizationWithGradients
+      s.cur_x = log(bl);
+      s.phase = kPhBrentInit;
+      opt_request(s, s.cur_x, true);
+      break;
+    case 2:  // GradientAscentOptimization
+      s.cur_x = bl;
+      s.x = bl;
+      s.phase = kPhGradientAscent;
+      opt_request(s, s.x, false);
+      break;
+    case 3:  // LogSpaceGradientAscentOptimization
+      s.cur_x = bl;
+      s.x = bl;
+      s.phase = kPhLogSpaceGradientAscent;
+      opt_request(s, s.x, false);
+      break;
+    default:  // NewtonOptimization
+      s.cur_x = bl;
+      s.x = log(bl);
+      s.phase = kPhNewton;
+      opt_request(s, s.x, true);
+      break;
+  }
+}
+
+__device__ void opt_finish_brent(OptState& s, const DeviceState& st) {
+  // dag_branch_handler.cpp:168-176: keep the old value if the search made things worse.
+  const double old_bl = exp(s.cur_x);
+  const double new_bl = (s.fx > s.cur_f) ? old_bl : exp(s.x);
+  st.bl[s.edge] = new_bl;
+  st.diff[s.edge] = fabs(old_bl - new_bl);
+  s.done = 1;
+}
+
+// Top of the do-while body of BrentMinimize up to the objective call (optimization.hpp:95-148).
+__device__ void brent_next(OptState& s, const DeviceState& st, const OptParams& prm) {
+  const double tolerance = ldexp(1.0, 1 - prm.significant_digits);
+  const double golden = 0.3819660f;
+  const double mid = (s.min + s.max) / 2;
+  const double fract1 = tolerance * fabs(s.x) + tolerance / 4;
+  const double fract2 = 2 * fract1;
+  if (fabs(s.x - mid) <= (fract2 - (s.max - s.min) / 2)) {
+    opt_finish_brent(s, st);
+    return;
+  }
+  bool use_bisection = true;
+  if (fabs(s.delta2) > fract1) {
+    double r = (s.x - s.w) * (s.fx - s.fv);
+    double q = (s.x - s.v) * (s.fx - s.fw);
+    double p = (s.x - s.v) * q - (s.x - s.w) * r;
+    q = 2 * (q - r);
+    if (q > 0) p = -p;
+    q = fabs(q);
+    const double td = s.delta2;
+    s.delta2 = s.delta;
+    if (((fabs(p) >= fabs(q * td / 2)) == false) && ((p <= q * (s.min - s.x)) == false) &&
+        ((p >= q * (s.max - s.x)) == false)) {
+      s.delta = p / q;
+      s.u = s.x + s.delta;
+      if (((s.u - s.min) < fract2) || ((s.max - s.u) < fract2)) {
+        s.delta = (mid - s.x) < 0 ? -fabs(fract1) : fabs(fract1);
+      }
+      use_bisection = false;
+    }
+  }
+  if (use_bisection) {
+    s.delta2 = (s.x >= mid) ? s.min - s.x : s.max - s.x;
+    s.delta = golden * s.delta2;
+  }
+  s.u = (fabs(s.delta) >= fract1) ? (s.x + s.delta)
+                                  : (s.delta > 0 ? (s.x + fabs(fract1)) : (s.x - fabs(fract1)));
+  s.phase = kPhBrentU;
+  opt_request(s, s.u, true);
+}
+
+__device__ void brent_accept(OptState& s, double u, double fu) {  // optimization.hpp:150-163
+  if (u >= s.x) s.min = s.x; else s.max = s.x;
+  s.v = s.w; s.w = s.x; s.x = u;
+  s.fv = s.fw; s.fw = s.fx; s.fx = fu;
+}
+__device__ void brent_reject(OptState& s, double u, double fu) {  // optimization.hpp:164-182
+  if (u < s.x) s.min = u; else s.max = u;
+  if ((fu <= s.fw) || (s.w == s.x)) {
+    s.v = s.w; s.w = u;
+    s.fv = s.fw; s.fw = fu;
+  } else if ((fu <= s.fv) || (s.v == s.x) || (s.v == s.w)) {
+    s.v = u;
+    s.fv = fu;
+  }
+}
+__device__ void brent_loop_end(OptState& s, const DeviceState& st, const OptParams& prm) {
+  if (--s.count) brent_next(s, st, prm); else opt_finish_brent(s, st);
+}
+
+// Consumes one objective evaluation (ll, dll/dt, d2ll/dt2 at t_eval) and advances the
+// optimiser to its next request or to completion. Decision-for-decision restatement of
+// optimization.hpp:71-402 driven as dag_branch_handler.cpp:150-280 drives it.
+__device__ void opt_advance(OptState& s, const DeviceState& st, const OptParams& prm, double ll,
+                            double d1, double d2) {
+  switch (s.phase) {
+    case kPhBrentInit: {
+      const double f = -ll;
+      s.cur_f = f;
+      s.w = s.v = s.x = s.cur_x;
+      s.fw = s.fv = s.fx = f;
+      s.delta2 = s.delta = 0;
+      s.min = prm.min_log_bl;
+      s.max = prm.max_log_bl;
+      s.count = prm.max_iter;
+      s.evals++;  // the reference evaluates the starting point twice (:161-162 and :89)
+      brent_next(s, st, prm);
+      break;
+    }
+    case kPhBrentU: {
+      s.fu = -ll;
+      if (s.fu <= s.fx) {
+        brent_accept(s, s.u, s.fu);
+        brent_loop_end(s, st, prm);
+      } else if (s.method == 1) {
+        // BrentMinimizeWithGradients: try a gradient step from x first (:286-289).
+        s.phase = kPhBrentGradGx;
+        opt_request(s, s.x, true);
+      } else {
+        brent_reject(s, s.u, s.fu);
+        brent_loop_end(s, st, prm);
+      }
+      break;
+    }
+    case kPhBrentGradGx: {
+      // brent_grad_func returns (-ll, -t * dll/dt), gp_engine.cpp:613-622.
+      const double f_prime_x = -s.t_eval * d1;
+      s.u_alt = s.x - prm.log_step_size * f_prime_x;
+      s.phase = kPhBrentGradU2;
+      opt_request(s, s.u_alt, true);
+      break;
+    }
+    case kPhBrentGradU2: {
+      const double fu_alt = -ll;
+      if (fu_alt <= s.fx) brent_accept(s, s.u_alt, fu_alt); else brent_reject(s, s.u, s.fu);
+      brent_loop_end(s, st, prm);
+      break;
+    }
+    case kPhGradientAscent: {  // optimization.hpp:331-345 (min_x is the LOG bound, as there)
+      const double tolerance = pow(10., static_cast<double>(-prm.significant_digits));
+      const double new_x = s.x + d1 * prm.step_size;
+      s.x = fmax(new_x, prm.min_log_bl);
+      if (fabs(d1) < fabs(ll) * tolerance || s.iter >= prm.max_iter) {
+        st.bl[s.edge] = s.x;
+        st.diff[s.edge] = fabs(s.cur_x - s.x);
+        s.done = 1;
+      } else {
+        ++s.iter;
+        opt_request(s, s.x, false);
+      }
+      break;
+    }
+    case kPhLogSpaceGradientAscent: {  // optimization.hpp:347-365
+      const double tolerance = pow(10., static_cast<double>(-prm.significant_digits));
+      const double y = log(s.x);
+      const double log_space_grad = s.x * d1;
+      const double new_x = exp(y + log_space_grad * prm.log_step_size);
+      s.x = fmax(new_x, exp(prm.min_log_bl));
+      if (fabs(d1) < fabs(ll) * tolerance || s.iter >= prm.max_iter) {
+        st.bl[s.edge] = s.x;
+        st.diff[s.edge] = fabs(s.cur_x - s.x);
+        s.done = 1;
+      } else {
+        ++s.iter;
+        opt_request(s, s.x, false);
+      }
+      break;
+    }
+    default: {  // Newton, optimization.hpp:367-402 on gp_engine.cpp:641-653
+      const double tolerance = pow(10., static_cast<double>(-prm.significant_digits));
+      const double t = s.t_eval;
+      const double f_prime_y = t * d1;
+      const double f_double_prime_y = f_prime_y + (t * t) * d2;
+      bool stop = fabs(f_double_prime_y) < prm.denominator_tolerance;
+      double new_x = s.x;
+      if (!stop) {
+        new_x = s.x - f_prime_y / f_double_prime_y;
+        if (new_x < prm.min_log_bl) new_x = s.x - 0.5 * (s.x - prm.min_log_bl);
+        if (new_x > prm.max_log_bl) new_x = s.x - 0.5 * (s.x - prm.max_log_bl);
+        const double delta = fabs(s.x - new_x);
+        stop = delta < tolerance || fabs(f_prime_y) < fabs(ll) * tolerance ||
+               s.iter == prm.max_iter;
+      }
+      if (stop) {
+        const double new_bl = exp(s.x);
+        st.bl[s.edge] = new_bl;
+        st.diff[s.edge] = fabs(s.cur_x - new_bl);
+        s.done = 1;
+      } else {
+        s.x = new_x;
+        ++s.iter;
+        opt_request(s, s.x, true);
+      }
+      break;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kTile)
+    k_opt_prepare(DeviceState st, const OptOp* __restrict__ ops, int tiles,
+                  OptState* __restrict__ states, OptParams prm, int method,
+                  double* __restrict__ coef, int init_states) {
+  const int o = blockIdx.x / tiles;
+  const int tile = blockIdx.x - o * tiles;
+  const OptOp op = ops[o];
+  if (init_states && tile == 0 && threadIdx.x == 0) {
+    OptState s;
+    opt_init(s, st, prm, method, op);
+    states[o] = s;
+  }
+  const int64_t p = static_cast<int64_t>(tile) * kTile + threadIdx.x;
+  if (p >= st.P) return;
+  const V4 r = load_plv(op.parent, p);
+  const V4 c = load_plv(op.child, p);
+  const int G = c_model.n_groups;
+  double cg[kMaxEigenGroups] = {0., 0., 0., 0.};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const double rv = r.a * c_model.V[k] + r.b * c_model.V[4 + k] + r.c * c_model.V[8 + k] +
+                      r.d * c_model.V[12 + k];
+    const double vp = c_model.Vinv[4 * k] * c.a + c_model.Vinv[4 * k + 1] * c.b +
+                      c_model.Vinv[4 * k + 2] * c.c + c_model.Vinv[4 * k + 3] * c.d;
+    const double term = rv * vp;
+    const int g = c_model.group[k];
+#pragma unroll
+    for (int gg = 0; gg < kMaxEigenGroups; ++gg)
+      if (gg == g) cg[gg] += term;
+  }
+  double* dst = coef + (static_cast<int64_t>(o) * st.P_stride + p) * G;
+  for (int g = 0; g < G; ++g) dst[g] = cg[g];
+}
+
+template <int G>
+__global__ void __launch_bounds__(kTile)
+    k_opt_eval(DeviceState st, int tiles, const OptState* __restrict__ states,
+               const double* __restrict__ coef, int n_derivatives,
+               double* __restrict__ partials) {
+  const int o = blockIdx.x / tiles;
+  const int tile = blockIdx.x - o * tiles;
+  if (states[o].done) return;  // sums of finished edges are never read
+  const double t = states[o].t_eval;
+  double e[G], e1[G], e2[G];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const double l = c_model.group_lambda[g];
+    e[g] = exp(l * t);
+    e1[g] = l * e[g];
+    e2[g] = l * l * e[g];
+  }
+  const int64_t p = static_cast<int64_t>(tile) * kTile + threadIdx.x;
+  double f = 0., g1 = 0., g2 = 0.;
+  if (p < st.P) {
+    const double* c = coef + (static_cast<int64_t>(o) * st.P_stride + p) * G;
+    double cg[G];
+    if (G == 2) {
+      const double2 v = *reinterpret_cast<const double2*>(c);
+      cg[0] = v.x;
+      cg[1] = v.y;
+    } else {
+#pragma unroll
+      for (int g = 0; g < G; ++g) cg[g] = c[g];
+    }
+    double L = 0., L1 = 0., L2 = 0.;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      L += cg[g] * e[g];
+      L1 += cg[g] * e1[g];
+      L2 += cg[g] * e2[g];
+    }
+    const double w = st.weights[p];
+    f = log(L) * w;
+    if (n_derivatives >= 1) g1 = (L1 / L) * w;                       // gp_engine.cpp:493-496
+    if (n_derivatives >= 2) g2 = ((L2 * L - L1 * L1) / (L * L)) * w;  // gp_engine.cpp:530-538
+  }
+  const int64_t base = static_cast<int64_t>(o) * 3 * tiles + tile;
+  f = block_reduce(f, SumOp(), 0.);
+  if (threadIdx.x == 0) partials[base] = f;
+  if (n_derivatives >= 1) {
+    g1 = block_reduce(g1, SumOp(), 0.);
+    if (threadIdx.x == 0) partials[base + tiles] = g1;
+  }
+  if (n_derivatives >= 2) {
+    g2 = block_reduce(g2, SumOp(), 0.);
+    if (threadIdx.x == 0) partials[base + 2 * tiles] = g2;
+  }
+}
+
+__global__ void k_opt_step(DeviceState st, int n_ops, OptState* __restrict__ states, OptParams prm,
+                           const double* __restrict__ sums, int32_t* __restrict__ active_counter) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n_ops) return;
+  OptState s = states[o];
+  if (s.done) return;
+  opt_advance(s, st, prm, sums[3 * o] + s.ll_offset, sums[3 * o + 1], sums[3 * o + 2]);
+  states[o] = s;
+  if (s.done) atomicAdd(st.feval_total, static_cast<unsigned long long>(s.evals));
+  if (!s.done && active_counter != nullptr) atomicAdd(active_counter, 1);
+}
+
+// ---- utilities ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTile)
+    k_export_plv(DeviceState st, PlvRef src, double* __restrict__ out) {
+  const int64_t p = static_cast<int64_t>(blockIdx.x) * kTile + threadIdx.x;
+  if (p < st.P) st256(out + 4 * p, load_plv(src, p));
+}
+
+__global__ void k_fill(double* __restrict__ dst, int64_t n, double value) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = value;
+}
+
+__global__ void k_transition_matrix(double t, double* out16) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) build_matrix(t, 0, 1., out16);
+}
+
+__global__ void __launch_bounds__(kTile)
+    k_weighted_sum(DeviceState st, const double* __restrict__ values, double* __restrict__ partials) {
+  const int64_t p = static_cast<int64_t>(blockIdx.x) * kTile + threadIdx.x;
+  double v = p < st.P ? values[p] * st.weights[p] : 0.;
+  v = block_reduce(v, SumOp(), 0.);
+  if (threadIdx.x == 0) partials[blockIdx.x] = v;
+}
+
+inline unsigned Grid(int64_t n_ops, int64_t tiles) { return static_cast<unsigned>(n_ops * tiles); }
+
+}  // namespace
+
+void LaunchAccum(cudaStream_t s, const DeviceState& st, const AccumGroup* groups,
+                 const AccumItem* items, const int32_t* pool, int n_groups) {
+  if (n_groups == 0) return;
+  const int tiles = static_cast<int>(TilesFor(st.P));
+  k_accum<<<Grid(n_groups, tiles), kTile, 0, s>>>(st, groups, items, pool, tiles);
+}
+void LaunchMultiply(cudaStream_t s, const DeviceState& st, const MultOp* ops, int n_ops,
+                    double* level_max) {
+  if (n_ops == 0) return;
+  const int tiles = static_cast<int>(TilesFor(st.P));
+  k_multiply<<<Grid(n_ops, tiles), kTile, 0, s>>>(
+      st, ops, tiles, reinterpret_cast<unsigned long long*>(level_max));
+}
+void LaunchRescale(cudaStream_t s, const DeviceState& st, const MultOp* ops, int n_ops,
+                   const double* level_max) {
+  if (n_ops == 0) return;
+  const int tiles = static_cast<int>(TilesFor(st.P));
+  k_rescale<<<Grid(n_ops, tiles), kTile, 0, s>>>(st, ops, tiles, level_max);
+}
+void LaunchLikelihood(cudaStream_t s, const DeviceState& st, const LikOp* ops, int n_ops,
+                      double* partials) {
+  if (n_ops == 0) return;
+  const int tiles = static_cast<int>(TilesFor(st.P));
+  k_likelihood<<<Grid(n_ops, tiles), kTile, 0, s>>>(st, ops, tiles, partials);
+}
+void LaunchMarginal(cudaStream_t s, const DeviceState& st, const MargItem* items, int n_items,
+                    int reset, double* partials) {
+  const int tiles = static_cast<int>(TilesFor(st.P));
+  k_marginal<<<tiles, kTile, 0, s>>>(st, items, n_items, reset, tiles, partials);
+}
+void LaunchStationary(cudaStream_t s, const DeviceState& st, const StatOp* ops, int n_ops) {
+  if (n_ops == 0) return;
+  const int tiles = static_cast<int>(TilesFor(st.P));
+  k_stationary<<<Grid(n_ops, tiles), kTile, 0, s>>>(st, ops, tiles);
+}
+void LaunchZero(cudaStream_t s, const DeviceState& st, const ZeroOp* ops, int n_ops) {
+  if (n_ops == 0) return;
+  const int tiles = static_cast<int>(TilesFor(st.P));
+  k_zero<<<Grid(n_ops, tiles), kTile, 0, s>>>(st, ops, tiles);
+}
+void LaunchScalar(cudaStream_t s, const DeviceState& st, const ScalarOp* ops,
+                  const int32_t* pool, int n_ops) {
+  if (n_ops == 0) return;
+  k_scalar<<<(n_ops + 63) / 64, 64, 0, s>>>(st, ops, pool, n_ops);
+}
+void LaunchReducePartials(cudaStream_t s, const double* partials, int n_out, int64_t tiles,
+                          double* out, const int32_t* scatter_idx, double* scatter_dst) {
+  if (n_out == 0) return;
+  const int warps_per_block = 8;
+  k_reduce_partials<<<(n_out + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0,
+                      s>>>(partials, n_out, tiles, out, scatter_idx, scatter_dst);
+}
+void LaunchScatter(cudaStream_t s, const double* packed, int n, const int32_t* scatter_idx,
+                   double* scatter_dst) {
+  if (n == 0) return;
+  k_scatter<<<(n + 127) / 128, 128, 0, s>>>(packed, n, scatter_idx, scatter_dst);
+}
+
+void LaunchOptPrepare(cudaStream_t s, const DeviceState& st, const OptOp* ops, int n_ops,
+                      OptState* states, const OptParams& params, int method, double* coef,
+                      int init_states) {
+  if (n_ops == 0) return;
+  const int tiles = static_cast<int>(TilesFor(st.P));
+  k_opt_prepare<<<Grid(n_ops, tiles), kTile, 0, s>>>(st, ops, tiles, states, params, method, coef,
+                                                     init_states);
+}
+void LaunchOptEval(cudaStream_t s, const DeviceState& st, int n_ops, const OptState* states,
+                   const double* coef, int n_derivatives, double* partials, int n_groups) {
+  if (n_ops == 0) return;
+  const int tiles = static_cast<int>(TilesFor(st.P));
+  const unsigned grid = Grid(n_ops, tiles);
+  switch (n_groups) {
+    case 1: k_opt_eval<1><<<grid, kTile, 0, s>>>(st, tiles, states, coef, n_derivatives, partials); break;
+    case 2: k_opt_eval<2><<<grid, kTile, 0, s>>>(st, tiles, states, coef, n_derivatives, partials); break;
+    case 3: k_opt_eval<3><<<grid, kTile, 0, s>>>(st, tiles, states, coef, n_derivatives, partials); break;
+    default: k_opt_eval<4><<<grid, kTile, 0, s>>>(st, tiles, states, coef, n_derivatives, partials); break;
+  }
+}
+void LaunchOptStep(cudaStream_t s, const DeviceState& st, int n_ops, OptState* states,
+                   const OptParams& params, const double* sums, int32_t* active_counter) {
+  if (n_ops == 0) return;
+  k_opt_step<<<(n_ops + 63) / 64, 64, 0, s>>>(st, n_ops, states, params, sums, active_counter);
+}
+
+void LaunchExportPlv(cudaStream_t s, const DeviceState& st, PlvRef src, double* dense_out) {
+  k_export_plv<<<static_cast<unsigned>(TilesFor(st.P)), kTile, 0, s>>>(st, src, dense_out);
+}
+void LaunchFill(cudaStream_t s, double* dst, int64_t n, double value) {
+  if (n == 0) return;
+  k_fill<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(dst, n, value);
+}
+void LaunchTransitionMatrix(cudaStream_t s, double t, double* out16) {
+  k_transition_matrix<<<1, 32, 0, s>>>(t, out16);
+}
+void LaunchWeightedSum(cudaStream_t s, const DeviceState& st, const double* values,
+                       double* partials) {
+  k_weighted_sum<<<static_cast<unsigned>(TilesFor(st.P)), kTile, 0, s>>>(st, values, partials);
+}
+
+}  // namespace bito_gp

@@ -1,0 +1,54 @@
+// bito_b200/csrc/gp_kernels.h — launch wrappers of the sm_100a GP kernels (gp_kernels.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "gp_types.h"
+
+namespace bito_gp {
+
+// Number of pattern tiles for P local patterns.
+inline int64_t TilesFor(int64_t P) { return (P + kTile - 1) / kTile; }
+
+cudaError_t UploadModel(const ModelConst& model);
+
+void LaunchAccum(cudaStream_t s, const DeviceState& st, const AccumGroup* groups,
+                 const AccumItem* items, const int32_t* pool, int n_groups);
+void LaunchMultiply(cudaStream_t s, const DeviceState& st, const MultOp* ops, int n_ops,
+                    double* level_max);
+void LaunchRescale(cudaStream_t s, const DeviceState& st, const MultOp* ops, int n_ops,
+                   const double* level_max);
+void LaunchLikelihood(cudaStream_t s, const DeviceState& st, const LikOp* ops, int n_ops,
+                      double* partials);
+void LaunchMarginal(cudaStream_t s, const DeviceState& st, const MargItem* items, int n_items,
+                    int reset, double* partials /* (n_items + 1) x tiles */);
+void LaunchStationary(cudaStream_t s, const DeviceState& st, const StatOp* ops, int n_ops);
+void LaunchZero(cudaStream_t s, const DeviceState& st, const ZeroOp* ops, int n_ops);
+void LaunchScalar(cudaStream_t s, const DeviceState& st, const ScalarOp* ops,
+                  const int32_t* pool, int n_ops);
+// out[i] = sum_t partials[i * tiles + t] (fixed order); when scatter_idx != nullptr also
+// scatter_dst[scatter_idx[i]] = out[i] for scatter_idx[i] >= 0.
+void LaunchReducePartials(cudaStream_t s, const double* partials, int n_out, int64_t tiles,
+                          double* out, const int32_t* scatter_idx, double* scatter_dst);
+void LaunchScatter(cudaStream_t s, const double* packed, int n, const int32_t* scatter_idx,
+                   double* scatter_dst);
+
+// Branch-length optimisation.
+void LaunchOptPrepare(cudaStream_t s, const DeviceState& st, const OptOp* ops, int n_ops,
+                      OptState* states, const OptParams& params, int method, double* coef,
+                      int init_states);
+void LaunchOptEval(cudaStream_t s, const DeviceState& st, int n_ops, const OptState* states,
+                   const double* coef, int n_derivatives, double* partials /* n_ops*3 x tiles */,
+                   int n_groups);
+void LaunchOptStep(cudaStream_t s, const DeviceState& st, int n_ops, OptState* states,
+                   const OptParams& params, const double* sums /* n_ops*3 */,
+                   int32_t* active_counter);
+
+// Utilities.
+void LaunchExportPlv(cudaStream_t s, const DeviceState& st, PlvRef src, double* dense_out);
+void LaunchFill(cudaStream_t s, double* dst, int64_t n, double value);
+void LaunchTransitionMatrix(cudaStream_t s, double t, double* out16);
+void LaunchWeightedSum(cudaStream_t s, const DeviceState& st, const double* values,
+                       double* partials);
+
+}  // namespace bito_gp

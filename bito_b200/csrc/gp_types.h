@@ -1,0 +1,185 @@
+// bito_b200/csrc/gp_types.h — device-visible tables of the level-scheduled GP engine.
+//
+// The host scheduler (gp_engine.cu) compiles a GPOperationVector
+// (/root/reference/src/gp_operation.hpp:163-170) into dependency levels of fused
+// "macro-ops"; each level is executed by a handful of kernels (gp_kernels.cu) that read
+// the tables below. PLV operands are resolved to device pointers at compile time.
+#pragma once
+
+#include <cstdint>
+
+namespace bito_gp {
+
+constexpr int kTile = 256;          // patterns per thread block (one pattern per thread)
+constexpr int kItemChunk = 32;      // transition matrices staged in shared memory at a time
+constexpr int kMaxEigenGroups = 4;  // distinct eigenvalues of the substitution model
+
+// How a PLV operand is stored in HBM.
+enum PlvKind : int32_t {
+  kPlvDense = 0,    // pattern_stride x 4 doubles, 32 B per pattern
+  kPlvSymbols = 1,  // leaf P-PLV kept as one byte per pattern (0..3 one-hot, 4 = all ones)
+  kPlvZero = 2      // never written since the last ZeroPLV / construction: reads as 0
+};
+
+struct PlvRef {
+  const void* ptr;
+  int32_t kind;
+  int32_t id;  // logical PLV id (indexes rescaling counts)
+};
+
+// Device error bits; each mirrors an Assert/Failwith on the reference path.
+enum StatusBits : uint32_t {
+  kErrRescalingDifference = 1u,  // gp_engine.cpp:237-238
+  kErrMultiplyNotFinite = 2u,    // gp_engine.cpp:283, 575-577
+  kErrNegativePLV = 4u,          // gp_engine.cpp:585-586
+  kErrRescaledStationary = 8u,   // gp_engine.cpp:256-257
+  kErrEmptyPrep = 16u            // gp_engine.cpp:325
+};
+
+// Per-engine device pointers handed to every kernel by value.
+struct DeviceState {
+  int64_t P;         // local pattern count
+  int64_t P_stride;  // allocation stride in patterns (multiple of 8)
+  int32_t* counts;   // rescaling count per logical PLV id          (gp_engine.hpp:317)
+  double* q;         // SBN parameters per edge, linear space       (gp_engine.hpp:337)
+  double* bl;        // branch lengths per edge                     (dag_branch_handler.hpp:249)
+  double* diff;      // last branch-length change per edge          (dag_branch_handler.hpp:252)
+  double* hybrid;    // hybrid marginal log-likelihoods per edge    (gp_engine.hpp:352)
+  double* ll_sum;    // per-edge sum_p w_p * log_likelihoods_(e,p), GLOBAL over ranks
+  double* weights;   // site pattern weights (local shard)
+  double* log_marg;  // per-pattern log marginal (local shard)      (gp_engine.hpp:349)
+  double* marg_sum;  // [0] = sum_p w_p * log_marg[p], GLOBAL over ranks
+  uint32_t* status;  // StatusBits
+  double thr;        // rescaling threshold
+  double log_thr;
+  double total_weight;  // sum of ALL ranks' weights
+  unsigned long long* feval_total;  // objective evaluations of finished optimisations
+};
+
+// Substitution-model eigensystem (JC69 today: substitution_model.cpp:20-26) in constant
+// memory. `group` maps each eigenvalue to its distinct-eigenvalue group for the
+// branch-length objective: L_p(t) = sum_g coef[p][g] * exp(group_lambda[g] * t).
+struct ModelConst {
+  double V[16];     // eigenvectors, row-major
+  double Vinv[16];  // inverse eigenvectors, row-major
+  double lambda[4];
+  double pi[4];
+  int32_t group[4];
+  int32_t n_groups;
+  double group_lambda[kMaxEigenGroups];
+};
+
+// ---- macro-ops ---------------------------------------------------------------------
+enum CountMode : int32_t {
+  kCountKeep = 0,  // dest count unchanged
+  kCountZero = 1,  // a folded ZeroPLV: count[dest] = 0
+  kCountPrep = 2   // a folded PrepForMarginalization: count[dest] = min count[src_vector]
+};
+
+// [ZeroPLV] [PrepForMarginalization] IncrementWithWeightedEvolvedPLV x n into one dest
+// (gp_engine.cpp:213-216, 323-333, 229-249): dest is read at most once, written once.
+struct AccumGroup {
+  double* dest;
+  int32_t dest_id;
+  int32_t init_zero;
+  int32_t count_mode;
+  int32_t n_items;
+  int32_t item_off;
+  int32_t prep_off;
+  int32_t prep_len;
+  int32_t pad;
+};
+struct AccumItem {
+  PlvRef src;
+  int32_t edge;
+  int32_t pad;
+};
+
+// Multiply (gp_engine.cpp:278-285); max_slot indexes the level's per-PLV maxima.
+struct MultOp {
+  double* dest;
+  PlvRef s1, s2;
+  int32_t dest_id;
+  int32_t max_slot;
+};
+
+// Likelihood (gp_engine.cpp:287-291).
+struct LikOp {
+  PlvRef parent, child;
+  double* row;  // may be null with BITO_GP_FLAG_NO_LOGLIK_MATRIX
+  int32_t edge;
+  int32_t pad;
+};
+
+// [ResetMarginalLikelihood] IncrementMarginalLikelihood x n (gp_engine.cpp:251-276).
+struct MargItem {
+  PlvRef stationary, p;
+  double* row;
+  int32_t edge;
+  int32_t pad;
+};
+
+struct StatOp {  // SetToStationaryDistribution (gp_engine.cpp:218-227)
+  double* dest;
+  int32_t dest_id;
+  int32_t edge;
+};
+
+struct ZeroOp {  // a ZeroPLV that could not be folded away
+  double* dest;
+  int32_t dest_id;
+  int32_t pad;
+};
+
+enum ScalarKind : int32_t {
+  kScalarCountZero = 0,  // ZeroPLV of a PLV that owns no memory: count only
+  kScalarPrep = 1,       // stand-alone PrepForMarginalization
+  kScalarSbn = 2         // UpdateSBNProbabilities (gp_engine.cpp:304-321)
+};
+struct ScalarOp {
+  int32_t kind;
+  int32_t a, b;  // count-zero/prep: a = dest id; sbn: [a, b)
+  int32_t vec_off, vec_len;
+  int32_t pad;
+};
+
+// OptimizeBranchLength (gp_engine.cpp:293-295, 667-670; dag_branch_handler.cpp:123-280).
+struct OptOp {
+  PlvRef parent, child;  // rootward_ (r-PLV of the parent), leafward_ (p-PLV of the child)
+  int32_t edge;
+  int32_t pad;
+};
+
+// Resumable optimiser state, one per OptimizeBranchLength in flight. The decision logic
+// of optimization.hpp:71-402 is run one objective evaluation at a time (gp_kernels.cu,
+// opt_step): `phase` says which evaluation is pending.
+struct OptState {
+  // pending evaluation
+  double t_eval;    // branch length at which the objective is being evaluated
+  double x_eval;    // the optimiser's own coordinate (log t for Brent/Newton, t for GA)
+  int32_t phase;
+  int32_t done;
+  int32_t method;
+  int32_t edge;
+  double ll_offset;  // (count[parent] + count[child]) * log thr * total_weight
+  // Brent (names as in optimization.hpp:75-83)
+  double x, w, v, u, delta, delta2, fu, fv, fw, fx, min, max;
+  double cur_x, cur_f;  // starting point and its objective value
+  double u_alt;         // gradient-step candidate of BrentMinimizeWithGradients
+  int64_t count;        // remaining iterations
+  int64_t iter;
+  int32_t evals;
+  int32_t pad;
+};
+
+struct OptParams {
+  int32_t significant_digits;
+  int32_t check_convergence;  // !IsFirstOptimization()
+  int64_t max_iter;
+  double min_log_bl, max_log_bl;
+  double denominator_tolerance;
+  double step_size, log_step_size;
+  double diff_threshold;
+};
+
+}  // namespace bito_gp

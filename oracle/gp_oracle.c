@@ -59,6 +59,7 @@ struct gpo {
   double* scratch;  /* P */
   int method, sig_digits;
   int64_t opt_count, fevals;
+  int strict; /* 1: the reference's Asserts fire (Debug build); 0: NDEBUG/Release semantics */
 };
 
 static char g_err[512];
@@ -533,7 +534,8 @@ int gpo_run(gpo* g, const int64_t* ops, int64_t n, const int64_t* vec) {
         double M[4][4];
         transition(g->bl[b], M);
         const int diff = g->counts[c] - g->counts[a];
-        if (diff < 0) return fail("dest_ rescaling too large in IncrementWithWeightedEvolvedPLV");
+        if (diff < 0 && g->strict)
+          return fail("dest_ rescaling too large in IncrementWithWeightedEvolvedPLV");
         const double factor = diff == 0 ? 1. : pow(g->thr, (double)diff);
         const double scale = factor * g->q[b];
         double* dest = PLV(g, a);
@@ -560,8 +562,9 @@ int gpo_run(gpo* g, const int64_t* ops, int64_t n, const int64_t* vec) {
           if (v < mn) mn = v;
         }
         g->counts[a] = g->counts[b] + g->counts[c];
-        if (!finite) return fail("Multiply dest_ is not finite");
-        if (mn < 0.) return fail("PLV with negative entry passed to RescalePLVIfNeeded");
+        if (!finite && g->strict) return fail("Multiply dest_ is not finite");
+        if (mn < 0. && g->strict)
+          return fail("PLV with negative entry passed to RescalePLVIfNeeded");
         if (mx == 0) break;
         int k = 0;
         while (mx < g->thr) {
@@ -608,7 +611,7 @@ int gpo_run(gpo* g, const int64_t* ops, int64_t n, const int64_t* vec) {
         break;
       case 8: { /* IncrementMarginalLikelihood :255-276 (a=stationary*prior, b=rootsplit, c=p) */
         if (check_plv(g, a) || check_edge(g, b) || check_plv(g, c)) return 1;
-        if (g->counts[a] != 0)
+        if (g->counts[a] != 0 && g->strict)
           return fail("Surprise! Rescaled stationary distribution in IncrementMarginalLikelihood");
         const double *st = PLV(g, a), *pp = PLV(g, c);
         const double resc = log_rescaling_for(g, c), logq = log(g->q[b]);
@@ -701,3 +704,4 @@ void gpo_set_null_prior(gpo* g) {
   for (int64_t i = 0; i < g->padded_edge_count; ++i) g->q[i] = 1.0;
 }
 int64_t gpo_feval_count(const gpo* g) { return g->fevals; }
+void gpo_set_strict(gpo* g, int strict) { g->strict = strict; }

@@ -60,6 +60,9 @@ void gpo_loglik_and_derivatives(gpo* g, int64_t gpcsp, int64_t rootward, int64_t
 void gpo_transition_matrix(double t, double* out /* 4x4 row-major */);
 /* number of objective evaluations performed by OptimizeBranchLength ops so far */
 int64_t gpo_feval_count(const gpo* g);
+/* strict != 0: the reference's Assert()s (sugar.hpp:103-111) raise errors, as in a Debug build.
+ * Default 0 = the Release build (-DNDEBUG) the reference ships, where they compile away. */
+void gpo_set_strict(gpo* g, int strict);
 
 /* Scalar helpers, exported so tests can pin them against the reference's goldens. */
 double gpo_log_add(double x, double y);

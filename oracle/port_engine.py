@@ -71,6 +71,7 @@ def _load():
     lib.gpo_transition_matrix.argtypes = [f64, vp]
     lib.gpo_feval_count.restype = i64
     lib.gpo_feval_count.argtypes = [vp]
+    lib.gpo_set_strict.argtypes = [vp, i32]
     lib.gpo_log_add.restype = f64
     lib.gpo_log_add.argtypes = [f64, f64]
     _lib = lib
@@ -236,6 +237,9 @@ class PortEngine:
 
     def transition_matrix(self, t):
         return transition_matrix(t)
+
+    def set_strict(self, strict=True):
+        _load().gpo_set_strict(self._h, int(strict))
 
     def feval_count(self):
         return int(_load().gpo_feval_count(self._h))

@@ -1,0 +1,131 @@
+"""Shared helpers for the parity tests: load a golden fixture (tests/golden/*.npz, written by
+tests/golden/make_golden.py from the unmodified reference) and drive any engine — the CUDA
+GPEngine, the plain-C oracle port or the reference itself — through the same protocol."""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ALL_CASES = ["hello", "hello_single_nucleotide", "hello_two_trees", "five_taxon", "ds1_reduced_5",
+             "seven_taxon", "six_taxon", "fluA", "ds1", "ds1_config1"]
+SMALL_CASES = ALL_CASES[:7]
+
+# Tolerances from BASELINE.json north_star.
+LL_RTOL = 1e-9       # per-pattern and per-edge log-likelihoods, relative, FP64
+BL_ATOL = 1e-6       # optimised branch lengths
+
+
+class Fixture:
+    def __init__(self, name):
+        self.name = name
+        self.z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+
+    def __getitem__(self, key):
+        v = self.z[key]
+        return v.item() if v.shape == () else v
+
+    def ops(self, which):
+        return self.z["ops_" + which], self.z["vec_" + which]
+
+    @property
+    def thresholds(self):
+        return [float(t) for t in self.z["thresholds"]]
+
+    @property
+    def methods(self):
+        return [str(m) for m in self.z["methods"]]
+
+    def engine_args(self, ti=0):
+        return dict(symbols=self["symbols"], weights=self["weights"], site_count=int(self["site_count"]),
+                    node_count=int(self["node_count"]), edge_count=int(self["edge_count"]),
+                    q=self["sbn_prior"], unconditional=self["unconditional_node_probabilities"],
+                    inverted=self["inverted_sbn_prior"], rescaling_threshold=self.thresholds[ti])
+
+
+def make_port(fx: Fixture, ti=0, use_gradients=False):
+    from oracle.port_engine import PortEngine
+    a = fx.engine_args(ti)
+    e = PortEngine(a["symbols"], a["weights"], a["site_count"], a["node_count"], a["edge_count"], a["q"],
+                   a["unconditional"], a["inverted"], a["rescaling_threshold"], use_gradients)
+    e.set_branch_lengths(fx["initial_branch_lengths"])
+    return e
+
+
+def make_cuda(fx: Fixture, ti=0, use_gradients=False, flags=0, pattern_slice=None, device=0):
+    from bito_b200.gp_engine import GPEngine
+    a = fx.engine_args(ti)
+    sym, w = a["symbols"], a["weights"]
+    if pattern_slice is not None:
+        sym, w = sym[:, pattern_slice], w[pattern_slice]
+    e = GPEngine(sym, w, a["site_count"], a["node_count"], a["edge_count"], a["rescaling_threshold"],
+                 a["q"], a["unconditional"], a["inverted"], use_gradients, device=device, flags=flags)
+    e.set_branch_lengths(fx["initial_branch_lengths"])
+    return e
+
+
+def rel_err(got, want):
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    both_ninf = np.isneginf(got) & np.isneginf(want)
+    # log-likelihoods of all-gap patterns are log(1 +- 1ulp) ~ 1e-16: relative error is only
+    # meaningful against max(|want|, 1)
+    denom = np.maximum(np.abs(want), 1.0)
+    err = np.where(both_ninf, 0.0, np.abs(got - want) / denom)
+    return float(np.max(err)) if err.size else 0.0
+
+
+def check_pass(engine, fx: Fixture, ti=0, rtol=LL_RTOL):
+    """PopulatePLVs + ComputeLikelihoods against the reference outputs."""
+    key = f"t{ti}"
+    engine.process_operations(*fx.ops("populate_plvs"))
+    engine.process_operations(*fx.ops("compute_likelihoods"))
+    assert rel_err(engine.per_gpcsp_log_likelihoods(), fx[f"{key}_pass_per_gpcsp_ll"]) <= rtol
+    assert rel_err(engine.log_marginal_likelihood(), fx[f"{key}_pass_log_marginal"]) <= rtol
+    assert rel_err(engine.per_pattern_log_marginal(), fx[f"{key}_pass_per_pattern_marginal"]) <= rtol
+    rows = fx[f"{key}_pass_ll_rows"]
+    assert rel_err(engine.log_likelihood_matrix()[rows], fx[f"{key}_pass_ll_matrix"]) <= rtol
+    # rescaling counts: bit-exact
+    want_counts = fx[f"{key}_pass_counts"]
+    got_counts = engine.rescaling_counts()
+    assert np.array_equal(got_counts[:want_counts.size], want_counts)
+    for plv_id, want in zip(fx[f"{key}_pass_plv_ids"], fx[f"{key}_pass_plvs"]):
+        got = engine.get_plv(int(plv_id))
+        scale = max(float(np.max(np.abs(want))), 1e-300)
+        assert float(np.max(np.abs(got - want))) <= rtol * scale, f"PLV {plv_id}"
+    assert rel_err(engine.per_gpcsp_components_of_full_log_marginal(), fx[f"{key}_pass_components"]) <= rtol
+    for (g, rw, lw), want in zip(fx[f"{key}_deriv_triples"], fx[f"{key}_deriv_values"]):
+        got = engine.log_likelihood_and_derivatives(int(g), int(rw), int(lw), two=True)
+        assert rel_err(got[0], want[0]) <= rtol
+        assert abs(got[1] - want[1]) <= 1e-7 * max(1.0, abs(want[1]))
+        assert abs(got[2] - want[2]) <= 1e-7 * max(1.0, abs(want[2]))
+
+
+def check_sbn(engine, fx: Fixture, ti=0):
+    """UpdateSBNProbabilities straight after a pass (GPInstance::EstimateSBNParameters)."""
+    engine.process_operations(*fx.ops("optimize_sbn_parameters"))
+    want = fx[f"t{ti}_sbn_q"]
+    got = engine.sbn_parameters()
+    # q = exp(x - logsum) with |x| ~ 1e3..1e4: 1e-9 relative on the log-likelihoods is ~1e-5 on q
+    assert np.max(np.abs(got - want)) <= 1e-6
+
+
+def check_sweeps(engine, fx: Fixture, ti, method, atol=BL_ATOL):
+    """EstimateBranchLengths' loop (gp_instance.cpp:241-308), one reference method."""
+    key = f"t{ti}_sweep_{method}"
+    engine.set_optimization_method(method)
+    engine.reset_optimization_count()
+    engine.process_operations(*fx.ops("populate_plvs"))
+    engine.process_operations(*fx.ops("marginal_likelihood"))
+    want_bl, want_diff, want_marg = fx[key + "_bl"], fx[key + "_diff"], fx[key + "_log_marginal"]
+    for s in range(int(fx["sweeps"])):
+        engine.process_operations(*fx.ops("branch_length_optimization"))
+        engine.process_operations(*fx.ops("populate_plvs"))
+        engine.process_operations(*fx.ops("marginal_likelihood"))
+        assert np.max(np.abs(engine.branch_lengths() - want_bl[s])) <= atol, f"sweep {s}"
+        assert np.max(np.abs(engine.branch_length_differences() - want_diff[s])) <= atol, f"sweep {s}"
+        assert rel_err(engine.log_marginal_likelihood(), want_marg[s]) <= 1e-7, f"sweep {s}"
+        engine.increment_optimization_count()
+    want_counts = fx[key + "_counts"]
+    assert np.array_equal(engine.rescaling_counts()[:want_counts.size], want_counts)

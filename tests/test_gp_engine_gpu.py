@@ -1,0 +1,235 @@
+"""GPU parity tests: the CUDA GPEngine, driven through the C-ABI, against (a) golden outputs of
+the unmodified reference GPEngine (tests/golden/*.npz) and (b) the plain-C oracle on seeded
+synthetic inputs. Tolerances are BASELINE.json's: log-likelihoods 1e-9 relative (FP64),
+optimised branch lengths 1e-6, rescaling counts bit-exact."""
+import numpy as np
+import pytest
+
+from gp_cases import (ALL_CASES, BL_ATOL, LL_RTOL, SMALL_CASES, Fixture, check_pass, check_sbn, check_sweeps,
+                      make_cuda, make_port, rel_err)
+
+pytestmark = pytest.mark.gpu
+
+
+def test_jc69_transition_matrix_golden(cuda_engine_lib):
+    # /root/reference/src/gp_engine.hpp:382-393, matrix built by the device code path
+    fx = Fixture("hello")
+    with make_cuda(fx) as e:
+        m = e.get_transition_matrix(0.75)
+    assert abs(0.52590958087 - m[0, 0]) < 1e-10
+    assert abs(0.1580301397 - m[0, 1]) < 1e-10
+
+
+def test_hello_goldens(cuda_engine_lib):
+    # gp_doctest.cpp:119-131 and 279-306
+    fx = Fixture("hello")
+    with make_cuda(fx) as e:
+        e.process_operations(*fx.ops("populate_plvs"))
+        e.process_operations(*fx.ops("compute_likelihoods"))
+        assert np.max(np.abs(e.get_per_gpcsp_log_likelihoods() - -84.77961943)) < 1e-6
+        assert abs(e.get_log_marginal_likelihood() - -84.77961943) < 1e-6
+        ll, d1, d2 = e.log_likelihood_and_first_two_derivatives(2, 29, 0)
+        assert abs(ll - -84.77961943) < 1e-6
+        assert abs(d1 - -18.22479569) < 1e-6
+        assert abs(d2 - -5.4460787413) < 1e-6
+    fx = Fixture("hello_single_nucleotide")
+    with make_cuda(fx) as e:
+        e.process_operations(*fx.ops("populate_plvs"))
+        e.process_operations(*fx.ops("compute_likelihoods"))
+        ll, d1 = e.log_likelihood_and_derivative(2, 29, 0)
+        assert abs(ll - -4.806671945) < 1e-6 and abs(d1 - -0.6109379521) < 1e-6
+
+
+@pytest.mark.parametrize("case", ALL_CASES)
+def test_pass_matches_reference(cuda_engine_lib, case):
+    """PopulatePLVs + ComputeLikelihoods: per-pattern / per-edge log-likelihoods, PLVs,
+    rescaling counts (thresholds {0.1, 0.5, 0.9} make them non-zero), then the SBN update."""
+    fx = Fixture(case)
+    for ti in range(len(fx.thresholds)):
+        with make_cuda(fx, ti) as e:
+            check_pass(e, fx, ti, rtol=LL_RTOL)
+            check_sbn(e, fx, ti)
+            # idempotence (gp_doctest.cpp:462-475): a second pass gives the same answer
+            check_pass(e, fx, ti, rtol=LL_RTOL) if case in SMALL_CASES else None
+
+
+@pytest.mark.parametrize("case", ALL_CASES)
+def test_branch_length_sweeps_match_reference(cuda_engine_lib, case):
+    fx = Fixture(case)
+    for ti in range(len(fx.thresholds)):
+        for method in fx.methods:
+            with make_cuda(fx, ti) as e:
+                check_sweeps(e, fx, ti, method, atol=BL_ATOL)
+
+
+@pytest.mark.parametrize("flags", [1, 2, 3])
+def test_unfused_and_graphless_modes_agree(cuda_engine_lib, flags):
+    """BITO_GP_FLAG_NO_CUDA_GRAPHS / NO_FUSION execute one kernel per reference op."""
+    fx = Fixture("fluA")
+    with make_cuda(fx, 3, flags=flags) as e:
+        check_pass(e, fx, 3)
+        check_sbn(e, fx, 3)
+
+
+def test_fluA_rescaling_invariance(cuda_engine_lib):
+    # gp_doctest.cpp:348-359
+    fx = Fixture("fluA")
+    vals = []
+    for ti in (0, 1, 4):
+        with make_cuda(fx, ti) as e:
+            e.process_operations(*fx.ops("populate_plvs"))
+            e.process_operations(*fx.ops("compute_likelihoods"))
+            vals.append(e.get_log_marginal_likelihood())
+    assert abs(vals[0] - vals[1]) < 1e-10
+    assert abs(vals[0] - vals[2]) < 1e-7
+
+
+def _random_problem(rng, taxa, patterns, gap_rate=0.05):
+    """A caterpillar-free random rooted binary tree as a one-tree DAG, hand-rolled op lists in
+    GPDAG's style, random symbols with gaps, ragged pattern counts."""
+    sym = rng.integers(0, 4, size=(taxa, patterns)).astype(np.uint8)
+    sym[rng.random(sym.shape) < gap_rate] = 4
+    w = rng.integers(1, 9, size=patterns).astype(np.float64)
+    # nodes: leaves 0..taxa-1, internal taxa..2*taxa-2 (root last)
+    avail = list(range(taxa))
+    children = {}
+    nxt = taxa
+    while len(avail) > 1:
+        i, j = sorted(rng.choice(len(avail), size=2, replace=False))
+        a, b = avail[i], avail[j]
+        avail = [x for k, x in enumerate(avail) if k not in (i, j)] + [nxt]
+        children[nxt] = (a, b)
+        nxt += 1
+    n_nodes = nxt
+    root = n_nodes - 1
+    edges = {}  # (parent, child) -> edge id; edge 0 = DAG root -> rootsplit
+    eid = 1
+    for p, (a, b) in children.items():
+        edges[(p, a)] = eid
+        edges[(p, b)] = eid + 1
+        eid += 2
+    n_edges = eid
+    N = n_nodes
+    P_, PHR, PHL, RH, RR, RL = (k * N for k in range(6))
+    from bito_b200.gp_operation import GPOperationVector
+    pop = GPOperationVector()
+    for n in range(taxa, N):
+        for t in (P_, PHR, PHL):
+            pop.zero_plv(t + n)
+    for n in range(N):
+        for t in (RH, RR, RL):
+            pop.zero_plv(t + n)
+    pop.set_to_stationary_distribution(RH + root, 0)
+    for p in sorted(children):  # children were created before parents: rootward order
+        a, b = children[p]
+        pop.append_after_prep_for_marginalization([(PHR + p, edges[(p, b)], P_ + b)])
+        pop.append_after_prep_for_marginalization([(PHL + p, edges[(p, a)], P_ + a)])
+        pop.multiply(P_ + p, PHR + p, PHL + p)
+    order = sorted(children, reverse=True)
+    visit = []
+    for p in order:
+        visit.append(p)
+    lik = GPOperationVector()
+    for n in [root] + [c for p in order for c in children[p]]:
+        if n != root:
+            par = next(p for p, ch in children.items() if n in ch)
+            on_left = children[par][0] == n
+            pop.append_after_prep_for_marginalization([(RH + n, edges[(par, n)], (RL if on_left else RR) + par)])
+            lik.likelihood(edges[(par, n)], P_ + n, (RL if on_left else RR) + par)
+        pop.multiply(RR + n, RH + n, PHL + n)
+        pop.multiply(RL + n, RH + n, PHR + n)
+    lik.reset_marginal_likelihood()
+    lik.increment_marginal_likelihood(RH + root, 0, P_ + root)
+    opt = GPOperationVector()
+    for (par, n), e in edges.items():
+        on_left = children[par][0] == n
+        opt.optimize_branch_length(P_ + n, (RL if on_left else RR) + par, e)
+    bl = rng.uniform(0.01, 0.3, size=n_edges)
+    return dict(symbols=sym, weights=w, node_count=N, edge_count=n_edges, populate=pop.arrays(),
+                likelihoods=lik.arrays(), optimize=opt.arrays(), branch_lengths=bl)
+
+
+@pytest.mark.parametrize("taxa,patterns,thr", [(4, 1, 1e-40), (7, 255, 1e-40), (9, 256, 0.5), (12, 257, 0.9),
+                                                (30, 3001, 0.7), (64, 20000, 1e-40)])
+def test_random_trees_match_oracle(cuda_engine_lib, taxa, patterns, thr):
+    """Seeded synthetic inputs, ragged tile edges (P = 1, 255, 256, 257, ...), gaps, and a
+    batched (Jacobi) optimisation of every edge at once: CUDA vs the plain-C oracle."""
+    from bito_b200.gp_engine import GPEngine
+    from oracle.port_engine import PortEngine
+    rng = np.random.default_rng(taxa * 1000 + patterns)
+    pb = _random_problem(rng, taxa, patterns)
+    site_count = int(pb["weights"].sum())
+    cpu = PortEngine(pb["symbols"], pb["weights"], site_count, pb["node_count"], pb["edge_count"],
+                     rescaling_threshold=thr)
+    with GPEngine(pb["symbols"], pb["weights"], site_count, pb["node_count"], pb["edge_count"], thr) as gpu:
+        for e in (cpu, gpu):
+            e.set_branch_lengths(pb["branch_lengths"])
+            e.process_operations(*pb["populate"])
+            e.process_operations(*pb["likelihoods"])
+        assert rel_err(gpu.get_log_likelihood_matrix(), cpu.log_likelihood_matrix()) <= LL_RTOL
+        assert rel_err(gpu.get_per_gpcsp_log_likelihoods(), cpu.per_gpcsp_log_likelihoods()) <= LL_RTOL
+        assert rel_err(gpu.get_log_marginal_likelihood(), cpu.log_marginal_likelihood()) <= LL_RTOL
+        assert np.array_equal(gpu.get_rescaling_counts(), cpu.rescaling_counts())
+        for method in ("brent", "newton"):
+            for e in (cpu, gpu):
+                e.set_branch_lengths(pb["branch_lengths"])
+                e.set_optimization_method(method)
+                e.reset_optimization_count()
+                e.process_operations(*pb["populate"])
+                e.process_operations(*pb["optimize"])
+            assert np.max(np.abs(gpu.get_branch_lengths() - cpu.branch_lengths())) <= BL_ATOL, method
+            assert np.max(np.abs(gpu.get_branch_length_differences() - cpu.branch_length_differences())) <= BL_ATOL
+
+
+def test_plv_roundtrip_and_copy(cuda_engine_lib):
+    fx = Fixture("five_taxon")
+    rng = np.random.default_rng(3)
+    with make_cuda(fx) as e:
+        P = e.pattern_count
+        # leaf P-PLVs are symbolic in HBM but read back one-hot / all-ones for gaps
+        sym = fx["symbols"]
+        leaf = e.get_plv(0)
+        for p in range(P):
+            s = sym[0, p]
+            want = np.ones(4) if s == 4 else np.eye(4)[s]
+            assert np.array_equal(leaf[p], want)
+        assert not e.get_plv(e.plv_count - 1).any()  # untouched PLVs read as zero
+        v = rng.random((P, 4))
+        e.set_plv(7, v, count=3)
+        assert np.array_equal(e.get_plv(7), v) and e.get_rescaling_counts()[7] == 3
+        spare = e.plv_count + 2  # spare PLV region starts at 6N (pv_handler.hpp:227-238)
+        e.copy_plv_data(7, spare)
+        assert np.array_equal(e.get_plv(spare), v) and e.get_rescaling_counts()[spare] == 3
+        e.copy_plv_data(0, spare + 1)
+        assert np.array_equal(e.get_plv(spare + 1), leaf)
+
+
+def test_errors_surface_as_exceptions(cuda_engine_lib):
+    fx = Fixture("hello")
+    with make_cuda(fx) as e:
+        ops = np.array([[2, 10 ** 6, 0, 0, 0, 0]], dtype=np.int64)
+        with pytest.raises(RuntimeError, match="out of range"):
+            e.process_operations(ops)
+        with pytest.raises(RuntimeError, match="unknown GPOperation"):
+            e.process_operations(np.array([[42, 0, 0, 0, 0, 0]], dtype=np.int64))
+        with pytest.raises(RuntimeError, match="Invalid OptimizationMethod"):
+            e.set_optimization_method(9)
+        # engine still usable afterwards
+        e.process_operations(*fx.ops("populate_plvs"))
+        e.process_operations(*fx.ops("compute_likelihoods"))
+        assert abs(e.get_log_marginal_likelihood() - -84.77961943) < 1e-6
+
+
+def test_stats_report_fusion_and_launches(cuda_engine_lib):
+    fx = Fixture("ds1")
+    with make_cuda(fx) as e:
+        e.process_operations(*fx.ops("populate_plvs"))
+        st = e.stats()
+        n_ops = fx.ops("populate_plvs")[0].shape[0]
+        assert 0 < st["fused_ops_last"] < n_ops / 2          # Zero/Prep/Increment chains were fused
+        assert 0 < st["levels_last"] < st["fused_ops_last"]  # and batched into dependency levels
+        assert st["kernel_launches"] > 0 and st["programs_compiled"] == 1
+        e.process_operations(*fx.ops("populate_plvs"))
+        assert e.stats()["programs_compiled"] == 1            # cached program (graph) replayed
+        # leaf PLVs are symbolic and leaf PHats never materialise: fewer resident PLVs than 6N
+        assert e.stats()["plvs_resident"] < e.plv_count
