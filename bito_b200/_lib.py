@@ -56,6 +56,11 @@ class Stats(C.Structure):
     ]
 
 
+class KernelProfile(C.Structure):
+    _fields_ = [("name", C.c_char * 32), ("launches", C.c_int64), ("total_ms", C.c_double),
+                ("algorithmic_bytes", C.c_double)]
+
+
 _vp, _i64, _i32, _f64 = C.c_void_p, C.c_int64, C.c_int32, C.c_double
 _int = C.c_int
 
@@ -111,6 +116,9 @@ SIGNATURES = {
     "bito_gp_set_stream": (_int, [_vp, _vp]),
     "bito_gp_synchronize": (_int, [_vp]),
     "bito_gp_get_stats": (_int, [_vp, C.POINTER(Stats)]),
+    "bito_gp_set_profiling": (_int, [_vp, _int]),
+    "bito_gp_reset_kernel_profile": (_int, [_vp]),
+    "bito_gp_get_kernel_profile": (_int, [_vp, C.POINTER(KernelProfile), _int, C.POINTER(_int)]),
 }
 
 _lib = None

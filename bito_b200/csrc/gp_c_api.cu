@@ -243,4 +243,18 @@ int bito_gp_get_stats(bito_gp_engine* e, bito_gp_stats* out) {
   return Guard([&] { e->impl.GetStats(out); });
 }
 
+int bito_gp_set_profiling(bito_gp_engine* e, int on) {
+  ENGINE_OR_FAIL(e);
+  return Guard([&] { e->impl.SetProfiling(on != 0); });
+}
+int bito_gp_reset_kernel_profile(bito_gp_engine* e) {
+  ENGINE_OR_FAIL(e);
+  return Guard([&] { e->impl.ResetKernelProfile(); });
+}
+int bito_gp_get_kernel_profile(bito_gp_engine* e, bito_gp_kernel_profile* out, int capacity,
+                               int* n_out) {
+  ENGINE_OR_FAIL(e);
+  return Guard([&] { *n_out = e->impl.GetKernelProfile(out, capacity); });
+}
+
 }  // extern "C"

@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <limits>
 #include <sstream>
@@ -335,8 +336,9 @@ void Engine::SetSitePatterns(const uint8_t* symbols, const double* weights, bool
   Activate();
   const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   if (!on_device) {
-    for (int64_t i = 0; i < taxon_count_ * P_; ++i)
-      if (symbols[i] > 4) Fail("bito_gp_set_site_patterns: symbol outside 0..4");
+    uint8_t worst = 0;
+    for (int64_t i = 0; i < taxon_count_ * P_; ++i) worst = symbols[i] > worst ? symbols[i] : worst;
+    if (worst > 4) Fail("bito_gp_set_site_patterns: symbol outside 0..4");
   }
   GP_CUDA(cudaMemcpy2DAsync(d_symbols_.ptr, static_cast<size_t>(P_stride_), symbols,
                             static_cast<size_t>(P_), static_cast<size_t>(P_),
@@ -344,11 +346,15 @@ void Engine::SetSitePatterns(const uint8_t* symbols, const double* weights, bool
   GP_CUDA(cudaMemcpyAsync(d_weights_.ptr, weights, static_cast<size_t>(P_) * sizeof(double), kind,
                           stream_));
   // Leaf P-PLVs (ids [0, taxa)) stay symbolic: 1 byte per pattern instead of 32.
+  bool slots_changed = false;
   for (int64_t t = 0; t < taxon_count_; ++t) {
     PlvSlot& s = plvs_[static_cast<size_t>(t)];
+    void* want = d_symbols_.ptr + t * P_stride_;
+    if (s.kind == kPlvSymbols && s.ptr == want) continue;
     if (s.kind == kPlvDense) plv_pool_.Free(s.ptr);
-    s.ptr = d_symbols_.ptr + t * P_stride_;
+    s.ptr = want;
     s.kind = kPlvSymbols;
+    slots_changed = true;
   }
   // Total weight (all ranks) for the rescaling term of the branch-length objective.
   const int64_t tiles = TilesFor(P_);
@@ -361,7 +367,8 @@ void Engine::SetSitePatterns(const uint8_t* symbols, const double* weights, bool
   GP_CUDA(cudaStreamSynchronize(stream_));
   total_weight_ = *static_cast<double*>(pinned_);
   have_patterns_ = true;
-  InvalidatePrograms();
+  // Re-uploading an alignment of the same shape leaves every compiled program valid.
+  if (slots_changed) InvalidatePrograms();
 }
 
 void Engine::InitializePriors(const double* sbn_prior, const double* unconditional,
@@ -559,7 +566,12 @@ Program* Engine::Compile(const bito_gp_op* ops, int64_t n, const int64_t* vec, i
         CheckPlv(op.a, "Multiply");
         CheckPlv(op.b, "Multiply");
         CheckPlv(op.c, "Multiply");
-        EnsureDense(op.a);
+        // A product with a PLV that is (and stays) identically zero is zero: if the
+        // destination owns no memory either it stays that way (e.g. the r-PLVs of leaves,
+        // RHat o PHat with PHat never written).
+        if (!(fuse && plvs_[op.a].kind == kPlvZero &&
+              (plvs_[op.b].kind == kPlvZero || plvs_[op.c].kind == kPlvZero)))
+          EnsureDense(op.a);
         break;
       case BITO_GP_LIKELIHOOD:
         CheckEdge(op.a, "Likelihood");
@@ -752,6 +764,22 @@ Program* Engine::Compile(const bito_gp_op* ops, int64_t n, const int64_t* vec, i
         if (op.c != op.a) before_read(op.c);
         if (op.b == op.a || op.c == op.a) before_read(op.a);
         pending_zero[op.a] = 0;
+        if (fuse && plvs_[op.a].kind == kPlvZero &&
+            (plvs_[op.b].kind == kPlvZero || plvs_[op.c].kind == kPlvZero)) {
+          // Kinds are final here (pass 0 made every really-written PLV dense): the product is
+          // identically zero and the destination keeps owning no memory. Only the count moves.
+          Macro z;
+          z.kind = kMkScalar;
+          z.idx = static_cast<int>(h_scalar.size());
+          h_scalar.push_back(ScalarOp{kScalarCountSum, static_cast<int32_t>(op.a),
+                                      static_cast<int32_t>(op.b), static_cast<int32_t>(op.c), 0, 0});
+          z.writes.push_back(op.a);
+          z.reads.push_back(op.b);
+          z.reads.push_back(op.c);
+          macros.push_back(std::move(z));
+          ++i;
+          break;
+        }
         Macro m;
         m.kind = kMkMult;
         m.idx = static_cast<int>(h_mult.size());
@@ -920,7 +948,11 @@ Program* Engine::Compile(const bito_gp_op* ops, int64_t n, const int64_t* vec, i
         case kMkZero: f_zero.push_back(h_zero[m.idx]); L.n_zero++; break;
         case kMkScalar: f_scalar.push_back(h_scalar[m.idx]); L.n_scalar++; break;
         case kMkStat: f_stat.push_back(h_stat[m.idx]); L.n_stat++; break;
-        case kMkAccum: f_accum.push_back(h_accum[m.idx]); L.n_accum++; break;
+        case kMkAccum:
+          f_accum.push_back(h_accum[m.idx]);
+          L.n_accum++;
+          L.accum_bytes_per_pattern += 32. * h_accum[m.idx].n_items + 32.;
+          break;
         case kMkMult: {
           MultOp mo = h_mult[m.idx];
           mo.max_slot = static_cast<int32_t>(f_mult.size());
@@ -1037,18 +1069,39 @@ void Engine::ExecuteLevels(Program& prog, size_t first, size_t last) {
   const int64_t tiles = TilesFor(P_);
   for (size_t li = first; li < last; ++li) {
     const Level& L = prog.levels[li];
-    LaunchZero(stream_, st, prog.d_zero + L.zero_off, L.n_zero);
-    LaunchScalar(stream_, st, prog.d_scalar + L.scalar_off, prog.d_pool, L.n_scalar);
-    LaunchStationary(stream_, st, prog.d_stat + L.stat_off, L.n_stat);
-    LaunchAccum(stream_, st, prog.d_accum + L.accum_off, prog.d_items, prog.d_pool, L.n_accum);
+    const double Pd = static_cast<double>(P_);
+    if (L.n_zero > 0) {
+      ProfScope ps(this, kProfZero, 32. * L.n_zero * Pd);
+      LaunchZero(stream_, st, prog.d_zero + L.zero_off, L.n_zero);
+    }
+    if (L.n_scalar > 0) {
+      ProfScope ps(this, kProfScalar, 0.);
+      LaunchScalar(stream_, st, prog.d_scalar + L.scalar_off, prog.d_pool, L.n_scalar);
+    }
+    if (L.n_stat > 0) {
+      ProfScope ps(this, kProfStationary, 32. * L.n_stat * Pd);
+      LaunchStationary(stream_, st, prog.d_stat + L.stat_off, L.n_stat);
+    }
+    if (L.n_accum > 0) {
+      ProfScope ps(this, kProfAccum, L.accum_bytes_per_pattern * Pd);
+      LaunchAccum(stream_, st, prog.d_accum + L.accum_off, prog.d_items, prog.d_pool, L.n_accum);
+    }
     if (L.n_mult > 0) {
-      LaunchMultiply(stream_, st, prog.d_mult + L.mult_off, L.n_mult, d_level_max_.ptr);
+      {
+        ProfScope ps(this, kProfMultiply, 96. * L.n_mult * Pd);
+        LaunchMultiply(stream_, st, prog.d_mult + L.mult_off, L.n_mult, d_level_max_.ptr);
+      }
       // The rescale decision needs the max over ALL patterns of the PLV (gp_engine.cpp:583-597).
       AllReduce(d_level_max_.ptr + L.mult_off, L.n_mult, true);
+      ProfScope ps(this, kProfRescale, 0.);
       LaunchRescale(stream_, st, prog.d_mult + L.mult_off, L.n_mult, d_level_max_.ptr);
     }
     if (L.n_lik > 0) {
-      LaunchLikelihood(stream_, st, prog.d_lik + L.lik_off, L.n_lik, d_partials_.ptr);
+      {
+        ProfScope ps(this, kProfLikelihood, 72. * L.n_lik * Pd);
+        LaunchLikelihood(stream_, st, prog.d_lik + L.lik_off, L.n_lik, d_partials_.ptr);
+      }
+      ProfScope ps(this, kProfReduce, 0.);
       if (n_ranks_ == 1) {
         LaunchReducePartials(stream_, d_partials_.ptr, L.n_lik, tiles, d_packed_.ptr,
                              prog.d_lik_scatter + L.lik_off, st.ll_sum);
@@ -1060,8 +1113,12 @@ void Engine::ExecuteLevels(Program& prog, size_t first, size_t last) {
       }
     }
     if (L.has_marg) {
-      LaunchMarginal(stream_, st, prog.d_marg + L.marg_off, L.n_marg, L.marg_reset,
-                     d_partials_.ptr);
+      {
+        ProfScope ps(this, kProfMarginal, 88. * L.n_marg * Pd);
+        LaunchMarginal(stream_, st, prog.d_marg + L.marg_off, L.n_marg, L.marg_reset,
+                       d_partials_.ptr);
+      }
+      ProfScope ps(this, kProfReduce, 0.);
       const int n_out = L.n_marg + 1;
       if (n_ranks_ == 1) {
         LaunchReducePartials(stream_, d_partials_.ptr, n_out, tiles, d_packed_.ptr,
@@ -1113,18 +1170,28 @@ void Engine::RunOptimizer(const OptOp* d_ops, int n_ops, int method, bool check_
 
   for (int c0 = 0; c0 < n_ops; c0 += chunk) {
     const int m = std::min(chunk, n_ops - c0);
-    LaunchOptPrepare(stream_, st, d_ops + c0, m, d_opt_states_.ptr, prm, method, d_coef_.ptr, 1);
+    {
+      ProfScope ps(this, kProfOptPrepare, 64. * m * static_cast<double>(P_));
+      LaunchOptPrepare(stream_, st, d_ops + c0, m, d_opt_states_.ptr, prm, method, d_coef_.ptr, 1);
+    }
     stats_.kernel_launches++;
     int64_t rounds = 0;
     int batch = method <= BITO_GP_BRENT_OPTIMIZATION_WITH_GRADIENTS ? 12 : 6;
     for (;;) {
       for (int r = 0; r < batch; ++r) {
         const bool last = (r == batch - 1);
-        LaunchOptEval(stream_, st, m, d_opt_states_.ptr, d_coef_.ptr, nd, d_partials_.ptr, G);
-        LaunchReducePartials(stream_, d_partials_.ptr, 3 * m, tiles, d_packed_.ptr, nullptr,
-                             nullptr);
+        {
+          ProfScope ps(this, kProfOptEval, 0.);
+          LaunchOptEval(stream_, st, m, d_opt_states_.ptr, d_coef_.ptr, nd, d_partials_.ptr, G);
+        }
+        {
+          ProfScope ps(this, kProfReduce, 0.);
+          LaunchReducePartials(stream_, d_partials_.ptr, 3 * m, tiles, d_packed_.ptr, nullptr,
+                               nullptr);
+        }
         AllReduce(d_packed_.ptr, 3 * m, false);
         if (last) GP_CUDA(cudaMemsetAsync(d_active_.ptr, 0, sizeof(int32_t), stream_));
+        ProfScope ps(this, kProfOptStep, 0.);
         LaunchOptStep(stream_, st, m, d_opt_states_.ptr, prm, d_packed_.ptr,
                       last ? d_active_.ptr : nullptr);
         stats_.kernel_launches += 3;
@@ -1151,7 +1218,8 @@ void Engine::Execute(Program& prog) {
       kv.second->graph_tried = false;
     }
   }
-  const bool want_graph = !(cfg_.flags & BITO_GP_FLAG_NO_CUDA_GRAPHS) && prog.n_opt_total == 0;
+  const bool want_graph =
+      !(cfg_.flags & BITO_GP_FLAG_NO_CUDA_GRAPHS) && prog.n_opt_total == 0 && !profiling_;
   auto body = [&]() {
     if (prog.n_mult_total > 0)
       GP_CUDA(cudaMemsetAsync(d_level_max_.ptr, 0, prog.n_mult_total * sizeof(double), stream_));
@@ -1586,6 +1654,65 @@ void Engine::CopyGpcspData(int64_t src, int64_t dest) {  // gp_engine.cpp:401-40
   cp(d_bl_);
   cp(d_q_);
   cp(d_inverted_);
+}
+
+// ---- per-kernel timing with CUDA events on the launching stream (bench.py's roofline) ---------------
+const char* const kProfNames[kProfKinds] = {"k_zero", "k_scalar", "k_stationary", "k_accum", "k_multiply",
+                                            "k_rescale", "k_likelihood", "k_marginal", "k_reduce_partials",
+                                            "k_opt_prepare", "k_opt_eval", "k_opt_step"};
+
+ProfScope::ProfScope(Engine* e, int kind, double bytes) : e_(e->profiling_ ? e : nullptr) {
+  if (e_ == nullptr) return;
+  Engine::ProfEvent ev{};
+  ev.kind = kind;
+  ev.bytes = bytes;
+  cudaEventCreate(&ev.begin);
+  cudaEventCreate(&ev.end);
+  cudaEventRecord(ev.begin, e_->stream_);
+  e_->prof_events_.push_back(ev);
+}
+ProfScope::~ProfScope() {
+  if (e_ != nullptr) cudaEventRecord(e_->prof_events_.back().end, e_->stream_);
+}
+
+void Engine::SetProfiling(bool on) {
+  Activate();
+  CollectProfile();
+  profiling_ = on;
+}
+
+void Engine::CollectProfile() {
+  if (prof_events_.empty()) return;
+  GP_CUDA(cudaStreamSynchronize(stream_));
+  for (ProfEvent& ev : prof_events_) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ev.begin, ev.end) == cudaSuccess) {
+      prof_[ev.kind].launches++;
+      prof_[ev.kind].total_ms += ms;
+      prof_[ev.kind].algorithmic_bytes += ev.bytes;
+    }
+    cudaEventDestroy(ev.begin);
+    cudaEventDestroy(ev.end);
+  }
+  prof_events_.clear();
+}
+
+int Engine::GetKernelProfile(bito_gp_kernel_profile* out, int capacity) {
+  Activate();
+  CollectProfile();
+  int n = 0;
+  for (int k = 0; k < kProfKinds && n < capacity; ++k) {
+    if (prof_[k].launches == 0) continue;
+    out[n] = prof_[k];
+    std::snprintf(out[n].name, sizeof out[n].name, "%s", kProfNames[k]);
+    ++n;
+  }
+  return n;
+}
+
+void Engine::ResetKernelProfile() {
+  CollectProfile();
+  for (auto& p : prof_) p = bito_gp_kernel_profile{};
 }
 
 void Engine::GetStats(bito_gp_stats* out) {

@@ -69,6 +69,7 @@ struct Level {
   int lik_off = 0, n_lik = 0;
   int marg_off = 0, n_marg = 0, marg_reset = 0, has_marg = 0, marg_scatter_off = 0;
   int opt_off = 0, n_opt = 0;
+  double accum_bytes_per_pattern = 0.;
 };
 
 struct Program {
@@ -100,8 +101,29 @@ struct Program {
   bool graph_tried = false;
 };
 
+enum ProfKind {
+  kProfZero, kProfScalar, kProfStationary, kProfAccum, kProfMultiply, kProfRescale, kProfLikelihood,
+  kProfMarginal, kProfReduce, kProfOptPrepare, kProfOptEval, kProfOptStep, kProfKinds
+};
+
+class Engine;
+// Brackets one kernel launch with CUDA events on the launching stream when profiling is on.
+class ProfScope {
+ public:
+  ProfScope(Engine* e, int kind, double bytes);
+  ~ProfScope();
+
+ private:
+  Engine* e_;
+};
+
 class Engine {
  public:
+  friend class ProfScope;
+  void SetProfiling(bool on);
+  int GetKernelProfile(bito_gp_kernel_profile* out, int capacity);
+  void ResetKernelProfile();
+
   explicit Engine(const bito_gp_config& cfg);
   ~Engine();
   Engine(const Engine&) = delete;
@@ -220,6 +242,16 @@ class Engine {
   int n_ranks_ = 1, rank_ = 0;
 
   bito_gp_stats stats_{};
+
+  struct ProfEvent {
+    cudaEvent_t begin, end;
+    int kind;
+    double bytes;
+  };
+  void CollectProfile();
+  bool profiling_ = false;
+  std::vector<ProfEvent> prof_events_;
+  bito_gp_kernel_profile prof_[kProfKinds] = {};
 };
 
 void MakeNcclUniqueId(uint8_t id[128]);

@@ -361,6 +361,8 @@ __global__ void k_scalar(DeviceState st, const ScalarOp* __restrict__ ops,
   const ScalarOp op = ops[o];
   if (op.kind == kScalarCountZero) {
     st.counts[op.a] = 0;
+  } else if (op.kind == kScalarCountSum) {  // gp_engine.cpp:281-282 (max == 0: no rescale, :587-589)
+    st.counts[op.a] = st.counts[op.b] + st.counts[op.vec_off];
   } else if (op.kind == kScalarPrep) {  // gp_engine.cpp:323-333
     if (op.vec_len <= 0) {
       atomicOr(st.status, kErrEmptyPrep);

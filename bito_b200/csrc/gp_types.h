@@ -134,11 +134,12 @@ struct ZeroOp {  // a ZeroPLV that could not be folded away
 enum ScalarKind : int32_t {
   kScalarCountZero = 0,  // ZeroPLV of a PLV that owns no memory: count only
   kScalarPrep = 1,       // stand-alone PrepForMarginalization
-  kScalarSbn = 2         // UpdateSBNProbabilities (gp_engine.cpp:304-321)
+  kScalarSbn = 2,        // UpdateSBNProbabilities (gp_engine.cpp:304-321)
+  kScalarCountSum = 3    // Multiply whose result is identically zero: count[a] = count[b] + count[c]
 };
 struct ScalarOp {
   int32_t kind;
-  int32_t a, b;  // count-zero/prep: a = dest id; sbn: [a, b)
+  int32_t a, b;  // count-zero/prep: a = dest id; sbn: [a, b); count-sum: dest, src1 (src2 in vec_off)
   int32_t vec_off, vec_len;
   int32_t pad;
 };

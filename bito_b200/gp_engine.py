@@ -283,6 +283,20 @@ class GPEngine:
     def synchronize(self):
         self._check(self._lib.bito_gp_synchronize(self._h))
 
+    def set_profiling(self, on: bool):
+        self._check(self._lib.bito_gp_set_profiling(self._h, int(bool(on))))
+
+    def reset_kernel_profile(self):
+        self._check(self._lib.bito_gp_reset_kernel_profile(self._h))
+
+    def kernel_profile(self) -> list:
+        """Per-kernel device time (CUDA events around each launch while profiling is on)."""
+        buf = (_lib.KernelProfile * 16)()
+        n = C.c_int()
+        self._check(self._lib.bito_gp_get_kernel_profile(self._h, buf, 16, C.byref(n)))
+        return [dict(name=buf[i].name.decode(), launches=buf[i].launches, total_ms=buf[i].total_ms,
+                     algorithmic_bytes=buf[i].algorithmic_bytes) for i in range(n.value)]
+
     def stats(self) -> dict:
         st = _lib.Stats()
         self._check(self._lib.bito_gp_get_stats(self._h, C.byref(st)))

@@ -216,6 +216,21 @@ typedef struct bito_gp_stats {
 } bito_gp_stats;
 BITO_GP_API int bito_gp_get_stats(bito_gp_engine* e, bito_gp_stats* out);
 
+/* Per-kernel device time, measured with CUDA events on the launching stream around every
+ * launch while profiling is on (graphs are bypassed meanwhile). algorithmic_bytes follows
+ * compulsory bytes of the ops each launch executed. */
+typedef struct bito_gp_kernel_profile {
+  char name[32];
+  int64_t launches;
+  double total_ms;
+  double algorithmic_bytes;
+} bito_gp_kernel_profile;
+BITO_GP_API int bito_gp_set_profiling(bito_gp_engine* e, int on);
+BITO_GP_API int bito_gp_reset_kernel_profile(bito_gp_engine* e);
+/* Writes up to `capacity` entries, returns the number written in *n_out. */
+BITO_GP_API int bito_gp_get_kernel_profile(bito_gp_engine* e, bito_gp_kernel_profile* out, int capacity,
+                               int* n_out);
+
 #ifdef __cplusplus
 }
 #endif
