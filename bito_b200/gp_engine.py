@@ -117,6 +117,15 @@ class GPEngine:
     def padded_gpcsp_count(self):
         return int(self._lib.bito_gp_get_padded_gpcsp_count(self._h))
 
+    # ---- site patterns ------------------------------------------------------------------------
+    def set_site_patterns(self, symbols, weights):
+        """Re-upload this shard's alignment (same shape) from host memory."""
+        symbols = np.ascontiguousarray(symbols, dtype=np.uint8)
+        weights = _f64(weights, self.pattern_count, "weights")
+        if symbols.shape != (self.taxon_count, self.pattern_count):
+            raise ValueError("symbols must keep the shape the engine was created with")
+        self._check(self._lib.bito_gp_set_site_patterns(self._h, _ptr(symbols), _ptr(weights)))
+
     # ---- priors ---------------------------------------------------------------------------
     def initialize_priors(self, sbn_prior, unconditional_node_probabilities, inverted_sbn_prior):
         q = _f64(sbn_prior, self.gpcsp_count, "sbn_prior")
