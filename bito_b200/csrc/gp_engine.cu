@@ -264,7 +264,7 @@ Engine::~Engine() {
   d_q_.Release(); d_bl_.Release(); d_diff_.Release(); d_hybrid_.Release(); d_ll_sum_.Release();
   d_inverted_.Release(); d_uncond_.Release(); d_status_.Release(); d_feval_total_.Release();
   d_partials_.Release(); d_packed_.Release(); d_level_max_.Release(); d_coef_.Release();
-  d_dense_tmp_.Release(); d_opt_states_.Release(); d_active_.Release(); d_single_opt_.Release();
+  d_dense_tmp_.Release(); d_mtab_.Release(); d_mtab_lik_.Release(); d_opt_states_.Release(); d_active_.Release(); d_single_opt_.Release();
   if (pinned_ != nullptr) cudaFreeHost(pinned_);
   if (ev_begin_) cudaEventDestroy(ev_begin_);
   if (ev_end_) cudaEventDestroy(ev_end_);
@@ -442,15 +442,16 @@ void Engine::EnsureScratch(int64_t partial_doubles, int64_t packed_doubles) {
   grow(d_partials_, partial_doubles);
   grow(d_packed_, packed_doubles);
   grow(d_dense_tmp_, 4 * P_stride_);
-  if (grew) {
-    // Captured graphs hold the old scratch addresses.
-    for (auto& kv : programs_) {
-      if (kv.second->graph != nullptr) {
-        cudaGraphExecDestroy(kv.second->graph);
-        kv.second->graph = nullptr;
-      }
-      kv.second->graph_tried = false;
+  if (grew) DropGraphs();  // captured graphs hold the old scratch addresses
+}
+
+void Engine::DropGraphs() {
+  for (auto& kv : programs_) {
+    if (kv.second->graph != nullptr) {
+      cudaGraphExecDestroy(kv.second->graph);
+      kv.second->graph = nullptr;
     }
+    kv.second->graph_tried = false;
   }
 }
 
@@ -526,7 +527,7 @@ void Engine::CheckStatus() {
 
 // ---- the op-list compiler -----------------------------------------------------------------
 namespace {
-enum MacroKind { kMkZero, kMkScalar, kMkStat, kMkAccum, kMkMult, kMkLik, kMkMarg, kMkOpt };
+enum MacroKind { kMkZero, kMkScalar, kMkStat, kMkAccum, kMkMult, kMkNode, kMkLik, kMkMarg, kMkOpt };
 struct Macro {
   MacroKind kind;
   int idx;  // into the per-kind host vector
@@ -900,6 +901,104 @@ Program* Engine::Compile(const bito_gp_op* ops, int64_t n, const int64_t* vec, i
       emit_zero(ops[k].a);
     }
 
+  // -- pass 1b: node fusion ------------------------------------------------------------------
+  // Adjacent macro-ops in program order are merged into one NodeOp when a Multiply consumes the
+  // result of the accumulate group(s) right before it: [A(X) [A(Y)] M(D = X o Y | X o Z) [M2]].
+  // A contiguous run of a sequential program executed as one step is always legal as long as the
+  // data flow inside the run is honoured; every site pattern is owned by one thread, which reads
+  // the products' operands from its own registers. Conservative extra conditions (no other
+  // aliasing inside the run) keep the kernel simple. Every remaining group / Multiply becomes a
+  // single-member node, so one kernel serves them all.
+  std::vector<NodeOp> h_node;
+  {
+    auto has = [](const std::vector<int64_t>& v, int64_t x) {
+      return std::find(v.begin(), v.end(), x) != v.end();
+    };
+    std::vector<Macro> fused;
+    fused.reserve(macros.size());
+    size_t k = 0;
+    while (k < macros.size()) {
+      if (macros[k].kind != kMkAccum && macros[k].kind != kMkMult) {
+        fused.push_back(std::move(macros[k]));
+        ++k;
+        continue;
+      }
+      NodeOp nd{};
+      Macro nm;
+      nm.kind = kMkNode;
+      auto add_group = [&](const Macro& a) {
+        nd.g[nd.n_groups++] = h_accum[a.idx];
+        nm.reads.insert(nm.reads.end(), a.reads.begin(), a.reads.end());
+        nm.writes.insert(nm.writes.end(), a.writes.begin(), a.writes.end());
+      };
+      auto group_of = [&](int64_t plv) {
+        for (int g = 0; g < nd.n_groups; ++g)
+          if (nd.g[g].dest_id == plv) return g;
+        return -1;
+      };
+      auto add_mult = [&](const Macro& mm) {
+        const MultOp& mo = h_mult[mm.idx];
+        NodeMult x{};
+        x.dest = mo.dest;
+        x.s1 = mo.s1;
+        x.s2 = mo.s2;
+        x.dest_id = mo.dest_id;
+        x.max_slot = 0;
+        x.s1_group = group_of(mo.s1.id);
+        x.s2_group = group_of(mo.s2.id);
+        nd.m[nd.n_mults++] = x;
+        for (int64_t r : mm.reads)
+          if (group_of(r) < 0) nm.reads.push_back(r);
+        nm.writes.insert(nm.writes.end(), mm.writes.begin(), mm.writes.end());
+      };
+      // A Multiply may join when it consumes a group result and aliases nothing else in the node.
+      auto mult_joins = [&](const Macro& mm) {
+        const MultOp& mo = h_mult[mm.idx];
+        const int g1 = group_of(mo.s1.id), g2 = group_of(mo.s2.id);
+        if (g1 < 0 && g2 < 0) return false;
+        if (has(nm.writes, mo.dest_id) || has(nm.reads, mo.dest_id)) return false;
+        if (g1 < 0 && has(nm.writes, mo.s1.id)) return false;
+        if (g2 < 0 && has(nm.writes, mo.s2.id)) return false;
+        return true;
+      };
+      size_t j = k + 1;
+      if (macros[k].kind == kMkMult) {
+        add_mult(macros[k]);
+      } else {
+        add_group(macros[k]);
+        if (fuse) {
+          // second group only if the Multiply right after it multiplies the two results
+          if (j + 1 < macros.size() && macros[j].kind == kMkAccum && macros[j + 1].kind == kMkMult) {
+            const AccumGroup& a1 = h_accum[macros[k].idx];
+            const AccumGroup& a2 = h_accum[macros[j].idx];
+            const MultOp& mo = h_mult[macros[j + 1].idx];
+            const bool both = (mo.s1.id == a1.dest_id && mo.s2.id == a2.dest_id) ||
+                              (mo.s1.id == a2.dest_id && mo.s2.id == a1.dest_id);
+            const bool contiguous = a2.item_off == a1.item_off + a1.n_items;
+            const bool clean = a1.dest_id != a2.dest_id && !has(macros[j].reads, a1.dest_id) &&
+                               !has(macros[k].reads, a2.dest_id) && mo.dest_id != a1.dest_id &&
+                               mo.dest_id != a2.dest_id && !has(macros[k].reads, mo.dest_id) &&
+                               !has(macros[j].reads, mo.dest_id);
+            if (both && contiguous && clean) {
+              add_group(macros[j]);
+              ++j;
+            }
+          }
+          while (j < macros.size() && macros[j].kind == kMkMult && nd.n_mults < 2 &&
+                 mult_joins(macros[j])) {
+            add_mult(macros[j]);
+            ++j;
+          }
+        }
+      }
+      nm.idx = static_cast<int>(h_node.size());
+      h_node.push_back(nd);
+      fused.push_back(std::move(nm));
+      k = j;
+    }
+    macros.swap(fused);
+  }
+
   // -- pass 2: dependency levels (RAW, WAW, WAR on PLVs, edge scalars, rows, marginal) ------
   const int64_t n_res = res_marg + 1;
   std::vector<int> last_write(static_cast<size_t>(n_res), -1), last_read(static_cast<size_t>(n_res), -1);
@@ -923,7 +1022,7 @@ Program* Engine::Compile(const bito_gp_op* ops, int64_t n, const int64_t* vec, i
   std::vector<ZeroOp> f_zero;
   std::vector<ScalarOp> f_scalar;
   std::vector<StatOp> f_stat;
-  std::vector<AccumGroup> f_accum;
+  std::vector<NodeOp> f_node;
   std::vector<MultOp> f_mult;
   std::vector<LikOp> f_lik;
   std::vector<MargItem> f_marg;
@@ -936,7 +1035,7 @@ Program* Engine::Compile(const bito_gp_op* ops, int64_t n, const int64_t* vec, i
     L.zero_off = static_cast<int>(f_zero.size());
     L.scalar_off = static_cast<int>(f_scalar.size());
     L.stat_off = static_cast<int>(f_stat.size());
-    L.accum_off = static_cast<int>(f_accum.size());
+    L.node_off = static_cast<int>(f_node.size());
     L.mult_off = static_cast<int>(f_mult.size());
     L.lik_off = static_cast<int>(f_lik.size());
     L.marg_off = static_cast<int>(f_marg.size());
@@ -948,18 +1047,29 @@ Program* Engine::Compile(const bito_gp_op* ops, int64_t n, const int64_t* vec, i
         case kMkZero: f_zero.push_back(h_zero[m.idx]); L.n_zero++; break;
         case kMkScalar: f_scalar.push_back(h_scalar[m.idx]); L.n_scalar++; break;
         case kMkStat: f_stat.push_back(h_stat[m.idx]); L.n_stat++; break;
-        case kMkAccum:
-          f_accum.push_back(h_accum[m.idx]);
-          L.n_accum++;
-          L.accum_bytes_per_pattern += 32. * h_accum[m.idx].n_items + 32.;
-          break;
-        case kMkMult: {
-          MultOp mo = h_mult[m.idx];
-          mo.max_slot = static_cast<int32_t>(f_mult.size());
-          f_mult.push_back(mo);
-          L.n_mult++;
+        case kMkNode: {
+          NodeOp nd = h_node[m.idx];
+          for (int g = 0; g < nd.n_groups; ++g)
+            L.node_bytes_per_pattern += 32. * nd.g[g].n_items + 32.;
+          for (int t = 0; t < nd.n_mults; ++t) {
+            nd.m[t].max_slot = static_cast<int32_t>(f_mult.size());
+            MultOp mo{};
+            mo.dest = nd.m[t].dest;
+            mo.s1 = nd.m[t].s1;
+            mo.s2 = nd.m[t].s2;
+            mo.dest_id = nd.m[t].dest_id;
+            mo.max_slot = nd.m[t].max_slot;
+            f_mult.push_back(mo);
+            L.n_mult++;
+            L.node_bytes_per_pattern += 96.;
+          }
+          f_node.push_back(nd);
+          L.n_node++;
           break;
         }
+        case kMkAccum:
+        case kMkMult:
+          Fail("internal: unfused accumulate/multiply macro after node fusion");
         case kMkLik:
           f_lik.push_back(h_lik[m.idx]);
           f_lik_scatter.push_back(h_lik[m.idx].edge);
@@ -985,11 +1095,13 @@ Program* Engine::Compile(const bito_gp_op* ops, int64_t n, const int64_t* vec, i
         prog->max_partials, std::max<int64_t>(L.n_lik, L.has_marg ? L.n_marg + 1 : 0) * tiles);
     prog->max_packed = std::max<int64_t>(prog->max_packed,
                                          std::max<int64_t>(L.n_lik, L.n_marg + 1));
-    prog->launches += (L.n_zero > 0) + (L.n_scalar > 0) + (L.n_stat > 0) + (L.n_accum > 0) +
-                      2 * (L.n_mult > 0) + 2 * (L.n_lik > 0) + 2 * L.has_marg;
+    prog->launches += (L.n_zero > 0) + (L.n_scalar > 0) + (L.n_stat > 0) + 2 * (L.n_node > 0) +
+                      (L.n_mult > 0) + 3 * (L.n_lik > 0) + 2 * L.has_marg;
+    prog->max_lik_level = std::max<int64_t>(prog->max_lik_level, L.n_lik);
   }
   prog->n_mult_total = static_cast<int>(f_mult.size());
   prog->n_opt_total = static_cast<int>(f_opt.size());
+  prog->n_items_total = static_cast<int64_t>(h_items.size());
   prog->n_macro = static_cast<int64_t>(macros.size());
   prog->alg_bytes_per_pattern = alg_bytes;
   prog->alloc_version = alloc_version_;
@@ -1004,7 +1116,7 @@ Program* Engine::Compile(const bito_gp_op* ops, int64_t n, const int64_t* vec, i
   const size_t o_zero = reserve(f_zero.size() * sizeof(ZeroOp));
   const size_t o_scalar = reserve(f_scalar.size() * sizeof(ScalarOp));
   const size_t o_stat = reserve(f_stat.size() * sizeof(StatOp));
-  const size_t o_accum = reserve(f_accum.size() * sizeof(AccumGroup));
+  const size_t o_node = reserve(f_node.size() * sizeof(NodeOp));
   const size_t o_items = reserve(h_items.size() * sizeof(AccumItem));
   const size_t o_mult = reserve(f_mult.size() * sizeof(MultOp));
   const size_t o_lik = reserve(f_lik.size() * sizeof(LikOp));
@@ -1021,7 +1133,7 @@ Program* Engine::Compile(const bito_gp_op* ops, int64_t n, const int64_t* vec, i
   put(o_zero, f_zero.data(), f_zero.size() * sizeof(ZeroOp));
   put(o_scalar, f_scalar.data(), f_scalar.size() * sizeof(ScalarOp));
   put(o_stat, f_stat.data(), f_stat.size() * sizeof(StatOp));
-  put(o_accum, f_accum.data(), f_accum.size() * sizeof(AccumGroup));
+  put(o_node, f_node.data(), f_node.size() * sizeof(NodeOp));
   put(o_items, h_items.data(), h_items.size() * sizeof(AccumItem));
   put(o_mult, f_mult.data(), f_mult.size() * sizeof(MultOp));
   put(o_lik, f_lik.data(), f_lik.size() * sizeof(LikOp));
@@ -1037,7 +1149,7 @@ Program* Engine::Compile(const bito_gp_op* ops, int64_t n, const int64_t* vec, i
   prog->d_zero = reinterpret_cast<ZeroOp*>(a + o_zero);
   prog->d_scalar = reinterpret_cast<ScalarOp*>(a + o_scalar);
   prog->d_stat = reinterpret_cast<StatOp*>(a + o_stat);
-  prog->d_accum = reinterpret_cast<AccumGroup*>(a + o_accum);
+  prog->d_node = reinterpret_cast<NodeOp*>(a + o_node);
   prog->d_items = reinterpret_cast<AccumItem*>(a + o_items);
   prog->d_mult = reinterpret_cast<MultOp*>(a + o_mult);
   prog->d_lik = reinterpret_cast<LikOp*>(a + o_lik);
@@ -1082,24 +1194,32 @@ void Engine::ExecuteLevels(Program& prog, size_t first, size_t last) {
       ProfScope ps(this, kProfStationary, 32. * L.n_stat * Pd);
       LaunchStationary(stream_, st, prog.d_stat + L.stat_off, L.n_stat);
     }
-    if (L.n_accum > 0) {
-      ProfScope ps(this, kProfAccum, L.accum_bytes_per_pattern * Pd);
-      LaunchAccum(stream_, st, prog.d_accum + L.accum_off, prog.d_items, prog.d_pool, L.n_accum);
-    }
-    if (L.n_mult > 0) {
+    if (L.n_node > 0) {
       {
-        ProfScope ps(this, kProfMultiply, 96. * L.n_mult * Pd);
-        LaunchMultiply(stream_, st, prog.d_mult + L.mult_off, L.n_mult, d_level_max_.ptr);
+        ProfScope ps(this, kProfPrologue, 0.);
+        LaunchNodePrologue(stream_, st, prog.d_node + L.node_off, prog.d_items, prog.d_pool, L.n_node,
+                           d_mtab_.ptr);
       }
-      // The rescale decision needs the max over ALL patterns of the PLV (gp_engine.cpp:583-597).
-      AllReduce(d_level_max_.ptr + L.mult_off, L.n_mult, true);
-      ProfScope ps(this, kProfRescale, 0.);
-      LaunchRescale(stream_, st, prog.d_mult + L.mult_off, L.n_mult, d_level_max_.ptr);
+      {
+        ProfScope ps(this, kProfNode, L.node_bytes_per_pattern * Pd);
+        LaunchNodes(stream_, st, prog.d_node + L.node_off, prog.d_items, d_mtab_.ptr, L.n_node,
+                    d_level_max_.ptr);
+      }
+      if (L.n_mult > 0) {
+        // The rescale decision needs the max over ALL patterns of the PLV (gp_engine.cpp:583-597).
+        AllReduce(d_level_max_.ptr + L.mult_off, L.n_mult, true);
+        ProfScope ps(this, kProfRescale, 0.);
+        LaunchRescale(stream_, st, prog.d_mult + L.mult_off, L.n_mult, d_level_max_.ptr);
+      }
     }
     if (L.n_lik > 0) {
       {
+        ProfScope ps(this, kProfPrologue, 0.);
+        LaunchLikPrologue(stream_, st, prog.d_lik + L.lik_off, L.n_lik, d_mtab_lik_.ptr);
+      }
+      {
         ProfScope ps(this, kProfLikelihood, 72. * L.n_lik * Pd);
-        LaunchLikelihood(stream_, st, prog.d_lik + L.lik_off, L.n_lik, d_partials_.ptr);
+        LaunchLikelihood(stream_, st, prog.d_lik + L.lik_off, L.n_lik, d_mtab_lik_.ptr, d_partials_.ptr);
       }
       ProfScope ps(this, kProfReduce, 0.);
       if (n_ranks_ == 1) {
@@ -1209,14 +1329,19 @@ void Engine::RunOptimizer(const OptOp* d_ops, int n_ops, int method, bool check_
 
 void Engine::Execute(Program& prog) {
   EnsureScratch(prog.max_partials, prog.max_packed);
-  if (static_cast<size_t>(prog.n_mult_total) > d_level_max_.n) {
-    GP_CUDA(cudaStreamSynchronize(stream_));
-    d_level_max_.Resize(static_cast<size_t>(prog.n_mult_total) + 64, false, stream_);
-    for (auto& kv : programs_) {
-      if (kv.second->graph != nullptr) cudaGraphExecDestroy(kv.second->graph);
-      kv.second->graph = nullptr;
-      kv.second->graph_tried = false;
-    }
+  {
+    bool grew = false;
+    auto grow = [&](DeviceArray<double>& a, int64_t want) {
+      if (static_cast<size_t>(want) > a.n) {
+        GP_CUDA(cudaStreamSynchronize(stream_));
+        a.Resize(static_cast<size_t>(want + want / 4 + 64), false, stream_);
+        grew = true;
+      }
+    };
+    grow(d_level_max_, prog.n_mult_total);
+    grow(d_mtab_, 16 * prog.n_items_total);
+    grow(d_mtab_lik_, 16 * prog.max_lik_level);
+    if (grew) DropGraphs();  // captured graphs hold the old scratch addresses
   }
   const bool want_graph =
       !(cfg_.flags & BITO_GP_FLAG_NO_CUDA_GRAPHS) && prog.n_opt_total == 0 && !profiling_;
@@ -1657,7 +1782,7 @@ void Engine::CopyGpcspData(int64_t src, int64_t dest) {  // gp_engine.cpp:401-40
 }
 
 // ---- per-kernel timing with CUDA events on the launching stream (bench.py's roofline) ---------------
-const char* const kProfNames[kProfKinds] = {"k_zero", "k_scalar", "k_stationary", "k_accum", "k_multiply",
+const char* const kProfNames[kProfKinds] = {"k_zero", "k_scalar", "k_stationary", "k_prologue", "k_node",
                                             "k_rescale", "k_likelihood", "k_marginal", "k_reduce_partials",
                                             "k_opt_prepare", "k_opt_eval", "k_opt_step"};
 

@@ -64,12 +64,12 @@ struct Level {
   int zero_off = 0, n_zero = 0;
   int scalar_off = 0, n_scalar = 0;
   int stat_off = 0, n_stat = 0;
-  int accum_off = 0, n_accum = 0;
-  int mult_off = 0, n_mult = 0;
+  int node_off = 0, n_node = 0;  // fused accumulate/multiply macro-ops (k_node)
+  int mult_off = 0, n_mult = 0;  // the Multiplies inside those nodes (rescale decisions)
   int lik_off = 0, n_lik = 0;
   int marg_off = 0, n_marg = 0, marg_reset = 0, has_marg = 0, marg_scatter_off = 0;
   int opt_off = 0, n_opt = 0;
-  double accum_bytes_per_pattern = 0.;
+  double node_bytes_per_pattern = 0.;
 };
 
 struct Program {
@@ -81,7 +81,7 @@ struct Program {
   ZeroOp* d_zero = nullptr;
   ScalarOp* d_scalar = nullptr;
   StatOp* d_stat = nullptr;
-  AccumGroup* d_accum = nullptr;
+  NodeOp* d_node = nullptr;
   AccumItem* d_items = nullptr;
   MultOp* d_mult = nullptr;
   LikOp* d_lik = nullptr;
@@ -92,6 +92,8 @@ struct Program {
   int32_t* d_marg_scatter = nullptr;  // per marginal level: n_marg edges + marginal slot
   int n_mult_total = 0;
   int n_opt_total = 0;
+  int64_t n_items_total = 0;  // transition matrices of all accumulate items (mtab slots)
+  int64_t max_lik_level = 0;  // most Likelihood ops in one level (lik mtab slots)
   int64_t max_partials = 0;  // doubles of tile partials needed by any level
   int64_t max_packed = 0;    // reduced scalars needed by any level
   int64_t n_macro = 0;
@@ -102,7 +104,7 @@ struct Program {
 };
 
 enum ProfKind {
-  kProfZero, kProfScalar, kProfStationary, kProfAccum, kProfMultiply, kProfRescale, kProfLikelihood,
+  kProfZero, kProfScalar, kProfStationary, kProfPrologue, kProfNode, kProfRescale, kProfLikelihood,
   kProfMarginal, kProfReduce, kProfOptPrepare, kProfOptEval, kProfOptStep, kProfKinds
 };
 
@@ -199,6 +201,7 @@ class Engine {
   void RunOptimizer(const OptOp* d_ops, int n_ops, int method, bool check_convergence);
   void FreeProgram(Program& p);
   void EnsureScratch(int64_t partial_doubles, int64_t packed_doubles);
+  void DropGraphs();
   void AllReduce(double* buf, int64_t n, bool max_op);
 
   bito_gp_config cfg_;
@@ -229,7 +232,7 @@ class Engine {
   DeviceArray<uint32_t> d_status_;
   DeviceArray<unsigned long long> d_feval_total_;
   // scratch
-  DeviceArray<double> d_partials_, d_packed_, d_level_max_, d_coef_, d_dense_tmp_;
+  DeviceArray<double> d_partials_, d_packed_, d_level_max_, d_coef_, d_dense_tmp_, d_mtab_, d_mtab_lik_;
   DeviceArray<OptState> d_opt_states_;
   DeviceArray<int32_t> d_active_;
   DeviceArray<OptOp> d_single_opt_;

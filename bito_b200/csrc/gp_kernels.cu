@@ -130,151 +130,233 @@ struct MaxOp {
   __device__ double operator()(double a, double b) const { return a > b ? a : b; }
 };
 
-// ---- IncrementWithWeightedEvolvedPLV groups -------------------------------------------
-// dest (+)= sum_i (thr^(count[src_i]-count[dest]) * q[e_i]) * M(t_{e_i}) * src_i, applied in
-// op-list order (gp_engine.cpp:229-249), with the preceding ZeroPLV /
-// PrepForMarginalization folded in (:213-216, :323-333).
-__global__ void __launch_bounds__(kTile)
-    k_accum(DeviceState st, const AccumGroup* __restrict__ groups,
-            const AccumItem* __restrict__ items, const int32_t* __restrict__ pool, int tiles) {
-  const int g = blockIdx.x / tiles;
-  const int tile = blockIdx.x - g * tiles;
-  const AccumGroup grp = groups[g];
-  __shared__ double sM[kItemChunk][16];
-  __shared__ int s_dest_count;
-
-  if (threadIdx.x == 0) {
+// ---- per-level prologue: rescaling counts and scaled transition matrices ---------------------
+// One warp per node macro-op. For every accumulate group: count[dest] (ZeroPLV -> 0,
+// PrepForMarginalization -> min over its src_vector, gp_engine.cpp:213-216, 323-333), then one
+// 4x4 matrix per IncrementWithWeightedEvolvedPLV, (thr^(count[src]-count[dest]) * q[e]) * M(t_e)
+// (gp_engine.cpp:229-249, 341-344), into `mtab` so that no pattern tile ever waits on exp().
+// For every Multiply: count[dest] = count[s1] + count[s2] (gp_engine.cpp:281-282).
+__global__ void k_node_prologue(DeviceState st, const NodeOp* __restrict__ nodes,
+                                const AccumItem* __restrict__ items,
+                                const int32_t* __restrict__ pool, int n_nodes,
+                                double* __restrict__ mtab) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= n_nodes) return;
+  const NodeOp* nd = nodes + w;
+  const int ng = nd->n_groups, nm = nd->n_mults;
+  int gcount0 = 0, gcount1 = 0;
+  for (int gi = 0; gi < ng; ++gi) {
+    const AccumGroup* grp = &nd->g[gi];
+    const int mode = grp->count_mode, dest_id = grp->dest_id;
     int c;
-    if (grp.count_mode == kCountPrep) {
+    if (mode == kCountPrep) {
       c = INT_MAX;
-      for (int i = 0; i < grp.prep_len; ++i) c = min(c, st.counts[pool[grp.prep_off + i]]);
-    } else if (grp.count_mode == kCountZero) {
+      for (int i = lane; i < grp->prep_len; i += 32) c = min(c, st.counts[pool[grp->prep_off + i]]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) c = min(c, __shfl_xor_sync(0xffffffffu, c, o));
+    } else if (mode == kCountZero) {
       c = 0;
     } else {
-      c = st.counts[grp.dest_id];
+      c = st.counts[dest_id];
     }
-    s_dest_count = c;
-    if (tile == 0 && grp.count_mode != kCountKeep) st.counts[grp.dest_id] = c;
-  }
-  __syncthreads();
-  const int dest_count = s_dest_count;
-
-  const int64_t p = static_cast<int64_t>(tile) * kTile + threadIdx.x;
-  const bool live = p < st.P;
-  V4 acc = {0., 0., 0., 0.};
-  if (live && !grp.init_zero) acc = ld256(grp.dest + 4 * p);
-
-  for (int base = 0; base < grp.n_items; base += kItemChunk) {
-    const int n = min(kItemChunk, grp.n_items - base);
-    if (threadIdx.x < n) {
-      const AccumItem it = items[grp.item_off + base + threadIdx.x];
-      const int diff = st.counts[it.src.id] - dest_count;
+    if (gi == 0) gcount0 = c; else gcount1 = c;
+    const int n_items = grp->n_items, item_off = grp->item_off;
+    for (int i = lane; i < n_items; i += 32) {
+      const AccumItem it = items[item_off + i];
+      const int src_count = it.src.id == dest_id ? c : st.counts[it.src.id];
+      const int diff = src_count - c;
       if (diff < 0) atomicOr(st.status, kErrRescalingDifference);
       const double factor = diff == 0 ? 1. : pow(st.thr, static_cast<double>(diff));
-      build_matrix(st.bl[it.edge], 0, factor * st.q[it.edge], sM[threadIdx.x]);
+      build_matrix(st.bl[it.edge], 0, factor * st.q[it.edge],
+                   mtab + 16 * static_cast<int64_t>(item_off + i));
+    }
+    __syncwarp();
+    if (lane == 0 && mode != kCountKeep) st.counts[dest_id] = c;
+  }
+  if (lane == 0) {
+    for (int mi = 0; mi < nm; ++mi) {
+      const NodeMult* m = &nd->m[mi];
+      const int c1 = m->s1_group == 0 ? gcount0 : (m->s1_group == 1 ? gcount1 : st.counts[m->s1.id]);
+      const int c2 = m->s2_group == 0 ? gcount0 : (m->s2_group == 1 ? gcount1 : st.counts[m->s2.id]);
+      st.counts[m->dest_id] = c1 + c2;
+    }
+  }
+}
+
+__device__ __forceinline__ V4 load_item(const void* ptr, int kind, int64_t p) {
+  PlvRef r;
+  r.ptr = ptr;
+  r.kind = kind;
+  r.id = 0;
+  return load_plv(r, p);
+}
+
+// acc += sum_{i in [b, e)} sM[i] * src_i[p], four independent 32-byte loads in flight.
+__device__ __forceinline__ void accumulate_items(V4& acc, const double (*sM)[16],
+                                                 const void* const* s_ptr, const int* s_kind,
+                                                 int b, int e, int64_t p) {
+  int i = b;
+  for (; i + 4 <= e; i += 4) {
+    const V4 x0 = load_item(s_ptr[i], s_kind[i], p);
+    const V4 x1 = load_item(s_ptr[i + 1], s_kind[i + 1], p);
+    const V4 x2 = load_item(s_ptr[i + 2], s_kind[i + 2], p);
+    const V4 x3 = load_item(s_ptr[i + 3], s_kind[i + 3], p);
+    const V4 y0 = matvec(sM[i], x0);
+    acc.a += y0.a; acc.b += y0.b; acc.c += y0.c; acc.d += y0.d;
+    const V4 y1 = matvec(sM[i + 1], x1);
+    acc.a += y1.a; acc.b += y1.b; acc.c += y1.c; acc.d += y1.d;
+    const V4 y2 = matvec(sM[i + 2], x2);
+    acc.a += y2.a; acc.b += y2.b; acc.c += y2.c; acc.d += y2.d;
+    const V4 y3 = matvec(sM[i + 3], x3);
+    acc.a += y3.a; acc.b += y3.b; acc.c += y3.c; acc.d += y3.d;
+  }
+  for (; i < e; ++i) {
+    const V4 x0 = load_item(s_ptr[i], s_kind[i], p);
+    const V4 y0 = matvec(sM[i], x0);
+    acc.a += y0.a; acc.b += y0.b; acc.c += y0.c; acc.d += y0.d;
+  }
+}
+
+// ---- node macro-ops: accumulate groups fused with the Multiplies that consume them -------------
+// Group g: dest (+)= sum_i Mtab_i * src_i in op-list order (gp_engine.cpp:229-249); Multiply:
+// dest = s1 o s2 with operands taken from registers when a group of this node produced them
+// (gp_engine.cpp:278-285), plus the per-PLV maximum for the rescale decision (:583-597).
+// Blocks are ordered tile-major (all macro-ops of one pattern tile are neighbours in the grid), so
+// a PLV tile read by several macro-ops of the level is served from L2 after its first use.
+__global__ void __launch_bounds__(kTile, 4)
+    k_node(DeviceState st, const NodeOp* __restrict__ nodes, const AccumItem* __restrict__ items,
+           const double* __restrict__ mtab, int n_nodes, unsigned long long* __restrict__ level_max) {
+  const int tile = blockIdx.x / n_nodes;
+  const int o = blockIdx.x - tile * n_nodes;
+  const NodeOp* nd = nodes + o;
+  __shared__ __align__(32) double sM[kItemChunk][16];
+  __shared__ const void* s_ptr[kItemChunk];
+  __shared__ int s_kind[kItemChunk];
+
+  const int ng = nd->n_groups, nm = nd->n_mults;
+  const int n0 = ng > 0 ? nd->g[0].n_items : 0;
+  const int n_tot = n0 + (ng > 1 ? nd->g[1].n_items : 0);
+  const int item_base = ng > 0 ? nd->g[0].item_off : 0;
+  const int64_t p = static_cast<int64_t>(tile) * kTile + threadIdx.x;
+  const bool live = p < st.P;
+
+  V4 acc0 = {0., 0., 0., 0.}, acc1 = {0., 0., 0., 0.};
+  if (live && ng > 0 && !nd->g[0].init_zero) acc0 = ld256(nd->g[0].dest + 4 * p);
+  if (live && ng > 1 && !nd->g[1].init_zero) acc1 = ld256(nd->g[1].dest + 4 * p);
+
+  for (int base = 0; base < n_tot; base += kItemChunk) {
+    const int n = min(kItemChunk, n_tot - base);
+    {
+      const int it = threadIdx.x >> 2, quarter = threadIdx.x & 3;
+      if (it < n) {
+        const int64_t gi = item_base + base + it;
+        const V4 m = ld256(mtab + 16 * gi + 4 * quarter);
+        double* dst = &sM[it][4 * quarter];
+        dst[0] = m.a; dst[1] = m.b; dst[2] = m.c; dst[3] = m.d;
+        if (quarter == 0) {
+          s_ptr[it] = items[gi].src.ptr;
+          s_kind[it] = items[gi].src.kind;
+        }
+      }
     }
     __syncthreads();
     if (live) {
-      int i = 0;
-      // Two independent 32-byte loads in flight per iteration.
-      for (; i + 1 < n; i += 2) {
-        const V4 x0 = load_plv(items[grp.item_off + base + i].src, p);
-        const V4 x1 = load_plv(items[grp.item_off + base + i + 1].src, p);
-        const V4 y0 = matvec(sM[i], x0);
-        acc.a += y0.a; acc.b += y0.b; acc.c += y0.c; acc.d += y0.d;
-        const V4 y1 = matvec(sM[i + 1], x1);
-        acc.a += y1.a; acc.b += y1.b; acc.c += y1.c; acc.d += y1.d;
-      }
-      if (i < n) {
-        const V4 x0 = load_plv(items[grp.item_off + base + i].src, p);
-        const V4 y0 = matvec(sM[i], x0);
-        acc.a += y0.a; acc.b += y0.b; acc.c += y0.c; acc.d += y0.d;
-      }
+      // chunk positions [0, n) hold items [base, base + n) of the node; the first n0 items
+      // of the node belong to group 0.
+      const int split = max(0, min(n, n0 - base));
+      accumulate_items(acc0, sM, s_ptr, s_kind, 0, split, p);
+      accumulate_items(acc1, sM, s_ptr, s_kind, split, n, p);
     }
     __syncthreads();
   }
-  if (live) st256(grp.dest + 4 * p, acc);
-}
-
-// ---- Multiply: dest = s1 o s2, count = c1 + c2, per-PLV max for the rescale decision ----
-__global__ void __launch_bounds__(kTile)
-    k_multiply(DeviceState st, const MultOp* __restrict__ ops, int tiles,
-               unsigned long long* __restrict__ level_max) {
-  const int o = blockIdx.x / tiles;
-  const int tile = blockIdx.x - o * tiles;
-  const MultOp op = ops[o];
-  const int64_t p = static_cast<int64_t>(tile) * kTile + threadIdx.x;
-  double mx = 0.;
-  if (p < st.P) {
-    const V4 x = load_plv(op.s1, p);
-    const V4 y = load_plv(op.s2, p);
-    V4 v = {x.a * y.a, x.b * y.b, x.c * y.c, x.d * y.d};
-    st256(op.dest + 4 * p, v);
-    const double hi = fmax(fmax(v.a, v.b), fmax(v.c, v.d));
-    const double lo = fmin(fmin(v.a, v.b), fmin(v.c, v.d));
-    // AssertPLVIsFinite (:575-577), non-negativity (:585-586). fmax/fmin drop NaNs, so
-    // test the sum as well.
-    if (!isfinite(v.a + v.b + v.c + v.d)) atomicOr(st.status, kErrMultiplyNotFinite);
-    else if (lo < 0.) atomicOr(st.status, kErrNegativePLV);
-    mx = hi > 0. ? hi : 0.;
+  if (live) {
+    if (ng > 0) st256(nd->g[0].dest + 4 * p, acc0);
+    if (ng > 1) st256(nd->g[1].dest + 4 * p, acc1);
   }
-  mx = block_reduce(mx, MaxOp(), 0.);
-  if (threadIdx.x == 0) {
+  for (int mi = 0; mi < nm; ++mi) {
+    const NodeMult* m = &nd->m[mi];
+    double mx = 0.;
+    if (live) {
+      const int g1 = m->s1_group, g2 = m->s2_group;
+      const V4 x = g1 == 0 ? acc0 : (g1 == 1 ? acc1 : load_plv(m->s1, p));
+      const V4 y = g2 == 0 ? acc0 : (g2 == 1 ? acc1 : load_plv(m->s2, p));
+      const V4 v = {x.a * y.a, x.b * y.b, x.c * y.c, x.d * y.d};
+      st256(m->dest + 4 * p, v);
+      const double hi = fmax(fmax(v.a, v.b), fmax(v.c, v.d));
+      const double lo = fmin(fmin(v.a, v.b), fmin(v.c, v.d));
+      // AssertPLVIsFinite (:575-577), non-negativity (:585-586). fmax/fmin drop NaNs, so
+      // test the sum as well.
+      if (!isfinite(v.a + v.b + v.c + v.d)) atomicOr(st.status, kErrMultiplyNotFinite);
+      else if (lo < 0.) atomicOr(st.status, kErrNegativePLV);
+      mx = hi > 0. ? hi : 0.;
+    }
+    mx = block_reduce(mx, MaxOp(), 0.);
     // Non-negative doubles order like their bit patterns.
-    if (mx > 0.) atomicMax(level_max + op.max_slot, static_cast<unsigned long long>(__double_as_longlong(mx)));
-    if (tile == 0) st.counts[op.dest_id] = st.counts[op.s1.id] + st.counts[op.s2.id];
+    if (threadIdx.x == 0 && mx > 0.)
+      atomicMax(level_max + m->max_slot, static_cast<unsigned long long>(__double_as_longlong(mx)));
   }
 }
 
-// RescalePLVIfNeeded + RescalePLV (gp_engine.cpp:564-573, 583-597). The maximum is over
-// the whole PLV (all patterns, all ranks); almost always a no-op.
+// RescalePLVIfNeeded + RescalePLV (gp_engine.cpp:564-573, 583-597). The maximum is over the
+// whole PLV (all patterns, all ranks); almost always nothing to do, so the grid is small and
+// fixed: each block walks the level's Multiplies and only touches the PLVs that need it.
 __global__ void __launch_bounds__(kTile)
-    k_rescale(DeviceState st, const MultOp* __restrict__ ops, int tiles,
+    k_rescale(DeviceState st, const MultOp* __restrict__ ops, int n_ops,
               const double* __restrict__ level_max) {
-  const int o = blockIdx.x / tiles;
-  const int tile = blockIdx.x - o * tiles;
-  const MultOp op = ops[o];
-  double max_entry = level_max[op.max_slot];
-  if (max_entry == 0.) return;
-  int rescaling_count = 0;
-  while (max_entry < st.thr) {
-    max_entry /= st.thr;
-    rescaling_count++;
+  for (int o = blockIdx.x; o < n_ops; o += gridDim.x) {
+    double max_entry = level_max[ops[o].max_slot];
+    if (max_entry == 0.) continue;
+    int rescaling_count = 0;
+    while (max_entry < st.thr) {
+      max_entry /= st.thr;
+      rescaling_count++;
+    }
+    if (rescaling_count == 0) continue;
+    const double divisor = pow(st.thr, static_cast<double>(rescaling_count));
+    double* dest = ops[o].dest;
+    for (int64_t p = threadIdx.x; p < st.P; p += kTile) {
+      V4 v = ld256(dest + 4 * p);
+      v.a /= divisor; v.b /= divisor; v.c /= divisor; v.d /= divisor;
+      st256(dest + 4 * p, v);
+    }
+    if (threadIdx.x == 0) st.counts[ops[o].dest_id] += rescaling_count;
   }
-  if (rescaling_count == 0) return;
-  const double divisor = pow(st.thr, static_cast<double>(rescaling_count));
-  const int64_t p = static_cast<int64_t>(tile) * kTile + threadIdx.x;
-  if (p < st.P) {
-    V4 v = ld256(op.dest + 4 * p);
-    v.a /= divisor; v.b /= divisor; v.c /= divisor; v.d /= divisor;
-    st256(op.dest + 4 * p, v);
-  }
-  // Every block of this op has read level_max before any could reach here only through
-  // its own copy; counts[dest] is written by one thread and read by none in this launch.
-  if (tile == 0 && threadIdx.x == 0) st.counts[op.dest_id] += rescaling_count;
 }
 
 // ---- Likelihood: row[p] = log(parent^T M(t_e) child) + (count_p + count_c) log thr -------
 // (gp_engine.cpp:287-291, gp_engine.hpp:273-282); also the weighted tile partial of the row.
+__global__ void k_lik_prologue(DeviceState st, const LikOp* __restrict__ ops, int n_ops,
+                               double* __restrict__ mtab) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o < n_ops) build_matrix(st.bl[ops[o].edge], 0, 1., mtab + 16 * static_cast<int64_t>(o));
+}
+
 __global__ void __launch_bounds__(kTile)
-    k_likelihood(DeviceState st, const LikOp* __restrict__ ops, int tiles,
-                 double* __restrict__ partials) {
-  const int o = blockIdx.x / tiles;
-  const int tile = blockIdx.x - o * tiles;
-  const LikOp op = ops[o];
+    k_likelihood(DeviceState st, const LikOp* __restrict__ ops, int n_ops,
+                 const double* __restrict__ mtab, double* __restrict__ partials) {
+  const int tile = blockIdx.x / n_ops;
+  const int o = blockIdx.x - tile * n_ops;
+  const int tiles = gridDim.x / n_ops;
+  const LikOp* op = ops + o;
   __shared__ double sM[16];
-  if (threadIdx.x == 0) build_matrix(st.bl[op.edge], 0, 1., sM);
+  const int64_t p = static_cast<int64_t>(tile) * kTile + threadIdx.x;
+  const bool live = p < st.P;
+  V4 r = {0., 0., 0., 0.}, c = {0., 0., 0., 0.};
+  if (live) {  // issued before the barrier: the PLV loads do not depend on the matrix
+    r = load_plv(op->parent, p);
+    c = load_plv(op->child, p);
+  }
+  if (threadIdx.x < 16) sM[threadIdx.x] = mtab[16 * static_cast<int64_t>(o) + threadIdx.x];
   __syncthreads();
   const double resc =
-      static_cast<double>(st.counts[op.parent.id]) * st.log_thr +
-      static_cast<double>(st.counts[op.child.id]) * st.log_thr;
-  const int64_t p = static_cast<int64_t>(tile) * kTile + threadIdx.x;
+      static_cast<double>(st.counts[op->parent.id]) * st.log_thr +
+      static_cast<double>(st.counts[op->child.id]) * st.log_thr;
   double wsum = 0.;
-  if (p < st.P) {
-    const V4 r = load_plv(op.parent, p);
-    const V4 c = load_plv(op.child, p);
+  if (live) {
     const double ll = log(quad(r, sM, c)) + resc;
-    if (op.row != nullptr) op.row[p] = ll;
+    double* row = op->row;
+    if (row != nullptr) row[p] = ll;
     wsum = ll * st.weights[p];
   }
   wsum = block_reduce(wsum, SumOp(), 0.);
@@ -784,30 +866,36 @@ inline unsigned Grid(int64_t n_ops, int64_t tiles) { return static_cast<unsigned
 
 }  // namespace
 
-void LaunchAccum(cudaStream_t s, const DeviceState& st, const AccumGroup* groups,
-                 const AccumItem* items, const int32_t* pool, int n_groups) {
-  if (n_groups == 0) return;
-  const int tiles = static_cast<int>(TilesFor(st.P));
-  k_accum<<<Grid(n_groups, tiles), kTile, 0, s>>>(st, groups, items, pool, tiles);
+void LaunchNodePrologue(cudaStream_t s, const DeviceState& st, const NodeOp* nodes,
+                         const AccumItem* items, const int32_t* pool, int n_nodes, double* mtab) {
+  if (n_nodes == 0) return;
+  const int warps_per_block = 4;
+  k_node_prologue<<<(n_nodes + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, s>>>(
+      st, nodes, items, pool, n_nodes, mtab);
 }
-void LaunchMultiply(cudaStream_t s, const DeviceState& st, const MultOp* ops, int n_ops,
-                    double* level_max) {
-  if (n_ops == 0) return;
+void LaunchNodes(cudaStream_t s, const DeviceState& st, const NodeOp* nodes, const AccumItem* items,
+                 const double* mtab, int n_nodes, double* level_max) {
+  if (n_nodes == 0) return;
   const int tiles = static_cast<int>(TilesFor(st.P));
-  k_multiply<<<Grid(n_ops, tiles), kTile, 0, s>>>(
-      st, ops, tiles, reinterpret_cast<unsigned long long*>(level_max));
+  k_node<<<Grid(n_nodes, tiles), kTile, 0, s>>>(st, nodes, items, mtab, n_nodes,
+                                                reinterpret_cast<unsigned long long*>(level_max));
 }
 void LaunchRescale(cudaStream_t s, const DeviceState& st, const MultOp* ops, int n_ops,
                    const double* level_max) {
   if (n_ops == 0) return;
-  const int tiles = static_cast<int>(TilesFor(st.P));
-  k_rescale<<<Grid(n_ops, tiles), kTile, 0, s>>>(st, ops, tiles, level_max);
+  const int grid = n_ops < 592 ? n_ops : 592;  // 148 SMs x 4 resident blocks
+  k_rescale<<<grid, kTile, 0, s>>>(st, ops, n_ops, level_max);
+}
+void LaunchLikPrologue(cudaStream_t s, const DeviceState& st, const LikOp* ops, int n_ops,
+                       double* mtab) {
+  if (n_ops == 0) return;
+  k_lik_prologue<<<(n_ops + 127) / 128, 128, 0, s>>>(st, ops, n_ops, mtab);
 }
 void LaunchLikelihood(cudaStream_t s, const DeviceState& st, const LikOp* ops, int n_ops,
-                      double* partials) {
+                      const double* mtab, double* partials) {
   if (n_ops == 0) return;
   const int tiles = static_cast<int>(TilesFor(st.P));
-  k_likelihood<<<Grid(n_ops, tiles), kTile, 0, s>>>(st, ops, tiles, partials);
+  k_likelihood<<<Grid(n_ops, tiles), kTile, 0, s>>>(st, ops, n_ops, mtab, partials);
 }
 void LaunchMarginal(cudaStream_t s, const DeviceState& st, const MargItem* items, int n_items,
                     int reset, double* partials) {

@@ -12,14 +12,17 @@ inline int64_t TilesFor(int64_t P) { return (P + kTile - 1) / kTile; }
 
 cudaError_t UploadModel(const ModelConst& model);
 
-void LaunchAccum(cudaStream_t s, const DeviceState& st, const AccumGroup* groups,
-                 const AccumItem* items, const int32_t* pool, int n_groups);
-void LaunchMultiply(cudaStream_t s, const DeviceState& st, const MultOp* ops, int n_ops,
-                    double* level_max);
+// Per level: counts + scaled transition matrices of every node macro-op into mtab[16 * item].
+void LaunchNodePrologue(cudaStream_t s, const DeviceState& st, const NodeOp* nodes,
+                        const AccumItem* items, const int32_t* pool, int n_nodes, double* mtab);
+void LaunchNodes(cudaStream_t s, const DeviceState& st, const NodeOp* nodes, const AccumItem* items,
+                 const double* mtab, int n_nodes, double* level_max);
 void LaunchRescale(cudaStream_t s, const DeviceState& st, const MultOp* ops, int n_ops,
                    const double* level_max);
+void LaunchLikPrologue(cudaStream_t s, const DeviceState& st, const LikOp* ops, int n_ops,
+                       double* mtab /* 16 * n_ops */);
 void LaunchLikelihood(cudaStream_t s, const DeviceState& st, const LikOp* ops, int n_ops,
-                      double* partials);
+                      const double* mtab, double* partials);
 void LaunchMarginal(cudaStream_t s, const DeviceState& st, const MargItem* items, int n_items,
                     int reset, double* partials /* (n_items + 1) x tiles */);
 void LaunchStationary(cudaStream_t s, const DeviceState& st, const StatOp* ops, int n_ops);

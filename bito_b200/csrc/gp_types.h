@@ -11,7 +11,7 @@
 namespace bito_gp {
 
 constexpr int kTile = 256;          // patterns per thread block (one pattern per thread)
-constexpr int kItemChunk = 32;      // transition matrices staged in shared memory at a time
+constexpr int kItemChunk = 64;      // transition matrices staged in shared memory at a time
 constexpr int kMaxEigenGroups = 4;  // distinct eigenvalues of the substitution model
 
 // How a PLV operand is stored in HBM.
@@ -101,6 +101,25 @@ struct MultOp {
   PlvRef s1, s2;
   int32_t dest_id;
   int32_t max_slot;
+};
+
+// A fused node macro-op: up to two accumulate groups followed by up to two Multiplies that
+// consume their results from registers. Rootward GPDAG node: PHatRight, PHatLeft, P = PHatRight o
+// PHatLeft (gp_dag.cpp:278-294); leafward node: RHat, RRight = RHat o PHatLeft, RLeft = RHat o
+// PHatRight (gp_dag.cpp:260-276). Unfused groups and Multiplies are nodes with one member.
+struct NodeMult {
+  double* dest;
+  PlvRef s1, s2;
+  int32_t dest_id;
+  int32_t max_slot;
+  int32_t s1_group;  // >= 0: operand is the result of that group of this node (registers)
+  int32_t s2_group;
+};
+struct NodeOp {
+  int32_t n_groups;  // 0..2
+  int32_t n_mults;   // 0..2
+  AccumGroup g[2];   // items of g[1] follow those of g[0] in the item table
+  NodeMult m[2];
 };
 
 // Likelihood (gp_engine.cpp:287-291).
