@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <sstream>
@@ -229,6 +230,8 @@ Engine::Engine(const bito_gp_config& cfg) : cfg_(cfg) {
     m.group[k] = g;
   }
   n_eigen_groups_ = m.n_groups;
+  for (int g = 0; g < m.n_groups; ++g) group_lambda_[g] = m.group_lambda[g];
+  if (const char* env = getenv("BITO_GP_OPT_CHUNK_MB")) opt_chunk_bytes_ = int64_t(atoll(env)) << 20;
   GP_CUDA(UploadModel(m));
 
   // PLV slabs: ~256 MiB chunks (or one PLV, whichever is larger).
@@ -264,7 +267,7 @@ Engine::~Engine() {
   d_q_.Release(); d_bl_.Release(); d_diff_.Release(); d_hybrid_.Release(); d_ll_sum_.Release();
   d_inverted_.Release(); d_uncond_.Release(); d_status_.Release(); d_feval_total_.Release();
   d_partials_.Release(); d_packed_.Release(); d_level_max_.Release(); d_coef_.Release();
-  d_dense_tmp_.Release(); d_mtab_.Release(); d_mtab_lik_.Release(); d_opt_states_.Release(); d_active_.Release(); d_single_opt_.Release();
+  d_dense_tmp_.Release(); d_mtab_.Release(); d_mtab_lik_.Release(); d_opt_states_.Release(); d_opt_const_.Release(); d_active_.Release(); d_single_opt_.Release();
   if (pinned_ != nullptr) cudaFreeHost(pinned_);
   if (ev_begin_) cudaEventDestroy(ev_begin_);
   if (ev_end_) cudaEventDestroy(ev_end_);
@@ -1222,11 +1225,12 @@ void Engine::ExecuteLevels(Program& prog, size_t first, size_t last) {
         LaunchLikelihood(stream_, st, prog.d_lik + L.lik_off, L.n_lik, d_mtab_lik_.ptr, d_partials_.ptr);
       }
       ProfScope ps(this, kProfReduce, 0.);
+      const int64_t lik_groups = LikelihoodTileGroups(L.n_lik, P_);
       if (n_ranks_ == 1) {
-        LaunchReducePartials(stream_, d_partials_.ptr, L.n_lik, tiles, d_packed_.ptr,
+        LaunchReducePartials(stream_, d_partials_.ptr, L.n_lik, lik_groups, d_packed_.ptr,
                              prog.d_lik_scatter + L.lik_off, st.ll_sum);
       } else {
-        LaunchReducePartials(stream_, d_partials_.ptr, L.n_lik, tiles, d_packed_.ptr, nullptr,
+        LaunchReducePartials(stream_, d_partials_.ptr, L.n_lik, lik_groups, d_packed_.ptr, nullptr,
                              nullptr);
         AllReduce(d_packed_.ptr, L.n_lik, false);
         LaunchScatter(stream_, d_packed_.ptr, L.n_lik, prog.d_lik_scatter + L.lik_off, st.ll_sum);
@@ -1259,19 +1263,29 @@ void Engine::RunOptimizeLevel(Program& prog, const Level& L) {
   RunOptimizer(prog.d_opt + L.opt_off, L.n_opt, method_, optimization_count_ != 0);
 }
 
-// Device-resident 1-D optimisers stepping every edge of the batch in lockstep: one
-// objective evaluation per round (eval -> reduce -> [all-reduce] -> step).
+// Device-resident 1-D optimisers stepping every edge of the batch in lockstep: one objective
+// evaluation per round (eval -> [reduce -> all-reduce] -> step). The PLVs of an edge are read once
+// (k_opt_prepare*); every round streams only the per-pattern coefficients.
 void Engine::RunOptimizer(const OptOp* d_ops, int n_ops, int method, bool check_convergence) {
   const DeviceState st = State();
   const int64_t tiles = TilesFor(P_);
   const int G = n_eigen_groups_;
-  const int64_t coef_per_op = P_stride_ * G;
-  const int64_t budget_doubles = (int64_t(256) << 20) / 8;
+  const int nd = method == BITO_GP_BRENT_OPTIMIZATION ? 0
+                 : method == BITO_GP_NEWTON_OPTIMIZATION ? 2 : 1;
+  // Plain Brent on a two-eigenvalue model (JC69, the only model GPEngine instantiates,
+  // gp_engine.hpp:366): ratio form, 8 B per pattern and one log per 8 patterns.
+  const bool ratio = (G == 2 && nd == 0);
+  const int64_t coef_per_op = P_stride_ * (ratio ? 1 : G);
+  const int64_t budget_doubles = (opt_chunk_bytes_ > 0 ? opt_chunk_bytes_ : (int64_t(1) << 30)) / 8;
   const int chunk = static_cast<int>(
       std::max<int64_t>(1, std::min<int64_t>(n_ops, budget_doubles / coef_per_op)));
   d_coef_.Resize(static_cast<size_t>(chunk * coef_per_op), false, stream_);
   d_opt_states_.Resize(static_cast<size_t>(chunk), false, stream_);
-  EnsureScratch(static_cast<int64_t>(chunk) * 3 * tiles, static_cast<int64_t>(chunk) * 3);
+  d_opt_const_.Resize(static_cast<size_t>(chunk), false, stream_);
+  const int64_t groups = ratio ? OptRatioTileGroups(P_) : tiles;
+  const int n_values = nd + 1, value_stride = ratio ? 1 : 3;
+  EnsureScratch(static_cast<int64_t>(chunk) * std::max<int64_t>(value_stride * groups, tiles),
+                static_cast<int64_t>(chunk) * 3);
 
   OptParams prm{};
   prm.significant_digits = significant_digits_;
@@ -1283,18 +1297,26 @@ void Engine::RunOptimizer(const OptOp* d_ops, int n_ops, int method, bool check_
   prm.step_size = kStepSizeForOptimization;
   prm.log_step_size = kStepSizeForLogSpaceOptimization;
   prm.diff_threshold = kBranchLengthDifferenceThreshold;
-  const int nd = method == BITO_GP_BRENT_OPTIMIZATION ? 0
-                 : method == BITO_GP_NEWTON_OPTIMIZATION ? 2 : 1;
   const int64_t max_rounds = 3 * kMaxIterForOptimization + 8;
   int32_t* h_active = static_cast<int32_t*>(pinned_);
 
   for (int c0 = 0; c0 < n_ops; c0 += chunk) {
     const int m = std::min(chunk, n_ops - c0);
-    {
+    if (ratio) {
+      {
+        ProfScope ps(this, kProfOptPrepare, 64. * m * static_cast<double>(P_));
+        LaunchOptPrepareRatio(stream_, st, d_ops + c0, m, d_opt_states_.ptr, prm, method, d_coef_.ptr,
+                              d_partials_.ptr);
+      }
+      ProfScope ps(this, kProfReduce, 0.);
+      LaunchReducePartials(stream_, d_partials_.ptr, m, tiles, d_opt_const_.ptr, nullptr, nullptr);
+      AllReduce(d_opt_const_.ptr, m, false);
+      stats_.kernel_launches += 2;
+    } else {
       ProfScope ps(this, kProfOptPrepare, 64. * m * static_cast<double>(P_));
       LaunchOptPrepare(stream_, st, d_ops + c0, m, d_opt_states_.ptr, prm, method, d_coef_.ptr, 1);
+      stats_.kernel_launches++;
     }
-    stats_.kernel_launches++;
     int64_t rounds = 0;
     int batch = method <= BITO_GP_BRENT_OPTIMIZATION_WITH_GRADIENTS ? 12 : 6;
     for (;;) {
@@ -1302,19 +1324,28 @@ void Engine::RunOptimizer(const OptOp* d_ops, int n_ops, int method, bool check_
         const bool last = (r == batch - 1);
         {
           ProfScope ps(this, kProfOptEval, 0.);
-          LaunchOptEval(stream_, st, m, d_opt_states_.ptr, d_coef_.ptr, nd, d_partials_.ptr, G);
+          if (ratio)
+            LaunchOptEvalRatio(stream_, st, m, d_opt_states_.ptr, d_coef_.ptr, d_partials_.ptr);
+          else
+            LaunchOptEval(stream_, st, m, d_opt_states_.ptr, d_coef_.ptr, nd, d_partials_.ptr, G);
         }
-        {
+        const double* sums = nullptr;
+        const double* parts = d_partials_.ptr;
+        if (n_ranks_ > 1) {
           ProfScope ps(this, kProfReduce, 0.);
-          LaunchReducePartials(stream_, d_partials_.ptr, 3 * m, tiles, d_packed_.ptr, nullptr,
-                               nullptr);
+          LaunchReducePartials(stream_, d_partials_.ptr, value_stride * m, groups, d_packed_.ptr,
+                               nullptr, nullptr);
+          AllReduce(d_packed_.ptr, static_cast<int64_t>(value_stride) * m, false);
+          sums = d_packed_.ptr;
+          parts = nullptr;
+          stats_.kernel_launches++;
         }
-        AllReduce(d_packed_.ptr, 3 * m, false);
         if (last) GP_CUDA(cudaMemsetAsync(d_active_.ptr, 0, sizeof(int32_t), stream_));
         ProfScope ps(this, kProfOptStep, 0.);
-        LaunchOptStep(stream_, st, m, d_opt_states_.ptr, prm, d_packed_.ptr,
+        LaunchOptStep(stream_, st, m, d_opt_states_.ptr, prm, sums, parts, static_cast<int>(groups),
+                      n_values, value_stride, ratio ? d_opt_const_.ptr : nullptr,
                       last ? d_active_.ptr : nullptr);
-        stats_.kernel_launches += 3;
+        stats_.kernel_launches += 2;
       }
       rounds += batch;
       GP_CUDA(cudaMemcpyAsync(h_active, d_active_.ptr, sizeof(int32_t), cudaMemcpyDeviceToHost,
@@ -1471,6 +1502,7 @@ void Engine::LogLikelihoodAndDerivatives(int64_t gpcsp, int64_t rootward, int64_
   OptState s{};
   s.t_eval = bl;
   s.done = 0;
+  for (int g = 0; g < n_eigen_groups_; ++g) s.e[g] = std::exp(group_lambda_[g] * bl);
   GP_CUDA(cudaMemcpyAsync(d_single_opt_.ptr, &op, sizeof op, cudaMemcpyHostToDevice, stream_));
   GP_CUDA(cudaMemcpyAsync(d_opt_states_.ptr, &s, sizeof s, cudaMemcpyHostToDevice, stream_));
   OptParams prm{};

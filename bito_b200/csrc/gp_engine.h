@@ -218,6 +218,8 @@ class Engine {
   bool have_patterns_ = false;
   bool timing_pending_ = false;
   int n_eigen_groups_ = 2;
+  double group_lambda_[kMaxEigenGroups] = {0., 0., 0., 0.};
+  int64_t opt_chunk_bytes_ = 0;  // coefficient scratch per optimiser batch (0: 1 GiB)
 
   SlabPool plv_pool_, row_pool_;
   std::vector<PlvSlot> plvs_;      // by logical PLV id (padded count)
@@ -234,6 +236,7 @@ class Engine {
   // scratch
   DeviceArray<double> d_partials_, d_packed_, d_level_max_, d_coef_, d_dense_tmp_, d_mtab_, d_mtab_lik_;
   DeviceArray<OptState> d_opt_states_;
+  DeviceArray<double> d_opt_const_;
   DeviceArray<int32_t> d_active_;
   DeviceArray<OptOp> d_single_opt_;
   void* pinned_ = nullptr;  // small pinned staging block

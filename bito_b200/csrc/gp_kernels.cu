@@ -10,6 +10,7 @@
 
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 
 namespace bito_gp {
 
@@ -224,11 +225,13 @@ __device__ __forceinline__ void accumulate_items(V4& acc, const double (*sM)[16]
 // (gp_engine.cpp:278-285), plus the per-PLV maximum for the rescale decision (:583-597).
 // Blocks are ordered tile-major (all macro-ops of one pattern tile are neighbours in the grid), so
 // a PLV tile read by several macro-ops of the level is served from L2 after its first use.
-__global__ void __launch_bounds__(kTile, 4)
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kTile, kMinBlocks)
     k_node(DeviceState st, const NodeOp* __restrict__ nodes, const AccumItem* __restrict__ items,
-           const double* __restrict__ mtab, int n_nodes, unsigned long long* __restrict__ level_max) {
-  const int tile = blockIdx.x / n_nodes;
-  const int o = blockIdx.x - tile * n_nodes;
+           const double* __restrict__ mtab, int n_nodes, int tiles, int tiles_per_block,
+           unsigned long long* __restrict__ level_max) {
+  const int tile_group = blockIdx.x / n_nodes;
+  const int o = blockIdx.x - tile_group * n_nodes;
   const NodeOp* nd = nodes + o;
   __shared__ __align__(32) double sM[kItemChunk][16];
   __shared__ const void* s_ptr[kItemChunk];
@@ -238,63 +241,87 @@ __global__ void __launch_bounds__(kTile, 4)
   const int n0 = ng > 0 ? nd->g[0].n_items : 0;
   const int n_tot = n0 + (ng > 1 ? nd->g[1].n_items : 0);
   const int item_base = ng > 0 ? nd->g[0].item_off : 0;
-  const int64_t p = static_cast<int64_t>(tile) * kTile + threadIdx.x;
-  const bool live = p < st.P;
+  double* const dest0 = ng > 0 ? nd->g[0].dest : nullptr;
+  double* const dest1 = ng > 1 ? nd->g[1].dest : nullptr;
+  const bool keep0 = ng > 0 && !nd->g[0].init_zero;
+  const bool keep1 = ng > 1 && !nd->g[1].init_zero;
 
-  V4 acc0 = {0., 0., 0., 0.}, acc1 = {0., 0., 0., 0.};
-  if (live && ng > 0 && !nd->g[0].init_zero) acc0 = ld256(nd->g[0].dest + 4 * p);
-  if (live && ng > 1 && !nd->g[1].init_zero) acc1 = ld256(nd->g[1].dest + 4 * p);
+  // Stage (a chunk of) the node's scaled transition matrices and source pointers: thread t
+  // moves quarter t&3 of item t>>2.
+  auto stage = [&](int base, int n) {
+    const int it = threadIdx.x >> 2, quarter = threadIdx.x & 3;
+    if (it < n) {
+      const int64_t gi = item_base + base + it;
+      const V4 m = ld256(mtab + 16 * gi + 4 * quarter);
+      double* dst = &sM[it][4 * quarter];
+      dst[0] = m.a; dst[1] = m.b; dst[2] = m.c; dst[3] = m.d;
+      if (quarter == 0) {
+        s_ptr[it] = items[gi].src.ptr;
+        s_kind[it] = items[gi].src.kind;
+      }
+    }
+  };
+  const bool single_chunk = n_tot <= kItemChunk;
+  if (n_tot > 0 && single_chunk) {
+    stage(0, n_tot);
+    __syncthreads();
+  }
 
-  for (int base = 0; base < n_tot; base += kItemChunk) {
-    const int n = min(kItemChunk, n_tot - base);
-    {
-      const int it = threadIdx.x >> 2, quarter = threadIdx.x & 3;
-      if (it < n) {
-        const int64_t gi = item_base + base + it;
-        const V4 m = ld256(mtab + 16 * gi + 4 * quarter);
-        double* dst = &sM[it][4 * quarter];
-        dst[0] = m.a; dst[1] = m.b; dst[2] = m.c; dst[3] = m.d;
-        if (quarter == 0) {
-          s_ptr[it] = items[gi].src.ptr;
-          s_kind[it] = items[gi].src.kind;
+  double mx0 = 0., mx1 = 0.;
+  const int tile_begin = tile_group * tiles_per_block;
+  const int tile_end = min(tiles, tile_begin + tiles_per_block);
+  for (int tile = tile_begin; tile < tile_end; ++tile) {
+    const int64_t p = static_cast<int64_t>(tile) * kTile + threadIdx.x;
+    const bool live = p < st.P;
+    V4 acc0 = {0., 0., 0., 0.}, acc1 = {0., 0., 0., 0.};
+    if (live && keep0) acc0 = ld256(dest0 + 4 * p);
+    if (live && keep1) acc1 = ld256(dest1 + 4 * p);
+    if (single_chunk) {
+      if (live) {
+        accumulate_items(acc0, sM, s_ptr, s_kind, 0, n0, p);
+        accumulate_items(acc1, sM, s_ptr, s_kind, n0, n_tot, p);
+      }
+    } else {
+      for (int base = 0; base < n_tot; base += kItemChunk) {
+        const int n = min(kItemChunk, n_tot - base);
+        __syncthreads();  // the previous chunk (or tile) is done with sM
+        stage(base, n);
+        __syncthreads();
+        if (live) {
+          // chunk positions [0, n) hold items [base, base + n) of the node; the first n0 items
+          // of the node belong to group 0.
+          const int split = max(0, min(n, n0 - base));
+          accumulate_items(acc0, sM, s_ptr, s_kind, 0, split, p);
+          accumulate_items(acc1, sM, s_ptr, s_kind, split, n, p);
         }
       }
     }
-    __syncthreads();
     if (live) {
-      // chunk positions [0, n) hold items [base, base + n) of the node; the first n0 items
-      // of the node belong to group 0.
-      const int split = max(0, min(n, n0 - base));
-      accumulate_items(acc0, sM, s_ptr, s_kind, 0, split, p);
-      accumulate_items(acc1, sM, s_ptr, s_kind, split, n, p);
+      if (ng > 0) st256(dest0 + 4 * p, acc0);
+      if (ng > 1) st256(dest1 + 4 * p, acc1);
+      for (int mi = 0; mi < nm; ++mi) {
+        const NodeMult* m = &nd->m[mi];
+        const int g1 = m->s1_group, g2 = m->s2_group;
+        const V4 x = g1 == 0 ? acc0 : (g1 == 1 ? acc1 : load_plv(m->s1, p));
+        const V4 y = g2 == 0 ? acc0 : (g2 == 1 ? acc1 : load_plv(m->s2, p));
+        const V4 v = {x.a * y.a, x.b * y.b, x.c * y.c, x.d * y.d};
+        st256(m->dest + 4 * p, v);
+        const double hi = fmax(fmax(v.a, v.b), fmax(v.c, v.d));
+        const double lo = fmin(fmin(v.a, v.b), fmin(v.c, v.d));
+        // AssertPLVIsFinite (:575-577), non-negativity (:585-586). fmax/fmin drop NaNs, so
+        // test the sum as well.
+        if (!isfinite(v.a + v.b + v.c + v.d)) atomicOr(st.status, kErrMultiplyNotFinite);
+        else if (lo < 0.) atomicOr(st.status, kErrNegativePLV);
+        if (mi == 0) mx0 = fmax(mx0, hi); else mx1 = fmax(mx1, hi);
+      }
     }
-    __syncthreads();
-  }
-  if (live) {
-    if (ng > 0) st256(nd->g[0].dest + 4 * p, acc0);
-    if (ng > 1) st256(nd->g[1].dest + 4 * p, acc1);
   }
   for (int mi = 0; mi < nm; ++mi) {
-    const NodeMult* m = &nd->m[mi];
-    double mx = 0.;
-    if (live) {
-      const int g1 = m->s1_group, g2 = m->s2_group;
-      const V4 x = g1 == 0 ? acc0 : (g1 == 1 ? acc1 : load_plv(m->s1, p));
-      const V4 y = g2 == 0 ? acc0 : (g2 == 1 ? acc1 : load_plv(m->s2, p));
-      const V4 v = {x.a * y.a, x.b * y.b, x.c * y.c, x.d * y.d};
-      st256(m->dest + 4 * p, v);
-      const double hi = fmax(fmax(v.a, v.b), fmax(v.c, v.d));
-      const double lo = fmin(fmin(v.a, v.b), fmin(v.c, v.d));
-      // AssertPLVIsFinite (:575-577), non-negativity (:585-586). fmax/fmin drop NaNs, so
-      // test the sum as well.
-      if (!isfinite(v.a + v.b + v.c + v.d)) atomicOr(st.status, kErrMultiplyNotFinite);
-      else if (lo < 0.) atomicOr(st.status, kErrNegativePLV);
-      mx = hi > 0. ? hi : 0.;
-    }
-    mx = block_reduce(mx, MaxOp(), 0.);
+    const double mx = block_reduce(mi == 0 ? mx0 : mx1, MaxOp(), 0.);
     // Non-negative doubles order like their bit patterns.
     if (threadIdx.x == 0 && mx > 0.)
-      atomicMax(level_max + m->max_slot, static_cast<unsigned long long>(__double_as_longlong(mx)));
+      atomicMax(level_max + nd->m[mi].max_slot,
+                static_cast<unsigned long long>(__double_as_longlong(mx)));
   }
 }
 
@@ -334,33 +361,35 @@ __global__ void k_lik_prologue(DeviceState st, const LikOp* __restrict__ ops, in
 
 __global__ void __launch_bounds__(kTile)
     k_likelihood(DeviceState st, const LikOp* __restrict__ ops, int n_ops,
-                 const double* __restrict__ mtab, double* __restrict__ partials) {
-  const int tile = blockIdx.x / n_ops;
-  const int o = blockIdx.x - tile * n_ops;
-  const int tiles = gridDim.x / n_ops;
+                 const double* __restrict__ mtab, int tiles, int tiles_per_block,
+                 double* __restrict__ partials) {
+  const int tile_group = blockIdx.x / n_ops;
+  const int o = blockIdx.x - tile_group * n_ops;
+  const int n_groups = gridDim.x / n_ops;
   const LikOp* op = ops + o;
   __shared__ double sM[16];
-  const int64_t p = static_cast<int64_t>(tile) * kTile + threadIdx.x;
-  const bool live = p < st.P;
-  V4 r = {0., 0., 0., 0.}, c = {0., 0., 0., 0.};
-  if (live) {  // issued before the barrier: the PLV loads do not depend on the matrix
-    r = load_plv(op->parent, p);
-    c = load_plv(op->child, p);
-  }
   if (threadIdx.x < 16) sM[threadIdx.x] = mtab[16 * static_cast<int64_t>(o) + threadIdx.x];
-  __syncthreads();
+  const PlvRef parent = op->parent, child = op->child;
+  double* const row = op->row;
   const double resc =
-      static_cast<double>(st.counts[op->parent.id]) * st.log_thr +
-      static_cast<double>(st.counts[op->child.id]) * st.log_thr;
+      static_cast<double>(st.counts[parent.id]) * st.log_thr +
+      static_cast<double>(st.counts[child.id]) * st.log_thr;
+  __syncthreads();
   double wsum = 0.;
-  if (live) {
-    const double ll = log(quad(r, sM, c)) + resc;
-    double* row = op->row;
-    if (row != nullptr) row[p] = ll;
-    wsum = ll * st.weights[p];
+  const int tile_begin = tile_group * tiles_per_block;
+  const int tile_end = min(tiles, tile_begin + tiles_per_block);
+  for (int tile = tile_begin; tile < tile_end; ++tile) {
+    const int64_t p = static_cast<int64_t>(tile) * kTile + threadIdx.x;
+    if (p < st.P) {
+      const V4 r = load_plv(parent, p);
+      const V4 c = load_plv(child, p);
+      const double ll = log(quad(r, sM, c)) + resc;
+      if (row != nullptr) row[p] = ll;
+      wsum += ll * st.weights[p];
+    }
   }
   wsum = block_reduce(wsum, SumOp(), 0.);
-  if (threadIdx.x == 0) partials[static_cast<int64_t>(o) * tiles + tile] = wsum;
+  if (threadIdx.x == 0) partials[static_cast<int64_t>(o) * n_groups + tile_group] = wsum;
 }
 
 // ---- [ResetMarginalLikelihood] IncrementMarginalLikelihood x n (gp_engine.cpp:251-276) ----
@@ -513,6 +542,8 @@ enum OptPhase : int32_t {
 __device__ void opt_request(OptState& s, double x, bool log_space) {
   s.x_eval = x;
   s.t_eval = log_space ? exp(x) : x;
+  // diag(e^{lambda t}) once per edge and request, not once per pattern (gp_engine.cpp:341-344)
+  for (int g = 0; g < c_model.n_groups; ++g) s.e[g] = exp(c_model.group_lambda[g] * s.t_eval);
   s.evals++;
 }
 
@@ -779,12 +810,11 @@ __global__ void __launch_bounds__(kTile)
   const int o = blockIdx.x / tiles;
   const int tile = blockIdx.x - o * tiles;
   if (states[o].done) return;  // sums of finished edges are never read
-  const double t = states[o].t_eval;
   double e[G], e1[G], e2[G];
 #pragma unroll
   for (int g = 0; g < G; ++g) {
     const double l = c_model.group_lambda[g];
-    e[g] = exp(l * t);
+    e[g] = states[o].e[g];
     e1[g] = l * e[g];
     e2[g] = l * l * e[g];
   }
@@ -826,13 +856,115 @@ __global__ void __launch_bounds__(kTile)
   }
 }
 
+// ---- Brent objective for two-eigenvalue models (JC69): ratio form -----------------------------
+// L_p(t) = c0_p e^{l0 t} + c1_p e^{l1 t} = c0_p e^{l0 t} (1 + rho_p x),  rho_p = c1_p / c0_p,
+// x = e^{(l1 - l0) t}. Hence  sum_p w_p log L_p = K + W l0 t + sum_p w_p log(1 + rho_p x)  with
+// K = sum_p w_p log c0_p computed once per edge. Only rho (8 B per pattern) is kept, and the last
+// sum is evaluated as the log of a running product with the binary exponents split off, so a
+// thread pays one log() per kOptPatternsPerThread patterns instead of one per pattern.
+__global__ void __launch_bounds__(kTile)
+    k_opt_prepare_ratio(DeviceState st, const OptOp* __restrict__ ops, int tiles,
+                        OptState* __restrict__ states, OptParams prm, int method,
+                        double* __restrict__ rho, double* __restrict__ partials) {
+  const int o = blockIdx.x / tiles;
+  const int t_idx = blockIdx.x - o * tiles;
+  const OptOp op = ops[o];
+  if (t_idx == 0 && threadIdx.x == 0) {
+    OptState s;
+    opt_init(s, st, prm, method, op);
+    states[o] = s;
+  }
+  const int64_t p = static_cast<int64_t>(t_idx) * kTile + threadIdx.x;
+  double k_part = 0.;
+  if (p < st.P) {
+    const V4 r = load_plv(op.parent, p);
+    const V4 c = load_plv(op.child, p);
+    double c0 = 0., c1 = 0.;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double rv = r.a * c_model.V[k] + r.b * c_model.V[4 + k] + r.c * c_model.V[8 + k] +
+                        r.d * c_model.V[12 + k];
+      const double vp = c_model.Vinv[4 * k] * c.a + c_model.Vinv[4 * k + 1] * c.b +
+                        c_model.Vinv[4 * k + 2] * c.c + c_model.Vinv[4 * k + 3] * c.d;
+      const double term = rv * vp;
+      if (c_model.group[k] == 0) c0 += term; else c1 += term;
+    }
+    rho[static_cast<int64_t>(o) * st.P_stride + p] = c0 != 0. ? c1 / c0 : 0.;
+    k_part = st.weights[p] * log(c0);
+  }
+  k_part = block_reduce(k_part, SumOp(), 0.);
+  if (threadIdx.x == 0) partials[static_cast<int64_t>(o) * tiles + t_idx] = k_part;
+}
+
+__global__ void __launch_bounds__(kTile)
+    k_opt_eval_ratio(DeviceState st, int tile_groups, const OptState* __restrict__ states,
+                     const double* __restrict__ rho, double* __restrict__ partials) {
+  const int o = blockIdx.x / tile_groups;
+  const int tg = blockIdx.x - o * tile_groups;
+  if (states[o].done) return;  // sums of finished edges are never read
+  const double x = states[o].e[1] / states[o].e[0];
+  const double* rh = rho + static_cast<int64_t>(o) * st.P_stride;
+  double prod = 1., slow = 0.;
+  int esum = 0;
+#pragma unroll
+  for (int k = 0; k < kOptPatternsPerThread; ++k) {
+    const int64_t p = (static_cast<int64_t>(tg) * kOptPatternsPerThread + k) * kTile + threadIdx.x;
+    if (p < st.P) {
+      const double t = fma(rh[p], x, 1.0);
+      const double w = st.weights[p];
+      const int wi = static_cast<int>(w);
+      if (t >= DBL_MIN && t < INFINITY && w == static_cast<double>(wi) && wi >= 1 && wi <= 7) {
+        // t = m * 2^e with m in [0.5, 1): multiply mantissas, add exponents; t^w by squaring.
+        const int hi = __double2hiint(t);
+        const int e = ((hi >> 20) & 0x7ff) - 1022;
+        const double m = __hiloint2double((hi & 0x800fffff) | 0x3fe00000, __double2loint(t));
+        double mw = m;
+        if (wi != 1) {
+          const double m2 = m * m;
+          mw = (wi & 1) ? m : 1.;
+          if (wi & 2) mw *= m2;
+          if (wi & 4) mw *= m2 * m2;
+        }
+        prod *= mw;  // >= 2^-(7 * kOptPatternsPerThread): no underflow
+        esum += e * wi;
+      } else {
+        slow += w * log(t);  // non-integer or large weights, non-positive likelihoods
+      }
+    }
+  }
+  double f = log(prod) + static_cast<double>(esum) * 0.6931471805599453094 + slow;
+  f = block_reduce(f, SumOp(), 0.);
+  if (threadIdx.x == 0) partials[static_cast<int64_t>(o) * tile_groups + tg] = f;
+}
+
+// Consumes this round's objective sums and advances every optimiser of the batch. Single rank:
+// `partials` holds n_parts partial sums per (edge, derivative) and is reduced here in a fixed
+// order; multi-rank: `sums` holds the all-reduced totals. edge_const/time_coef add the terms of the
+// ratio form that do not depend on the pattern: K_e + W * lambda_0 * t.
 __global__ void k_opt_step(DeviceState st, int n_ops, OptState* __restrict__ states, OptParams prm,
-                           const double* __restrict__ sums, int32_t* __restrict__ active_counter) {
+                           const double* __restrict__ sums, const double* __restrict__ partials,
+                           int n_parts, int n_values, int value_stride,
+                           const double* __restrict__ edge_const,
+                           int32_t* __restrict__ active_counter) {
   const int o = blockIdx.x * blockDim.x + threadIdx.x;
   if (o >= n_ops) return;
   OptState s = states[o];
   if (s.done) return;
-  opt_advance(s, st, prm, sums[3 * o] + s.ll_offset, sums[3 * o + 1], sums[3 * o + 2]);
+  double v[3] = {0., 0., 0.};
+  if (partials != nullptr) {
+    for (int k = 0; k < n_values; ++k) {
+      const double* row = partials + (static_cast<int64_t>(o) * value_stride + k) * n_parts;
+      double acc = 0.;
+      for (int t = 0; t < n_parts; ++t) acc += row[t];
+      v[k] = acc;
+    }
+  } else {
+    for (int k = 0; k < n_values; ++k) v[k] = sums[static_cast<int64_t>(o) * value_stride + k];
+  }
+  double ll = v[0] + s.ll_offset;
+  if (edge_const != nullptr)
+    ll += edge_const[o] + st.total_weight * c_model.group_lambda[0] * s.t_eval;
+  opt_advance(s, st, prm, ll, v[1], v[2]);
   states[o] = s;
   if (s.done) atomicAdd(st.feval_total, static_cast<unsigned long long>(s.evals));
   if (!s.done && active_counter != nullptr) atomicAdd(active_counter, 1);
@@ -873,12 +1005,34 @@ void LaunchNodePrologue(cudaStream_t s, const DeviceState& st, const NodeOp* nod
   k_node_prologue<<<(n_nodes + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, s>>>(
       st, nodes, items, pool, n_nodes, mtab);
 }
+// Pattern tiles one block walks: enough to amortise the per-block prologue (macro-op record,
+// matrix staging, final reduction) while leaving >= ~8 waves of blocks on 148 SMs.
+int TilesPerBlock(int64_t n_ops, int64_t tiles, const char* env_name, int max_tiles) {
+  const char* e = getenv(env_name);
+  const int forced = e != nullptr ? atoi(e) : 0;
+  if (forced > 0) return forced;
+  const int64_t blocks_one = n_ops * tiles;
+  const int64_t target = 148 * 4 * 8;
+  int t = static_cast<int>(blocks_one / target);
+  if (t < 1) t = 1;
+  if (t > max_tiles) t = max_tiles;
+  return t;
+}
 void LaunchNodes(cudaStream_t s, const DeviceState& st, const NodeOp* nodes, const AccumItem* items,
                  const double* mtab, int n_nodes, double* level_max) {
   if (n_nodes == 0) return;
   const int tiles = static_cast<int>(TilesFor(st.P));
-  k_node<<<Grid(n_nodes, tiles), kTile, 0, s>>>(st, nodes, items, mtab, n_nodes,
-                                                reinterpret_cast<unsigned long long*>(level_max));
+  const int tpb = TilesPerBlock(n_nodes, tiles, "BITO_GP_TILES_PER_BLOCK", 8);
+  static const int occ = [] {
+    const char* e = getenv("BITO_GP_NODE_OCC");
+    return e != nullptr ? atoi(e) : 4;
+  }();
+  const unsigned grid = Grid(n_nodes, (tiles + tpb - 1) / tpb);
+  unsigned long long* mx = reinterpret_cast<unsigned long long*>(level_max);
+  if (occ >= 4)
+    k_node<4><<<grid, kTile, 0, s>>>(st, nodes, items, mtab, n_nodes, tiles, tpb, mx);
+  else
+    k_node<3><<<grid, kTile, 0, s>>>(st, nodes, items, mtab, n_nodes, tiles, tpb, mx);
 }
 void LaunchRescale(cudaStream_t s, const DeviceState& st, const MultOp* ops, int n_ops,
                    const double* level_max) {
@@ -891,11 +1045,18 @@ void LaunchLikPrologue(cudaStream_t s, const DeviceState& st, const LikOp* ops, 
   if (n_ops == 0) return;
   k_lik_prologue<<<(n_ops + 127) / 128, 128, 0, s>>>(st, ops, n_ops, mtab);
 }
+int64_t LikelihoodTileGroups(int n_ops, int64_t P) {
+  const int64_t tiles = TilesFor(P);
+  const int tpb = TilesPerBlock(n_ops, tiles, "BITO_GP_LIK_TILES_PER_BLOCK", 8);
+  return (tiles + tpb - 1) / tpb;
+}
 void LaunchLikelihood(cudaStream_t s, const DeviceState& st, const LikOp* ops, int n_ops,
                       const double* mtab, double* partials) {
   if (n_ops == 0) return;
   const int tiles = static_cast<int>(TilesFor(st.P));
-  k_likelihood<<<Grid(n_ops, tiles), kTile, 0, s>>>(st, ops, n_ops, mtab, partials);
+  const int tpb = TilesPerBlock(n_ops, tiles, "BITO_GP_LIK_TILES_PER_BLOCK", 8);
+  k_likelihood<<<Grid(n_ops, (tiles + tpb - 1) / tpb), kTile, 0, s>>>(st, ops, n_ops, mtab, tiles, tpb,
+                                                                     partials);
 }
 void LaunchMarginal(cudaStream_t s, const DeviceState& st, const MargItem* items, int n_items,
                     int reset, double* partials) {
@@ -951,9 +1112,30 @@ void LaunchOptEval(cudaStream_t s, const DeviceState& st, int n_ops, const OptSt
   }
 }
 void LaunchOptStep(cudaStream_t s, const DeviceState& st, int n_ops, OptState* states,
-                   const OptParams& params, const double* sums, int32_t* active_counter) {
+                   const OptParams& params, const double* sums, const double* partials, int n_parts,
+                   int n_values, int value_stride, const double* edge_const,
+                   int32_t* active_counter) {
   if (n_ops == 0) return;
-  k_opt_step<<<(n_ops + 63) / 64, 64, 0, s>>>(st, n_ops, states, params, sums, active_counter);
+  k_opt_step<<<(n_ops + 63) / 64, 64, 0, s>>>(st, n_ops, states, params, sums, partials, n_parts,
+                                              n_values, value_stride, edge_const, active_counter);
+}
+void LaunchOptPrepareRatio(cudaStream_t s, const DeviceState& st, const OptOp* ops, int n_ops,
+                           OptState* states, const OptParams& params, int method, double* rho,
+                           double* partials) {
+  if (n_ops == 0) return;
+  const int tiles = static_cast<int>(TilesFor(st.P));
+  k_opt_prepare_ratio<<<Grid(n_ops, tiles), kTile, 0, s>>>(st, ops, tiles, states, params, method, rho,
+                                                           partials);
+}
+int64_t OptRatioTileGroups(int64_t P) {
+  const int64_t per_block = static_cast<int64_t>(kTile) * kOptPatternsPerThread;
+  return (P + per_block - 1) / per_block;
+}
+void LaunchOptEvalRatio(cudaStream_t s, const DeviceState& st, int n_ops, const OptState* states,
+                        const double* rho, double* partials) {
+  if (n_ops == 0) return;
+  const int groups = static_cast<int>(OptRatioTileGroups(st.P));
+  k_opt_eval_ratio<<<Grid(n_ops, groups), kTile, 0, s>>>(st, groups, states, rho, partials);
 }
 
 void LaunchExportPlv(cudaStream_t s, const DeviceState& st, PlvRef src, double* dense_out) {

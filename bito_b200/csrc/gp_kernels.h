@@ -21,6 +21,8 @@ void LaunchRescale(cudaStream_t s, const DeviceState& st, const MultOp* ops, int
                    const double* level_max);
 void LaunchLikPrologue(cudaStream_t s, const DeviceState& st, const LikOp* ops, int n_ops,
                        double* mtab /* 16 * n_ops */);
+// partials: n_ops rows of LikelihoodTileGroups(n_ops, P) tile-group sums.
+int64_t LikelihoodTileGroups(int n_ops, int64_t P);
 void LaunchLikelihood(cudaStream_t s, const DeviceState& st, const LikOp* ops, int n_ops,
                       const double* mtab, double* partials);
 void LaunchMarginal(cudaStream_t s, const DeviceState& st, const MargItem* items, int n_items,
@@ -43,9 +45,20 @@ void LaunchOptPrepare(cudaStream_t s, const DeviceState& st, const OptOp* ops, i
 void LaunchOptEval(cudaStream_t s, const DeviceState& st, int n_ops, const OptState* states,
                    const double* coef, int n_derivatives, double* partials /* n_ops*3 x tiles */,
                    int n_groups);
+// Value k of edge o is sums[o * value_stride + k] (multi-rank, after the all-reduce), or the sum of
+// the n_parts entries of row (o * value_stride + k) of `partials`, reduced inside the step in a
+// fixed order (single rank). edge_const (ratio form only): K_e, see k_opt_prepare_ratio.
 void LaunchOptStep(cudaStream_t s, const DeviceState& st, int n_ops, OptState* states,
-                   const OptParams& params, const double* sums /* n_ops*3 */,
+                   const OptParams& params, const double* sums, const double* partials, int n_parts,
+                   int n_values, int value_stride, const double* edge_const,
                    int32_t* active_counter);
+// Two-eigenvalue (JC69) Brent path: rho = c1 / c0 per pattern (8 B), K_e partials per tile.
+void LaunchOptPrepareRatio(cudaStream_t s, const DeviceState& st, const OptOp* ops, int n_ops,
+                           OptState* states, const OptParams& params, int method, double* rho,
+                           double* partials /* n_ops x tiles */);
+int64_t OptRatioTileGroups(int64_t P);
+void LaunchOptEvalRatio(cudaStream_t s, const DeviceState& st, int n_ops, const OptState* states,
+                        const double* rho, double* partials /* n_ops x OptRatioTileGroups(P) */);
 
 // Utilities.
 void LaunchExportPlv(cudaStream_t s, const DeviceState& st, PlvRef src, double* dense_out);

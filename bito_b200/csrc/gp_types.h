@@ -13,6 +13,7 @@ namespace bito_gp {
 constexpr int kTile = 256;          // patterns per thread block (one pattern per thread)
 constexpr int kItemChunk = 64;      // transition matrices staged in shared memory at a time
 constexpr int kMaxEigenGroups = 4;  // distinct eigenvalues of the substitution model
+constexpr int kOptPatternsPerThread = 8;  // k_opt_eval_ratio: patterns one thread folds into one log
 
 // How a PLV operand is stored in HBM.
 enum PlvKind : int32_t {
@@ -177,6 +178,7 @@ struct OptState {
   // pending evaluation
   double t_eval;    // branch length at which the objective is being evaluated
   double x_eval;    // the optimiser's own coordinate (log t for Brent/Newton, t for GA)
+  double e[kMaxEigenGroups];  // exp(group_lambda[g] * t_eval), set with every request
   int32_t phase;
   int32_t done;
   int32_t method;
