@@ -197,16 +197,16 @@ def main():
     import torch
     import torch.distributed as dist
     from bito_b200 import _lib
+    from bito_b200 import distributed as D
     from bito_b200.gp_engine import GPEngine
-    from bito_b200.synthetic import CONFIGS, make_named_workload
+    from bito_b200.synthetic import make_named_workload
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the GP engine has no CPU fallback")
     if world != args.gpus:
         raise SystemExit(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; launch with torchrun")
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    D.init("nccl")
 
     name = args.workload or (SINGLE_GPU_WORKLOAD if world == 1 else MULTI_GPU_WORKLOAD)
     t_setup = time.time()
@@ -226,23 +226,8 @@ def main():
                       inverted_sbn_prior=wl.inverted, device=local_rank, flags=flags)
     stream = torch.cuda.current_stream()
     engine.set_stream(stream.cuda_stream)
-    if world > 1:
-        uid = [GPEngine.make_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        engine.comm_init(world, rank, uid[0])
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    barrier, max_over_ranks = D.barrier, D.max_over_ranks
 
     def device_step():
         engine.process_operations(*pop)
@@ -269,6 +254,16 @@ def main():
         barrier()
         ms = max_over_ranks(ev0.elapsed_time(ev1))
         return ms / steps, engine.stats()["kernel_launches"] - launches0
+
+    # ---- N > 1: the same shard on one GPU with no communicator (weak-scaling reference) ----------
+    standalone = None
+    if world > 1:
+        ms_alone, _ = timed(device_step, max(3, args.steps // 2), 3)
+        standalone = {"value_per_gpu": wl.updates_per_pass() * P_local / (ms_alone * 1e-3), "unit": UNIT,
+                      "ms_per_step": ms_alone,
+                      "what": "this rank's shard (same DAG, same patterns per GPU) before joining the NCCL "
+                              "communicator; max over ranks"}
+        D.connect_engine(engine)
 
     # ---- device-resident throughput (`value`) ---------------------------------------------------
     sampler = ClockSampler(local_rank)
@@ -304,7 +299,8 @@ def main():
     achieved = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9
     traffic = None
     traffic_path = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(traffic_path):
+    if os.path.exists(traffic_path) and world == 1 and name == SINGLE_GPU_WORKLOAD and args.patterns is None:
+        # ncu dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel on this workload
         with open(traffic_path) as f:
             traffic = json.load(f).get(top["name"], {}).get("dram_bytes_per_launch")
     pass_alg_bytes = sum(k["algorithmic_bytes"] for k in prof) / prof_steps
@@ -373,6 +369,7 @@ def main():
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "sweep": sweep,
+            "single_gpu_same_shard": standalone,
             "log_marginal": log_marginal,
             "full_pass_ms": ms_per_step,
         }

@@ -1047,14 +1047,14 @@ void LaunchLikPrologue(cudaStream_t s, const DeviceState& st, const LikOp* ops, 
 }
 int64_t LikelihoodTileGroups(int n_ops, int64_t P) {
   const int64_t tiles = TilesFor(P);
-  const int tpb = TilesPerBlock(n_ops, tiles, "BITO_GP_LIK_TILES_PER_BLOCK", 8);
+  const int tpb = TilesPerBlock(n_ops, tiles, "BITO_GP_LIK_TILES_PER_BLOCK", 32);
   return (tiles + tpb - 1) / tpb;
 }
 void LaunchLikelihood(cudaStream_t s, const DeviceState& st, const LikOp* ops, int n_ops,
                       const double* mtab, double* partials) {
   if (n_ops == 0) return;
   const int tiles = static_cast<int>(TilesFor(st.P));
-  const int tpb = TilesPerBlock(n_ops, tiles, "BITO_GP_LIK_TILES_PER_BLOCK", 8);
+  const int tpb = TilesPerBlock(n_ops, tiles, "BITO_GP_LIK_TILES_PER_BLOCK", 32);
   k_likelihood<<<Grid(n_ops, (tiles + tpb - 1) / tpb), kTile, 0, s>>>(st, ops, n_ops, mtab, tiles, tpb,
                                                                      partials);
 }
