@@ -1033,6 +1033,7 @@ Program* Engine::Compile(const bito_gp_op* ops, int64_t n, const int64_t* vec, i
   std::vector<int32_t> f_lik_scatter, f_marg_scatter;
   const int64_t tiles = TilesFor(P_);
   const int32_t marg_slot = static_cast<int32_t>(d_ll_sum_.n - 1);
+  bool dirty_matrices = false;
   for (int lv = 0; lv < n_levels; ++lv) {
     Level& L = prog->levels[lv];
     L.zero_off = static_cast<int>(f_zero.size());
@@ -1098,13 +1099,18 @@ Program* Engine::Compile(const bito_gp_op* ops, int64_t n, const int64_t* vec, i
         prog->max_partials, std::max<int64_t>(L.n_lik, L.has_marg ? L.n_marg + 1 : 0) * tiles);
     prog->max_packed = std::max<int64_t>(prog->max_packed,
                                          std::max<int64_t>(L.n_lik, L.n_marg + 1));
-    prog->launches += (L.n_zero > 0) + (L.n_scalar > 0) + (L.n_stat > 0) + 2 * (L.n_node > 0) +
-                      (L.n_mult > 0) + 3 * (L.n_lik > 0) + 2 * L.has_marg;
-    prog->max_lik_level = std::max<int64_t>(prog->max_lik_level, L.n_lik);
+    // Transition matrices are (re)built before the first level and after any level that may have
+    // changed branch lengths (OptimizeBranchLength) or q (UpdateSBNProbabilities).
+    L.rebuild_matrices = (lv == 0) || dirty_matrices;
+    dirty_matrices = L.n_opt > 0;
+    for (int t = 0; t < L.n_scalar; ++t) dirty_matrices |= (f_scalar[L.scalar_off + t].kind == kScalarSbn);
+    prog->launches += (L.n_zero > 0) + (L.n_scalar > 0) + (L.n_stat > 0) + (L.n_node > 0) +
+                      (L.n_mult > 0) + 2 * (L.n_lik > 0) + 2 * L.has_marg + L.rebuild_matrices;
   }
   prog->n_mult_total = static_cast<int>(f_mult.size());
   prog->n_opt_total = static_cast<int>(f_opt.size());
   prog->n_items_total = static_cast<int64_t>(h_items.size());
+  prog->n_lik_total = static_cast<int>(f_lik.size());
   prog->n_macro = static_cast<int64_t>(macros.size());
   prog->alg_bytes_per_pattern = alg_bytes;
   prog->alloc_version = alloc_version_;
@@ -1197,16 +1203,16 @@ void Engine::ExecuteLevels(Program& prog, size_t first, size_t last) {
       ProfScope ps(this, kProfStationary, 32. * L.n_stat * Pd);
       LaunchStationary(stream_, st, prog.d_stat + L.stat_off, L.n_stat);
     }
+    if (L.rebuild_matrices && (prog.n_items_total > 0 || prog.n_lik_total > 0)) {
+      ProfScope ps(this, kProfPrologue, 0.);
+      LaunchBuildMatrices(stream_, st, prog.d_items, static_cast<int>(prog.n_items_total), prog.d_lik,
+                          prog.n_lik_total, d_mtab_.ptr, d_mtab_lik_.ptr);
+    }
     if (L.n_node > 0) {
       {
-        ProfScope ps(this, kProfPrologue, 0.);
-        LaunchNodePrologue(stream_, st, prog.d_node + L.node_off, prog.d_items, prog.d_pool, L.n_node,
-                           d_mtab_.ptr);
-      }
-      {
         ProfScope ps(this, kProfNode, L.node_bytes_per_pattern * Pd);
-        LaunchNodes(stream_, st, prog.d_node + L.node_off, prog.d_items, d_mtab_.ptr, L.n_node,
-                    d_level_max_.ptr);
+        LaunchNodes(stream_, st, prog.d_node + L.node_off, prog.d_items, prog.d_pool, d_mtab_.ptr,
+                    L.n_node, d_level_max_.ptr);
       }
       if (L.n_mult > 0) {
         // The rescale decision needs the max over ALL patterns of the PLV (gp_engine.cpp:583-597).
@@ -1217,12 +1223,9 @@ void Engine::ExecuteLevels(Program& prog, size_t first, size_t last) {
     }
     if (L.n_lik > 0) {
       {
-        ProfScope ps(this, kProfPrologue, 0.);
-        LaunchLikPrologue(stream_, st, prog.d_lik + L.lik_off, L.n_lik, d_mtab_lik_.ptr);
-      }
-      {
         ProfScope ps(this, kProfLikelihood, 72. * L.n_lik * Pd);
-        LaunchLikelihood(stream_, st, prog.d_lik + L.lik_off, L.n_lik, d_mtab_lik_.ptr, d_partials_.ptr);
+        LaunchLikelihood(stream_, st, prog.d_lik + L.lik_off, L.n_lik,
+                         d_mtab_lik_.ptr + 16 * static_cast<int64_t>(L.lik_off), d_partials_.ptr);
       }
       ProfScope ps(this, kProfReduce, 0.);
       const int64_t lik_groups = LikelihoodTileGroups(L.n_lik, P_);
@@ -1371,7 +1374,7 @@ void Engine::Execute(Program& prog) {
     };
     grow(d_level_max_, prog.n_mult_total);
     grow(d_mtab_, 16 * prog.n_items_total);
-    grow(d_mtab_lik_, 16 * prog.max_lik_level);
+    grow(d_mtab_lik_, 16 * static_cast<int64_t>(prog.n_lik_total));
     if (grew) DropGraphs();  // captured graphs hold the old scratch addresses
   }
   const bool want_graph =

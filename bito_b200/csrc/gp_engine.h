@@ -70,6 +70,7 @@ struct Level {
   int marg_off = 0, n_marg = 0, marg_reset = 0, has_marg = 0, marg_scatter_off = 0;
   int opt_off = 0, n_opt = 0;
   double node_bytes_per_pattern = 0.;
+  bool rebuild_matrices = false;  // branch lengths / q may have changed since the tables were built
 };
 
 struct Program {
@@ -93,7 +94,7 @@ struct Program {
   int n_mult_total = 0;
   int n_opt_total = 0;
   int64_t n_items_total = 0;  // transition matrices of all accumulate items (mtab slots)
-  int64_t max_lik_level = 0;  // most Likelihood ops in one level (lik mtab slots)
+  int n_lik_total = 0;        // Likelihood ops (lik mtab slots)
   int64_t max_partials = 0;  // doubles of tile partials needed by any level
   int64_t max_packed = 0;    // reduced scalars needed by any level
   int64_t n_macro = 0;

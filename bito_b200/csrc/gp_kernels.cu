@@ -131,57 +131,21 @@ struct MaxOp {
   __device__ double operator()(double a, double b) const { return a > b ? a : b; }
 };
 
-// ---- per-level prologue: rescaling counts and scaled transition matrices ---------------------
-// One warp per node macro-op. For every accumulate group: count[dest] (ZeroPLV -> 0,
-// PrepForMarginalization -> min over its src_vector, gp_engine.cpp:213-216, 323-333), then one
-// 4x4 matrix per IncrementWithWeightedEvolvedPLV, (thr^(count[src]-count[dest]) * q[e]) * M(t_e)
-// (gp_engine.cpp:229-249, 341-344), into `mtab` so that no pattern tile ever waits on exp().
-// For every Multiply: count[dest] = count[s1] + count[s2] (gp_engine.cpp:281-282).
-__global__ void k_node_prologue(DeviceState st, const NodeOp* __restrict__ nodes,
-                                const AccumItem* __restrict__ items,
-                                const int32_t* __restrict__ pool, int n_nodes,
-                                double* __restrict__ mtab) {
-  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (w >= n_nodes) return;
-  const NodeOp* nd = nodes + w;
-  const int ng = nd->n_groups, nm = nd->n_mults;
-  int gcount0 = 0, gcount1 = 0;
-  for (int gi = 0; gi < ng; ++gi) {
-    const AccumGroup* grp = &nd->g[gi];
-    const int mode = grp->count_mode, dest_id = grp->dest_id;
-    int c;
-    if (mode == kCountPrep) {
-      c = INT_MAX;
-      for (int i = lane; i < grp->prep_len; i += 32) c = min(c, st.counts[pool[grp->prep_off + i]]);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) c = min(c, __shfl_xor_sync(0xffffffffu, c, o));
-    } else if (mode == kCountZero) {
-      c = 0;
-    } else {
-      c = st.counts[dest_id];
-    }
-    if (gi == 0) gcount0 = c; else gcount1 = c;
-    const int n_items = grp->n_items, item_off = grp->item_off;
-    for (int i = lane; i < n_items; i += 32) {
-      const AccumItem it = items[item_off + i];
-      const int src_count = it.src.id == dest_id ? c : st.counts[it.src.id];
-      const int diff = src_count - c;
-      if (diff < 0) atomicOr(st.status, kErrRescalingDifference);
-      const double factor = diff == 0 ? 1. : pow(st.thr, static_cast<double>(diff));
-      build_matrix(st.bl[it.edge], 0, factor * st.q[it.edge],
-                   mtab + 16 * static_cast<int64_t>(item_off + i));
-    }
-    __syncwarp();
-    if (lane == 0 && mode != kCountKeep) st.counts[dest_id] = c;
-  }
-  if (lane == 0) {
-    for (int mi = 0; mi < nm; ++mi) {
-      const NodeMult* m = &nd->m[mi];
-      const int c1 = m->s1_group == 0 ? gcount0 : (m->s1_group == 1 ? gcount1 : st.counts[m->s1.id]);
-      const int c2 = m->s2_group == 0 ? gcount0 : (m->s2_group == 1 ? gcount1 : st.counts[m->s2.id]);
-      st.counts[m->dest_id] = c1 + c2;
-    }
+// ---- transition-matrix tables ------------------------------------------------------------------
+// q[e] * M(t_e) for every IncrementWithWeightedEvolvedPLV of a program and M(t_e) for every
+// Likelihood (gp_engine.cpp:229-249, 287-291, 341-344), built once per program execution (again
+// after any level that changes branch lengths or q), so that no pattern tile ever waits on exp().
+// The rescaling factor thr^(count[src]-count[dest]) is applied where the matrix is used.
+__global__ void k_build_matrices(DeviceState st, const AccumItem* __restrict__ items, int n_items,
+                                 const LikOp* __restrict__ liks, int n_liks,
+                                 double* __restrict__ mtab, double* __restrict__ mtab_lik) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_items) {
+    const int e = items[i].edge;
+    build_matrix(st.bl[e], 0, st.q[e], mtab + 16 * static_cast<int64_t>(i));
+  } else if (i < n_items + n_liks) {
+    const int j = i - n_items;
+    build_matrix(st.bl[liks[j].edge], 0, 1., mtab_lik + 16 * static_cast<int64_t>(j));
   }
 }
 
@@ -228,14 +192,16 @@ __device__ __forceinline__ void accumulate_items(V4& acc, const double (*sM)[16]
 template <int kMinBlocks>
 __global__ void __launch_bounds__(kTile, kMinBlocks)
     k_node(DeviceState st, const NodeOp* __restrict__ nodes, const AccumItem* __restrict__ items,
-           const double* __restrict__ mtab, int n_nodes, int tiles, int tiles_per_block,
-           unsigned long long* __restrict__ level_max) {
+           const int32_t* __restrict__ pool, const double* __restrict__ mtab, int n_nodes, int tiles,
+           int tiles_per_block, unsigned long long* __restrict__ level_max) {
   const int tile_group = blockIdx.x / n_nodes;
   const int o = blockIdx.x - tile_group * n_nodes;
   const NodeOp* nd = nodes + o;
   __shared__ __align__(32) double sM[kItemChunk][16];
   __shared__ const void* s_ptr[kItemChunk];
   __shared__ int s_kind[kItemChunk];
+  __shared__ int s_src_count[kItemChunk];
+  __shared__ int s_gcount[2];
 
   const int ng = nd->n_groups, nm = nd->n_mults;
   const int n0 = ng > 0 ? nd->g[0].n_items : 0;
@@ -246,8 +212,50 @@ __global__ void __launch_bounds__(kTile, kMinBlocks)
   const bool keep0 = ng > 0 && !nd->g[0].init_zero;
   const bool keep1 = ng > 1 && !nd->g[1].init_zero;
 
-  // Stage (a chunk of) the node's scaled transition matrices and source pointers: thread t
-  // moves quarter t&3 of item t>>2.
+  // Rescaling counts (the last warp; every block derives them, the block of tile group 0
+  // publishes them): count[dest] of a group is 0 after a folded ZeroPLV, the minimum over the
+  // src_vector after a folded PrepForMarginalization (gp_engine.cpp:213-216, 323-333), else
+  // unchanged; count[dest] of a Multiply = count[s1] + count[s2] (gp_engine.cpp:281-282).
+  if (threadIdx.x >= kTile - 32) {
+    const int lane = threadIdx.x & 31;
+    int gc0 = 0, gc1 = 0;
+    for (int gi = 0; gi < ng; ++gi) {
+      const AccumGroup* grp = &nd->g[gi];
+      const int mode = grp->count_mode;
+      int c;
+      if (mode == kCountPrep) {
+        c = INT_MAX;
+        for (int i = lane; i < grp->prep_len; i += 32) c = min(c, st.counts[pool[grp->prep_off + i]]);
+#pragma unroll
+        for (int sh = 16; sh > 0; sh >>= 1) c = min(c, __shfl_xor_sync(0xffffffffu, c, sh));
+      } else if (mode == kCountZero) {
+        c = 0;
+      } else {
+        c = st.counts[grp->dest_id];
+      }
+      if (gi == 0) gc0 = c; else gc1 = c;
+    }
+    if (lane == 0) {
+      s_gcount[0] = gc0;
+      s_gcount[1] = gc1;
+      if (tile_group == 0) {
+        // Multiplies first: an in-place product reads its own old count.
+        int mc[2] = {0, 0};
+        for (int mi = 0; mi < nm; ++mi) {
+          const NodeMult* m = &nd->m[mi];
+          const int c1 = m->s1_group == 0 ? gc0 : (m->s1_group == 1 ? gc1 : st.counts[m->s1.id]);
+          const int c2 = m->s2_group == 0 ? gc0 : (m->s2_group == 1 ? gc1 : st.counts[m->s2.id]);
+          mc[mi] = c1 + c2;
+        }
+        if (ng > 0 && nd->g[0].count_mode != kCountKeep) st.counts[nd->g[0].dest_id] = gc0;
+        if (ng > 1 && nd->g[1].count_mode != kCountKeep) st.counts[nd->g[1].dest_id] = gc1;
+        for (int mi = 0; mi < nm; ++mi) st.counts[nd->m[mi].dest_id] = mc[mi];
+      }
+    }
+  }
+
+  // Stage (a chunk of) the node's transition matrices and sources: thread t moves quarter t&3 of
+  // item t>>2.
   auto stage = [&](int base, int n) {
     const int it = threadIdx.x >> 2, quarter = threadIdx.x & 3;
     if (it < n) {
@@ -256,15 +264,45 @@ __global__ void __launch_bounds__(kTile, kMinBlocks)
       double* dst = &sM[it][4 * quarter];
       dst[0] = m.a; dst[1] = m.b; dst[2] = m.c; dst[3] = m.d;
       if (quarter == 0) {
-        s_ptr[it] = items[gi].src.ptr;
-        s_kind[it] = items[gi].src.kind;
+        const PlvRef src = items[gi].src;
+        s_ptr[it] = src.ptr;
+        s_kind[it] = src.kind;
+        const int dest_id = base + it < n0 ? nd->g[0].dest_id : nd->g[1].dest_id;
+        // an increment that reads its own destination sees the count just set for it
+        s_src_count[it] = src.id == dest_id ? INT_MIN : st.counts[src.id];
+      }
+    }
+  };
+  // Rescaling factor thr^(count[src] - count[dest]) (gp_engine.cpp:236-242): after the barrier
+  // that follows stage(), fold it into the staged matrix. Almost always 1 (nothing to do).
+  auto apply_factors = [&](int base, int n) {
+    const int it = threadIdx.x >> 2, quarter = threadIdx.x & 3;
+    if (it < n) {
+      const int c = s_gcount[base + it < n0 ? 0 : 1];
+      const int sc = s_src_count[it];
+      const int diff = sc == INT_MIN ? 0 : sc - c;
+      if (diff != 0) {
+        if (diff < 0 && tile_group == 0 && quarter == 0) atomicOr(st.status, kErrRescalingDifference);
+        const double factor = pow(st.thr, static_cast<double>(diff));
+        double* dst = &sM[it][4 * quarter];
+        dst[0] *= factor; dst[1] *= factor; dst[2] *= factor; dst[3] *= factor;
       }
     }
   };
   const bool single_chunk = n_tot <= kItemChunk;
+  if (n_tot > 0 && single_chunk) stage(0, n_tot);
+  __syncthreads();
+  bool any_factor = false;
   if (n_tot > 0 && single_chunk) {
-    stage(0, n_tot);
-    __syncthreads();
+    // block-uniform decision, so the extra barrier is only paid when some factor is not 1
+    for (int i = 0; i < n_tot; ++i) {
+      const int sc = s_src_count[i];
+      any_factor |= (sc != INT_MIN && sc != s_gcount[i < n0 ? 0 : 1]);
+    }
+    if (any_factor) {
+      apply_factors(0, n_tot);
+      __syncthreads();
+    }
   }
 
   double mx0 = 0., mx1 = 0.;
@@ -286,6 +324,8 @@ __global__ void __launch_bounds__(kTile, kMinBlocks)
         const int n = min(kItemChunk, n_tot - base);
         __syncthreads();  // the previous chunk (or tile) is done with sM
         stage(base, n);
+        __syncthreads();
+        apply_factors(base, n);
         __syncthreads();
         if (live) {
           // chunk positions [0, n) hold items [base, base + n) of the node; the first n0 items
@@ -353,12 +393,6 @@ __global__ void __launch_bounds__(kTile)
 
 // ---- Likelihood: row[p] = log(parent^T M(t_e) child) + (count_p + count_c) log thr -------
 // (gp_engine.cpp:287-291, gp_engine.hpp:273-282); also the weighted tile partial of the row.
-__global__ void k_lik_prologue(DeviceState st, const LikOp* __restrict__ ops, int n_ops,
-                               double* __restrict__ mtab) {
-  const int o = blockIdx.x * blockDim.x + threadIdx.x;
-  if (o < n_ops) build_matrix(st.bl[ops[o].edge], 0, 1., mtab + 16 * static_cast<int64_t>(o));
-}
-
 __global__ void __launch_bounds__(kTile)
     k_likelihood(DeviceState st, const LikOp* __restrict__ ops, int n_ops,
                  const double* __restrict__ mtab, int tiles, int tiles_per_block,
@@ -998,31 +1032,33 @@ inline unsigned Grid(int64_t n_ops, int64_t tiles) { return static_cast<unsigned
 
 }  // namespace
 
-void LaunchNodePrologue(cudaStream_t s, const DeviceState& st, const NodeOp* nodes,
-                         const AccumItem* items, const int32_t* pool, int n_nodes, double* mtab) {
-  if (n_nodes == 0) return;
-  const int warps_per_block = 4;
-  k_node_prologue<<<(n_nodes + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, s>>>(
-      st, nodes, items, pool, n_nodes, mtab);
+void LaunchBuildMatrices(cudaStream_t s, const DeviceState& st, const AccumItem* items, int n_items,
+                          const LikOp* liks, int n_liks, double* mtab, double* mtab_lik) {
+  const int n = n_items + n_liks;
+  if (n == 0) return;
+  k_build_matrices<<<(n + 127) / 128, 128, 0, s>>>(st, items, n_items, liks, n_liks, mtab, mtab_lik);
 }
-// Pattern tiles one block walks: enough to amortise the per-block prologue (macro-op record,
-// matrix staging, final reduction) while leaving >= ~8 waves of blocks on 148 SMs.
+// Pattern tiles one block walks. Small levels (the long tail of a DAG: a few nodes each) get
+// exactly one wave of blocks on the 148 SMs x 4 resident blocks, each walking up to 16 tiles, so
+// the per-block prologue (macro-op record, counts, matrix staging) is paid once per SM slot
+// instead of once per tile; large levels use 8 tiles per block and many waves.
 int TilesPerBlock(int64_t n_ops, int64_t tiles, const char* env_name, int max_tiles) {
   const char* e = getenv(env_name);
   const int forced = e != nullptr ? atoi(e) : 0;
   if (forced > 0) return forced;
   const int64_t blocks_one = n_ops * tiles;
-  const int64_t target = 148 * 4 * 8;
-  int t = static_cast<int>(blocks_one / target);
+  const int64_t slots = 148 * 4;
+  int64_t t = blocks_one <= slots * 16 ? (blocks_one + slots - 1) / slots
+                                       : (blocks_one >= slots * 256 ? max_tiles : 8);
   if (t < 1) t = 1;
   if (t > max_tiles) t = max_tiles;
-  return t;
+  return static_cast<int>(t);
 }
 void LaunchNodes(cudaStream_t s, const DeviceState& st, const NodeOp* nodes, const AccumItem* items,
-                 const double* mtab, int n_nodes, double* level_max) {
+                 const int32_t* pool, const double* mtab, int n_nodes, double* level_max) {
   if (n_nodes == 0) return;
   const int tiles = static_cast<int>(TilesFor(st.P));
-  const int tpb = TilesPerBlock(n_nodes, tiles, "BITO_GP_TILES_PER_BLOCK", 8);
+  const int tpb = TilesPerBlock(n_nodes, tiles, "BITO_GP_TILES_PER_BLOCK", 16);
   static const int occ = [] {
     const char* e = getenv("BITO_GP_NODE_OCC");
     return e != nullptr ? atoi(e) : 4;
@@ -1030,20 +1066,15 @@ void LaunchNodes(cudaStream_t s, const DeviceState& st, const NodeOp* nodes, con
   const unsigned grid = Grid(n_nodes, (tiles + tpb - 1) / tpb);
   unsigned long long* mx = reinterpret_cast<unsigned long long*>(level_max);
   if (occ >= 4)
-    k_node<4><<<grid, kTile, 0, s>>>(st, nodes, items, mtab, n_nodes, tiles, tpb, mx);
+    k_node<4><<<grid, kTile, 0, s>>>(st, nodes, items, pool, mtab, n_nodes, tiles, tpb, mx);
   else
-    k_node<3><<<grid, kTile, 0, s>>>(st, nodes, items, mtab, n_nodes, tiles, tpb, mx);
+    k_node<3><<<grid, kTile, 0, s>>>(st, nodes, items, pool, mtab, n_nodes, tiles, tpb, mx);
 }
 void LaunchRescale(cudaStream_t s, const DeviceState& st, const MultOp* ops, int n_ops,
                    const double* level_max) {
   if (n_ops == 0) return;
   const int grid = n_ops < 592 ? n_ops : 592;  // 148 SMs x 4 resident blocks
   k_rescale<<<grid, kTile, 0, s>>>(st, ops, n_ops, level_max);
-}
-void LaunchLikPrologue(cudaStream_t s, const DeviceState& st, const LikOp* ops, int n_ops,
-                       double* mtab) {
-  if (n_ops == 0) return;
-  k_lik_prologue<<<(n_ops + 127) / 128, 128, 0, s>>>(st, ops, n_ops, mtab);
 }
 int64_t LikelihoodTileGroups(int n_ops, int64_t P) {
   const int64_t tiles = TilesFor(P);

@@ -12,15 +12,14 @@ inline int64_t TilesFor(int64_t P) { return (P + kTile - 1) / kTile; }
 
 cudaError_t UploadModel(const ModelConst& model);
 
-// Per level: counts + scaled transition matrices of every node macro-op into mtab[16 * item].
-void LaunchNodePrologue(cudaStream_t s, const DeviceState& st, const NodeOp* nodes,
-                        const AccumItem* items, const int32_t* pool, int n_nodes, double* mtab);
+// q[e] * M(t_e) per accumulate item into mtab[16 * item], M(t_e) per Likelihood into
+// mtab_lik[16 * lik]: once per program execution and after every level that changes t or q.
+void LaunchBuildMatrices(cudaStream_t s, const DeviceState& st, const AccumItem* items, int n_items,
+                         const LikOp* liks, int n_liks, double* mtab, double* mtab_lik);
 void LaunchNodes(cudaStream_t s, const DeviceState& st, const NodeOp* nodes, const AccumItem* items,
-                 const double* mtab, int n_nodes, double* level_max);
+                 const int32_t* pool, const double* mtab, int n_nodes, double* level_max);
 void LaunchRescale(cudaStream_t s, const DeviceState& st, const MultOp* ops, int n_ops,
                    const double* level_max);
-void LaunchLikPrologue(cudaStream_t s, const DeviceState& st, const LikOp* ops, int n_ops,
-                       double* mtab /* 16 * n_ops */);
 // partials: n_ops rows of LikelihoodTileGroups(n_ops, P) tile-group sums.
 int64_t LikelihoodTileGroups(int n_ops, int64_t P);
 void LaunchLikelihood(cudaStream_t s, const DeviceState& st, const LikOp* ops, int n_ops,
