@@ -267,7 +267,7 @@ Engine::~Engine() {
   d_q_.Release(); d_bl_.Release(); d_diff_.Release(); d_hybrid_.Release(); d_ll_sum_.Release();
   d_inverted_.Release(); d_uncond_.Release(); d_status_.Release(); d_feval_total_.Release();
   d_partials_.Release(); d_packed_.Release(); d_level_max_.Release(); d_coef_.Release();
-  d_dense_tmp_.Release(); d_mtab_.Release(); d_mtab_lik_.Release(); d_opt_states_.Release(); d_opt_const_.Release(); d_active_.Release(); d_single_opt_.Release();
+  d_dense_tmp_.Release(); d_mtab_.Release(); d_mtab_lik_.Release(); d_opt_states_.Release(); d_opt_const_.Release(); d_opt_active_.Release(); d_perm_.Release(); d_wperm_.Release(); d_row_class_.Release(); d_active_.Release(); d_single_opt_.Release();
   if (pinned_ != nullptr) cudaFreeHost(pinned_);
   if (ev_begin_) cudaEventDestroy(ev_begin_);
   if (ev_end_) cudaEventDestroy(ev_end_);
@@ -370,8 +370,68 @@ void Engine::SetSitePatterns(const uint8_t* symbols, const double* weights, bool
   GP_CUDA(cudaStreamSynchronize(stream_));
   total_weight_ = *static_cast<double*>(pinned_);
   have_patterns_ = true;
+  BuildWeightClasses(on_device ? nullptr : weights);
   // Re-uploading an alignment of the same shape leaves every compiled program valid.
   if (slots_changed) InvalidatePrograms();
+}
+
+// The Brent objective (k_opt_eval_ratio) folds the per-pattern factors (1 + rho_p x)^{w_p} into a
+// running product. To keep that branch-free the optimiser stores rho in a pattern order grouped by
+// weight class: weights 1..7 (site-pattern multiplicities, almost always 1) get one class each,
+// every other weight goes to a last "general" class evaluated with an explicit log. Classes are
+// padded to whole tile groups; the padding holds rho = 0, i.e. a factor of exactly 1.
+void Engine::BuildWeightClasses(const double* host_weights) {
+  std::vector<double> w(static_cast<size_t>(P_));
+  if (host_weights != nullptr) {
+    std::memcpy(w.data(), host_weights, w.size() * sizeof(double));
+  } else {
+    GP_CUDA(cudaMemcpyAsync(w.data(), d_weights_.ptr, w.size() * sizeof(double), cudaMemcpyDeviceToHost,
+                            stream_));
+    GP_CUDA(cudaStreamSynchronize(stream_));
+  }
+  if (w == host_weights_cache_ && P_perm_ > 0) return;  // same weights: the layout is current
+  host_weights_cache_ = w;
+  auto cls = [](double x) {
+    const int wi = static_cast<int>(x);
+    return (x == static_cast<double>(wi) && wi >= 1 && wi <= 7) ? wi - 1 : 7;
+  };
+  // Classes are padded to whole tile groups (kTile * kOptPatternsPerThread patterns), so one
+  // block-item of k_opt_eval_ratio sees a single weight.
+  const int64_t group = static_cast<int64_t>(kTile) * kOptPatternsPerThread;
+  int64_t n_in[8] = {0, 0, 0, 0, 0, 0, 0, 0}, start[8];
+  for (double x : w) n_in[cls(x)]++;
+  int64_t pos = 0;
+  for (int c = 0; c < 8; ++c) {
+    start[c] = pos;
+    pos += RoundUp(n_in[c], group);
+  }
+  P_perm_ = std::max<int64_t>(pos, group);
+  std::vector<int32_t> perm(static_cast<size_t>(P_));
+  std::vector<double> wperm(static_cast<size_t>(P_perm_), 0.);
+  std::vector<uint8_t> row_class(static_cast<size_t>(P_perm_ / group), 0);
+  int64_t next[8];
+  for (int c = 0; c < 8; ++c) {
+    next[c] = start[c];
+    for (int64_t r = start[c] / group; r < (start[c] + RoundUp(n_in[c], group)) / group; ++r)
+      row_class[static_cast<size_t>(r)] = static_cast<uint8_t>(c);
+  }
+  for (int64_t p = 0; p < P_; ++p) {
+    const int c = cls(w[static_cast<size_t>(p)]);
+    perm[static_cast<size_t>(p)] = static_cast<int32_t>(next[c]);
+    wperm[static_cast<size_t>(next[c]++)] = w[static_cast<size_t>(p)];
+  }
+  GP_CUDA(cudaStreamSynchronize(stream_));
+  d_perm_.Resize(perm.size(), false, stream_);
+  d_wperm_.Resize(wperm.size(), false, stream_);
+  d_row_class_.Resize(row_class.size(), false, stream_);
+  GP_CUDA(cudaMemcpyAsync(d_perm_.ptr, perm.data(), perm.size() * sizeof(int32_t), cudaMemcpyHostToDevice,
+                          stream_));
+  GP_CUDA(cudaMemcpyAsync(d_wperm_.ptr, wperm.data(), wperm.size() * sizeof(double),
+                          cudaMemcpyHostToDevice, stream_));
+  GP_CUDA(cudaMemcpyAsync(d_row_class_.ptr, row_class.data(), row_class.size(), cudaMemcpyHostToDevice,
+                          stream_));
+  GP_CUDA(cudaStreamSynchronize(stream_));  // host vectors die here
+  coef_padding_zeroed_ = false;
 }
 
 void Engine::InitializePriors(const double* sbn_prior, const double* unconditional,
@@ -1278,14 +1338,23 @@ void Engine::RunOptimizer(const OptOp* d_ops, int n_ops, int method, bool check_
   // Plain Brent on a two-eigenvalue model (JC69, the only model GPEngine instantiates,
   // gp_engine.hpp:366): ratio form, 8 B per pattern and one log per 8 patterns.
   const bool ratio = (G == 2 && nd == 0);
-  const int64_t coef_per_op = P_stride_ * (ratio ? 1 : G);
+  const int64_t coef_per_op = ratio ? P_perm_ : P_stride_ * G;
   const int64_t budget_doubles = (opt_chunk_bytes_ > 0 ? opt_chunk_bytes_ : (int64_t(1) << 30)) / 8;
   const int chunk = static_cast<int>(
       std::max<int64_t>(1, std::min<int64_t>(n_ops, budget_doubles / coef_per_op)));
-  d_coef_.Resize(static_cast<size_t>(chunk * coef_per_op), false, stream_);
+  if (static_cast<size_t>(chunk * coef_per_op) > d_coef_.n) {
+    d_coef_.Resize(static_cast<size_t>(chunk * coef_per_op), false, stream_);
+    coef_padding_zeroed_ = false;
+  }
+  if (ratio && !coef_padding_zeroed_) {  // padding rows of the weight-class layout: rho = 0
+    GP_CUDA(cudaMemsetAsync(d_coef_.ptr, 0, d_coef_.n * sizeof(double), stream_));
+    coef_padding_zeroed_ = true;
+  }
+  if (!ratio) coef_padding_zeroed_ = false;
   d_opt_states_.Resize(static_cast<size_t>(chunk), false, stream_);
   d_opt_const_.Resize(static_cast<size_t>(chunk), false, stream_);
-  const int64_t groups = ratio ? OptRatioTileGroups(P_) : tiles;
+  d_opt_active_.Resize(static_cast<size_t>(4 + 2 * chunk), false, stream_);
+  const int64_t groups = ratio ? OptRatioPartials(P_perm_) : tiles;
   const int n_values = nd + 1, value_stride = ratio ? 1 : 3;
   EnsureScratch(static_cast<int64_t>(chunk) * std::max<int64_t>(value_stride * groups, tiles),
                 static_cast<int64_t>(chunk) * 3);
@@ -1309,7 +1378,7 @@ void Engine::RunOptimizer(const OptOp* d_ops, int n_ops, int method, bool check_
       {
         ProfScope ps(this, kProfOptPrepare, 64. * m * static_cast<double>(P_));
         LaunchOptPrepareRatio(stream_, st, d_ops + c0, m, d_opt_states_.ptr, prm, method, d_coef_.ptr,
-                              d_partials_.ptr);
+                              d_perm_.ptr, P_perm_, d_partials_.ptr, d_opt_active_.ptr, chunk);
       }
       ProfScope ps(this, kProfReduce, 0.);
       LaunchReducePartials(stream_, d_partials_.ptr, m, tiles, d_opt_const_.ptr, nullptr, nullptr);
@@ -1322,13 +1391,17 @@ void Engine::RunOptimizer(const OptOp* d_ops, int n_ops, int method, bool check_
     }
     int64_t rounds = 0;
     int batch = method <= BITO_GP_BRENT_OPTIMIZATION_WITH_GRADIENTS ? 12 : 6;
+    int32_t* act = ratio ? d_opt_active_.ptr : nullptr;
     for (;;) {
+      int32_t* counter = nullptr;
       for (int r = 0; r < batch; ++r) {
         const bool last = (r == batch - 1);
+        const int parity = static_cast<int>((rounds + r) & 1);
         {
           ProfScope ps(this, kProfOptEval, 0.);
           if (ratio)
-            LaunchOptEvalRatio(stream_, st, m, d_opt_states_.ptr, d_coef_.ptr, d_partials_.ptr);
+            LaunchOptEvalRatio(stream_, st, m, d_opt_states_.ptr, d_coef_.ptr, P_perm_, d_wperm_.ptr,
+                               d_row_class_.ptr, d_partials_.ptr, act, chunk, parity);
           else
             LaunchOptEval(stream_, st, m, d_opt_states_.ptr, d_coef_.ptr, nd, d_partials_.ptr, G);
         }
@@ -1343,16 +1416,20 @@ void Engine::RunOptimizer(const OptOp* d_ops, int n_ops, int method, bool check_
           parts = nullptr;
           stats_.kernel_launches++;
         }
-        if (last) GP_CUDA(cudaMemsetAsync(d_active_.ptr, 0, sizeof(int32_t), stream_));
+        if (ratio) {
+          counter = act + (parity ^ 1);  // edges still active after this round
+        } else {
+          counter = d_active_.ptr;
+          if (last) GP_CUDA(cudaMemsetAsync(d_active_.ptr, 0, sizeof(int32_t), stream_));
+        }
         ProfScope ps(this, kProfOptStep, 0.);
         LaunchOptStep(stream_, st, m, d_opt_states_.ptr, prm, sums, parts, static_cast<int>(groups),
                       n_values, value_stride, ratio ? d_opt_const_.ptr : nullptr,
-                      last ? d_active_.ptr : nullptr);
+                      (!ratio && last) ? d_active_.ptr : nullptr, act, chunk, parity);
         stats_.kernel_launches += 2;
       }
       rounds += batch;
-      GP_CUDA(cudaMemcpyAsync(h_active, d_active_.ptr, sizeof(int32_t), cudaMemcpyDeviceToHost,
-                              stream_));
+      GP_CUDA(cudaMemcpyAsync(h_active, counter, sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
       GP_CUDA(cudaStreamSynchronize(stream_));
       if (*h_active == 0) break;
       if (rounds > max_rounds) Fail("OptimizeBranchLength: optimiser did not terminate");
@@ -1487,6 +1564,7 @@ void Engine::LogLikelihoodAndDerivatives(int64_t gpcsp, int64_t rootward, int64_
   const int64_t tiles = TilesFor(P_);
   const int G = n_eigen_groups_;
   d_coef_.Resize(static_cast<size_t>(P_stride_ * G), false, stream_);
+  coef_padding_zeroed_ = false;
   d_opt_states_.Resize(1, false, stream_);
   d_single_opt_.Resize(1, false, stream_);
   EnsureScratch(3 * tiles, 3);

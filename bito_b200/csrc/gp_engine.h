@@ -202,6 +202,7 @@ class Engine {
   void RunOptimizer(const OptOp* d_ops, int n_ops, int method, bool check_convergence);
   void FreeProgram(Program& p);
   void EnsureScratch(int64_t partial_doubles, int64_t packed_doubles);
+  void BuildWeightClasses(const double* host_weights);
   void DropGraphs();
   void AllReduce(double* buf, int64_t n, bool max_op);
 
@@ -238,7 +239,12 @@ class Engine {
   DeviceArray<double> d_partials_, d_packed_, d_level_max_, d_coef_, d_dense_tmp_, d_mtab_, d_mtab_lik_;
   DeviceArray<OptState> d_opt_states_;
   DeviceArray<double> d_opt_const_;
-  DeviceArray<int32_t> d_active_;
+  DeviceArray<int32_t> d_active_, d_opt_active_, d_perm_;
+  DeviceArray<double> d_wperm_;
+  DeviceArray<uint8_t> d_row_class_;
+  int64_t P_perm_ = 0;  // patterns in weight-class order, classes padded to 256-pattern rows
+  bool coef_padding_zeroed_ = false;
+  std::vector<double> host_weights_cache_;
   DeviceArray<OptOp> d_single_opt_;
   void* pinned_ = nullptr;  // small pinned staging block
 

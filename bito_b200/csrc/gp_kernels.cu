@@ -578,6 +578,7 @@ __device__ void opt_request(OptState& s, double x, bool log_space) {
   s.t_eval = log_space ? exp(x) : x;
   // diag(e^{lambda t}) once per edge and request, not once per pattern (gp_engine.cpp:341-344)
   for (int g = 0; g < c_model.n_groups; ++g) s.e[g] = exp(c_model.group_lambda[g] * s.t_eval);
+  s.x_ratio = s.e[1] / s.e[0];  // two-eigenvalue ratio form, k_opt_eval_ratio
   s.evals++;
 }
 
@@ -899,15 +900,28 @@ __global__ void __launch_bounds__(kTile)
 __global__ void __launch_bounds__(kTile)
     k_opt_prepare_ratio(DeviceState st, const OptOp* __restrict__ ops, int tiles,
                         OptState* __restrict__ states, OptParams prm, int method,
-                        double* __restrict__ rho, double* __restrict__ partials) {
-  const int o = blockIdx.x / tiles;
-  const int t_idx = blockIdx.x - o * tiles;
+                        double* __restrict__ rho, const int32_t* __restrict__ perm,
+                        int64_t rho_stride, double* __restrict__ partials,
+                        int32_t* __restrict__ active, int active_capacity) {
+  // tile-major: the edges of one pattern tile are neighbours in the grid, so a parent r-PLV or
+  // child p-PLV tile shared by several edges is read from HBM once and from L2 afterwards
+  const int n_ops = gridDim.x / tiles;
+  const int t_idx = blockIdx.x / n_ops;
+  const int o = blockIdx.x - t_idx * n_ops;
   const OptOp op = ops[o];
   if (t_idx == 0 && threadIdx.x == 0) {
     OptState s;
     opt_init(s, st, prm, method, op);
     states[o] = s;
+    // active[0..1]: number of edges still optimising, double-buffered by round parity;
+    // active[4 + parity * capacity + i]: their indices (see k_opt_step).
+    active[4 + o] = o;
+    if (o == 0) {
+      active[0] = n_ops;
+      active[1] = 0;
+    }
   }
+  (void)active_capacity;
   const int64_t p = static_cast<int64_t>(t_idx) * kTile + threadIdx.x;
   double k_part = 0.;
   if (p < st.P) {
@@ -923,52 +937,94 @@ __global__ void __launch_bounds__(kTile)
       const double term = rv * vp;
       if (c_model.group[k] == 0) c0 += term; else c1 += term;
     }
-    rho[static_cast<int64_t>(o) * st.P_stride + p] = c0 != 0. ? c1 / c0 : 0.;
+    rho[static_cast<int64_t>(o) * rho_stride + perm[p]] = c0 != 0. ? c1 / c0 : 0.;
     k_part = st.weights[p] * log(c0);
   }
   k_part = block_reduce(k_part, SumOp(), 0.);
   if (threadIdx.x == 0) partials[static_cast<int64_t>(o) * tiles + t_idx] = k_part;
 }
 
+// Splits t > 0 (finite, normal) into m * 2^e with m in [0.5, 1).
+__device__ __forceinline__ bool split_positive(double t, double& m, int& e) {
+  const int hi = __double2hiint(t);
+  // biased exponent in [1, 2046] and sign bit clear
+  if (static_cast<unsigned>(hi - 0x00100000) >= 0x7fe00000u) return false;
+  e = (hi >> 20) - 1022;
+  m = __hiloint2double((hi & 0x000fffff) | 0x3fe00000, __double2loint(t));
+  return true;
+}
+
 __global__ void __launch_bounds__(kTile)
     k_opt_eval_ratio(DeviceState st, int tile_groups, const OptState* __restrict__ states,
-                     const double* __restrict__ rho, double* __restrict__ partials) {
-  const int o = blockIdx.x / tile_groups;
-  const int tg = blockIdx.x - o * tile_groups;
-  if (states[o].done) return;  // sums of finished edges are never read
-  const double x = states[o].e[1] / states[o].e[0];
-  const double* rh = rho + static_cast<int64_t>(o) * st.P_stride;
-  double prod = 1., slow = 0.;
-  int esum = 0;
+                     const double* __restrict__ rho, int64_t rho_stride,
+                     const double* __restrict__ wperm, const uint8_t* __restrict__ group_class,
+                     double* __restrict__ partials, int32_t* __restrict__ active,
+                     int active_capacity, int parity) {
+  // Fixed grid walking the (still active edge, tile group) items: late rounds, when most edges
+  // of the batch have converged, cost only the work that is left.
+  const int n_active = active[parity];
+  const int32_t* list = active + 4 + parity * active_capacity;
+  if (blockIdx.x == 0 && threadIdx.x == 0) active[parity ^ 1] = 0;  // filled by this round's step
+  const int n_items = n_active * tile_groups;  // < 2^31: the batch's rho buffer is at most a few GiB
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int a = item / tile_groups;
+    const int tg = item - a * tile_groups;
+    const int o = list[a];
+    const double x = states[o].x_ratio;
+    const int cls = group_class[tg];  // block-uniform: weight - 1, or 7 = general weights
+    const int64_t pos0 = static_cast<int64_t>(tg) * (kTile * kOptPatternsPerThread) + threadIdx.x;
+    const double* base = rho + static_cast<int64_t>(o) * rho_stride + pos0;
+    double t[kOptPatternsPerThread];
 #pragma unroll
-  for (int k = 0; k < kOptPatternsPerThread; ++k) {
-    const int64_t p = (static_cast<int64_t>(tg) * kOptPatternsPerThread + k) * kTile + threadIdx.x;
-    if (p < st.P) {
-      const double t = fma(rh[p], x, 1.0);
-      const double w = st.weights[p];
-      const int wi = static_cast<int>(w);
-      if (t >= DBL_MIN && t < INFINITY && w == static_cast<double>(wi) && wi >= 1 && wi <= 7) {
-        // t = m * 2^e with m in [0.5, 1): multiply mantissas, add exponents; t^w by squaring.
-        const int hi = __double2hiint(t);
-        const int e = ((hi >> 20) & 0x7ff) - 1022;
-        const double m = __hiloint2double((hi & 0x800fffff) | 0x3fe00000, __double2loint(t));
-        double mw = m;
-        if (wi != 1) {
+    for (int k = 0; k < kOptPatternsPerThread; ++k) t[k] = base[k * kTile];  // all loads first
+    double prod = 1., slow = 0.;
+    int esum = 0;
+    if (cls == 0) {  // weight 1: the bulk of any alignment
+#pragma unroll
+      for (int k = 0; k < kOptPatternsPerThread; ++k) {
+        const double tk = fma(t[k], x, 1.0);
+        double m;
+        int e;
+        if (split_positive(tk, m, e)) {
+          prod *= m;  // >= 2^-kOptPatternsPerThread
+          esum += e;
+        } else {
+          slow += log(tk);
+        }
+      }
+    } else if (cls < 7) {  // weights 2..7: (m 2^e)^w by squaring
+      const int wi = cls + 1;
+#pragma unroll
+      for (int k = 0; k < kOptPatternsPerThread; ++k) {
+        const double tk = fma(t[k], x, 1.0);
+        double m;
+        int e;
+        if (split_positive(tk, m, e)) {
           const double m2 = m * m;
-          mw = (wi & 1) ? m : 1.;
+          double mw = (wi & 1) ? m : 1.;
           if (wi & 2) mw *= m2;
           if (wi & 4) mw *= m2 * m2;
+          prod *= mw;  // >= 2^-(7 * kOptPatternsPerThread): no underflow
+          esum += e * wi;
+        } else {
+          slow += static_cast<double>(wi) * log(tk);
         }
-        prod *= mw;  // >= 2^-(7 * kOptPatternsPerThread): no underflow
-        esum += e * wi;
-      } else {
-        slow += w * log(t);  // non-integer or large weights, non-positive likelihoods
+      }
+    } else {  // general weights: explicit log
+#pragma unroll
+      for (int k = 0; k < kOptPatternsPerThread; ++k) {
+        const double w = wperm[pos0 + k * kTile];
+        if (w != 0.) slow += w * log(fma(t[k], x, 1.0));
       }
     }
+    double f = log(prod) + static_cast<double>(esum) * 0.6931471805599453094 + slow;
+    // One partial per warp (fixed shuffle tree) and no block barrier: warps of a block run ahead
+    // independently into the next item; k_opt_step sums the kTile/32 * tile_groups partials.
+#pragma unroll
+    for (int sh = 16; sh > 0; sh >>= 1) f += __shfl_down_sync(0xffffffffu, f, sh);
+    if ((threadIdx.x & 31) == 0)
+      partials[(static_cast<int64_t>(o) * tile_groups + tg) * (kTile / 32) + (threadIdx.x >> 5)] = f;
   }
-  double f = log(prod) + static_cast<double>(esum) * 0.6931471805599453094 + slow;
-  f = block_reduce(f, SumOp(), 0.);
-  if (threadIdx.x == 0) partials[static_cast<int64_t>(o) * tile_groups + tg] = f;
 }
 
 // Consumes this round's objective sums and advances every optimiser of the batch. Single rank:
@@ -979,29 +1035,46 @@ __global__ void k_opt_step(DeviceState st, int n_ops, OptState* __restrict__ sta
                            const double* __restrict__ sums, const double* __restrict__ partials,
                            int n_parts, int n_values, int value_stride,
                            const double* __restrict__ edge_const,
-                           int32_t* __restrict__ active_counter) {
-  const int o = blockIdx.x * blockDim.x + threadIdx.x;
-  if (o >= n_ops) return;
-  OptState s = states[o];
-  if (s.done) return;
+                           int32_t* __restrict__ active_counter, int32_t* __restrict__ active,
+                           int active_capacity, int parity) {
+  // One warp per edge: the lanes sum the partials (lane-strided, then a fixed shuffle tree), lane
+  // 0 advances the optimiser.
+  const int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  int o = a;
+  if (active != nullptr) {  // compacted list of the edges still optimising
+    if (a >= active[parity]) return;
+    o = active[4 + parity * active_capacity + a];
+  } else if (a >= n_ops) {
+    return;
+  }
+  if (states[o].done) return;
   double v[3] = {0., 0., 0.};
   if (partials != nullptr) {
     for (int k = 0; k < n_values; ++k) {
       const double* row = partials + (static_cast<int64_t>(o) * value_stride + k) * n_parts;
       double acc = 0.;
-      for (int t = 0; t < n_parts; ++t) acc += row[t];
+      for (int t = lane; t < n_parts; t += 32) acc += row[t];
+#pragma unroll
+      for (int sh = 16; sh > 0; sh >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, sh);
       v[k] = acc;
     }
   } else {
     for (int k = 0; k < n_values; ++k) v[k] = sums[static_cast<int64_t>(o) * value_stride + k];
   }
+  if (lane != 0) return;
+  OptState s = states[o];
   double ll = v[0] + s.ll_offset;
   if (edge_const != nullptr)
     ll += edge_const[o] + st.total_weight * c_model.group_lambda[0] * s.t_eval;
   opt_advance(s, st, prm, ll, v[1], v[2]);
   states[o] = s;
   if (s.done) atomicAdd(st.feval_total, static_cast<unsigned long long>(s.evals));
-  if (!s.done && active_counter != nullptr) atomicAdd(active_counter, 1);
+  if (!s.done) {
+    if (active != nullptr)
+      active[4 + (parity ^ 1) * active_capacity + atomicAdd(active + (parity ^ 1), 1)] = o;
+    if (active_counter != nullptr) atomicAdd(active_counter, 1);
+  }
 }
 
 // ---- utilities ---------------------------------------------------------------------------------
@@ -1145,28 +1218,45 @@ void LaunchOptEval(cudaStream_t s, const DeviceState& st, int n_ops, const OptSt
 void LaunchOptStep(cudaStream_t s, const DeviceState& st, int n_ops, OptState* states,
                    const OptParams& params, const double* sums, const double* partials, int n_parts,
                    int n_values, int value_stride, const double* edge_const,
-                   int32_t* active_counter) {
+                   int32_t* active_counter, int32_t* active, int active_capacity, int parity) {
   if (n_ops == 0) return;
-  k_opt_step<<<(n_ops + 63) / 64, 64, 0, s>>>(st, n_ops, states, params, sums, partials, n_parts,
-                                              n_values, value_stride, edge_const, active_counter);
+  k_opt_step<<<(n_ops + 7) / 8, 256, 0, s>>>(st, n_ops, states, params, sums, partials, n_parts,
+                                              n_values, value_stride, edge_const, active_counter,
+                                              active, active_capacity, parity);
 }
 void LaunchOptPrepareRatio(cudaStream_t s, const DeviceState& st, const OptOp* ops, int n_ops,
                            OptState* states, const OptParams& params, int method, double* rho,
-                           double* partials) {
+                           const int32_t* perm, int64_t rho_stride, double* partials,
+                           int32_t* active, int active_capacity) {
   if (n_ops == 0) return;
   const int tiles = static_cast<int>(TilesFor(st.P));
   k_opt_prepare_ratio<<<Grid(n_ops, tiles), kTile, 0, s>>>(st, ops, tiles, states, params, method, rho,
-                                                           partials);
+                                                           perm, rho_stride, partials, active,
+                                                           active_capacity);
 }
 int64_t OptRatioTileGroups(int64_t P) {
   const int64_t per_block = static_cast<int64_t>(kTile) * kOptPatternsPerThread;
   return (P + per_block - 1) / per_block;
 }
+int64_t OptRatioPartials(int64_t P) { return OptRatioTileGroups(P) * (kTile / 32); }
 void LaunchOptEvalRatio(cudaStream_t s, const DeviceState& st, int n_ops, const OptState* states,
-                        const double* rho, double* partials) {
+                        const double* rho, int64_t rho_stride, const double* wperm,
+                        const uint8_t* row_class, double* partials, int32_t* active,
+                        int active_capacity, int parity) {
   if (n_ops == 0) return;
-  const int groups = static_cast<int>(OptRatioTileGroups(st.P));
-  k_opt_eval_ratio<<<Grid(n_ops, groups), kTile, 0, s>>>(st, groups, states, rho, partials);
+  const int groups = static_cast<int>(OptRatioTileGroups(rho_stride));
+  const int64_t items = static_cast<int64_t>(n_ops) * groups;
+  static const int64_t cap = [] {  // exactly one resident wave: every SM slot walks the same share
+    int per_sm = 0, sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_opt_eval_ratio, kTile, 0) != cudaSuccess ||
+        per_sm < 1)
+      per_sm = 4;
+    return static_cast<int64_t>(per_sm) * sms;
+  }();
+  k_opt_eval_ratio<<<static_cast<unsigned>(items < cap ? items : cap), kTile, 0, s>>>(
+      st, groups, states, rho, rho_stride, wperm, row_class, partials, active, active_capacity, parity);
 }
 
 void LaunchExportPlv(cudaStream_t s, const DeviceState& st, PlvRef src, double* dense_out) {

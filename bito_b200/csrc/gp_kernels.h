@@ -50,14 +50,20 @@ void LaunchOptEval(cudaStream_t s, const DeviceState& st, int n_ops, const OptSt
 void LaunchOptStep(cudaStream_t s, const DeviceState& st, int n_ops, OptState* states,
                    const OptParams& params, const double* sums, const double* partials, int n_parts,
                    int n_values, int value_stride, const double* edge_const,
-                   int32_t* active_counter);
-// Two-eigenvalue (JC69) Brent path: rho = c1 / c0 per pattern (8 B), K_e partials per tile.
+                   int32_t* active_counter, int32_t* active, int active_capacity, int parity);
+// Two-eigenvalue (JC69) Brent path: rho = c1 / c0 per pattern (8 B) stored at perm[p] (weight-class
+// order, Engine::BuildWeightClasses), K_e partials per tile.
 void LaunchOptPrepareRatio(cudaStream_t s, const DeviceState& st, const OptOp* ops, int n_ops,
                            OptState* states, const OptParams& params, int method, double* rho,
-                           double* partials /* n_ops x tiles */);
+                           const int32_t* perm, int64_t rho_stride, double* partials /* n_ops x tiles */,
+                           int32_t* active, int active_capacity);
 int64_t OptRatioTileGroups(int64_t P);
+int64_t OptRatioPartials(int64_t P);  // partial sums per edge written by LaunchOptEvalRatio
 void LaunchOptEvalRatio(cudaStream_t s, const DeviceState& st, int n_ops, const OptState* states,
-                        const double* rho, double* partials /* n_ops x OptRatioTileGroups(P) */);
+                        const double* rho, int64_t rho_stride, const double* wperm,
+                        const uint8_t* row_class, double* partials /* n_ops x OptRatioPartials */,
+                        int32_t* active /* [4 + 2 * capacity]: counts by parity, then the two lists */,
+                        int active_capacity, int parity);
 
 // Utilities.
 void LaunchExportPlv(cudaStream_t s, const DeviceState& st, PlvRef src, double* dense_out);

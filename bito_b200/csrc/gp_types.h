@@ -179,6 +179,7 @@ struct OptState {
   double t_eval;    // branch length at which the objective is being evaluated
   double x_eval;    // the optimiser's own coordinate (log t for Brent/Newton, t for GA)
   double e[kMaxEigenGroups];  // exp(group_lambda[g] * t_eval), set with every request
+  double x_ratio;             // e[1] / e[0]
   int32_t phase;
   int32_t done;
   int32_t method;
