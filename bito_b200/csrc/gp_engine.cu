@@ -1381,7 +1381,8 @@ void Engine::RunOptimizer(const OptOp* d_ops, int n_ops, int method, bool check_
                               d_perm_.ptr, P_perm_, d_partials_.ptr, d_opt_active_.ptr, chunk);
       }
       ProfScope ps(this, kProfReduce, 0.);
-      LaunchReducePartials(stream_, d_partials_.ptr, m, tiles, d_opt_const_.ptr, nullptr, nullptr);
+      LaunchReducePartials(stream_, d_partials_.ptr, m, OptPrepareTileGroups(m, P_), d_opt_const_.ptr,
+                           nullptr, nullptr);
       AllReduce(d_opt_const_.ptr, m, false);
       stats_.kernel_launches += 2;
     } else {

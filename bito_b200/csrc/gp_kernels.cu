@@ -898,18 +898,18 @@ __global__ void __launch_bounds__(kTile)
 // sum is evaluated as the log of a running product with the binary exponents split off, so a
 // thread pays one log() per kOptPatternsPerThread patterns instead of one per pattern.
 __global__ void __launch_bounds__(kTile)
-    k_opt_prepare_ratio(DeviceState st, const OptOp* __restrict__ ops, int tiles,
-                        OptState* __restrict__ states, OptParams prm, int method,
+    k_opt_prepare_ratio(DeviceState st, const OptOp* __restrict__ ops, int n_ops, int tiles,
+                        int tiles_per_block, OptState* __restrict__ states, OptParams prm, int method,
                         double* __restrict__ rho, const int32_t* __restrict__ perm,
                         int64_t rho_stride, double* __restrict__ partials,
                         int32_t* __restrict__ active, int active_capacity) {
-  // tile-major: the edges of one pattern tile are neighbours in the grid, so a parent r-PLV or
-  // child p-PLV tile shared by several edges is read from HBM once and from L2 afterwards
-  const int n_ops = gridDim.x / tiles;
-  const int t_idx = blockIdx.x / n_ops;
-  const int o = blockIdx.x - t_idx * n_ops;
+  // tile-major: the edges of one pattern tile group are neighbours in the grid, so a parent r-PLV
+  // or child p-PLV tile shared by several edges is read from HBM once and from L2 afterwards
+  const int n_groups = gridDim.x / n_ops;
+  const int tile_group = blockIdx.x / n_ops;
+  const int o = blockIdx.x - tile_group * n_ops;
   const OptOp op = ops[o];
-  if (t_idx == 0 && threadIdx.x == 0) {
+  if (tile_group == 0 && threadIdx.x == 0) {
     OptState s;
     opt_init(s, st, prm, method, op);
     states[o] = s;
@@ -922,26 +922,31 @@ __global__ void __launch_bounds__(kTile)
     }
   }
   (void)active_capacity;
-  const int64_t p = static_cast<int64_t>(t_idx) * kTile + threadIdx.x;
   double k_part = 0.;
-  if (p < st.P) {
-    const V4 r = load_plv(op.parent, p);
-    const V4 c = load_plv(op.child, p);
-    double c0 = 0., c1 = 0.;
+  const int tile_begin = tile_group * tiles_per_block;
+  const int tile_end = min(tiles, tile_begin + tiles_per_block);
+  double* const rho_o = rho + static_cast<int64_t>(o) * rho_stride;
+  for (int tile = tile_begin; tile < tile_end; ++tile) {
+    const int64_t p = static_cast<int64_t>(tile) * kTile + threadIdx.x;
+    if (p < st.P) {
+      const V4 r = load_plv(op.parent, p);
+      const V4 c = load_plv(op.child, p);
+      double c0 = 0., c1 = 0.;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const double rv = r.a * c_model.V[k] + r.b * c_model.V[4 + k] + r.c * c_model.V[8 + k] +
-                        r.d * c_model.V[12 + k];
-      const double vp = c_model.Vinv[4 * k] * c.a + c_model.Vinv[4 * k + 1] * c.b +
-                        c_model.Vinv[4 * k + 2] * c.c + c_model.Vinv[4 * k + 3] * c.d;
-      const double term = rv * vp;
-      if (c_model.group[k] == 0) c0 += term; else c1 += term;
+      for (int k = 0; k < 4; ++k) {
+        const double rv = r.a * c_model.V[k] + r.b * c_model.V[4 + k] + r.c * c_model.V[8 + k] +
+                          r.d * c_model.V[12 + k];
+        const double vp = c_model.Vinv[4 * k] * c.a + c_model.Vinv[4 * k + 1] * c.b +
+                          c_model.Vinv[4 * k + 2] * c.c + c_model.Vinv[4 * k + 3] * c.d;
+        const double term = rv * vp;
+        if (c_model.group[k] == 0) c0 += term; else c1 += term;
+      }
+      rho_o[perm[p]] = c0 != 0. ? c1 / c0 : 0.;
+      k_part += st.weights[p] * log(c0);
     }
-    rho[static_cast<int64_t>(o) * rho_stride + perm[p]] = c0 != 0. ? c1 / c0 : 0.;
-    k_part = st.weights[p] * log(c0);
   }
   k_part = block_reduce(k_part, SumOp(), 0.);
-  if (threadIdx.x == 0) partials[static_cast<int64_t>(o) * tiles + t_idx] = k_part;
+  if (threadIdx.x == 0) partials[static_cast<int64_t>(o) * n_groups + tile_group] = k_part;
 }
 
 // Splits t > 0 (finite, normal) into m * 2^e with m in [0.5, 1).
@@ -1224,15 +1229,21 @@ void LaunchOptStep(cudaStream_t s, const DeviceState& st, int n_ops, OptState* s
                                               n_values, value_stride, edge_const, active_counter,
                                               active, active_capacity, parity);
 }
+int64_t OptPrepareTileGroups(int n_ops, int64_t P) {
+  const int64_t tiles = TilesFor(P);
+  const int tpb = TilesPerBlock(n_ops, tiles, "BITO_GP_OPT_TILES_PER_BLOCK", 32);
+  return (tiles + tpb - 1) / tpb;
+}
 void LaunchOptPrepareRatio(cudaStream_t s, const DeviceState& st, const OptOp* ops, int n_ops,
                            OptState* states, const OptParams& params, int method, double* rho,
                            const int32_t* perm, int64_t rho_stride, double* partials,
                            int32_t* active, int active_capacity) {
   if (n_ops == 0) return;
   const int tiles = static_cast<int>(TilesFor(st.P));
-  k_opt_prepare_ratio<<<Grid(n_ops, tiles), kTile, 0, s>>>(st, ops, tiles, states, params, method, rho,
-                                                           perm, rho_stride, partials, active,
-                                                           active_capacity);
+  const int tpb = TilesPerBlock(n_ops, tiles, "BITO_GP_OPT_TILES_PER_BLOCK", 32);
+  k_opt_prepare_ratio<<<Grid(n_ops, (tiles + tpb - 1) / tpb), kTile, 0, s>>>(
+      st, ops, n_ops, tiles, tpb, states, params, method, rho, perm, rho_stride, partials, active,
+      active_capacity);
 }
 int64_t OptRatioTileGroups(int64_t P) {
   const int64_t per_block = static_cast<int64_t>(kTile) * kOptPatternsPerThread;

@@ -55,8 +55,10 @@ void LaunchOptStep(cudaStream_t s, const DeviceState& st, int n_ops, OptState* s
 // order, Engine::BuildWeightClasses), K_e partials per tile.
 void LaunchOptPrepareRatio(cudaStream_t s, const DeviceState& st, const OptOp* ops, int n_ops,
                            OptState* states, const OptParams& params, int method, double* rho,
-                           const int32_t* perm, int64_t rho_stride, double* partials /* n_ops x tiles */,
+                           const int32_t* perm, int64_t rho_stride,
+                           double* partials /* n_ops x OptPrepareTileGroups(n_ops, P) */,
                            int32_t* active, int active_capacity);
+int64_t OptPrepareTileGroups(int n_ops, int64_t P);
 int64_t OptRatioTileGroups(int64_t P);
 int64_t OptRatioPartials(int64_t P);  // partial sums per edge written by LaunchOptEvalRatio
 void LaunchOptEvalRatio(cudaStream_t s, const DeviceState& st, int n_ops, const OptState* states,
