@@ -240,3 +240,118 @@ def test_stats_report_fusion_and_launches(cuda_engine_lib):
         assert e.stats()["programs_compiled"] == 1            # cached program (graph) replayed
         # leaf PLVs are symbolic and leaf PHats never materialise: fewer resident PLVs than 6N
         assert e.stats()["plvs_resident"] < e.plv_count
+
+
+def test_weight_classes_general_weights_match_oracle(cuda_engine_lib):
+    """The Brent objective stores patterns grouped by weight class (1..7 folded into a running
+    product, everything else through an explicit log): non-integer, zero-adjacent and large weights
+    must give the oracle's optimised branch lengths too."""
+    from bito_b200.gp_engine import GPEngine
+    from oracle.port_engine import PortEngine
+    rng = np.random.default_rng(11)
+    pb = _random_problem(rng, 10, 1500)
+    w = pb["weights"].copy()
+    w[::7] = rng.uniform(0.25, 3.5, size=w[::7].size)   # non-integer
+    w[5::31] = rng.integers(8, 400, size=w[5::31].size)  # large multiplicities (constant sites)
+    site_count = int(round(w.sum()))
+    cpu = PortEngine(pb["symbols"], w, site_count, pb["node_count"], pb["edge_count"])
+    with GPEngine(pb["symbols"], w, site_count, pb["node_count"], pb["edge_count"]) as gpu:
+        for e in (cpu, gpu):
+            e.set_branch_lengths(pb["branch_lengths"])
+            e.process_operations(*pb["populate"])
+            e.process_operations(*pb["likelihoods"])
+            e.process_operations(*pb["optimize"])
+        assert rel_err(gpu.get_per_gpcsp_log_likelihoods(), cpu.per_gpcsp_log_likelihoods()) <= LL_RTOL
+        assert np.max(np.abs(gpu.get_branch_lengths() - cpu.branch_lengths())) <= BL_ATOL
+        # a second alignment with other weights on the same engine re-derives the class layout
+        w2 = np.ones_like(w)
+        cpu2 = PortEngine(pb["symbols"], w2, int(w2.sum()), pb["node_count"], pb["edge_count"])
+        gpu.set_site_patterns(pb["symbols"], w2)
+        for e in (cpu2, gpu):
+            e.set_branch_lengths(pb["branch_lengths"])
+            e.reset_optimization_count()
+            e.process_operations(*pb["populate"])
+            e.process_operations(*pb["optimize"])
+        assert np.max(np.abs(gpu.get_branch_lengths() - cpu2.branch_lengths())) <= BL_ATOL
+
+
+def test_bench_size_properties(cuda_engine_lib):
+    """BASELINE.json configs[3] at full size (200 taxa x 100 000 patterns, 3474 nodes, 8369 edges),
+    where the CPU oracle is too slow to be the checker: size-independent properties instead.
+      * idempotence: a second PopulatePLVs + ComputeLikelihoods reproduces every output bit for bit
+        (gp_doctest.cpp:462-475);
+      * weight linearity: doubling every pattern weight doubles every per-edge log-likelihood
+        exactly (a power-of-two scaling of each term of the sum);
+      * shard additivity (the multi-GPU identity): per-edge sums over two half alignments add up to
+        the full alignment's;
+      * the oracle agrees on the first 1500 patterns (same DAG, same op lists)."""
+    from bito_b200 import _lib
+    from bito_b200.gp_engine import GPEngine
+    from bito_b200.synthetic import make_named_workload
+    from oracle.port_engine import PortEngine
+    wl = make_named_workload("synthetic-200taxa-100kpat-1000trees")
+    dag = wl.dag
+    pop, lik = wl.ops("populate_plvs"), wl.ops("compute_likelihoods")
+
+    def run(symbols, weights, flags=_lib.FLAG_NO_LOGLIK_MATRIX):
+        with GPEngine(symbols, weights, int(weights.sum()), dag.node_count, dag.edge_count, sbn_prior=wl.sbn_prior,
+                      unconditional_node_probabilities=wl.unconditional, inverted_sbn_prior=wl.inverted,
+                      flags=flags) as e:
+            e.process_operations(*pop)
+            e.process_operations(*lik)
+            first = (e.get_per_gpcsp_log_likelihoods(), e.get_log_marginal_likelihood(), e.get_rescaling_counts())
+            e.process_operations(*pop)
+            e.process_operations(*lik)
+            again = (e.get_per_gpcsp_log_likelihoods(), e.get_log_marginal_likelihood(), e.get_rescaling_counts())
+            assert e.stats()["device_status_bits"] == 0
+        assert np.array_equal(first[0], again[0]) and first[1] == again[1] and np.array_equal(first[2], again[2])
+        return first
+
+    full = run(wl.symbols, wl.weights)
+    assert np.all(np.isfinite(full[0])) and np.isfinite(full[1])
+    doubled = run(wl.symbols, 2.0 * wl.weights)
+    assert np.array_equal(doubled[0], 2.0 * full[0]) and doubled[1] == 2.0 * full[1]
+    half = wl.pattern_count // 2
+    lo = run(wl.symbols[:, :half], wl.weights[:half])
+    hi = run(wl.symbols[:, half:], wl.weights[half:])
+    assert rel_err(lo[0] + hi[0], full[0]) <= 1e-12
+    assert rel_err(lo[1] + hi[1], full[1]) <= 1e-12
+    n = 1500
+    sub = wl.subsample(n)
+    cpu = PortEngine(sub.symbols, sub.weights, sub.site_count, dag.node_count, dag.edge_count, wl.sbn_prior,
+                     wl.unconditional, wl.inverted)
+    cpu.process_operations(*pop)
+    cpu.process_operations(*lik)
+    with GPEngine(sub.symbols, sub.weights, sub.site_count, dag.node_count, dag.edge_count, sbn_prior=wl.sbn_prior,
+                  unconditional_node_probabilities=wl.unconditional, inverted_sbn_prior=wl.inverted) as e:
+        e.process_operations(*pop)
+        e.process_operations(*lik)
+        assert rel_err(e.get_per_gpcsp_log_likelihoods(), cpu.per_gpcsp_log_likelihoods()) <= LL_RTOL
+        assert rel_err(e.get_log_marginal_likelihood(), cpu.log_marginal_likelihood()) <= LL_RTOL
+        assert rel_err(e.get_log_likelihood_matrix(), cpu.log_likelihood_matrix()) <= LL_RTOL
+        assert np.array_equal(e.get_rescaling_counts(), cpu.rescaling_counts())
+        # One batched (Jacobi) Brent sweep over all 8356 edges from the common start t = 0.1. Brent's
+        # first parabolic step then sits on an acceptance boundary for ~0.1 % of the edges, where
+        # 1e-11 relative noise in the objective flips the decision: two builds of the UNMODIFIED
+        # reference disagree with each other on 3-10 of these 8369 edges by up to 2e-4
+        # (oracle/ref_jacobi_sweep_sensitivity.py; DESIGN.md section 5). So: >= 99.5 % of the edges
+        # within 1e-6, the rest inside Brent's own tolerance (2^-9 relative in log t,
+        # optimization.hpp:71-188) with an objective value as good as the oracle's to 1e-9.
+        blo = wl.ops("batched_branch_length_optimization")
+        for eng in (cpu, e):
+            eng.process_operations(*blo)
+        got, want = e.get_branch_lengths(), cpu.branch_lengths()
+        off = np.nonzero(np.abs(got - want) > BL_ATOL)[0]
+        assert off.size <= 0.005 * want.size, off.size
+        tol = 2.0 ** -9
+        assert np.all(np.abs(np.log(got[off]) - np.log(want[off])) <= 4 * (tol * np.abs(np.log(want[off])) + tol / 4))
+        by_edge = {int(r[3]): (int(r[1]), int(r[2])) for r in blo[0]}
+        for g in off:
+            leafward, rootward = by_edge[int(g)]
+            values = []
+            for t in (got[g], want[g]):
+                bl = want.copy()
+                bl[g] = t
+                cpu.set_branch_lengths(bl)
+                values.append(cpu.log_likelihood_and_derivatives(int(g), rootward, leafward)[0])
+            assert abs(values[0] - values[1]) <= 1e-9 * abs(values[1])
