@@ -166,9 +166,8 @@ void DeviceArray<T>::Release() {
 // ---- construction: GPEngine::GPEngine, gp_engine.cpp:9-43 ------------------------------
 Engine::Engine(const bito_gp_config& cfg) : cfg_(cfg) {
   if (cfg.abi_version != BITO_GP_ABI_VERSION) Fail("bito_gp_config.abi_version mismatch");
-  if (cfg.taxon_count <= 0 || cfg.pattern_count <= 0 || cfg.node_count <= 0 ||
-      cfg.gpcsp_count <= 0)
-    Fail("bito_gp_create: taxon, pattern, node and gpcsp counts must be positive");
+  if (cfg.taxon_count <= 0 || cfg.pattern_count < 0 || cfg.node_count <= 0 || cfg.gpcsp_count <= 0)
+    Fail("bito_gp_create: taxon, node and gpcsp counts must be positive and pattern_count >= 0");
   if (!(cfg.rescaling_threshold > 0.) || !(cfg.rescaling_threshold < 1.))
     Fail("bito_gp_create: rescaling_threshold must lie in (0, 1)");
   int n_dev = 0;
@@ -190,7 +189,7 @@ Engine::Engine(const bito_gp_config& cfg) : cfg_(cfg) {
 
   taxon_count_ = cfg.taxon_count;
   P_ = cfg.pattern_count;
-  P_stride_ = RoundUp(P_, 8);
+  P_stride_ = std::max<int64_t>(8, RoundUp(P_, 8));  // an empty shard still owns (unused) storage
   site_count_ = cfg.site_count;
   node_count_ = cfg.node_count;
   gpcsp_count_ = cfg.gpcsp_count;
@@ -338,6 +337,23 @@ void Engine::InvalidatePrograms() { alloc_version_++; }
 void Engine::SetSitePatterns(const uint8_t* symbols, const double* weights, bool on_device) {
   Activate();
   const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  if (P_ == 0) {  // empty shard: nothing to upload
+    bool slots_changed = false;
+    for (int64_t t = 0; t < taxon_count_; ++t) {
+      PlvSlot& s = plvs_[static_cast<size_t>(t)];
+      void* want = d_symbols_.ptr + t * P_stride_;
+      if (s.kind == kPlvSymbols && s.ptr == want) continue;
+      if (s.kind == kPlvDense) plv_pool_.Free(s.ptr);
+      s.ptr = want;
+      s.kind = kPlvSymbols;
+      slots_changed = true;
+    }
+    total_weight_ = 0.;
+    have_patterns_ = true;
+    BuildWeightClasses(weights);
+    if (slots_changed) InvalidatePrograms();
+    return;
+  }
   if (!on_device) {
     uint8_t worst = 0;
     for (int64_t i = 0; i < taxon_count_ * P_; ++i) worst = symbols[i] > worst ? symbols[i] : worst;
@@ -382,14 +398,16 @@ void Engine::SetSitePatterns(const uint8_t* symbols, const double* weights, bool
 // padded to whole tile groups; the padding holds rho = 0, i.e. a factor of exactly 1.
 void Engine::BuildWeightClasses(const double* host_weights) {
   std::vector<double> w(static_cast<size_t>(P_));
-  if (host_weights != nullptr) {
+  if (P_ == 0) {
+    // nothing to read
+  } else if (host_weights != nullptr) {
     std::memcpy(w.data(), host_weights, w.size() * sizeof(double));
   } else {
     GP_CUDA(cudaMemcpyAsync(w.data(), d_weights_.ptr, w.size() * sizeof(double), cudaMemcpyDeviceToHost,
                             stream_));
     GP_CUDA(cudaStreamSynchronize(stream_));
   }
-  if (w == host_weights_cache_ && P_perm_ > 0) return;  // same weights: the layout is current
+  if (w == host_weights_cache_ && P_perm_ > 0 && P_ > 0) return;  // same weights: layout is current
   host_weights_cache_ = w;
   auto cls = [](double x) {
     const int wi = static_cast<int>(x);
@@ -539,6 +557,7 @@ void Engine::CommInit(int n_ranks, int rank, const uint8_t id[128]) {
   NcclCheck(Nccl().CommInitRank(&comm, n_ranks, uid, rank), "ncclCommInitRank");
   nccl_comm_ = comm;
   if (have_patterns_) {  // total weight must now be global
+    EnsureScratch(TilesFor(P_), 2);
     GP_CUDA(cudaMemcpyAsync(d_packed_.ptr, &total_weight_, sizeof(double), cudaMemcpyHostToDevice,
                             stream_));
     AllReduce(d_packed_.ptr, 1, false);

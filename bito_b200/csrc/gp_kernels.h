@@ -8,7 +8,10 @@
 namespace bito_gp {
 
 // Number of pattern tiles for P local patterns.
-inline int64_t TilesFor(int64_t P) { return (P + kTile - 1) / kTile; }
+// Number of pattern tiles for P local patterns. An empty shard (P = 0, a rank of a multi-GPU run
+// that owns no pattern) still gets one tile, so the per-macro-op bookkeeping (rescaling counts,
+// optimiser states) runs there too; no thread of that tile is live.
+inline int64_t TilesFor(int64_t P) { return P > 0 ? (P + kTile - 1) / kTile : 1; }
 
 cudaError_t UploadModel(const ModelConst& model);
 

@@ -355,3 +355,17 @@ def test_bench_size_properties(cuda_engine_lib):
                 cpu.set_branch_lengths(bl)
                 values.append(cpu.log_likelihood_and_derivatives(int(g), rootward, leafward)[0])
             assert abs(values[0] - values[1]) <= 1e-9 * abs(values[1])
+
+
+def test_empty_shard_is_a_valid_engine(cuda_engine_lib):
+    """A rank of a pattern-sharded run may own no pattern at all (P < number of GPUs): its engine
+    must run every op list, keep its rescaling counts and optimiser states in step, and contribute
+    zeros to the sums."""
+    fx = Fixture("five_taxon")
+    with make_cuda(fx, 0, pattern_slice=slice(0, 0)) as e:
+        assert e.pattern_count == 0
+        for name in ("populate_plvs", "compute_likelihoods", "optimize_sbn_parameters"):
+            e.process_operations(*fx.ops(name))
+        assert not e.get_per_gpcsp_log_likelihoods().any() and e.get_log_marginal_likelihood() == 0.0
+        assert e.get_plv(0).shape == (0, 4) and e.get_log_likelihood_matrix().shape[1] == 0
+        assert not e.get_rescaling_counts().any()

@@ -33,7 +33,8 @@ def check(name, ok):
         print(("ok   " if ok else "FAIL ") + name, flush=True)
 
 
-for case, thresholds in (("ds1", (0, 2)), ("fluA", (0, 4)), ("five_taxon", (0, 1))):
+# hello_single_nucleotide has ONE pattern: every rank but the first owns an empty shard
+for case, thresholds in (("ds1", (0, 2)), ("fluA", (0, 4)), ("five_taxon", (0, 1)), ("hello_single_nucleotide", (0,))):
     fx = Fixture(case)
     P = fx["symbols"].shape[1]
     lo, hi = shard_bounds(P, world, rank)
