@@ -307,6 +307,10 @@ def main():
     roofline = {
         "bound": "hbm", "kernel": top["name"], "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
         "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
+        # bytes the kernel actually moved (ncu, per launch) over the live launch time: the fused node
+        # kernel moves fewer bytes than the op list's algorithmic bytes, so `frac` can exceed 1
+        "dram_achieved": (traffic / (per_launch_ms * 1e-3) / 1e9) if traffic else None,
+        "dram_frac": (traffic / (per_launch_ms * 1e-3) / 1e9 / peak_gbs) if traffic else None,
         "launches_per_step": top["launches"] / prof_steps, "kernel_share_of_step": top["total_ms"] / total_prof_ms,
         "algorithmic_bytes_per_launch": per_launch_bytes, "ms_per_launch": per_launch_ms,
         "whole_pass": {"algorithmic_bytes": pass_alg_bytes,

@@ -34,7 +34,8 @@ enum StatusBits : uint32_t {
   kErrMultiplyNotFinite = 2u,    // gp_engine.cpp:283, 575-577
   kErrNegativePLV = 4u,          // gp_engine.cpp:585-586
   kErrRescaledStationary = 8u,   // gp_engine.cpp:256-257
-  kErrEmptyPrep = 16u            // gp_engine.cpp:325
+  kErrEmptyPrep = 16u,           // gp_engine.cpp:325
+  kErrQuartetRescaled = 32u      // gp_engine.cpp:750-753
 };
 
 // Per-engine device pointers handed to every kernel by value.
@@ -46,6 +47,8 @@ struct DeviceState {
   double* bl;        // branch lengths per edge                     (dag_branch_handler.hpp:249)
   double* diff;      // last branch-length change per edge          (dag_branch_handler.hpp:252)
   double* hybrid;    // hybrid marginal log-likelihoods per edge    (gp_engine.hpp:352)
+  double* inverted;  // inverted SBN prior per edge                 (gp_engine.hpp:338)
+  double* uncond;    // unconditional node probabilities per node   (gp_engine.hpp:315)
   double* ll_sum;    // per-edge sum_p w_p * log_likelihoods_(e,p), GLOBAL over ranks
   double* weights;   // site pattern weights (local shard)
   double* log_marg;  // per-pattern log marginal (local shard)      (gp_engine.hpp:349)
@@ -169,6 +172,15 @@ struct OptOp {
   PlvRef parent, child;  // rootward_ (r-PLV of the parent), leafward_ (p-PLV of the child)
   int32_t edge;
   int32_t pad;
+};
+
+// One summand of a quartet hybrid marginal (gp_engine.cpp:748-808, quartet_hybrid_request.hpp):
+// a choice of (rootward, sister, rotated, sorted) tips around one central edge. mats points at
+// the five transition matrices rootward, sister, central, rotated, sorted (80 doubles).
+struct QuartetItem {
+  PlvRef rootward, sister, rotated, sorted;
+  int32_t edge[5];        // rootward, sister, central, rotated, sorted
+  int32_t rootward_node;  // indexes the unconditional node probabilities
 };
 
 // Resumable optimiser state, one per OptimizeBranchLength in flight. The decision logic
