@@ -98,6 +98,9 @@ SIGNATURES = {
     "bito_gp_set_sbn_parameters": (_int, [_vp, _vp]),
     "bito_gp_get_plv": (_int, [_vp, _i64, _vp]),
     "bito_gp_set_plv": (_int, [_vp, _i64, _vp, _i32]),
+    "bito_gp_calculate_quartet_hybrid_likelihoods": (_int, [_vp, _i64, _vp, _vp, _vp]),
+    "bito_gp_process_quartet_hybrid_requests": (_int, [_vp, _i64, _vp, _vp, _vp]),
+    "bito_gp_get_hybrid_marginals": (_int, [_vp, _vp]),
     "bito_gp_get_rescaling_counts": (_int, [_vp, _vp]),
     "bito_gp_get_node_count": (_i64, [_vp]),
     "bito_gp_get_plv_count": (_i64, [_vp]),
@@ -109,6 +112,7 @@ SIGNATURES = {
     "bito_gp_grow_gpcsps": (_int, [_vp, _i64, _vp, _i64]),
     "bito_gp_grow_spare_plvs": (_int, [_vp, _i64]),
     "bito_gp_grow_spare_gpcsps": (_int, [_vp, _i64]),
+    "bito_gp_copy_node_data": (_int, [_vp, _i64, _i64]),
     "bito_gp_copy_plv_data": (_int, [_vp, _i64, _i64]),
     "bito_gp_copy_gpcsp_data": (_int, [_vp, _i64, _i64]),
     "bito_gp_comm_make_unique_id": (_int, [_vp]),

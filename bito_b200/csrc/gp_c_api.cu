@@ -177,6 +177,25 @@ int bito_gp_set_plv(bito_gp_engine* e, int64_t plv_id, const double* in, int32_t
   ENGINE_OR_FAIL(e);
   return Guard([&] { e->impl.SetPlv(plv_id, in, rescaling_count); });
 }
+int bito_gp_calculate_quartet_hybrid_likelihoods(bito_gp_engine* e, int64_t central_gpcsp_idx,
+                                                 const bito_gp_quartet_tip* tips,
+                                                 const int32_t tip_counts[4], double* out) {
+  ENGINE_OR_FAIL(e);
+  return Guard([&] { e->impl.QuartetHybrid(1, &central_gpcsp_idx, tip_counts, tips, out, false); });
+}
+int bito_gp_process_quartet_hybrid_requests(bito_gp_engine* e, int64_t n_requests,
+                                            const int64_t* central_gpcsp_idx,
+                                            const int32_t* tip_counts,
+                                            const bito_gp_quartet_tip* tips) {
+  ENGINE_OR_FAIL(e);
+  return Guard([&] {
+    e->impl.QuartetHybrid(n_requests, central_gpcsp_idx, tip_counts, tips, nullptr, true);
+  });
+}
+int bito_gp_get_hybrid_marginals(bito_gp_engine* e, double* out) {
+  ENGINE_OR_FAIL(e);
+  return Guard([&] { e->impl.GetHybridMarginals(out); });
+}
 int bito_gp_get_rescaling_counts(bito_gp_engine* e, int32_t* out) {
   ENGINE_OR_FAIL(e);
   return Guard([&] { e->impl.GetRescalingCounts(out); });
@@ -212,6 +231,10 @@ int bito_gp_grow_spare_plvs(bito_gp_engine* e, int64_t new_node_spare_count) {
 int bito_gp_grow_spare_gpcsps(bito_gp_engine* e, int64_t new_gpcsp_spare_count) {
   ENGINE_OR_FAIL(e);
   return Guard([&] { e->impl.GrowSpareGpcsps(new_gpcsp_spare_count); });
+}
+int bito_gp_copy_node_data(bito_gp_engine* e, int64_t src_node_idx, int64_t dest_node_idx) {
+  ENGINE_OR_FAIL(e);
+  return Guard([&] { e->impl.CopyNodeData(src_node_idx, dest_node_idx); });
 }
 int bito_gp_copy_plv_data(bito_gp_engine* e, int64_t src_plv_idx, int64_t dest_plv_idx) {
   ENGINE_OR_FAIL(e);

@@ -266,7 +266,7 @@ Engine::~Engine() {
   d_q_.Release(); d_bl_.Release(); d_diff_.Release(); d_hybrid_.Release(); d_ll_sum_.Release();
   d_inverted_.Release(); d_uncond_.Release(); d_status_.Release(); d_feval_total_.Release();
   d_partials_.Release(); d_packed_.Release(); d_level_max_.Release(); d_coef_.Release();
-  d_dense_tmp_.Release(); d_mtab_.Release(); d_mtab_lik_.Release(); d_opt_states_.Release(); d_opt_const_.Release(); d_opt_active_.Release(); d_perm_.Release(); d_wperm_.Release(); d_row_class_.Release(); d_active_.Release(); d_single_opt_.Release();
+  d_dense_tmp_.Release(); d_mtab_.Release(); d_mtab_lik_.Release(); d_opt_states_.Release(); d_opt_const_.Release(); d_opt_active_.Release(); d_perm_.Release(); d_wperm_.Release(); d_row_class_.Release(); d_active_.Release(); d_single_opt_.Release(); d_quartet_items_.Release(); d_quartet_mats_.Release();
   if (pinned_ != nullptr) cudaFreeHost(pinned_);
   if (ev_begin_) cudaEventDestroy(ev_begin_);
   if (ev_end_) cudaEventDestroy(ev_end_);
@@ -296,7 +296,12 @@ void Engine::AllocEdgeArrays(int64_t padded) {
   LaunchFill(stream_, d_diff_.ptr + old_n, fresh, 0.0);
   LaunchFill(stream_, d_hybrid_.ptr + old_n, fresh, -std::numeric_limits<double>::infinity());
   LaunchFill(stream_, d_ll_sum_.ptr + old_n, fresh + 1, 0.0);
-  d_uncond_.Resize(static_cast<size_t>(node_count_ + spare_nodes_), true, stream_);
+  {
+    const size_t old_u = d_uncond_.n;
+    d_uncond_.Resize(static_cast<size_t>(node_count_ + spare_nodes_), true, stream_);
+    if (d_uncond_.n > old_u)
+      LaunchFill(stream_, d_uncond_.ptr + old_u, static_cast<int64_t>(d_uncond_.n - old_u), 1.0);
+  }
 }
 
 DeviceState Engine::State() const {
@@ -308,6 +313,8 @@ DeviceState Engine::State() const {
   st.bl = d_bl_.ptr;
   st.diff = d_diff_.ptr;
   st.hybrid = d_hybrid_.ptr;
+  st.inverted = d_inverted_.ptr;
+  st.uncond = d_uncond_.ptr;
   st.ll_sum = d_ll_sum_.ptr;
   st.weights = d_weights_.ptr;
   st.log_marg = d_log_marg_.ptr;
@@ -603,6 +610,8 @@ void Engine::CheckStatus() {
   if (bits & kErrRescaledStationary)
     msg += "Surprise! Rescaled stationary distribution in IncrementMarginalLikelihood; ";
   if (bits & kErrEmptyPrep) msg += "Empty src_vector in PrepForMarginalization; ";
+  if (bits & kErrQuartetRescaled)
+    msg += "Rescaling not implemented in CalculateQuartetHybridLikelihoods.; ";
   msg += "(bito_gp device status " + std::to_string(bits) + ")";
   Fail(msg);
 }
@@ -1618,6 +1627,109 @@ void Engine::LogLikelihoodAndDerivatives(int64_t gpcsp, int64_t rootward, int64_
             total_weight_;
 }
 
+// ---- quartet hybrid marginals: gp_engine.cpp:748-816 ---------------------------------------------
+namespace {
+// NumericalUtils::LogAdd (numerical_utils.hpp:35-52); LogSum is its left fold (numerical_utils.cpp).
+double HostLogAdd(double x, double y) {
+  if (y > x) std::swap(x, y);
+  if (x == -std::numeric_limits<double>::infinity()) return x;
+  const double neg_diff = y - x;
+  if (neg_diff < std::log(std::numeric_limits<double>::epsilon())) return x;
+  return x + std::log(1.0 + std::exp(neg_diff));
+}
+}  // namespace
+
+void Engine::QuartetHybrid(int64_t n_requests, const int64_t* central, const int32_t* tip_counts,
+                           const bito_gp_quartet_tip* tips, double* likelihoods, bool store) {
+  Activate();
+  if (n_requests < 0) Fail("QuartetHybrid: negative request count");
+  std::vector<QuartetItem> items;
+  std::vector<int64_t> first_item(static_cast<size_t>(n_requests) + 1, 0);
+  int64_t tip_off = 0;
+  for (int64_t r = 0; r < n_requests; ++r) {
+    const int32_t* n = tip_counts + 4 * r;
+    for (int k = 0; k < 4; ++k)
+      if (n[k] < 0) Fail("QuartetHybrid: negative tip count");
+    const bito_gp_quartet_tip* rw = tips + tip_off;
+    const bito_gp_quartet_tip* sis = rw + n[0];
+    const bito_gp_quartet_tip* rot = sis + n[1];
+    const bito_gp_quartet_tip* sorted = rot + n[2];
+    tip_off += static_cast<int64_t>(n[0]) + n[1] + n[2] + n[3];
+    CheckEdge(central[r], "QuartetHybridRequest");
+    for (const bito_gp_quartet_tip* t = rw; t < sorted + n[3]; ++t) {
+      CheckPlv(t->plv_idx, "QuartetHybridRequest");
+      CheckEdge(t->gpcsp_idx, "QuartetHybridRequest");
+    }
+    first_item[r] = static_cast<int64_t>(items.size());
+    // Loop nest of CalculateQuartetHybridLikelihoods: rootward, sister, rotated, sorted (innermost).
+    for (int a = 0; a < n[0]; ++a) {
+      if (rw[a].tip_node_id < 0 || rw[a].tip_node_id >= node_count_ + spare_nodes_)
+        Fail("QuartetHybridRequest: rootward tip node id out of range");
+      for (int b = 0; b < n[1]; ++b)
+        for (int c = 0; c < n[2]; ++c)
+          for (int d = 0; d < n[3]; ++d) {
+            QuartetItem it{};
+            it.rootward = Ref(rw[a].plv_idx);
+            it.sister = Ref(sis[b].plv_idx);
+            it.rotated = Ref(rot[c].plv_idx);
+            it.sorted = Ref(sorted[d].plv_idx);
+            it.edge[0] = static_cast<int32_t>(rw[a].gpcsp_idx);
+            it.edge[1] = static_cast<int32_t>(sis[b].gpcsp_idx);
+            it.edge[2] = static_cast<int32_t>(central[r]);
+            it.edge[3] = static_cast<int32_t>(rot[c].gpcsp_idx);
+            it.edge[4] = static_cast<int32_t>(sorted[d].gpcsp_idx);
+            it.rootward_node = static_cast<int32_t>(rw[a].tip_node_id);
+            items.push_back(it);
+          }
+    }
+  }
+  first_item[static_cast<size_t>(n_requests)] = static_cast<int64_t>(items.size());
+  const int64_t n_items = static_cast<int64_t>(items.size());
+  std::vector<double> result(static_cast<size_t>(n_items));
+  if (n_items > 0) {
+    if (n_items > (int64_t{1} << 30) / TilesFor(P_)) Fail("QuartetHybrid: too many summands in one call");
+    const DeviceState st = State();
+    const int64_t tiles = TilesFor(P_);
+    d_quartet_items_.Resize(static_cast<size_t>(n_items), false, stream_);
+    d_quartet_mats_.Resize(static_cast<size_t>(80 * n_items), false, stream_);
+    EnsureScratch(n_items * tiles, 2 * n_items);
+    GP_CUDA(cudaMemcpyAsync(d_quartet_items_.ptr, items.data(), items.size() * sizeof(QuartetItem),
+                            cudaMemcpyHostToDevice, stream_));
+    LaunchQuartetMatrices(stream_, st, d_quartet_items_.ptr, static_cast<int>(n_items), d_quartet_mats_.ptr);
+    LaunchQuartet(stream_, st, d_quartet_items_.ptr, static_cast<int>(n_items), d_quartet_mats_.ptr,
+                  d_partials_.ptr);
+    LaunchReducePartials(stream_, d_partials_.ptr, static_cast<int>(n_items), tiles, d_packed_.ptr, nullptr,
+                         nullptr);
+    AllReduce(d_packed_.ptr, n_items, false);
+    LaunchQuartetFinish(stream_, st, d_quartet_items_.ptr, static_cast<int>(n_items), d_packed_.ptr,
+                        d_packed_.ptr + n_items);
+    GP_CUDA(cudaMemcpyAsync(result.data(), d_packed_.ptr + n_items, n_items * sizeof(double),
+                            cudaMemcpyDeviceToHost, stream_));
+    GP_CUDA(cudaStreamSynchronize(stream_));
+    stats_.kernel_launches += 4;
+    CheckStatus();
+  }
+  if (likelihoods != nullptr && n_items > 0) std::memcpy(likelihoods, result.data(), n_items * sizeof(double));
+  if (store) {
+    for (int64_t r = 0; r < n_requests; ++r) {
+      const int64_t b = first_item[r], e = first_item[r + 1];
+      if (e == b) continue;  // not fully formed (gp_engine.cpp:811): entry stays as it is
+      double acc = result[b];
+      for (int64_t i = b + 1; i < e; ++i) acc = HostLogAdd(acc, result[i]);
+      GP_CUDA(cudaMemcpyAsync(d_hybrid_.ptr + central[r], &acc, sizeof(double), cudaMemcpyHostToDevice,
+                              stream_));
+      GP_CUDA(cudaStreamSynchronize(stream_));
+    }
+  }
+}
+
+void Engine::GetHybridMarginals(double* out) {
+  Activate();
+  GP_CUDA(cudaMemcpyAsync(out, d_hybrid_.ptr, gpcsp_count_ * sizeof(double), cudaMemcpyDeviceToHost,
+                          stream_));
+  GP_CUDA(cudaStreamSynchronize(stream_));
+}
+
 void Engine::GetTransitionMatrix(double t, double out[16]) {
   Activate();
   EnsureScratch(16, 16);
@@ -1764,7 +1876,22 @@ void Engine::GrowPlvs(int64_t new_node_count, const int64_t* reindexer, int64_t 
   d_counts_.Resize(static_cast<size_t>(new_padded), false, stream_);
   GP_CUDA(cudaMemcpyAsync(d_counts_.ptr, counts.data(), counts.size() * sizeof(int32_t),
                           cudaMemcpyHostToDevice, stream_));
-  d_uncond_.Resize(static_cast<size_t>(node_count_ + spare_nodes_), true, stream_);
+  // unconditional_node_probabilities_: reindexed with the nodes, 1 for nodes that are new
+  // (gp_engine.cpp:100-104, 171-172).
+  {
+    std::vector<double> old_u(static_cast<size_t>(old_n + spare_nodes_), 1.);
+    if (d_uncond_.ptr != nullptr)
+      GP_CUDA(cudaMemcpyAsync(old_u.data(), d_uncond_.ptr,
+                              std::min(old_u.size(), d_uncond_.n) * sizeof(double),
+                              cudaMemcpyDeviceToHost, stream_));
+    GP_CUDA(cudaStreamSynchronize(stream_));
+    std::vector<double> u(static_cast<size_t>(node_count_ + spare_nodes_), 1.);
+    for (int64_t node = 0; node < std::min(old_n, new_node_count); ++node)
+      u[static_cast<size_t>(reindexer != nullptr ? reindexer[node] : node)] = old_u[static_cast<size_t>(node)];
+    d_uncond_.Resize(u.size(), false, stream_);
+    GP_CUDA(cudaMemcpyAsync(d_uncond_.ptr, u.data(), u.size() * sizeof(double), cudaMemcpyHostToDevice,
+                            stream_));
+  }
   GP_CUDA(cudaStreamSynchronize(stream_));
   InvalidatePrograms();
 }
@@ -1837,7 +1964,11 @@ void Engine::GrowSparePlvs(int64_t new_spare) {
   GP_CUDA(cudaMemsetAsync(d_counts_.ptr + old_padded, 0,
                           static_cast<size_t>(padded_plv_count() - old_padded) * sizeof(int32_t),
                           stream_));
-  d_uncond_.Resize(static_cast<size_t>(node_count_ + spare_nodes_), true, stream_);
+  {
+    const size_t old_n = d_uncond_.n;
+    d_uncond_.Resize(static_cast<size_t>(node_count_ + spare_nodes_), true, stream_);
+    if (d_uncond_.n > old_n) LaunchFill(stream_, d_uncond_.ptr + old_n, static_cast<int64_t>(d_uncond_.n - old_n), 1.0);
+  }
   InvalidatePrograms();
 }
 
@@ -1869,6 +2000,16 @@ void Engine::GrowSpareGpcsps(int64_t new_spare) {
   spare_gpcsps_ = new_spare;
   rows_.resize(static_cast<size_t>(new_padded), nullptr);
   InvalidatePrograms();
+}
+
+void Engine::CopyNodeData(int64_t src, int64_t dest) {  // gp_engine.cpp:384-390
+  Activate();
+  const int64_t padded = node_count_ + spare_nodes_;
+  if (src < 0 || dest < 0 || src >= padded || dest >= padded)
+    Fail("Cannot copy node data with src or dest index out-of-range.");
+  if (src == dest) return;
+  GP_CUDA(cudaMemcpyAsync(d_uncond_.ptr + dest, d_uncond_.ptr + src, sizeof(double),
+                          cudaMemcpyDeviceToDevice, stream_));
 }
 
 void Engine::CopyPlvData(int64_t src, int64_t dest) {  // gp_engine.cpp:394-399

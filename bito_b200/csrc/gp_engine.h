@@ -161,6 +161,13 @@ class Engine {
   void GetPlv(int64_t id, double* out);
   void SetPlv(int64_t id, const double* in, int32_t count);
   void GetRescalingCounts(int32_t* out);
+  // Quartet hybrid marginals (gp_engine.cpp:748-816). Request r owns tip_counts[4r..4r+3] tips
+  // (rootward, sister, rotated, sorted) taken consecutively from `tips`. likelihoods (nullable):
+  // every summand in the reference's loop order; store: LogSum of each fully formed request goes to
+  // hybrid_marginal_log_likelihoods_[central].
+  void QuartetHybrid(int64_t n_requests, const int64_t* central, const int32_t* tip_counts,
+                     const bito_gp_quartet_tip* tips, double* likelihoods, bool store);
+  void GetHybridMarginals(double* out);
 
   int64_t node_count() const { return node_count_; }
   int64_t plv_count() const { return 6 * node_count_; }
@@ -173,6 +180,7 @@ class Engine {
   void GrowGpcsps(int64_t new_count, const int64_t* reindexer, int64_t explicit_alloc);
   void GrowSparePlvs(int64_t new_spare);
   void GrowSpareGpcsps(int64_t new_spare);
+  void CopyNodeData(int64_t src, int64_t dest);
   void CopyPlvData(int64_t src, int64_t dest);
   void CopyGpcspData(int64_t src, int64_t dest);
 
@@ -246,6 +254,8 @@ class Engine {
   bool coef_padding_zeroed_ = false;
   std::vector<double> host_weights_cache_;
   DeviceArray<OptOp> d_single_opt_;
+  DeviceArray<QuartetItem> d_quartet_items_;
+  DeviceArray<double> d_quartet_mats_;
   void* pinned_ = nullptr;  // small pinned staging block
 
   std::unordered_map<uint64_t, std::unique_ptr<Program>> programs_;

@@ -1106,6 +1106,61 @@ __global__ void __launch_bounds__(kTile)
   if (threadIdx.x == 0) partials[blockIdx.x] = v;
 }
 
+// ---- quartet hybrid marginal (gp_engine.cpp:748-808) -------------------------------------------
+// The five transition matrices of every summand: rootward, sister, central, rotated, sorted.
+__global__ void k_quartet_matrices(DeviceState st, const QuartetItem* __restrict__ items, int n_items,
+                                   double* __restrict__ mats) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 5 * n_items) return;
+  const int item = i / 5, which = i - 5 * item;
+  build_matrix(st.bl[items[item].edge[which]], 0, 1., mats + 16 * static_cast<int64_t>(i));
+}
+
+// One block = one 256-pattern tile of one summand. Per pattern, in the reference's order:
+//   root = M_rw * plv_rw;  r_s = root o (M_sis * plv_sis);  q_s = M_central * r_s;
+//   r_sorted = q_s o (M_rot * plv_rot);  L = r_sorted^T M_sorted plv_sorted;
+//   partial += w_p * (log L - log(unconditional[rootward node])).
+__global__ void __launch_bounds__(kTile)
+    k_quartet(DeviceState st, const QuartetItem* __restrict__ items, const double* __restrict__ mats,
+              int tiles, double* __restrict__ partials) {
+  const int item = blockIdx.x / tiles;
+  const int tile = blockIdx.x - item * tiles;
+  const QuartetItem* it = items + item;
+  __shared__ double sM[5][16];
+  if (threadIdx.x < 80) (&sM[0][0])[threadIdx.x] = mats[80 * static_cast<int64_t>(item) + threadIdx.x];
+  if (threadIdx.x == 0 && tile == 0 &&
+      (st.counts[it->rootward.id] | st.counts[it->sister.id] | st.counts[it->rotated.id] |
+       st.counts[it->sorted.id]) != 0)
+    atomicOr(st.status, kErrQuartetRescaled);
+  const double log_prior = log(st.uncond[it->rootward_node]);
+  __syncthreads();
+  const int64_t p = static_cast<int64_t>(tile) * kTile + threadIdx.x;
+  double v = 0.;
+  if (p < st.P) {
+    const V4 x_rw = load_plv(it->rootward, p), x_sis = load_plv(it->sister, p);
+    const V4 x_rot = load_plv(it->rotated, p), x_sorted = load_plv(it->sorted, p);
+    const V4 root = matvec(sM[0], x_rw);
+    const V4 sis = matvec(sM[1], x_sis);
+    const V4 r_s = {root.a * sis.a, root.b * sis.b, root.c * sis.c, root.d * sis.d};
+    const V4 q_s = matvec(sM[2], r_s);
+    const V4 rot = matvec(sM[3], x_rot);
+    const V4 r_sorted = {q_s.a * rot.a, q_s.b * rot.b, q_s.c * rot.c, q_s.d * rot.d};
+    v = (log(quad(r_sorted, sM[4], x_sorted)) - log_prior) * st.weights[p];
+  }
+  v = block_reduce(v, SumOp(), 0.);
+  if (threadIdx.x == 0) partials[blockIdx.x] = v;
+}
+
+// out[i] = log(inverted[rootward edge] * q[sister] * q[rotated] * q[sorted]) + sums[i]
+__global__ void k_quartet_finish(DeviceState st, const QuartetItem* __restrict__ items, int n_items,
+                                 const double* __restrict__ sums, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_items) return;
+  const QuartetItem* it = items + i;
+  out[i] = log(st.inverted[it->edge[0]] * st.q[it->edge[1]] * st.q[it->edge[3]] * st.q[it->edge[4]]) +
+           sums[i];
+}
+
 inline unsigned Grid(int64_t n_ops, int64_t tiles) { return static_cast<unsigned>(n_ops * tiles); }
 
 }  // namespace
@@ -1283,6 +1338,23 @@ void LaunchTransitionMatrix(cudaStream_t s, double t, double* out16) {
 void LaunchWeightedSum(cudaStream_t s, const DeviceState& st, const double* values,
                        double* partials) {
   k_weighted_sum<<<static_cast<unsigned>(TilesFor(st.P)), kTile, 0, s>>>(st, values, partials);
+}
+
+void LaunchQuartetMatrices(cudaStream_t s, const DeviceState& st, const QuartetItem* items, int n_items,
+                           double* mats) {
+  if (n_items == 0) return;
+  k_quartet_matrices<<<(5 * n_items + 127) / 128, 128, 0, s>>>(st, items, n_items, mats);
+}
+void LaunchQuartet(cudaStream_t s, const DeviceState& st, const QuartetItem* items, int n_items,
+                   const double* mats, double* partials) {
+  if (n_items == 0) return;
+  const int64_t tiles = TilesFor(st.P);
+  k_quartet<<<Grid(n_items, tiles), kTile, 0, s>>>(st, items, mats, static_cast<int>(tiles), partials);
+}
+void LaunchQuartetFinish(cudaStream_t s, const DeviceState& st, const QuartetItem* items, int n_items,
+                         const double* sums, double* out) {
+  if (n_items == 0) return;
+  k_quartet_finish<<<(n_items + 127) / 128, 128, 0, s>>>(st, items, n_items, sums, out);
 }
 
 }  // namespace bito_gp

@@ -70,6 +70,15 @@ void LaunchOptEvalRatio(cudaStream_t s, const DeviceState& st, int n_ops, const 
                         int32_t* active /* [4 + 2 * capacity]: counts by parity, then the two lists */,
                         int active_capacity, int parity);
 
+// Quartet hybrid marginals (gp_engine.cpp:748-808): mats = 80 doubles per summand, partials =
+// n_items x TilesFor(P) weighted tile sums, out[i] = non-sequence log-probability + sums[i].
+void LaunchQuartetMatrices(cudaStream_t s, const DeviceState& st, const QuartetItem* items, int n_items,
+                           double* mats);
+void LaunchQuartet(cudaStream_t s, const DeviceState& st, const QuartetItem* items, int n_items,
+                   const double* mats, double* partials);
+void LaunchQuartetFinish(cudaStream_t s, const DeviceState& st, const QuartetItem* items, int n_items,
+                         const double* sums, double* out);
+
 // Utilities.
 void LaunchExportPlv(cudaStream_t s, const DeviceState& st, PlvRef src, double* dense_out);
 void LaunchFill(cudaStream_t s, double* dst, int64_t n, double value);

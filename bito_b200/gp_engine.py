@@ -250,6 +250,34 @@ class GPEngine:
         self._check(self._lib.bito_gp_get_rescaling_counts(self._h, _ptr(out)))
         return out
 
+    # ---- quartet hybrid marginals: gp_engine.cpp:748-816 --------------------------------------------
+    def calculate_quartet_hybrid_likelihoods(self, central_gpcsp_idx, tip_counts, tips):
+        """GPEngine::CalculateQuartetHybridLikelihoods. tip_counts = (rootward, sister, rotated,
+        sorted); tips = rows (tip_node_id, plv_idx, gpcsp_idx) in that order."""
+        counts = np.ascontiguousarray(tip_counts, dtype=np.int32).reshape(4)
+        tips = np.ascontiguousarray(tips, dtype=np.int64).reshape(-1, 3)
+        if tips.shape[0] != int(counts.sum()):
+            raise ValueError("tips must hold sum(tip_counts) rows")
+        out = np.zeros(int(np.prod(counts.astype(np.int64))))
+        self._check(self._lib.bito_gp_calculate_quartet_hybrid_likelihoods(
+            self._h, int(central_gpcsp_idx), _ptr(tips), _ptr(counts), _ptr(out)))
+        return out
+
+    def process_quartet_hybrid_requests(self, central_gpcsp_idx, tip_counts, tips):
+        """GPEngine::ProcessQuartetHybridRequest for a batch of requests in one launch."""
+        central = np.ascontiguousarray(central_gpcsp_idx, dtype=np.int64).reshape(-1)
+        counts = np.ascontiguousarray(tip_counts, dtype=np.int32).reshape(-1, 4)
+        tips = np.ascontiguousarray(tips, dtype=np.int64).reshape(-1, 3)
+        if counts.shape[0] != central.size or tips.shape[0] != int(counts.sum()):
+            raise ValueError("tip_counts / tips do not match the request count")
+        self._check(self._lib.bito_gp_process_quartet_hybrid_requests(
+            self._h, central.size, _ptr(central), _ptr(counts), _ptr(tips)))
+
+    def get_hybrid_marginals(self):
+        out = np.zeros(self.gpcsp_count)
+        self._check(self._lib.bito_gp_get_hybrid_marginals(self._h, _ptr(out)))
+        return out
+
     # ---- resize / copy -------------------------------------------------------------------------
     def grow_plvs(self, node_count, node_reindexer=None, explicit_allocation=None):
         r = None if node_reindexer is None else np.ascontiguousarray(node_reindexer, dtype=np.int64)
@@ -266,6 +294,9 @@ class GPEngine:
 
     def grow_spare_gpcsps(self, new_gpcsp_spare_count):
         self._check(self._lib.bito_gp_grow_spare_gpcsps(self._h, int(new_gpcsp_spare_count)))
+
+    def copy_node_data(self, src_node_idx, dest_node_idx):
+        self._check(self._lib.bito_gp_copy_node_data(self._h, int(src_node_idx), int(dest_node_idx)))
 
     def copy_plv_data(self, src_plv_idx, dest_plv_idx):
         self._check(self._lib.bito_gp_copy_plv_data(self._h, int(src_plv_idx), int(dest_plv_idx)))
@@ -321,6 +352,7 @@ class GPEngine:
     branch_lengths = get_branch_lengths
     branch_length_differences = get_branch_length_differences
     rescaling_counts = get_rescaling_counts
+    hybrid_marginals = get_hybrid_marginals
     optimization_count = get_optimization_count
     transition_matrix = get_transition_matrix
 

@@ -3,7 +3,7 @@ a seed tree, JC69-simulated site columns, and a subsplit DAG from trees that are
 moves away from the seed (heavy subsplit sharing, so the DAG stays HBM-sized)."""
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -111,6 +111,38 @@ def nni_neighbourhood_dag(seed: RootedTree, tree_count: int, moves_per_tree: int
             for token in reversed(undo):
                 mt.undo(token)
     return GPDAG(seed.taxon_count, pcsps)
+
+
+def nni_walk_trees(seed: RootedTree, tree_count: int, moves_per_tree: int,
+                   rng: np.random.Generator) -> List[RootedTree]:
+    """The seed tree plus `tree_count - 1` trees of an NNI random walk from it, as explicit
+    trees (for callers that need a tree file, e.g. the reference's own newick parser)."""
+    mt = _MutableTree(seed)
+    internal = [v for v in seed.children if v != seed.root]
+    trees = [seed]
+    for _ in range(max(0, tree_count - 1)):
+        for _m in range(moves_per_tree):
+            mt.nni(int(rng.choice(internal)), int(rng.integers(0, 2)))
+        bl = {v: float(rng.exponential(0.08)) + 1e-3 for v in list(mt.children) + list(range(mt.n))
+              if v != mt.root}
+        trees.append(RootedTree(mt.n, dict(mt.children), mt.root, bl))
+    return trees
+
+
+def tree_to_newick(tree: RootedTree, taxon_names: Sequence[str]) -> str:
+    def rec(v):
+        label = taxon_names[v] if v < tree.taxon_count else "(" + ",".join(rec(c) for c in tree.children[v]) + ")"
+        return label + (f":{tree.branch_lengths[v]:.6f}" if v in tree.branch_lengths else "")
+    return rec(tree.root) + ";"
+
+
+def write_fasta(path: str, symbols: np.ndarray, taxon_names: Sequence[str]) -> None:
+    """symbols: taxa x sites of 0..3 (ACGT) / 4 (gap), the engine's symbol table
+    (site_pattern.cpp: SitePattern::GetSymbolTable)."""
+    alphabet = np.frombuffer(b"ACGT-", dtype=np.uint8)
+    with open(path, "w") as f:
+        for name, row in zip(taxon_names, symbols):
+            f.write(f">{name}\n{alphabet[row].tobytes().decode()}\n")
 
 
 class Workload:

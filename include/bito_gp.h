@@ -165,6 +165,30 @@ BITO_GP_API int bito_gp_set_sbn_parameters(bito_gp_engine* e, const double* q /*
  * an Eigen::Ref; writes go through bito_gp_set_plv. out/in: pattern_count x 4. */
 BITO_GP_API int bito_gp_get_plv(bito_gp_engine* e, int64_t plv_id, double* out);
 BITO_GP_API int bito_gp_set_plv(bito_gp_engine* e, int64_t plv_id, const double* in, int32_t rescaling_count);
+/* ---- quartet hybrid marginals: gp_engine.cpp:748-816, quartet_hybrid_request.hpp:11-43 -- */
+/* QuartetTip (quartet_hybrid_request.hpp:11-18). */
+typedef struct bito_gp_quartet_tip {
+  int64_t tip_node_id;
+  int64_t plv_idx;
+  int64_t gpcsp_idx;
+} bito_gp_quartet_tip;
+/* GPEngine::CalculateQuartetHybridLikelihoods (gp_engine.cpp:748-808). tips = the request's
+ * rootward, sister, rotated and sorted tips concatenated, tip_counts[4] of each. out receives
+ * tip_counts[0]*[1]*[2]*[3] log-likelihoods in the reference's loop order (sorted innermost). */
+BITO_GP_API int bito_gp_calculate_quartet_hybrid_likelihoods(bito_gp_engine* e, int64_t central_gpcsp_idx,
+                                                 const bito_gp_quartet_tip* tips,
+                                                 const int32_t tip_counts[4], double* out);
+/* GPEngine::ProcessQuartetHybridRequest (gp_engine.cpp:810-816) for n_requests requests in one
+ * launch (GPInstance::CalculateHybridMarginals, gp_instance.cpp:408-417, issues one per edge):
+ * request r owns tip_counts[4r..4r+3] tips taken consecutively from `tips`; requests that are not
+ * fully formed (an empty tip vector) leave their entry untouched. */
+BITO_GP_API int bito_gp_process_quartet_hybrid_requests(bito_gp_engine* e, int64_t n_requests,
+                                            const int64_t* central_gpcsp_idx,
+                                            const int32_t* tip_counts,
+                                            const bito_gp_quartet_tip* tips);
+/* GPEngine::GetHybridMarginals (gp_engine.cpp:464-466); -inf where none was computed. */
+BITO_GP_API int bito_gp_get_hybrid_marginals(bito_gp_engine* e, double* out /* gpcsp_count */);
+
 /* rescaling_counts_ (gp_engine.hpp:317; private in the reference, exposed for parity). */
 BITO_GP_API int bito_gp_get_rescaling_counts(bito_gp_engine* e, int32_t* out /* padded_plv_count */);
 
@@ -185,6 +209,8 @@ BITO_GP_API int bito_gp_grow_gpcsps(bito_gp_engine* e, int64_t new_gpcsp_count,
                         const int64_t* gpcsp_reindexer, int64_t explicit_allocation);
 BITO_GP_API int bito_gp_grow_spare_plvs(bito_gp_engine* e, int64_t new_node_spare_count);
 BITO_GP_API int bito_gp_grow_spare_gpcsps(bito_gp_engine* e, int64_t new_gpcsp_spare_count);
+/* GPEngine::CopyNodeData (gp_engine.cpp:384-390): the unconditional node probability. */
+BITO_GP_API int bito_gp_copy_node_data(bito_gp_engine* e, int64_t src_node_idx, int64_t dest_node_idx);
 BITO_GP_API int bito_gp_copy_plv_data(bito_gp_engine* e, int64_t src_plv_idx, int64_t dest_plv_idx);
 BITO_GP_API int bito_gp_copy_gpcsp_data(bito_gp_engine* e, int64_t src_gpcsp_idx, int64_t dest_gpcsp_idx);
 

@@ -53,6 +53,7 @@ struct gpo {
   int32_t* counts;
   double *q, *inverted, *uncond;
   double *bl, *diff;
+  double* hybrid;   /* hybrid marginal log-likelihoods per edge, -inf until computed (gp_engine.hpp:352) */
   double* ll;       /* padded_edge_count x P, row-major (gp_engine.hpp:345) */
   double* log_marg; /* P */
   double* weights;  /* P */
@@ -154,6 +155,7 @@ gpo* gpo_create(int64_t taxa, int64_t P, const uint8_t* symbols, const double* w
   g->uncond = (double*)malloc(sizeof(double) * (node_count + SPARE_NODES));
   g->bl = (double*)malloc(sizeof(double) * g->padded_edge_count);
   g->diff = (double*)calloc((size_t)g->padded_edge_count, sizeof(double));
+  g->hybrid = (double*)malloc(sizeof(double) * g->padded_edge_count);
   g->ll = (double*)calloc((size_t)(g->padded_edge_count * P), sizeof(double));
   g->log_marg = (double*)malloc(sizeof(double) * P);
   g->weights = (double*)malloc(sizeof(double) * P);
@@ -167,6 +169,7 @@ gpo* gpo_create(int64_t taxa, int64_t P, const uint8_t* symbols, const double* w
     g->q[i] = (sbn_prior && i < edge_count) ? sbn_prior[i] : 1.0;
     g->inverted[i] = (inverted && i < edge_count) ? inverted[i] : 1.0;
     g->bl[i] = kDefaultBranchLength;
+    g->hybrid[i] = -INFINITY;
   }
   for (int64_t i = 0; i < node_count + SPARE_NODES; ++i)
     g->uncond[i] = (uncond && i < node_count) ? uncond[i] : 1.0;
@@ -198,6 +201,7 @@ void gpo_destroy(gpo* g) {
   free(g->uncond);
   free(g->bl);
   free(g->diff);
+  free(g->hybrid);
   free(g->ll);
   free(g->log_marg);
   free(g->weights);
@@ -590,15 +594,19 @@ int gpo_run(gpo* g, const int64_t* ops, int64_t n, const int64_t* vec) {
         optimize_branch_length(g, c, b, a);
         break;
       }
-      case 6: { /* UpdateSBNProbabilities :297-321 (hybrid marginals unavailable -> -inf) */
+      case 6: { /* UpdateSBNProbabilities :297-321 */
         const int64_t len = b - a;
         if (check_edge(g, a) || len < 1 || check_edge(g, b - 1)) return 1;
         if (len == 1) {
           g->q[a] = 1.;
         } else {
           double* x = (double*)malloc(sizeof(double) * len);
+          double hybrid_min = INFINITY; /* :309-316: hybrid marginals win when all are set */
           for (int64_t i = 0; i < len; ++i)
-            x[i] = dot_weights(g, g->ll + (a + i) * P) + log(g->q[a + i]);
+            if (g->hybrid[a + i] < hybrid_min) hybrid_min = g->hybrid[a + i];
+          for (int64_t i = 0; i < len; ++i)
+            x[i] = (hybrid_min > -INFINITY ? g->hybrid[a + i] : dot_weights(g, g->ll + (a + i) * P)) +
+                   log(g->q[a + i]);
           double norm = x[0]; /* NumericalUtils::LogSum = left fold, numerical_utils.cpp:8 */
           for (int64_t i = 1; i < len; ++i) norm = gpo_log_add(norm, x[i]);
           for (int64_t i = 0; i < len; ++i) g->q[a + i] = exp(x[i] - norm);
@@ -645,6 +653,93 @@ int gpo_run(gpo* g, const int64_t* ops, int64_t n, const int64_t* vec) {
 }
 
 /* ---- getters: gp_engine.cpp:413-468 --------------------------------------------------- */
+/* ---- quartet hybrid marginals: gp_engine.cpp:748-816 ---------------------------------- */
+static void matvec4(const double M[4][4], const double* x, double* y) {
+  for (int i = 0; i < 4; ++i) {
+    double s = 0.0;
+    for (int k = 0; k < 4; ++k) s += M[i][k] * x[k];
+    y[i] = s;
+  }
+}
+
+/* CalculateQuartetHybridLikelihoods (:748-808): tips = (tip_node_id, plv_idx, gpcsp_idx)
+ * triples of the rootward, sister, rotated and sorted tips, counts[4] of each; out receives
+ * one log-likelihood per (rootward, sister, rotated, sorted) choice, sorted innermost. */
+int gpo_quartet_likelihoods(gpo* g, int64_t central, const int32_t* counts, const int64_t* tips,
+                            double* out) {
+  const int64_t* rw = tips;
+  const int64_t* sis = rw + 3 * counts[0];
+  const int64_t* rot = sis + 3 * counts[1];
+  const int64_t* srt = rot + 3 * counts[2];
+  const int64_t n_tips = (int64_t)counts[0] + counts[1] + counts[2] + counts[3];
+  if (check_edge(g, central)) return 1;
+  for (int64_t i = 0; i < n_tips; ++i) {
+    if (check_plv(g, tips[3 * i + 1]) || check_edge(g, tips[3 * i + 2])) return 1;
+    if (g->strict && g->counts[tips[3 * i + 1]] != 0)
+      return fail("Rescaling not implemented in CalculateQuartetHybridLikelihoods.");
+  }
+  double Mrw[4][4], Ms[4][4], Mc[4][4], Mrot[4][4], Msrt[4][4];
+  int64_t k = 0;
+  for (int a = 0; a < counts[0]; ++a) {
+    const double log_prior = log(g->uncond[rw[3 * a]]);
+    transition(g->bl[rw[3 * a + 2]], Mrw);
+    for (int b = 0; b < counts[1]; ++b) {
+      transition(g->bl[sis[3 * b + 2]], Ms);
+      transition(g->bl[central], Mc);
+      for (int c = 0; c < counts[2]; ++c) {
+        transition(g->bl[rot[3 * c + 2]], Mrot);
+        for (int d = 0; d < counts[3]; ++d, ++k) {
+          const double non_seq = log(g->inverted[rw[3 * a + 2]] * g->q[sis[3 * b + 2]] *
+                                     g->q[rot[3 * c + 2]] * g->q[srt[3 * d + 2]]);
+          transition(g->bl[srt[3 * d + 2]], Msrt);
+          const double *x_rw = PLV(g, rw[3 * a + 1]), *x_s = PLV(g, sis[3 * b + 1]);
+          const double *x_rot = PLV(g, rot[3 * c + 1]), *x_srt = PLV(g, srt[3 * d + 1]);
+          for (int64_t p = 0; p < g->P; ++p) {
+            double root[4], s[4], r_s[4], q_s[4], r[4], r_sorted[4];
+            matvec4(Mrw, x_rw + 4 * p, root);
+            matvec4(Ms, x_s + 4 * p, s);
+            for (int i = 0; i < 4; ++i) r_s[i] = root[i] * s[i];
+            matvec4(Mc, r_s, q_s);
+            matvec4(Mrot, x_rot + 4 * p, r);
+            for (int i = 0; i < 4; ++i) r_sorted[i] = q_s[i] * r[i];
+            g->scratch[p] = log(quad(r_sorted, Msrt, x_srt + 4 * p)) - log_prior;
+          }
+          out[k] = non_seq + dot_weights(g, g->scratch);
+        }
+      }
+    }
+  }
+  return 0;
+}
+
+/* ProcessQuartetHybridRequest (:810-816): LogSum (left fold of LogAdd, numerical_utils.cpp)
+ * of a fully formed request's summands goes to hybrid_marginal_log_likelihoods_[central]. */
+int gpo_process_quartet_requests(gpo* g, int64_t n, const int64_t* central, const int32_t* counts,
+                                 const int64_t* tips) {
+  const int64_t* t = tips;
+  for (int64_t r = 0; r < n; ++r) {
+    const int32_t* c = counts + 4 * r;
+    const int64_t n_out = (int64_t)c[0] * c[1] * c[2] * c[3];
+    if (n_out > 0) {
+      double* out = (double*)malloc(sizeof(double) * (size_t)n_out);
+      if (gpo_quartet_likelihoods(g, central[r], c, t, out) != 0) {
+        free(out);
+        return 1;
+      }
+      double acc = out[0];
+      for (int64_t i = 1; i < n_out; ++i) acc = gpo_log_add(acc, out[i]);
+      g->hybrid[central[r]] = acc;
+      free(out);
+    }
+    t += 3 * ((int64_t)c[0] + c[1] + c[2] + c[3]);
+  }
+  return 0;
+}
+
+void gpo_get_hybrid_marginals(const gpo* g, double* out) {
+  memcpy(out, g->hybrid, sizeof(double) * g->E);
+}
+
 int64_t gpo_plv_count(const gpo* g) { return g->plv_count; }
 int64_t gpo_padded_plv_count(const gpo* g) { return g->padded_plv_count; }
 int gpo_get_plv(const gpo* g, int64_t id, double* out) {

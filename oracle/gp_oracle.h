@@ -58,6 +58,13 @@ void gpo_set_null_prior(gpo* g);
 void gpo_loglik_and_derivatives(gpo* g, int64_t gpcsp, int64_t rootward, int64_t leafward,
                                 double* out);
 void gpo_transition_matrix(double t, double* out /* 4x4 row-major */);
+/* Quartet hybrid marginals (gp_engine.cpp:748-816); tips = (tip_node_id, plv_idx, gpcsp_idx)
+ * triples, counts[4] = rootward, sister, rotated, sorted. */
+int gpo_quartet_likelihoods(gpo* g, int64_t central, const int32_t* counts, const int64_t* tips,
+                            double* out);
+int gpo_process_quartet_requests(gpo* g, int64_t n, const int64_t* central, const int32_t* counts,
+                                 const int64_t* tips);
+void gpo_get_hybrid_marginals(const gpo* g, double* out /* E */);
 /* number of objective evaluations performed by OptimizeBranchLength ops so far */
 int64_t gpo_feval_count(const gpo* g);
 /* strict != 0: the reference's Assert()s (sugar.hpp:103-111) raise errors, as in a Debug build.

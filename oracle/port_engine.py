@@ -69,6 +69,9 @@ def _load():
     lib.gpo_set_null_prior.argtypes = [vp]
     lib.gpo_loglik_and_derivatives.argtypes = [vp, i64, i64, i64, vp]
     lib.gpo_transition_matrix.argtypes = [f64, vp]
+    lib.gpo_quartet_likelihoods.argtypes = [vp, i64, vp, vp, vp]
+    lib.gpo_process_quartet_requests.argtypes = [vp, i64, vp, vp, vp]
+    lib.gpo_get_hybrid_marginals.argtypes = [vp, vp]
     lib.gpo_feval_count.restype = i64
     lib.gpo_feval_count.argtypes = [vp]
     lib.gpo_set_strict.argtypes = [vp, i32]
@@ -243,3 +246,23 @@ class PortEngine:
 
     def feval_count(self):
         return int(_load().gpo_feval_count(self._h))
+
+    # ---- quartet hybrid marginals (gp_engine.cpp:748-816) ----------------------------------
+    def calculate_quartet_hybrid_likelihoods(self, central, counts, tips):
+        counts = np.ascontiguousarray(counts, dtype=np.int32).reshape(4)
+        tips = np.ascontiguousarray(tips, dtype=np.int64).reshape(-1, 3)
+        out = np.zeros(int(np.prod(counts.astype(np.int64))))
+        self._check(_load().gpo_quartet_likelihoods(self._h, int(central), _ptr(counts), _ptr(tips), _ptr(out)))
+        return out
+
+    def process_quartet_hybrid_requests(self, central, counts, tips):
+        central = np.ascontiguousarray(central, dtype=np.int64).reshape(-1)
+        counts = np.ascontiguousarray(counts, dtype=np.int32).reshape(-1, 4)
+        tips = np.ascontiguousarray(tips, dtype=np.int64).reshape(-1, 3)
+        self._check(_load().gpo_process_quartet_requests(self._h, central.size, _ptr(central), _ptr(counts),
+                                                         _ptr(tips)))
+
+    def hybrid_marginals(self):
+        out = np.zeros(self.edge_count)
+        _load().gpo_get_hybrid_marginals(self._h, _ptr(out))
+        return out

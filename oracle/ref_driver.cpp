@@ -522,4 +522,89 @@ void ref_transition_matrix(void* h, double t, double* out) {
     for (int j = 0; j < 4; ++j) out[4 * i + j] = e.GetTransitionMatrix()(i, j);
 }
 
+// ---- quartet hybrid marginals (gp_engine.cpp:748-816, gp_dag.cpp:413-458) --------------------
+
+namespace {
+QuartetHybridRequest RequestOf(int64_t central, const int32_t* counts, const int64_t* tips) {
+  QuartetTipVector v[4];
+  const int64_t* t = tips;
+  for (int k = 0; k < 4; ++k)
+    for (int32_t i = 0; i < counts[k]; ++i, t += 3)
+      v[k].emplace_back(static_cast<size_t>(t[0]), static_cast<size_t>(t[1]),
+                        static_cast<size_t>(t[2]));
+  return QuartetHybridRequest(static_cast<size_t>(central), std::move(v[0]), std::move(v[1]),
+                              std::move(v[2]), std::move(v[3]));
+}
+}  // namespace
+
+// Every request GPInstance::CalculateHybridMarginals issues (gp_instance.cpp:408-417), in its
+// TopologicalEdgeTraversal order, flattened: central[r], tip_counts[4r..] (rootward, sister,
+// rotated, sorted), tips = (tip_node_id, plv_idx, gpcsp_idx) triples. Call with central == nullptr
+// to size. Returns the request count, -1 on error.
+int64_t ref_quartet_requests(void* h, int64_t* central, int32_t* tip_counts, int64_t* tips,
+                             int64_t cap_requests, int64_t cap_tips, int64_t* n_tips) {
+  auto* inst = static_cast<RefInst*>(h);
+  std::vector<int64_t> c, t;
+  std::vector<int32_t> n;
+  const int rc = Guard([&] {
+    auto& dag = *inst->dag;
+    dag.TopologicalEdgeTraversal([&](const NodeId parent_id, const bool is_edge_on_left,
+                                     const NodeId child_id, const EdgeId edge_idx) {
+      const QuartetHybridRequest req =
+          dag.QuartetHybridRequestOf(parent_id, is_edge_on_left, child_id);
+      c.push_back(static_cast<int64_t>(req.central_gpcsp_idx_));
+      for (const QuartetTipVector* v : {&req.rootward_tips_, &req.sister_tips_,
+                                        &req.rotated_tips_, &req.sorted_tips_}) {
+        n.push_back(static_cast<int32_t>(v->size()));
+        for (const auto& tip : *v) {
+          t.push_back(static_cast<int64_t>(tip.tip_node_id_));
+          t.push_back(static_cast<int64_t>(tip.plv_idx_));
+          t.push_back(static_cast<int64_t>(tip.gpcsp_idx_));
+        }
+      }
+    });
+  });
+  if (rc != 0) return -1;
+  *n_tips = static_cast<int64_t>(t.size() / 3);
+  if (central != nullptr) {
+    if (static_cast<int64_t>(c.size()) > cap_requests || *n_tips > cap_tips) {
+      g_error = "ref_quartet_requests: buffer too small";
+      return -1;
+    }
+    std::copy(c.begin(), c.end(), central);
+    std::copy(n.begin(), n.end(), tip_counts);
+    std::copy(t.begin(), t.end(), tips);
+  }
+  return static_cast<int64_t>(c.size());
+}
+
+// GPEngine::CalculateQuartetHybridLikelihoods; out has prod(counts) entries.
+int ref_quartet_likelihoods(void* h, int64_t central, const int32_t* counts, const int64_t* tips,
+                            double* out) {
+  auto* inst = static_cast<RefInst*>(h);
+  return Guard([&] {
+    EigenVectorXd v = inst->engine->CalculateQuartetHybridLikelihoods(RequestOf(central, counts, tips));
+    std::copy(v.data(), v.data() + v.size(), out);
+  });
+}
+
+// GPEngine::ProcessQuartetHybridRequest for each flattened request.
+int ref_process_quartet_requests(void* h, int64_t n, const int64_t* central, const int32_t* counts,
+                                 const int64_t* tips) {
+  auto* inst = static_cast<RefInst*>(h);
+  return Guard([&] {
+    const int64_t* t = tips;
+    for (int64_t r = 0; r < n; ++r) {
+      const int32_t* c = counts + 4 * r;
+      inst->engine->ProcessQuartetHybridRequest(RequestOf(central[r], c, t));
+      t += 3 * (static_cast<int64_t>(c[0]) + c[1] + c[2] + c[3]);
+    }
+  });
+}
+
+void ref_get_hybrid_marginals(void* h, double* out /* E */) {
+  auto& e = *static_cast<RefInst*>(h)->engine;
+  for (size_t i = 0; i < e.GetGPCSPCount(); ++i) out[i] = e.hybrid_marginal_log_likelihoods_[i];
+}
+
 }  // extern "C"

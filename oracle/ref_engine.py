@@ -98,6 +98,11 @@ def _load():
     lib.ref_set_null_prior.argtypes = [vp]
     lib.ref_loglik_and_derivatives.argtypes = [vp, i64, i64, i64, i32, vp]
     lib.ref_transition_matrix.argtypes = [vp, f64, vp]
+    lib.ref_quartet_requests.restype = i64
+    lib.ref_quartet_requests.argtypes = [vp, vp, vp, vp, i64, i64, P(i64)]
+    lib.ref_quartet_likelihoods.argtypes = [vp, i64, vp, vp, vp]
+    lib.ref_process_quartet_requests.argtypes = [vp, i64, vp, vp, vp]
+    lib.ref_get_hybrid_marginals.argtypes = [vp, vp]
     _lib = lib
     return lib
 
@@ -327,4 +332,41 @@ class RefEngine:
     def transition_matrix(self, t):
         out = np.zeros((4, 4))
         _load().ref_transition_matrix(self._h, float(t), _ptr(out))
+        return out
+
+    # ---- quartet hybrid marginals (gp_engine.cpp:748-816, gp_dag.cpp:413-458) ------------
+    def quartet_requests(self):
+        """Every request GPInstance::CalculateHybridMarginals issues, flattened: central (n),
+        tip_counts (n x 4: rootward, sister, rotated, sorted), tips (total x 3: node, plv, gpcsp)."""
+        lib = _load()
+        n_tips = C.c_int64(0)
+        n = lib.ref_quartet_requests(self._h, None, None, None, 0, 0, C.byref(n_tips))
+        if n < 0:
+            raise RuntimeError(lib.ref_last_error().decode())
+        central = np.zeros(n, dtype=np.int64)
+        counts = np.zeros((n, 4), dtype=np.int32)
+        tips = np.zeros((max(1, n_tips.value), 3), dtype=np.int64)
+        n2 = lib.ref_quartet_requests(self._h, _ptr(central), _ptr(counts), _ptr(tips), n, tips.shape[0],
+                                      C.byref(n_tips))
+        if n2 != n:
+            raise RuntimeError(lib.ref_last_error().decode())
+        return central, counts, tips[:n_tips.value]
+
+    def calculate_quartet_hybrid_likelihoods(self, central, counts, tips):
+        counts = np.ascontiguousarray(counts, dtype=np.int32)
+        tips = np.ascontiguousarray(tips, dtype=np.int64)
+        out = np.zeros(int(np.prod(counts.astype(np.int64))))
+        self._check(_load().ref_quartet_likelihoods(self._h, int(central), _ptr(counts), _ptr(tips), _ptr(out)))
+        return out
+
+    def process_quartet_hybrid_requests(self, central, counts, tips):
+        central = np.ascontiguousarray(central, dtype=np.int64)
+        counts = np.ascontiguousarray(counts, dtype=np.int32)
+        tips = np.ascontiguousarray(tips, dtype=np.int64)
+        self._check(_load().ref_process_quartet_requests(self._h, central.size, _ptr(central), _ptr(counts),
+                                                         _ptr(tips)))
+
+    def hybrid_marginals(self):
+        out = np.zeros(self.edge_count)
+        _load().ref_get_hybrid_marginals(self._h, _ptr(out))
         return out

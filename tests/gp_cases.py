@@ -11,6 +11,7 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 ALL_CASES = ["hello", "hello_single_nucleotide", "hello_two_trees", "five_taxon", "ds1_reduced_5",
              "seven_taxon", "six_taxon", "fluA", "ds1", "ds1_config1"]
 SMALL_CASES = ALL_CASES[:7]
+QUARTET_CASES = ["hello_two_trees", "five_taxon", "six_taxon", "seven_taxon", "ds1_reduced_5", "ds1"]
 
 # Tolerances from BASELINE.json north_star.
 LL_RTOL = 1e-9       # per-pattern and per-edge log-likelihoods, relative, FP64
@@ -72,7 +73,8 @@ def rel_err(got, want):
     # log-likelihoods of all-gap patterns are log(1 +- 1ulp) ~ 1e-16: relative error is only
     # meaningful against max(|want|, 1)
     denom = np.maximum(np.abs(want), 1.0)
-    err = np.where(both_ninf, 0.0, np.abs(got - want) / denom)
+    with np.errstate(invalid="ignore"):  # -inf - -inf on entries both engines leave at -inf
+        err = np.where(both_ninf, 0.0, np.abs(got - want) / denom)
     return float(np.max(err)) if err.size else 0.0
 
 
@@ -129,3 +131,29 @@ def check_sweeps(engine, fx: Fixture, ti, method, atol=BL_ATOL):
         engine.increment_optimization_count()
     want_counts = fx[key + "_counts"]
     assert np.array_equal(engine.rescaling_counts()[:want_counts.size], want_counts)
+
+
+def check_quartet_hybrid(engine, fx: Fixture, rtol=LL_RTOL):
+    """Quartet hybrid marginals (gp_engine.cpp:748-816) against tests/golden/quartet_<case>.npz:
+    every summand, the stored per-edge LogSum, and the SBN update that then prefers them
+    (gp_engine.cpp:304-321). The requests are the reference GPDAG's own (gp_dag.cpp:413-458)."""
+    z = np.load(os.path.join(GOLDEN_DIR, f"quartet_{fx.name}.npz"))
+    central, counts, tips, well = z["central"], z["tip_counts"], z["tips"], z["well_defined"]
+    engine.process_operations(*fx.ops("populate_plvs"))
+    engine.process_operations(*fx.ops("compute_likelihoods"))
+    got, off, keep = [], 0, []
+    for r in range(central.size):
+        n = int(counts[r].sum())
+        t = tips[off:off + n]
+        off += n
+        if well[r]:
+            got.append(engine.calculate_quartet_hybrid_likelihoods(int(central[r]), counts[r], t))
+            keep.append(t)
+    got = np.concatenate(got) if got else np.zeros(0)
+    assert rel_err(got, z["likelihoods"]) <= rtol
+    assert np.all(np.isneginf(engine.hybrid_marginals()))  # Calculate... stores nothing
+    engine.process_quartet_hybrid_requests(central[well == 1], counts[well == 1],
+                                           np.concatenate(keep) if keep else np.zeros((0, 3), dtype=np.int64))
+    assert rel_err(engine.hybrid_marginals(), z["hybrid_marginals"]) <= rtol
+    engine.process_operations(*fx.ops("optimize_sbn_parameters"))
+    assert np.max(np.abs(engine.sbn_parameters() - z["sbn_q_after"])) <= 1e-6

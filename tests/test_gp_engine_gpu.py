@@ -5,8 +5,8 @@ optimised branch lengths 1e-6, rescaling counts bit-exact."""
 import numpy as np
 import pytest
 
-from gp_cases import (ALL_CASES, BL_ATOL, LL_RTOL, SMALL_CASES, Fixture, check_pass, check_sbn, check_sweeps,
-                      make_cuda, make_port, rel_err)
+from gp_cases import (ALL_CASES, BL_ATOL, LL_RTOL, QUARTET_CASES, SMALL_CASES, Fixture, check_pass,
+                      check_quartet_hybrid, check_sbn, check_sweeps, make_cuda, make_port, rel_err)
 
 pytestmark = pytest.mark.gpu
 
@@ -369,3 +369,12 @@ def test_empty_shard_is_a_valid_engine(cuda_engine_lib):
         assert not e.get_per_gpcsp_log_likelihoods().any() and e.get_log_marginal_likelihood() == 0.0
         assert e.get_plv(0).shape == (0, 4) and e.get_log_likelihood_matrix().shape[1] == 0
         assert not e.get_rescaling_counts().any()
+
+
+@pytest.mark.parametrize("case", QUARTET_CASES)
+def test_quartet_hybrid_marginals_match_reference(cuda_engine_lib, case):
+    """SURVEY 8f-2: GPEngine::CalculateQuartetHybridLikelihoods / ProcessQuartetHybridRequest on the
+    reference GPDAG's own requests, one batched launch for the whole DAG."""
+    fx = Fixture(case)
+    with make_cuda(fx) as e:
+        check_quartet_hybrid(e, fx)

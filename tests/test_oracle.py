@@ -7,8 +7,8 @@ import numpy as np
 import pytest
 
 from oracle import port_engine, ref_engine
-from gp_cases import (ALL_CASES, SMALL_CASES, Fixture, check_pass, check_sbn, check_sweeps, make_port,
-                      rel_err)
+from gp_cases import (ALL_CASES, QUARTET_CASES, SMALL_CASES, Fixture, check_pass, check_quartet_hybrid, check_sbn,
+                      check_sweeps, make_port, rel_err)
 
 
 def test_jc69_transition_matrix_golden():
@@ -145,3 +145,9 @@ def test_port_matches_live_reference(case):
     assert np.max(np.abs(p.branch_lengths() - r.branch_lengths())) < 1e-9
     assert rel_err(p.log_likelihood_matrix(), r.log_likelihood_matrix()) < 1e-8
     assert np.array_equal(p.rescaling_counts(), r.rescaling_counts())
+
+
+@pytest.mark.parametrize("case", QUARTET_CASES)
+def test_port_quartet_hybrid_marginals_match_reference(case):
+    fx = Fixture(case)
+    check_quartet_hybrid(make_port(fx), fx)
