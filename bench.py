@@ -8,10 +8,11 @@ One *step* = one full-DAG likelihood pass: GPDAG::PopulatePLVs + GPDAG::ComputeL
 (gp_instance.cpp:231-235) through GPEngine::ProcessOperations, over one synthetic alignment.
 metric = GP pattern x edge PLV updates / s  =  2 (E - R) P_total / pass time  (SURVEY.md 8d).
 
-N = 1 runs BASELINE.json configs[3] (200 taxa x 100k patterns, DAG from 1000 trees);
-N > 1 runs configs[4] (1000 taxa, DAG from 5000 trees) weak-scaled at 125k patterns per
-GPU (N = 8 is the full 1M-pattern alignment), patterns sharded, per-edge scalars
-all-reduced with NCCL inside the engine.
+Every N runs BASELINE.json configs[4] (1000 taxa, DAG from 5000 trees) weak-scaled at 125k
+site patterns per GPU (N = 8 is the full 1M-pattern alignment; one shard fills 127 GB of
+HBM), patterns sharded, per-edge scalars all-reduced with NCCL inside the engine. At N = 1
+the line also carries configs[3] (200 taxa x 100k patterns, DAG from 1000 trees, "single
+B200") under `config3_single_b200`, measured in the same run.
 
   value  : device-resident throughput (alignment already in HBM), CUDA events, max over ranks
   e2e    : same metric through the C-ABI with HOST buffers: every step uploads the alignment,
@@ -38,8 +39,11 @@ sys.path.insert(0, ROOT)
 
 METRIC = "gp_pattern_edge_plv_updates_per_s"
 UNIT = "updates/s"
-SINGLE_GPU_WORKLOAD = "synthetic-200taxa-100kpat-1000trees"
-MULTI_GPU_WORKLOAD = "synthetic-1000taxa-1Mpat-5000trees"
+# Every N runs the SAME per-GPU work (weak scaling): BASELINE.json configs[4], 1000 taxa, DAG from 5000
+# trees, 125k site patterns per GPU (N = 8 is the full 1M-pattern alignment; one shard is 127 GB of HBM).
+BENCH_WORKLOAD = "synthetic-1000taxa-1Mpat-5000trees"
+# configs[3] (200 taxa x 100k patterns, DAG from 1000 trees) is reported beside it at N = 1.
+SINGLE_B200_WORKLOAD = "synthetic-200taxa-100kpat-1000trees"
 
 
 def parse_args():
@@ -52,6 +56,7 @@ def parse_args():
     ap.add_argument("--patterns", type=int, default=None, help="patterns per GPU (default: the config's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--no-config3", action="store_true", help="N = 1: skip the extra configs[3] measurement")
     ap.add_argument("--ref-procs", type=int, default=0, help="--impl reference: processes (default: all cores, <= 32)")
     return ap.parse_args()
 
@@ -162,11 +167,11 @@ def cpu_sample_size(workload):
 def _reference_worker(job):
     """One process of the reference arm: the unmodified single-threaded reference GPEngine on its own
     slice of the workload's site patterns (the path is pattern-parallel)."""
-    name, index, patterns, warmup, steps, start_at = job
+    name, index, patterns, warmup, steps, gate = job
     from bito_b200.synthetic import make_named_workload
     wl = make_named_workload(name, rank=1000 + index, pattern_count=patterns)
-    while time.time() < start_at:  # all workers enter the timed passes together
-        time.sleep(0.01)
+    if gate is not None:
+        gate.wait()  # all workers enter the timed passes together
     t0 = time.time()
     kind, times, marginal = cpu_pass_seconds(wl, wl.pattern_count, warmup + steps)
     return dict(kind=kind, times=times.tolist(), marginal=marginal, began=t0, updates=wl.updates_per_pass(),
@@ -180,19 +185,19 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     import multiprocessing as mp
-    name = args.workload or (SINGLE_GPU_WORKLOAD if args.gpus == 1 else MULTI_GPU_WORKLOAD)
+    name = args.workload or BENCH_WORKLOAD
     procs = args.ref_procs or min(32, os.cpu_count() or 1)
     # per process: ~1 s of CPU work per step and ~1.3 GB of touched PLV pages (the reference's PLVs are
     # an mmap'd file); all processes together stay under ~21 GB
-    patterns = args.patterns or max(512, min(2048, 32768 // procs))
-    setup_allowance = 25.0 if "1000taxa" not in name else 120.0
-    start_at = time.time() + setup_allowance
-    jobs = [(name, i, patterns, args.warmup, args.steps, start_at) for i in range(procs)]
+    patterns = args.patterns or max(512, min(1024 if "1000taxa" in name else 2048, 32768 // procs))
     if procs == 1:
-        results = [_reference_worker(jobs[0])]
+        results = [_reference_worker((name, 0, patterns, args.warmup, args.steps, None))]
     else:
-        with mp.get_context("spawn").Pool(procs) as pool:
-            results = pool.map(_reference_worker, jobs)
+        ctx = mp.get_context("spawn")
+        with ctx.Manager() as manager, ctx.Pool(procs) as pool:
+            gate = manager.Barrier(procs)
+            results = pool.map(_reference_worker,
+                               [(name, i, patterns, args.warmup, args.steps, gate) for i in range(procs)], chunksize=1)
     # every process repeats `steps` timed passes; aggregate throughput = all updates / slowest process
     per_proc = [float(np.sum(r["times"][args.warmup:])) for r in results]
     sec = max(per_proc) / args.steps
@@ -215,30 +220,14 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
-def main():
-    args = parse_args()
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-        return
-
+def measure(args, name, rank, world, local_rank, extras=True):
+    """One workload on this rank's GPU: device-resident pass, e2e pass, per-kernel roofline, sweep,
+    CPU baseline. Returns the JSON line (rank 0) or None."""
     import torch
-    import torch.distributed as dist
     from bito_b200 import _lib
     from bito_b200 import distributed as D
     from bito_b200.gp_engine import GPEngine
     from bito_b200.synthetic import make_named_workload
-
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the GP engine has no CPU fallback")
-    if world != args.gpus:
-        raise SystemExit(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; launch with torchrun")
-    torch.cuda.set_device(local_rank)
-    D.init("nccl")
-
-    name = args.workload or (SINGLE_GPU_WORKLOAD if world == 1 else MULTI_GPU_WORKLOAD)
     t_setup = time.time()
     wl = make_named_workload(name, rank=rank, pattern_count=args.patterns)
     P_local = wl.pattern_count
@@ -329,10 +318,11 @@ def main():
     achieved = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9
     traffic = None
     traffic_path = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(traffic_path) and world == 1 and name == SINGLE_GPU_WORKLOAD and args.patterns is None:
-        # ncu dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel on this workload
+    if os.path.exists(traffic_path) and args.patterns is None:
+        # ncu dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel on this workload's
+        # per-GPU shard (every rank moves the same bytes)
         with open(traffic_path) as f:
-            traffic = json.load(f).get(top["name"], {}).get("dram_bytes_per_launch")
+            traffic = json.load(f).get(name, {}).get(top["name"], {}).get("dram_bytes_per_launch")
     pass_alg_bytes = sum(k["algorithmic_bytes"] for k in prof) / prof_steps
     roofline = {
         "bound": "hbm", "kernel": top["name"], "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
@@ -376,7 +366,7 @@ def main():
 
     # ---- CPU baseline: the reference's own engine on this box's host cores (rank 0, N = 1) -------
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and extras and not args.no_cpu_baseline:
         sample = cpu_sample_size(wl)
         kind, times, cpu_marginal = cpu_pass_seconds(wl, sample, 3)
         sec = float(np.min(times))
@@ -385,6 +375,7 @@ def main():
                                   f"passes ({sec:.2f} s each); host has {os.cpu_count()} cores, the reference "
                                   "GPEngine uses 1"}
 
+    line = None
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -407,8 +398,43 @@ def main():
             "log_marginal": log_marginal,
             "full_pass_ms": ms_per_step,
         }
-        print(json.dumps(line))
     engine.close()
+    return line
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from bito_b200 import _lib
+    from bito_b200 import distributed as D
+    from bito_b200.gp_engine import GPEngine
+    from bito_b200.synthetic import make_named_workload
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the GP engine has no CPU fallback")
+    if world != args.gpus:
+        raise SystemExit(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; launch with torchrun")
+    torch.cuda.set_device(local_rank)
+    D.init("nccl")
+
+    name = args.workload or BENCH_WORKLOAD
+    line = measure(args, name, rank, world, local_rank)
+    if world == 1 and args.workload is None and not args.no_config3:
+        # BASELINE.json configs[3] (the "single B200" shape) beside the weak-scaling shard, same run
+        other = measure(args, SINGLE_B200_WORKLOAD, rank, world, local_rank, extras=False)
+        if line is not None and other is not None:
+            line["config3_single_b200"] = {k: other[k] for k in ("value", "unit", "ms_per_step", "e2e", "config",
+                                                                 "roofline", "sweep", "log_marginal")}
+    if rank == 0:
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 

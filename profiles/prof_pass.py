@@ -6,7 +6,7 @@ from bito_b200 import _lib
 from bito_b200.gp_engine import GPEngine
 from bito_b200.synthetic import make_named_workload
 
-name = sys.argv[1] if len(sys.argv) > 1 else "synthetic-200taxa-100kpat-1000trees"
+name = sys.argv[1] if len(sys.argv) > 1 else "synthetic-1000taxa-1Mpat-5000trees"
 patterns = int(sys.argv[2]) if len(sys.argv) > 2 else None
 passes = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 with_sweep = len(sys.argv) > 4 and sys.argv[4] == "sweep"
