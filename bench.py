@@ -345,23 +345,28 @@ def measure(args, name, rank, world, local_rank, extras=True):
     sweep = None
     if not args.no_sweep:
         blo = wl.ops("batched_branch_length_optimization")
-        engine.reset_optimization_count()
-        device_step()
-        barrier()
-        f0 = engine.stats()["objective_evaluations"]
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record(stream)
-        engine.process_operations(*blo)
-        ev1.record(stream)
-        barrier()
-        sweep_ms = max_over_ranks(ev0.elapsed_time(ev1))
-        fevals = engine.stats()["objective_evaluations"] - f0
         n_edges_opt = blo[0].shape[0]
+        sweep_runs = []
+        for _ in range(2):  # same starting point twice: the first run also compiles the list and allocates
+            engine.set_branch_lengths(bl_pinned.numpy())
+            engine.reset_optimization_count()
+            device_step()
+            barrier()
+            f0 = engine.stats()["objective_evaluations"]
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(stream)
+            engine.process_operations(*blo)
+            ev1.record(stream)
+            barrier()
+            sweep_runs.append((max_over_ranks(ev0.elapsed_time(ev1)), engine.stats()["objective_evaluations"] - f0))
+        sweep_ms, fevals = min(sweep_runs)
         device_step()
-        sweep = {"schedule": "batched (all edges in one level, Brent)", "ms": sweep_ms, "edges": n_edges_opt,
-                 "objective_evaluations": fevals,
+        sweep = {"schedule": "batched (all edges in one level, Brent)", "ms": sweep_ms, "ms_first_call": sweep_runs[0][0],
+                 "edges": n_edges_opt, "objective_evaluations": fevals,
                  "algorithmic_bytes": 64.0 * n_edges_opt * P_local,
                  "frac_of_hbm_peak": 64.0 * n_edges_opt * P_local / (sweep_ms * 1e-3) / 1e9 / peak_gbs,
+                 "as_executed_bytes": (64.0 * n_edges_opt + 8.0 * fevals) * P_local,
+                 "as_executed_frac_of_hbm_peak": (64.0 * n_edges_opt + 8.0 * fevals) * P_local / (sweep_ms * 1e-3) / 1e9 / peak_gbs,
                  "log_marginal_after": engine.get_log_marginal_likelihood()}
 
     # ---- CPU baseline: the reference's own engine on this box's host cores (rank 0, N = 1) -------

@@ -361,11 +361,6 @@ void Engine::SetSitePatterns(const uint8_t* symbols, const double* weights, bool
     if (slots_changed) InvalidatePrograms();
     return;
   }
-  if (!on_device) {
-    uint8_t worst = 0;
-    for (int64_t i = 0; i < taxon_count_ * P_; ++i) worst = symbols[i] > worst ? symbols[i] : worst;
-    if (worst > 4) Fail("bito_gp_set_site_patterns: symbol outside 0..4");
-  }
   GP_CUDA(cudaMemcpy2DAsync(d_symbols_.ptr, static_cast<size_t>(P_stride_), symbols,
                             static_cast<size_t>(P_), static_cast<size_t>(P_),
                             static_cast<size_t>(taxon_count_), kind, stream_));
@@ -389,9 +384,16 @@ void Engine::SetSitePatterns(const uint8_t* symbols, const double* weights, bool
   LaunchWeightedSum(stream_, State(), d_dense_tmp_.ptr, d_partials_.ptr);
   LaunchReducePartials(stream_, d_partials_.ptr, 1, tiles, d_packed_.ptr, nullptr, nullptr);
   AllReduce(d_packed_.ptr, 1, false);
-  GP_CUDA(cudaMemcpyAsync(pinned_, d_packed_.ptr, sizeof(double), cudaMemcpyDeviceToHost, stream_));
+  // The symbols are validated where they now live (a host-side scan of taxa x P bytes costs more
+  // than the upload); the result rides on the read-back of the total weight.
+  LaunchMaxSymbol(stream_, d_symbols_.ptr, taxon_count_, P_, P_stride_, d_packed_.ptr + 1);
+  GP_CUDA(cudaMemcpyAsync(pinned_, d_packed_.ptr, 2 * sizeof(double), cudaMemcpyDeviceToHost, stream_));
   GP_CUDA(cudaStreamSynchronize(stream_));
-  total_weight_ = *static_cast<double*>(pinned_);
+  total_weight_ = static_cast<double*>(pinned_)[0];
+  if (static_cast<double*>(pinned_)[1] > 4.) {
+    have_patterns_ = false;
+    Fail("bito_gp_set_site_patterns: symbol outside 0..4");
+  }
   have_patterns_ = true;
   BuildWeightClasses(on_device ? nullptr : weights);
   // Re-uploading an alignment of the same shape leaves every compiled program valid.
@@ -1306,7 +1308,7 @@ void Engine::ExecuteLevels(Program& prog, size_t first, size_t last) {
         // The rescale decision needs the max over ALL patterns of the PLV (gp_engine.cpp:583-597).
         AllReduce(d_level_max_.ptr + L.mult_off, L.n_mult, true);
         ProfScope ps(this, kProfRescale, 0.);
-        LaunchRescale(stream_, st, prog.d_mult + L.mult_off, L.n_mult, d_level_max_.ptr);
+        LaunchRescale(stream_, st, prog.d_mult + L.mult_off, L.n_mult, d_level_max_.ptr + L.mult_off);
       }
     }
     if (L.n_lik > 0) {

@@ -366,28 +366,69 @@ __global__ void __launch_bounds__(kTile, kMinBlocks)
 }
 
 // RescalePLVIfNeeded + RescalePLV (gp_engine.cpp:564-573, 583-597). The maximum is over the
-// whole PLV (all patterns, all ranks); almost always nothing to do, so the grid is small and
-// fixed: each block walks the level's Multiplies and only touches the PLVs that need it.
+// whole PLV (all patterns, all ranks). Almost always there is nothing to do, so the grid is small
+// and fixed. Every block scans the level's maxima (level_max[o] belongs to ops[o]) in chunks of
+// kRescaleChunk Multiplies and compacts, in op order, the ones that need rescaling into shared
+// memory; all blocks then share the (PLV, pattern tile) items of that list, so a PLV that does
+// need it (deep DAGs: the levels next to the rootsplits) is rescaled by the whole machine, not by
+// one block.
+constexpr int kRescaleChunk = 4 * kTile;
 __global__ void __launch_bounds__(kTile)
     k_rescale(DeviceState st, const MultOp* __restrict__ ops, int n_ops,
-              const double* __restrict__ level_max) {
-  for (int o = blockIdx.x; o < n_ops; o += gridDim.x) {
-    double max_entry = level_max[ops[o].max_slot];
-    if (max_entry == 0.) continue;
-    int rescaling_count = 0;
-    while (max_entry < st.thr) {
-      max_entry /= st.thr;
-      rescaling_count++;
+              const double* __restrict__ level_max, int tiles) {
+  __shared__ int s_op[kRescaleChunk];
+  __shared__ double s_divisor[kRescaleChunk];
+  __shared__ int s_warp_count[kTile / 32];
+  __shared__ int s_n;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int chunk0 = 0; chunk0 < n_ops; chunk0 += kRescaleChunk) {
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    for (int base = chunk0; base < min(n_ops, chunk0 + kRescaleChunk); base += kTile) {
+      const int o = base + threadIdx.x;
+      int rescaling_count = 0;
+      if (o < n_ops) {
+        double max_entry = level_max[o];
+        if (max_entry != 0.) {  // max == 0: no rescale (gp_engine.cpp:587-589)
+          while (max_entry < st.thr) {
+            max_entry /= st.thr;
+            rescaling_count++;
+          }
+        }
+      }
+      const unsigned ballot = __ballot_sync(0xffffffffu, rescaling_count > 0);
+      if (lane == 0) s_warp_count[warp] = __popc(ballot);
+      __syncthreads();
+      int at = s_n;
+      for (int w = 0; w < warp; ++w) at += s_warp_count[w];
+      if (rescaling_count > 0) {
+        at += __popc(ballot & ((1u << lane) - 1u));
+        s_op[at] = o;
+        s_divisor[at] = pow(st.thr, static_cast<double>(rescaling_count));
+        if (blockIdx.x == 0) st.counts[ops[o].dest_id] += rescaling_count;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int total = s_n;
+        for (int w = 0; w < kTile / 32; ++w) total += s_warp_count[w];
+        s_n = total;
+      }
+      __syncthreads();
     }
-    if (rescaling_count == 0) continue;
-    const double divisor = pow(st.thr, static_cast<double>(rescaling_count));
-    double* dest = ops[o].dest;
-    for (int64_t p = threadIdx.x; p < st.P; p += kTile) {
-      V4 v = ld256(dest + 4 * p);
-      v.a /= divisor; v.b /= divisor; v.c /= divisor; v.d /= divisor;
-      st256(dest + 4 * p, v);
+    const int64_t n_items = static_cast<int64_t>(s_n) * tiles;
+    for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int k = static_cast<int>(item / tiles);
+      const int tile = static_cast<int>(item - static_cast<int64_t>(k) * tiles);
+      const int64_t p = static_cast<int64_t>(tile) * kTile + threadIdx.x;
+      if (p < st.P) {
+        double* dest = ops[s_op[k]].dest;
+        const double divisor = s_divisor[k];
+        V4 v = ld256(dest + 4 * p);
+        v.a /= divisor; v.b /= divisor; v.c /= divisor; v.d /= divisor;
+        st256(dest + 4 * p, v);
+      }
     }
-    if (threadIdx.x == 0) st.counts[ops[o].dest_id] += rescaling_count;
+    __syncthreads();  // the list is rebuilt for the next chunk
   }
 }
 
@@ -412,7 +453,30 @@ __global__ void __launch_bounds__(kTile)
   double wsum = 0.;
   const int tile_begin = tile_group * tiles_per_block;
   const int tile_end = min(tiles, tile_begin + tiles_per_block);
-  for (int tile = tile_begin; tile < tile_end; ++tile) {
+  // Two pattern tiles per trip: the four 32-byte loads are issued before the first log(), so a
+  // thread keeps 128 B in flight (the kernel is bound by load latency, not by the FP64 pipe).
+  // The weighted sum keeps the one-tile-at-a-time order.
+  int tile = tile_begin;
+  for (; tile + 2 <= tile_end; tile += 2) {
+    const int64_t p0 = static_cast<int64_t>(tile) * kTile + threadIdx.x;
+    const int64_t p1 = p0 + kTile;
+    const bool live0 = p0 < st.P, live1 = p1 < st.P;
+    V4 r0 = {0., 0., 0., 0.}, c0 = r0, r1 = r0, c1 = r0;
+    double w0 = 0., w1 = 0.;
+    if (live0) { r0 = load_plv(parent, p0); c0 = load_plv(child, p0); w0 = st.weights[p0]; }
+    if (live1) { r1 = load_plv(parent, p1); c1 = load_plv(child, p1); w1 = st.weights[p1]; }
+    if (live0) {
+      const double ll = log(quad(r0, sM, c0)) + resc;
+      if (row != nullptr) row[p0] = ll;
+      wsum += ll * w0;
+    }
+    if (live1) {
+      const double ll = log(quad(r1, sM, c1)) + resc;
+      if (row != nullptr) row[p1] = ll;
+      wsum += ll * w1;
+    }
+  }
+  for (; tile < tile_end; ++tile) {
     const int64_t p = static_cast<int64_t>(tile) * kTile + threadIdx.x;
     if (p < st.P) {
       const V4 r = load_plv(parent, p);
@@ -1106,6 +1170,33 @@ __global__ void __launch_bounds__(kTile)
   if (threadIdx.x == 0) partials[blockIdx.x] = v;
 }
 
+// Largest symbol of the uploaded alignment (valid symbols are 0..4, site_pattern.cpp symbol table):
+// one 8-byte word per thread, the row padding beyond P masked out.
+__global__ void k_max_symbol(const uint8_t* __restrict__ symbols, int64_t rows, int64_t P,
+                             int64_t P_stride, unsigned* __restrict__ out) {
+  const int64_t words_per_row = P_stride / 8;
+  const int64_t n_words = rows * words_per_row;
+  unsigned worst = 0;
+  for (int64_t w = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; w < n_words;
+       w += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t row = w / words_per_row;
+    const int64_t col = (w - row * words_per_row) * 8;
+    unsigned long long word = *reinterpret_cast<const unsigned long long*>(symbols + row * P_stride + col);
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const unsigned v = static_cast<unsigned>(word & 0xffull);
+      word >>= 8;
+      if (col + b < P) worst = max(worst, v);
+    }
+  }
+#pragma unroll
+  for (int sh = 16; sh > 0; sh >>= 1) worst = max(worst, __shfl_xor_sync(0xffffffffu, worst, sh));
+  if ((threadIdx.x & 31) == 0 && worst > 0) atomicMax(out, worst);
+}
+__global__ void k_u32_to_double(const unsigned* __restrict__ in, double* __restrict__ out) {
+  *out = static_cast<double>(*in);
+}
+
 // ---- quartet hybrid marginal (gp_engine.cpp:748-808) -------------------------------------------
 // The five transition matrices of every summand: rootward, sister, central, rotated, sorted.
 __global__ void k_quartet_matrices(DeviceState st, const QuartetItem* __restrict__ items, int n_items,
@@ -1206,8 +1297,10 @@ void LaunchNodes(cudaStream_t s, const DeviceState& st, const NodeOp* nodes, con
 void LaunchRescale(cudaStream_t s, const DeviceState& st, const MultOp* ops, int n_ops,
                    const double* level_max) {
   if (n_ops == 0) return;
-  const int grid = n_ops < 592 ? n_ops : 592;  // 148 SMs x 4 resident blocks
-  k_rescale<<<grid, kTile, 0, s>>>(st, ops, n_ops, level_max);
+  const int tiles = static_cast<int>(TilesFor(st.P));
+  const int64_t items = static_cast<int64_t>(n_ops) * tiles;
+  const int grid = items < 592 ? static_cast<int>(items) : 592;  // 148 SMs x 4 resident blocks
+  k_rescale<<<grid, kTile, 0, s>>>(st, ops, n_ops, level_max, tiles);
 }
 int64_t LikelihoodTileGroups(int n_ops, int64_t P) {
   const int64_t tiles = TilesFor(P);
@@ -1334,6 +1427,19 @@ void LaunchFill(cudaStream_t s, double* dst, int64_t n, double value) {
 }
 void LaunchTransitionMatrix(cudaStream_t s, double t, double* out16) {
   k_transition_matrix<<<1, 32, 0, s>>>(t, out16);
+}
+void LaunchMaxSymbol(cudaStream_t s, const uint8_t* symbols, int64_t rows, int64_t P, int64_t P_stride,
+                     double* out) {
+  // *out doubles as the 4-byte accumulator (its low word), converted in place afterwards
+  unsigned* acc = reinterpret_cast<unsigned*>(out);
+  cudaMemsetAsync(out, 0, sizeof(double), s);
+  const int64_t n_words = rows * (P_stride / 8);
+  if (n_words > 0) {
+    const int64_t want = (n_words + 255) / 256;
+    k_max_symbol<<<static_cast<unsigned>(want < 148 * 8 ? want : 148 * 8), 256, 0, s>>>(symbols, rows, P,
+                                                                                     P_stride, acc);
+  }
+  k_u32_to_double<<<1, 1, 0, s>>>(acc, out);
 }
 void LaunchWeightedSum(cudaStream_t s, const DeviceState& st, const double* values,
                        double* partials) {

@@ -21,8 +21,12 @@ void LaunchBuildMatrices(cudaStream_t s, const DeviceState& st, const AccumItem*
                          const LikOp* liks, int n_liks, double* mtab, double* mtab_lik);
 void LaunchNodes(cudaStream_t s, const DeviceState& st, const NodeOp* nodes, const AccumItem* items,
                  const int32_t* pool, const double* mtab, int n_nodes, double* level_max);
+// level_max[o] = maximum entry of ops[o].dest over all patterns (and ranks).
 void LaunchRescale(cudaStream_t s, const DeviceState& st, const MultOp* ops, int n_ops,
                    const double* level_max);
+// max over taxa x P symbols (rows of stride P_stride bytes) as a double into *out.
+void LaunchMaxSymbol(cudaStream_t s, const uint8_t* symbols, int64_t rows, int64_t P, int64_t P_stride,
+                     double* out);
 // partials: n_ops rows of LikelihoodTileGroups(n_ops, P) tile-group sums.
 int64_t LikelihoodTileGroups(int n_ops, int64_t P);
 void LaunchLikelihood(cudaStream_t s, const DeviceState& st, const LikOp* ops, int n_ops,

@@ -15,11 +15,12 @@ timeout 900 python bench.py --steps 10 --warmup 3 > $out/${tag}_bench.json 2> $o
 cat $out/${tag}_bench.json | cut -c1-600
 timeout 400 python bench.py --impl reference --steps 3 --warmup 1 > $out/${tag}_bench_ref.json 2> $out/${tag}_bench_ref.err; echo "bench ref rc=$?"
 cat $out/${tag}_bench_ref.json | cut -c1-400
-timeout 300 python tools/time_pass.py $WL $PAT 5 sweep > $out/${tag}_time_pass.log 2>&1; cat $out/${tag}_time_pass.log | tail -1
+timeout 300 python tools/time_small.py > $out/${tag}_time_small.log 2>&1; cat $out/${tag}_time_small.log
 timeout 300 python tools/profile_sweep.py $WL $PAT > $out/${tag}_profile_sweep.log 2>&1; tail -12 $out/${tag}_profile_sweep.log
 # launch list: one pass + one batched sweep, graphs off
 timeout 500 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 6000 --csv \
   --log-file $out/${tag}_launches_pass.csv python profiles/prof_pass.py $WL $PAT 1 > $out/${tag}_prof_pass.log 2>&1; echo "ncu list rc=$?"
+[ -n "$QUICK" ] && { ls -la $out; exit 0; }
 # full captures (at 40k / 20k patterns so that ncu's save/restore of device memory stays small): the two
 # largest k_node launches (first rootward levels), the likelihood kernel, the sweep objective
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_node -s 1 -c 2 -f -o $out/${tag}_k_node \
