@@ -18,6 +18,7 @@ FLAG_NO_CUDA_GRAPHS = 1
 FLAG_NO_FUSION = 2
 FLAG_NO_LOGLIK_MATRIX = 4
 FLAG_STRICT_ASSERTS = 8
+FLAG_NO_ONCHIP_OPTIMIZER = 16
 
 
 class Config(C.Structure):

@@ -43,6 +43,8 @@ constexpr double kStepSizeForOptimization = 5e-4;
 constexpr double kStepSizeForLogSpaceOptimization = 1.0005;
 constexpr int64_t kMaxIterForOptimization = 1000;
 constexpr double kBranchLengthDifferenceThreshold = 1e-15;
+// k_opt_block keeps G doubles per pattern in shared memory: up to 10240 patterns under JC69 (G = 2)
+constexpr size_t kOptBlockMaxSharedBytes = 160 * 1024;
 
 uint64_t HashOps(const bito_gp_op* ops, int64_t n, const int64_t* vec, int64_t vec_len) {
   uint64_t h = 1469598103934665603ull;
@@ -265,7 +267,7 @@ Engine::~Engine() {
   d_symbols_.Release(); d_weights_.Release(); d_log_marg_.Release(); d_counts_.Release();
   d_q_.Release(); d_bl_.Release(); d_diff_.Release(); d_hybrid_.Release(); d_ll_sum_.Release();
   d_inverted_.Release(); d_uncond_.Release(); d_status_.Release(); d_feval_total_.Release();
-  d_partials_.Release(); d_packed_.Release(); d_level_max_.Release(); d_coef_.Release();
+  d_partials_.Release(); d_packed_.Release(); d_level_max_.Release(); d_coef_.Release(); d_opt_ctl_.Release();
   d_dense_tmp_.Release(); d_mtab_.Release(); d_mtab_lik_.Release(); d_opt_states_.Release(); d_opt_const_.Release(); d_opt_active_.Release(); d_perm_.Release(); d_wperm_.Release(); d_row_class_.Release(); d_active_.Release(); d_single_opt_.Release(); d_quartet_items_.Release(); d_quartet_mats_.Release();
   if (pinned_ != nullptr) cudaFreeHost(pinned_);
   if (ev_begin_) cudaEventDestroy(ev_begin_);
@@ -1199,6 +1201,7 @@ Program* Engine::Compile(const bito_gp_op* ops, int64_t n, const int64_t* vec, i
   }
   prog->n_mult_total = static_cast<int>(f_mult.size());
   prog->n_opt_total = static_cast<int>(f_opt.size());
+  for (const Level& L : prog->levels) prog->n_opt_levels += (L.n_opt > 0);
   prog->n_items_total = static_cast<int64_t>(h_items.size());
   prog->n_lik_total = static_cast<int>(f_lik.size());
   prog->n_macro = static_cast<int64_t>(macros.size());
@@ -1352,6 +1355,27 @@ void Engine::ExecuteLevels(Program& prog, size_t first, size_t last) {
   }
 }
 
+// One block per edge can hold the per-pattern coefficients of its edge in shared memory: the whole
+// 1-D search runs on chip. Needs every pattern on this rank (the objective is a sum over ALL patterns).
+OptParams Engine::OptimizerParams(bool check_convergence) const {
+  OptParams prm{};
+  prm.significant_digits = significant_digits_;
+  prm.check_convergence = check_convergence ? 1 : 0;
+  prm.max_iter = kMaxIterForOptimization;
+  prm.min_log_bl = kMinLogBranchLength;
+  prm.max_log_bl = kMaxLogBranchLength;
+  prm.denominator_tolerance = kDenominatorToleranceForNewton;
+  prm.step_size = kStepSizeForOptimization;
+  prm.log_step_size = kStepSizeForLogSpaceOptimization;
+  prm.diff_threshold = kBranchLengthDifferenceThreshold;
+  return prm;
+}
+
+bool Engine::OptimizerOnChip() const {
+  return n_ranks_ == 1 && P_ > 0 && !(cfg_.flags & BITO_GP_FLAG_NO_ONCHIP_OPTIMIZER) &&
+         OptBlockSharedBytes(P_, n_eigen_groups_) <= kOptBlockMaxSharedBytes;
+}
+
 void Engine::RunOptimizeLevel(Program& prog, const Level& L) {
   RunOptimizer(prog.d_opt + L.opt_off, L.n_opt, method_, optimization_count_ != 0);
 }
@@ -1367,6 +1391,14 @@ void Engine::RunOptimizer(const OptOp* d_ops, int n_ops, int method, bool check_
                  : method == BITO_GP_NEWTON_OPTIMIZATION ? 2 : 1;
   // Plain Brent on a two-eigenvalue model (JC69, the only model GPEngine instantiates,
   // gp_engine.hpp:366): ratio form, 8 B per pattern and one log per 8 patterns.
+  if (OptimizerOnChip()) {
+    // small alignment, single rank: every edge's whole search in one launch (k_opt_block); the
+    // settings were written to d_opt_ctl_ by Execute, outside any captured graph
+    ProfScope ps(this, kProfOptBlock, 64. * n_ops * static_cast<double>(P_));
+    LaunchOptBlock(stream_, st, d_ops, n_ops, d_opt_ctl_.ptr, G);
+    return;
+  }
+  const OptParams prm = OptimizerParams(check_convergence);
   const bool ratio = (G == 2 && nd == 0);
   const int64_t coef_per_op = ratio ? P_perm_ : P_stride_ * G;
   const int64_t budget_doubles = (opt_chunk_bytes_ > 0 ? opt_chunk_bytes_ : (int64_t(1) << 30)) / 8;
@@ -1389,16 +1421,6 @@ void Engine::RunOptimizer(const OptOp* d_ops, int n_ops, int method, bool check_
   EnsureScratch(static_cast<int64_t>(chunk) * std::max<int64_t>(value_stride * groups, tiles),
                 static_cast<int64_t>(chunk) * 3);
 
-  OptParams prm{};
-  prm.significant_digits = significant_digits_;
-  prm.check_convergence = check_convergence ? 1 : 0;
-  prm.max_iter = kMaxIterForOptimization;
-  prm.min_log_bl = kMinLogBranchLength;
-  prm.max_log_bl = kMaxLogBranchLength;
-  prm.denominator_tolerance = kDenominatorToleranceForNewton;
-  prm.step_size = kStepSizeForOptimization;
-  prm.log_step_size = kStepSizeForLogSpaceOptimization;
-  prm.diff_threshold = kBranchLengthDifferenceThreshold;
   const int64_t max_rounds = 3 * kMaxIterForOptimization + 8;
   int32_t* h_active = static_cast<int32_t*>(pinned_);
 
@@ -1486,7 +1508,19 @@ void Engine::Execute(Program& prog) {
     if (grew) DropGraphs();  // captured graphs hold the old scratch addresses
   }
   const bool want_graph =
-      !(cfg_.flags & BITO_GP_FLAG_NO_CUDA_GRAPHS) && prog.n_opt_total == 0 && !profiling_;
+      !(cfg_.flags & BITO_GP_FLAG_NO_CUDA_GRAPHS) && (prog.n_opt_total == 0 || OptimizerOnChip()) &&
+      !profiling_;
+  // the round-per-launch optimiser counts its own launches; the on-chip one is one per level
+  const int64_t launches = prog.launches + (OptimizerOnChip() ? prog.n_opt_levels : 0);
+  if (prog.n_opt_total > 0 && OptimizerOnChip()) {
+    OptControl ctl{};
+    ctl.prm = OptimizerParams(optimization_count_ != 0);
+    ctl.method = method_;
+    ctl.n_derivatives = method_ == BITO_GP_BRENT_OPTIMIZATION ? 0
+                        : method_ == BITO_GP_NEWTON_OPTIMIZATION ? 2 : 1;
+    if (d_opt_ctl_.n == 0) d_opt_ctl_.Resize(1, false, stream_);
+    LaunchSetOptControl(stream_, d_opt_ctl_.ptr, ctl);
+  }
   auto body = [&]() {
     if (prog.n_mult_total > 0)
       GP_CUDA(cudaMemsetAsync(d_level_max_.ptr, 0, prog.n_mult_total * sizeof(double), stream_));
@@ -1515,12 +1549,12 @@ void Engine::Execute(Program& prog) {
     if (prog.graph != nullptr) {
       GP_CUDA(cudaGraphLaunch(prog.graph, stream_));
       stats_.graph_launches++;
-      stats_.kernel_launches += prog.launches;
+      stats_.kernel_launches += launches;
       return;
     }
   }
   body();
-  stats_.kernel_launches += prog.launches;
+  stats_.kernel_launches += launches;
 }
 
 void Engine::ProcessOperations(const bito_gp_op* ops, int64_t n, const int64_t* vec,
@@ -2060,7 +2094,7 @@ void Engine::CopyGpcspData(int64_t src, int64_t dest) {  // gp_engine.cpp:401-40
 // ---- per-kernel timing with CUDA events on the launching stream (bench.py's roofline) ---------------
 const char* const kProfNames[kProfKinds] = {"k_zero", "k_scalar", "k_stationary", "k_prologue", "k_node",
                                             "k_rescale", "k_likelihood", "k_marginal", "k_reduce_partials",
-                                            "k_opt_prepare", "k_opt_eval", "k_opt_step"};
+                                            "k_opt_prepare", "k_opt_eval", "k_opt_step", "k_opt_block"};
 
 ProfScope::ProfScope(Engine* e, int kind, double bytes) : e_(e->profiling_ ? e : nullptr) {
   if (e_ == nullptr) return;

@@ -93,6 +93,7 @@ struct Program {
   int32_t* d_marg_scatter = nullptr;  // per marginal level: n_marg edges + marginal slot
   int n_mult_total = 0;
   int n_opt_total = 0;
+  int n_opt_levels = 0;       // levels that hold OptimizeBranchLength ops
   int64_t n_items_total = 0;  // transition matrices of all accumulate items (mtab slots)
   int n_lik_total = 0;        // Likelihood ops (lik mtab slots)
   int64_t max_partials = 0;  // doubles of tile partials needed by any level
@@ -106,7 +107,7 @@ struct Program {
 
 enum ProfKind {
   kProfZero, kProfScalar, kProfStationary, kProfPrologue, kProfNode, kProfRescale, kProfLikelihood,
-  kProfMarginal, kProfReduce, kProfOptPrepare, kProfOptEval, kProfOptStep, kProfKinds
+  kProfMarginal, kProfReduce, kProfOptPrepare, kProfOptEval, kProfOptStep, kProfOptBlock, kProfKinds
 };
 
 class Engine;
@@ -207,6 +208,8 @@ class Engine {
   void Execute(Program& prog);
   void ExecuteLevels(Program& prog, size_t first, size_t last);
   void RunOptimizeLevel(Program& prog, const Level& lv);
+  bool OptimizerOnChip() const;
+  OptParams OptimizerParams(bool check_convergence) const;
   void RunOptimizer(const OptOp* d_ops, int n_ops, int method, bool check_convergence);
   void FreeProgram(Program& p);
   void EnsureScratch(int64_t partial_doubles, int64_t packed_doubles);
@@ -238,6 +241,7 @@ class Engine {
   int64_t max_device_bytes_ = 0;
 
   DeviceArray<uint8_t> d_symbols_;
+  DeviceArray<OptControl> d_opt_ctl_;  // optimiser settings read by k_opt_block
   DeviceArray<double> d_weights_, d_log_marg_;
   DeviceArray<int32_t> d_counts_;
   DeviceArray<double> d_q_, d_bl_, d_diff_, d_hybrid_, d_ll_sum_, d_inverted_, d_uncond_;

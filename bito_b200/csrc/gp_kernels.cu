@@ -1146,6 +1146,86 @@ __global__ void k_opt_step(DeviceState st, int n_ops, OptState* __restrict__ sta
   }
 }
 
+// ---- OptimizeBranchLength on chip (small alignments) -------------------------------------------
+// Real alignments have 1e2..1e4 site patterns: there the round-per-launch scheme above is bound by
+// launch and host-check latency, not by HBM. Here one block owns one edge for its whole 1-D search:
+// it reads the two PLVs once (64 B per pattern), keeps the per-pattern eigen-coefficients in shared
+// memory (G doubles per pattern), and loops objective evaluation -> block reduction -> optimiser
+// decision (thread 0, the same opt_init/opt_advance state machine) until the optimiser is done. A
+// level of k independent edges is k blocks of ONE launch with no host round trip, so whole
+// Gauss-Seidel sweeps (GPDAG::BranchLengthOptimization) replay as a CUDA graph.
+__global__ void __launch_bounds__(kTile)
+    k_opt_block(DeviceState st, const OptOp* __restrict__ ops, const OptControl* __restrict__ ctl) {
+  extern __shared__ __align__(16) double s_coef[];  // [G][P]
+  __shared__ OptState s_state;
+  const OptParams prm = ctl->prm;
+  const int method = ctl->method, n_derivatives = ctl->n_derivatives;
+  const OptOp op = ops[blockIdx.x];
+  const int G = c_model.n_groups;
+  const int P = static_cast<int>(st.P);
+  if (threadIdx.x == 0) {
+    OptState s;
+    opt_init(s, st, prm, method, op);
+    s_state = s;
+  }
+  for (int p = threadIdx.x; p < P; p += kTile) {
+    const V4 r = load_plv(op.parent, p);
+    const V4 c = load_plv(op.child, p);
+    double cg[kMaxEigenGroups] = {0., 0., 0., 0.};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double rv = r.a * c_model.V[k] + r.b * c_model.V[4 + k] + r.c * c_model.V[8 + k] +
+                        r.d * c_model.V[12 + k];
+      const double vp = c_model.Vinv[4 * k] * c.a + c_model.Vinv[4 * k + 1] * c.b +
+                        c_model.Vinv[4 * k + 2] * c.c + c_model.Vinv[4 * k + 3] * c.d;
+      const double term = rv * vp;
+      const int g = c_model.group[k];
+#pragma unroll
+      for (int gg = 0; gg < kMaxEigenGroups; ++gg)
+        if (gg == g) cg[gg] += term;
+    }
+    for (int g = 0; g < G; ++g) s_coef[g * P + p] = cg[g];
+  }
+  __syncthreads();
+  while (!s_state.done) {  // block-uniform: s_state only changes between the barriers below
+    double e[kMaxEigenGroups], e1[kMaxEigenGroups], e2[kMaxEigenGroups];
+#pragma unroll
+    for (int g = 0; g < kMaxEigenGroups; ++g) {
+      const double l = g < G ? c_model.group_lambda[g] : 0.;
+      e[g] = g < G ? s_state.e[g] : 0.;
+      e1[g] = l * e[g];
+      e2[g] = l * l * e[g];
+    }
+    double f = 0., g1 = 0., g2 = 0.;
+    for (int p = threadIdx.x; p < P; p += kTile) {
+      double L = 0., L1 = 0., L2 = 0.;
+#pragma unroll
+      for (int g = 0; g < kMaxEigenGroups; ++g) {
+        if (g < G) {
+          const double c = s_coef[g * P + p];
+          L += c * e[g];
+          L1 += c * e1[g];
+          L2 += c * e2[g];
+        }
+      }
+      const double w = st.weights[p];
+      f += log(L) * w;
+      if (n_derivatives >= 1) g1 += (L1 / L) * w;                       // gp_engine.cpp:493-496
+      if (n_derivatives >= 2) g2 += ((L2 * L - L1 * L1) / (L * L)) * w;  // gp_engine.cpp:530-538
+    }
+    f = block_reduce(f, SumOp(), 0.);
+    if (n_derivatives >= 1) g1 = block_reduce(g1, SumOp(), 0.);
+    if (n_derivatives >= 2) g2 = block_reduce(g2, SumOp(), 0.);
+    if (threadIdx.x == 0) {
+      OptState s = s_state;
+      opt_advance(s, st, prm, f + s.ll_offset, g1, g2);
+      s_state = s;
+      if (s.done) atomicAdd(st.feval_total, static_cast<unsigned long long>(s.evals));
+    }
+    __syncthreads();
+  }
+}
+
 // ---- utilities ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kTile)
     k_export_plv(DeviceState st, PlvRef src, double* __restrict__ out) {
@@ -1376,6 +1456,24 @@ void LaunchOptStep(cudaStream_t s, const DeviceState& st, int n_ops, OptState* s
   k_opt_step<<<(n_ops + 7) / 8, 256, 0, s>>>(st, n_ops, states, params, sums, partials, n_parts,
                                               n_values, value_stride, edge_const, active_counter,
                                               active, active_capacity, parity);
+}
+size_t OptBlockSharedBytes(int64_t P, int n_groups) {
+  return static_cast<size_t>(P) * static_cast<size_t>(n_groups) * sizeof(double);
+}
+__global__ void k_set_opt_control(OptControl* ctl, OptControl value) { *ctl = value; }
+void LaunchSetOptControl(cudaStream_t s, OptControl* ctl, const OptControl& value) {
+  k_set_opt_control<<<1, 1, 0, s>>>(ctl, value);
+}
+void LaunchOptBlock(cudaStream_t s, const DeviceState& st, const OptOp* ops, int n_ops,
+                    const OptControl* ctl, int n_groups) {
+  if (n_ops == 0) return;
+  const size_t smem = OptBlockSharedBytes(st.P, n_groups);
+  static size_t opted_in = 0;
+  if (smem > 48 * 1024 && smem > opted_in) {
+    cudaFuncSetAttribute(k_opt_block, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    opted_in = smem;
+  }
+  k_opt_block<<<n_ops, kTile, smem, s>>>(st, ops, ctl);
 }
 int64_t OptPrepareTileGroups(int n_ops, int64_t P) {
   const int64_t tiles = TilesFor(P);

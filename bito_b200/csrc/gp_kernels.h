@@ -65,6 +65,14 @@ void LaunchOptPrepareRatio(cudaStream_t s, const DeviceState& st, const OptOp* o
                            const int32_t* perm, int64_t rho_stride,
                            double* partials /* n_ops x OptPrepareTileGroups(n_ops, P) */,
                            int32_t* active, int active_capacity);
+// Small alignments: one block per edge runs the whole 1-D search on chip (coefficients in
+// OptBlockSharedBytes(P, G) of dynamic shared memory), one launch per level, no host round trip.
+size_t OptBlockSharedBytes(int64_t P, int n_groups);
+// The optimiser settings live in device memory (*ctl, written in-stream by LaunchSetOptControl
+// before the program runs) so that a captured launch picks up the settings of each replay.
+void LaunchSetOptControl(cudaStream_t s, OptControl* ctl, const OptControl& value);
+void LaunchOptBlock(cudaStream_t s, const DeviceState& st, const OptOp* ops, int n_ops,
+                    const OptControl* ctl, int n_groups);
 int64_t OptPrepareTileGroups(int n_ops, int64_t P);
 int64_t OptRatioTileGroups(int64_t P);
 int64_t OptRatioPartials(int64_t P);  // partial sums per edge written by LaunchOptEvalRatio

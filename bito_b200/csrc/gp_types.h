@@ -217,4 +217,13 @@ struct OptParams {
   double diff_threshold;
 };
 
+// What a captured OptimizeBranchLength launch must not bake in: the optimiser settings can change
+// between replays of the same op list (method, significant digits, first-vs-later optimisation,
+// dag_branch_handler.hpp:49-52), so k_opt_block reads them from device memory.
+struct OptControl {
+  OptParams prm;
+  int32_t method;
+  int32_t n_derivatives;
+};
+
 }  // namespace bito_gp

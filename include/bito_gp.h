@@ -101,7 +101,10 @@ enum {
   /* The reference's Assert()s on this path (gp_engine.cpp:237-238, 256-257, 283, 585-586) compile
    * away in its Release build (sugar.hpp:103-111). Default: same - violations are only recorded in
    * bito_gp_stats.device_status_bits. With this flag they fail the call, as in a Debug build. */
-  BITO_GP_FLAG_STRICT_ASSERTS = 8
+  BITO_GP_FLAG_STRICT_ASSERTS = 8,
+  /* OptimizeBranchLength on small alignments runs each edge's whole 1-D search inside one thread
+   * block (no host round trips). This flag forces the round-per-launch scheme used for large ones. */
+  BITO_GP_FLAG_NO_ONCHIP_OPTIMIZER = 16
 };
 
 typedef struct bito_gp_engine bito_gp_engine;

@@ -54,8 +54,14 @@ def test_pass_matches_reference(cuda_engine_lib, case):
             check_sbn(e, fx, ti)
 
 
+@pytest.mark.parametrize("scheme", ["on_chip", "rounds"])
 @pytest.mark.parametrize("case", ALL_CASES)
-def test_branch_length_sweeps_match_reference(cuda_engine_lib, case):
+def test_branch_length_sweeps_match_reference(cuda_engine_lib, case, scheme):
+    """Gauss-Seidel sweeps (GPInstance::EstimateBranchLengths) through both optimiser schemes: the
+    one-block-per-edge on-chip search these small alignments get by default, and the
+    round-per-launch scheme large alignments and multi-GPU runs use."""
+    from bito_b200 import _lib
+    flags = 0 if scheme == "on_chip" else _lib.FLAG_NO_ONCHIP_OPTIMIZER
     fx = Fixture(case)
     for ti in range(len(fx.thresholds)):
         for method in fx.methods:
@@ -65,8 +71,32 @@ def test_branch_length_sweeps_match_reference(cuda_engine_lib, case):
             # to 7.7e-7 on `hello` with this method and agree to <= 1e-9 on every other method/fixture
             # (oracle/ref_rounding_sensitivity.py, table in DESIGN.md section 5). 1e-6 everywhere else.
             atol = 5e-6 if method == "brent_with_gradients" else BL_ATOL
-            with make_cuda(fx, ti) as e:
+            with make_cuda(fx, ti, flags=flags) as e:
                 check_sweeps(e, fx, ti, method, atol=atol)
+
+
+def test_on_chip_sweep_replays_as_one_graph(cuda_engine_lib):
+    """With the on-chip optimiser an op list that holds OptimizeBranchLength ops has no host round
+    trip left, so it is captured and replayed as a CUDA graph like any other list; the
+    round-per-launch scheme (host check every few rounds) is launched directly. Both count the same
+    objective evaluations as they take the same optimiser decisions."""
+    from bito_b200 import _lib
+    fx = Fixture("ds1_reduced_5")
+    evals = {}
+    for flags in (0, _lib.FLAG_NO_ONCHIP_OPTIMIZER):
+        with make_cuda(fx, 0, flags=flags) as e:
+            e.set_optimization_method("brent")
+            e.process_operations(*fx.ops("populate_plvs"))
+            before = e.stats()
+            e.process_operations(*fx.ops("branch_length_optimization"))
+            after = e.stats()
+            assert after["graph_launches"] - before["graph_launches"] == (1 if flags == 0 else 0)
+            assert after["kernel_launches"] > before["kernel_launches"]
+            evals[flags] = after["objective_evaluations"] - before["objective_evaluations"]
+            bl = e.get_branch_lengths()
+        evals[(flags, "bl")] = bl
+    assert evals[0] > 0 and abs(evals[0] - evals[_lib.FLAG_NO_ONCHIP_OPTIMIZER]) <= max(2, evals[0] // 100)
+    assert np.max(np.abs(evals[(0, "bl")] - evals[(_lib.FLAG_NO_ONCHIP_OPTIMIZER, "bl")])) <= BL_ATOL
 
 
 @pytest.mark.parametrize("flags", [1, 2, 3])
@@ -168,7 +198,15 @@ def test_random_trees_match_oracle(cuda_engine_lib, taxa, patterns, thr):
     site_count = int(pb["weights"].sum())
     cpu = PortEngine(pb["symbols"], pb["weights"], site_count, pb["node_count"], pb["edge_count"],
                      rescaling_threshold=thr)
-    with GPEngine(pb["symbols"], pb["weights"], site_count, pb["node_count"], pb["edge_count"], thr) as gpu:
+    from bito_b200 import _lib
+    for flags in (0, _lib.FLAG_NO_ONCHIP_OPTIMIZER):
+        _random_tree_case(pb, cpu, site_count, thr, flags)
+
+
+def _random_tree_case(pb, cpu, site_count, thr, flags):
+    from bito_b200.gp_engine import GPEngine
+    with GPEngine(pb["symbols"], pb["weights"], site_count, pb["node_count"], pb["edge_count"], thr,
+                  flags=flags) as gpu:
         for e in (cpu, gpu):
             e.set_branch_lengths(pb["branch_lengths"])
             e.process_operations(*pb["populate"])
@@ -254,8 +292,11 @@ def test_weight_classes_general_weights_match_oracle(cuda_engine_lib):
     w[::7] = rng.uniform(0.25, 3.5, size=w[::7].size)   # non-integer
     w[5::31] = rng.integers(8, 400, size=w[5::31].size)  # large multiplicities (constant sites)
     site_count = int(round(w.sum()))
+    from bito_b200 import _lib
     cpu = PortEngine(pb["symbols"], w, site_count, pb["node_count"], pb["edge_count"])
-    with GPEngine(pb["symbols"], w, site_count, pb["node_count"], pb["edge_count"]) as gpu:
+    # the weight-class layout belongs to the round-per-launch Brent objective: force that scheme
+    with GPEngine(pb["symbols"], w, site_count, pb["node_count"], pb["edge_count"],
+                  flags=_lib.FLAG_NO_ONCHIP_OPTIMIZER) as gpu:
         for e in (cpu, gpu):
             e.set_branch_lengths(pb["branch_lengths"])
             e.process_operations(*pb["populate"])
