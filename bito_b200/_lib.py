@@ -54,6 +54,10 @@ class Stats(C.Structure):
         ("algorithmic_bytes_last", C.c_double),
         ("last_process_ms", C.c_double),
         ("device_status_bits", C.c_int64),
+        ("optimizer_scheme", C.c_int64),
+        ("optimizer_cluster_size", C.c_int64),
+        ("optimizer_cluster_threads", C.c_int64),
+        ("optimizer_edges_in_flight", C.c_int64),
     ]
 
 

@@ -233,6 +233,11 @@ Engine::Engine(const bito_gp_config& cfg) : cfg_(cfg) {
   n_eigen_groups_ = m.n_groups;
   for (int g = 0; g < m.n_groups; ++g) group_lambda_[g] = m.group_lambda[g];
   if (const char* env = getenv("BITO_GP_OPT_CHUNK_MB")) opt_chunk_bytes_ = int64_t(atoll(env)) << 20;
+  // BITO_GP_OPT_CLUSTER: 0 = never use the cluster-resident optimiser; N > 0 = use it with clusters
+  // of exactly N blocks even where one block would do (tests); unset = automatic
+  if (const char* env = getenv("BITO_GP_OPT_CLUSTER")) opt_cluster_env_ = atoi(env);
+  // BITO_GP_OPT_CLUSTER_THREADS: 256 | 1024 = only that block size (with a forced cluster size: tests)
+  if (const char* env = getenv("BITO_GP_OPT_CLUSTER_THREADS")) opt_cluster_threads_env_ = atoi(env);
   GP_CUDA(UploadModel(m));
 
   // PLV slabs: ~256 MiB chunks (or one PLV, whichever is larger).
@@ -268,7 +273,7 @@ Engine::~Engine() {
   d_q_.Release(); d_bl_.Release(); d_diff_.Release(); d_hybrid_.Release(); d_ll_sum_.Release();
   d_inverted_.Release(); d_uncond_.Release(); d_status_.Release(); d_feval_total_.Release();
   d_partials_.Release(); d_packed_.Release(); d_level_max_.Release(); d_coef_.Release(); d_opt_ctl_.Release();
-  d_dense_tmp_.Release(); d_mtab_.Release(); d_mtab_lik_.Release(); d_opt_states_.Release(); d_opt_const_.Release(); d_opt_active_.Release(); d_perm_.Release(); d_wperm_.Release(); d_row_class_.Release(); d_active_.Release(); d_single_opt_.Release(); d_quartet_items_.Release(); d_quartet_mats_.Release();
+  d_dense_tmp_.Release(); d_mtab_.Release(); d_mtab_lik_.Release(); d_opt_states_.Release(); d_opt_const_.Release(); d_opt_active_.Release(); d_perm_.Release(); d_wperm_.Release(); d_row_class_.Release(); d_active_.Release(); d_single_opt_.Release(); d_cluster_inv_perm_.Release(); d_cluster_wperm_.Release(); d_quartet_items_.Release(); d_quartet_mats_.Release();
   if (pinned_ != nullptr) cudaFreeHost(pinned_);
   if (ev_begin_) cudaEventDestroy(ev_begin_);
   if (ev_end_) cudaEventDestroy(ev_end_);
@@ -459,6 +464,55 @@ void Engine::BuildWeightClasses(const double* host_weights) {
                           cudaMemcpyHostToDevice, stream_));
   GP_CUDA(cudaMemcpyAsync(d_row_class_.ptr, row_class.data(), row_class.size(), cudaMemcpyHostToDevice,
                           stream_));
+  // The cluster-resident optimiser (k_opt_cluster) uses the same idea at a finer grain: classes
+  // padded to rows of kClusterThreads patterns, addressed through the INVERSE permutation (a block
+  // fills its own shared-memory rows, so it asks "which pattern sits at position q").
+  std::vector<int32_t> inv(0);
+  std::vector<double> cw(0);
+  {
+    const int64_t row = kClusterThreads;
+    int64_t cstart[9];
+    int64_t cpos = 0;
+    for (int c = 0; c < 8; ++c) {
+      cstart[c] = cpos;
+      cpos += RoundUp(n_in[c], row);
+    }
+    cstart[8] = cpos;
+    for (int c = 0; c < 9; ++c) cluster_class_row_start_[c] = static_cast<int32_t>(cstart[c] / row);
+    inv.assign(static_cast<size_t>(std::max<int64_t>(cpos, row)), -1);
+    cw.assign(inv.size(), 0.);
+    int64_t cnext[8];
+    for (int c = 0; c < 8; ++c) cnext[c] = cstart[c];
+    for (int64_t p = 0; p < P_; ++p) {
+      const int c = cls(w[static_cast<size_t>(p)]);
+      inv[static_cast<size_t>(cnext[c])] = static_cast<int32_t>(p);
+      cw[static_cast<size_t>(cnext[c]++)] = w[static_cast<size_t>(p)];
+    }
+    d_cluster_inv_perm_.Resize(inv.size(), false, stream_);
+    d_cluster_wperm_.Resize(cw.size(), false, stream_);
+    GP_CUDA(cudaMemcpyAsync(d_cluster_inv_perm_.ptr, inv.data(), inv.size() * sizeof(int32_t),
+                            cudaMemcpyHostToDevice, stream_));
+    GP_CUDA(cudaMemcpyAsync(d_cluster_wperm_.ptr, cw.data(), cw.size() * sizeof(double),
+                            cudaMemcpyHostToDevice, stream_));
+    // every cluster shape this device can run for this alignment; RunOptimizer picks one per level
+    const size_t had = cluster_plans_.size();
+    const int had_rows = had > 0 ? cluster_plans_[0].rows_total : -1;
+    cluster_plans_.clear();
+    if (opt_cluster_env_ != 0 && P_ > 0) {
+      for (int threads : {256, 1024}) {
+        if (opt_cluster_threads_env_ > 0 && threads != opt_cluster_threads_env_) continue;
+        if (opt_cluster_env_ > 0 && opt_cluster_threads_env_ <= 0 && threads != 256) continue;
+        for (int c = 1; c <= kMaxOptCluster; c *= 2) {
+          if (opt_cluster_env_ > 0 && c != opt_cluster_env_) continue;
+          OptClusterPlan plan;
+          if (PlanOptCluster(cpos / row, threads, c, &plan)) cluster_plans_.push_back(plan);
+        }
+      }
+    }
+    if (had != cluster_plans_.size() ||
+        (had > 0 && had_rows != cluster_plans_[0].rows_total))
+      DropGraphs();  // captured optimiser launches bake the cluster shape in
+  }
   GP_CUDA(cudaStreamSynchronize(stream_));  // host vectors die here
   coef_padding_zeroed_ = false;
 }
@@ -1371,9 +1425,52 @@ OptParams Engine::OptimizerParams(bool check_convergence) const {
   return prm;
 }
 
-bool Engine::OptimizerOnChip() const {
-  return n_ranks_ == 1 && P_ > 0 && !(cfg_.flags & BITO_GP_FLAG_NO_ONCHIP_OPTIMIZER) &&
-         OptBlockSharedBytes(P_, n_eigen_groups_) <= kOptBlockMaxSharedBytes;
+// How a level of n_ops OptimizeBranchLength ops runs. 0: round-per-launch scheme (rho streamed from
+// HBM every objective round; the host looks at a counter every few rounds, so no graph capture);
+// 1: one block per edge (k_opt_block, every method); 2: one thread-block cluster per edge
+// (k_opt_cluster: plain Brent on a two-eigenvalue model), *plan = its shape.
+// The on-chip searches are bound by latency per edge (~16 dependent objective evaluations), the
+// round scheme by HBM bandwidth: few edges -> spread each over as many SMs as a cluster has; a level
+// with thousands of edges at 1e5 patterns -> stream. The constants below are B200 measurements
+// (profiles/r01f_*: 3-4 us per on-chip evaluation, 2.5 us per two-row load trip, 5.2 TB/s streamed).
+int Engine::OptScheme(int n_ops, const OptClusterPlan** plan) const {
+  if (plan != nullptr) *plan = nullptr;
+  if (n_ranks_ != 1 || P_ <= 0 || (cfg_.flags & BITO_GP_FLAG_NO_ONCHIP_OPTIMIZER)) return 0;
+  const bool cluster_ok = !cluster_plans_.empty() && n_eigen_groups_ == 2 &&
+                          method_ == BITO_GP_BRENT_OPTIMIZATION;
+  const bool forced = opt_cluster_env_ > 0;
+  if (!(cluster_ok && forced) && OptBlockSharedBytes(P_, n_eigen_groups_) <= kOptBlockMaxSharedBytes)
+    return 1;
+  if (!cluster_ok) return 0;
+  const double n_evals = 16.;
+  double best = 0.;
+  const OptClusterPlan* best_plan = nullptr;
+  for (const OptClusterPlan& c : cluster_plans_) {
+    const int rows_per_thread = (c.rows_per_block * kClusterThreads + c.threads - 1) / c.threads;
+    const double load_us = 1.0 + 2.5 * ((rows_per_thread + 1) / 2);
+    const double eval_us = 3.2 + 0.06 * rows_per_thread;
+    const double waves = std::ceil(static_cast<double>(n_ops) / c.active_clusters);
+    const double us = waves * (load_us + n_evals * eval_us);
+    if (best_plan == nullptr || us < best) {
+      best = us;
+      best_plan = &c;
+    }
+  }
+  if (!forced) {
+    const double streamed_bytes = static_cast<double>(n_ops) * static_cast<double>(P_) * (64. + 8. + 8. * n_evals);
+    const double rounds_us = streamed_bytes / 5.2e6 + 26. * 10. + 60.;
+    if (rounds_us < best) return 0;
+  }
+  if (plan != nullptr) *plan = best_plan;
+  return 2;
+}
+
+// True when every OptimizeBranchLength level of the program runs on chip, i.e. the whole program
+// is free of host round trips and can be captured as one CUDA graph.
+bool Engine::ProgramOptimizesOnChip(const Program& prog) const {
+  for (const Level& L : prog.levels)
+    if (L.n_opt > 0 && OptScheme(L.n_opt, nullptr) == 0) return false;
+  return true;
 }
 
 void Engine::RunOptimizeLevel(Program& prog, const Level& L) {
@@ -1391,11 +1488,23 @@ void Engine::RunOptimizer(const OptOp* d_ops, int n_ops, int method, bool check_
                  : method == BITO_GP_NEWTON_OPTIMIZATION ? 2 : 1;
   // Plain Brent on a two-eigenvalue model (JC69, the only model GPEngine instantiates,
   // gp_engine.hpp:366): ratio form, 8 B per pattern and one log per 8 patterns.
-  if (OptimizerOnChip()) {
+  const OptClusterPlan* plan = nullptr;
+  const int on_chip = OptScheme(n_ops, &plan);
+  last_opt_scheme_ = on_chip;
+  last_opt_plan_ = plan != nullptr ? *plan : OptClusterPlan();
+  if (on_chip != 0 && !capturing_) stats_.kernel_launches++;
+  if (on_chip == 1) {
     // small alignment, single rank: every edge's whole search in one launch (k_opt_block); the
     // settings were written to d_opt_ctl_ by Execute, outside any captured graph
     ProfScope ps(this, kProfOptBlock, 64. * n_ops * static_cast<double>(P_));
     LaunchOptBlock(stream_, st, d_ops, n_ops, d_opt_ctl_.ptr, G);
+    return;
+  }
+  if (on_chip == 2) {
+    // large alignment, single rank, plain Brent: one thread-block cluster per edge (k_opt_cluster)
+    ProfScope ps(this, kProfOptCluster, 64. * n_ops * static_cast<double>(P_));
+    GP_CUDA(LaunchOptCluster(stream_, st, d_ops, n_ops, d_opt_ctl_.ptr, d_cluster_inv_perm_.ptr,
+                             d_cluster_wperm_.ptr, cluster_class_row_start_, *plan));
     return;
   }
   const OptParams prm = OptimizerParams(check_convergence);
@@ -1507,12 +1616,14 @@ void Engine::Execute(Program& prog) {
     grow(d_mtab_lik_, 16 * static_cast<int64_t>(prog.n_lik_total));
     if (grew) DropGraphs();  // captured graphs hold the old scratch addresses
   }
-  const bool want_graph =
-      !(cfg_.flags & BITO_GP_FLAG_NO_CUDA_GRAPHS) && (prog.n_opt_total == 0 || OptimizerOnChip()) &&
-      !profiling_;
-  // the round-per-launch optimiser counts its own launches; the on-chip one is one per level
-  const int64_t launches = prog.launches + (OptimizerOnChip() ? prog.n_opt_levels : 0);
-  if (prog.n_opt_total > 0 && OptimizerOnChip()) {
+  const bool opt_on_chip = prog.n_opt_total > 0 && ProgramOptimizesOnChip(prog);
+  const bool want_graph = !(cfg_.flags & BITO_GP_FLAG_NO_CUDA_GRAPHS) &&
+                          (prog.n_opt_total == 0 || opt_on_chip) && !profiling_;
+  // optimiser launches are counted where they are issued (RunOptimizer), except inside a graph
+  // replay, where every OptimizeBranchLength level is exactly one on-chip launch
+  const int64_t launches = prog.launches;
+  const int64_t graph_launches = prog.launches + (opt_on_chip ? prog.n_opt_levels : 0);
+  if (prog.n_opt_total > 0) {  // read by k_opt_block / k_opt_cluster, whichever levels use them
     OptControl ctl{};
     ctl.prm = OptimizerParams(optimization_count_ != 0);
     ctl.method = method_;
@@ -1531,13 +1642,16 @@ void Engine::Execute(Program& prog) {
       prog.graph_tried = true;
       cudaGraph_t graph = nullptr;
       GP_CUDA(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+      capturing_ = true;
       try {
         body();
       } catch (...) {
+        capturing_ = false;
         cudaStreamEndCapture(stream_, &graph);
         if (graph != nullptr) cudaGraphDestroy(graph);
         throw;
       }
+      capturing_ = false;
       GP_CUDA(cudaStreamEndCapture(stream_, &graph));
       cudaError_t err = cudaGraphInstantiate(&prog.graph, graph, 0);
       cudaGraphDestroy(graph);
@@ -1549,7 +1663,7 @@ void Engine::Execute(Program& prog) {
     if (prog.graph != nullptr) {
       GP_CUDA(cudaGraphLaunch(prog.graph, stream_));
       stats_.graph_launches++;
-      stats_.kernel_launches += launches;
+      stats_.kernel_launches += graph_launches;
       return;
     }
   }
@@ -1611,6 +1725,7 @@ void Engine::GetBranchLengthDifferences(double* out) {
 }
 void Engine::SetOptimizationMethod(int m) {
   if (m < 0 || m > 4) Fail("DAGBranchHandler::Optimization(): Invalid OptimizationMethod given.");
+  if (m != method_) DropGraphs();  // which optimiser kernel a captured level launches depends on it
   method_ = m;
 }
 void Engine::ResetOptimizationCount() {  // dag_branch_handler.hpp:49-52
@@ -2094,7 +2209,7 @@ void Engine::CopyGpcspData(int64_t src, int64_t dest) {  // gp_engine.cpp:401-40
 // ---- per-kernel timing with CUDA events on the launching stream (bench.py's roofline) ---------------
 const char* const kProfNames[kProfKinds] = {"k_zero", "k_scalar", "k_stationary", "k_prologue", "k_node",
                                             "k_rescale", "k_likelihood", "k_marginal", "k_reduce_partials",
-                                            "k_opt_prepare", "k_opt_eval", "k_opt_step", "k_opt_block"};
+                                            "k_opt_prepare", "k_opt_eval", "k_opt_step", "k_opt_block", "k_opt_cluster"};
 
 ProfScope::ProfScope(Engine* e, int kind, double bytes) : e_(e->profiling_ ? e : nullptr) {
   if (e_ == nullptr) return;
@@ -2166,6 +2281,10 @@ void Engine::GetStats(bito_gp_stats* out) {
   int64_t resident = 0;
   for (const PlvSlot& s : plvs_) resident += (s.kind == kPlvDense);
   stats_.plvs_resident = resident;
+  stats_.optimizer_scheme = last_opt_scheme_;
+  stats_.optimizer_cluster_size = last_opt_scheme_ == 2 ? last_opt_plan_.cluster_size : 0;
+  stats_.optimizer_cluster_threads = last_opt_scheme_ == 2 ? last_opt_plan_.threads : 0;
+  stats_.optimizer_edges_in_flight = last_opt_scheme_ == 2 ? last_opt_plan_.active_clusters : 0;
   *out = stats_;
 }
 

@@ -107,7 +107,8 @@ struct Program {
 
 enum ProfKind {
   kProfZero, kProfScalar, kProfStationary, kProfPrologue, kProfNode, kProfRescale, kProfLikelihood,
-  kProfMarginal, kProfReduce, kProfOptPrepare, kProfOptEval, kProfOptStep, kProfOptBlock, kProfKinds
+  kProfMarginal, kProfReduce, kProfOptPrepare, kProfOptEval, kProfOptStep, kProfOptBlock, kProfOptCluster,
+  kProfKinds
 };
 
 class Engine;
@@ -208,7 +209,8 @@ class Engine {
   void Execute(Program& prog);
   void ExecuteLevels(Program& prog, size_t first, size_t last);
   void RunOptimizeLevel(Program& prog, const Level& lv);
-  bool OptimizerOnChip() const;
+  int OptScheme(int n_ops, const OptClusterPlan** plan) const;
+  bool ProgramOptimizesOnChip(const Program& prog) const;
   OptParams OptimizerParams(bool check_convergence) const;
   void RunOptimizer(const OptOp* d_ops, int n_ops, int method, bool check_convergence);
   void FreeProgram(Program& p);
@@ -255,6 +257,16 @@ class Engine {
   DeviceArray<double> d_wperm_;
   DeviceArray<uint8_t> d_row_class_;
   int64_t P_perm_ = 0;  // patterns in weight-class order, classes padded to 256-pattern rows
+  // k_opt_cluster's layout: position -> pattern (-1 = padding), weights by position, class rows
+  DeviceArray<int32_t> d_cluster_inv_perm_;
+  DeviceArray<double> d_cluster_wperm_;
+  int32_t cluster_class_row_start_[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  std::vector<OptClusterPlan> cluster_plans_;  // every shape this device runs for this alignment
+  int opt_cluster_env_ = -1;          // BITO_GP_OPT_CLUSTER (-1: automatic)
+  int opt_cluster_threads_env_ = -1;  // BITO_GP_OPT_CLUSTER_THREADS
+  int last_opt_scheme_ = 0;           // scheme and shape of the most recent optimiser level
+  OptClusterPlan last_opt_plan_;
+  bool capturing_ = false;            // inside cudaStreamBeginCapture .. EndCapture
   bool coef_padding_zeroed_ = false;
   std::vector<double> host_weights_cache_;
   DeviceArray<OptOp> d_single_opt_;

@@ -12,6 +12,10 @@
 #include <cmath>
 #include <cstdlib>
 
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
+
 namespace bito_gp {
 
 __constant__ ModelConst c_model;
@@ -1226,6 +1230,196 @@ __global__ void __launch_bounds__(kTile)
   }
 }
 
+// ---- OptimizeBranchLength on chip (large alignments): one thread-block CLUSTER per edge -----------
+// At 1e5 patterns the ratio stream of an edge (8 B per pattern, see k_opt_prepare_ratio) is ~1 MB:
+// too big for one SM, but it fits the shared memory of a cluster of 8-16 SMs. The cluster reads the
+// edge's two PLVs from HBM exactly once (64 B per pattern, the algorithmic minimum of SURVEY 8d),
+// keeps rho distributed over its blocks' shared memory, and runs the whole Brent search there: each
+// evaluation is a pass over shared memory, a block reduction, one 8-byte store per peer block over
+// distributed shared memory and one cluster barrier; every block then takes the (bitwise
+// identical) optimiser decision itself, so there is no broadcast. The round-per-launch scheme
+// re-streams rho from HBM for each of the ~16 evaluations instead.
+// Pattern order: the cluster weight-class layout of Engine::BuildWeightClasses (classes padded to
+// rows of kClusterThreads patterns; padding has inv_perm = -1 and contributes rho = 0).
+// c0, c1 = the two eigen-group coefficients of L_p(t) for one pattern (see k_opt_prepare_ratio);
+// rho = c1 / c0.
+__device__ __forceinline__ void ratio_coefficients(const V4& r, const V4& c, double& rho, double& c0_out) {
+  double c0 = 0., c1 = 0.;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const double rv = r.a * c_model.V[k] + r.b * c_model.V[4 + k] + r.c * c_model.V[8 + k] +
+                      r.d * c_model.V[12 + k];
+    const double vp = c_model.Vinv[4 * k] * c.a + c_model.Vinv[4 * k + 1] * c.b +
+                      c_model.Vinv[4 * k + 2] * c.c + c_model.Vinv[4 * k + 3] * c.d;
+    const double term = rv * vp;
+    if (c_model.group[k] == 0) c0 += term; else c1 += term;
+  }
+  rho = c0 != 0. ? c1 / c0 : 0.;
+  c0_out = c0;
+}
+
+// Sum of `v` over every thread of every block of the cluster, returned to all threads. s_slots is
+// double-buffered by `parity`: a block can only be one barrier ahead of its peers.
+template <int T>
+__device__ __forceinline__ double cluster_sum(cg::cluster_group& cluster, double v, double* s_warp,
+                                              double (*s_slots)[kMaxOptCluster], int parity) {
+#pragma unroll
+  for (int sh = 16; sh > 0; sh >>= 1) v += __shfl_down_sync(0xffffffffu, v, sh);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) s_warp[warp] = v;
+  __syncthreads();
+  const unsigned n_blocks = cluster.num_blocks();
+  if (warp == 0) {
+    double t = lane < T / 32 ? s_warp[lane] : 0.;
+#pragma unroll
+    for (int sh = 16; sh > 0; sh >>= 1) t += __shfl_down_sync(0xffffffffu, t, sh);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (lane < static_cast<int>(n_blocks))  // lane k hands this block's sum to block k
+      *cluster.map_shared_rank(&s_slots[parity][cluster.block_rank()], lane) = t;
+  }
+  cluster.sync();  // release/acquire: the remote stores above are visible to every block
+  double total = 0.;
+  for (unsigned k = 0; k < n_blocks; ++k) total += s_slots[parity][k];  // same order in every block
+  return total;
+}
+
+// T = threads per block: 256 (several blocks per SM: many edges resident, for levels with many
+// edges) or 1024 (one edge spread over as many threads as a cluster has: the shortest time per
+// edge, for the one-or-two-edge levels of a Gauss-Seidel sweep). Rows are kClusterThreads = 256
+// patterns whatever T is; a block of T threads walks T / 256 rows at a time.
+template <int T>
+__global__ void __launch_bounds__(T, T == 256 ? 3 : 1)
+    k_opt_cluster(DeviceState st, const OptOp* __restrict__ ops, const OptControl* __restrict__ ctl,
+                  const int32_t* __restrict__ inv_perm, const double* __restrict__ wperm,
+                  OptClusterLayout lay) {
+  constexpr int S = T / kClusterThreads;           // rows walked per step
+  constexpr int kStep = S * kClusterThreads;       // = T positions
+  extern __shared__ __align__(16) double s_rho[];  // rows_per_block x kClusterThreads
+  __shared__ OptState s_state;
+  __shared__ double s_warp[T / 32];
+  __shared__ double s_slots[2][kMaxOptCluster];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = static_cast<int>(cluster.block_rank());
+  const int o = blockIdx.x / cluster.num_blocks();
+  const OptOp op = ops[o];
+  const OptParams prm = ctl->prm;
+  if (threadIdx.x == 0) opt_init(s_state, st, prm, ctl->method, op);
+  __syncthreads();
+  // converged edges (dag_branch_handler.cpp:126-131): the same decision in every block
+  if (s_state.done) return;
+  const int row0 = rank * lay.rows_per_block;
+  const int n_rows = max(0, min(lay.rows_per_block, lay.rows_total - row0));
+  const int64_t q0 = static_cast<int64_t>(row0) * kClusterThreads;
+  const int sub = threadIdx.x / kClusterThreads;  // this thread's rows: sub, sub + S, sub + 2 S, ...
+  // the edge's PLVs, once: rho into shared memory, K_e = sum_p w_p log c0_p. Two rows per trip
+  // with all four 256-bit loads issued before the first use (padding reads pattern 0 and is masked).
+  double k_part = 0.;
+  for (int r = sub; r < n_rows; r += 2 * S) {
+    const int i0 = r * kClusterThreads + (threadIdx.x & (kClusterThreads - 1)), i1 = i0 + kStep;
+    const bool two = r + S < n_rows;
+    const int32_t pa = inv_perm[q0 + i0];
+    const int32_t pb = two ? inv_perm[q0 + i1] : -1;
+    const V4 ra = load_plv(op.parent, max(pa, 0));
+    const V4 ca = load_plv(op.child, max(pa, 0));
+    const V4 rb = load_plv(op.parent, max(pb, 0));
+    const V4 cb = load_plv(op.child, max(pb, 0));
+    double rho, c0;
+    ratio_coefficients(ra, ca, rho, c0);
+    if (pa >= 0) k_part += wperm[q0 + i0] * log(c0);
+    s_rho[i0] = pa >= 0 ? rho : 0.;
+    if (two) {
+      ratio_coefficients(rb, cb, rho, c0);
+      if (pb >= 0) k_part += wperm[q0 + i1] * log(c0);
+      s_rho[i1] = pb >= 0 ? rho : 0.;
+    }
+  }
+  int round = 0;
+  const double edge_const = cluster_sum<T>(cluster, k_part, s_warp, s_slots, (round++) & 1);
+  // this thread's rows by weight class: first row >= the class's first row that is = sub (mod S)
+  int seg_begin[8], seg_end[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int b = min(max(lay.class_row_start[c] - row0, 0), n_rows);
+    seg_begin[c] = b + ((sub - b) % S + S) % S;
+    seg_end[c] = min(max(lay.class_row_start[c + 1] - row0, 0), n_rows);
+  }
+  const double* mine = s_rho + (threadIdx.x & (kClusterThreads - 1));
+  for (;;) {
+    const double x = s_state.x_ratio;
+    double prod = 1., slow = 0.;
+    int esum = 0;
+    // weight 1: the bulk of any alignment; four independent chains, renormalised as they go
+    {
+      double p0 = 1., p1 = 1., p2 = 1., p3 = 1.;
+      int r = seg_begin[0], trip = 0;
+      for (; r + 3 * S < seg_end[0]; r += 4 * S, ++trip) {
+        const double t0 = fma(mine[(r + 0 * S) * kClusterThreads], x, 1.0);
+        const double t1 = fma(mine[(r + 1 * S) * kClusterThreads], x, 1.0);
+        const double t2 = fma(mine[(r + 2 * S) * kClusterThreads], x, 1.0);
+        const double t3 = fma(mine[(r + 3 * S) * kClusterThreads], x, 1.0);
+        double m;
+        int e;
+        if (split_positive(t0, m, e)) { p0 *= m; esum += e; } else slow += log(t0);
+        if (split_positive(t1, m, e)) { p1 *= m; esum += e; } else slow += log(t1);
+        if (split_positive(t2, m, e)) { p2 *= m; esum += e; } else slow += log(t2);
+        if (split_positive(t3, m, e)) { p3 *= m; esum += e; } else slow += log(t3);
+        if ((trip & 7) == 7) {  // every 8th trip: each chain >= 2^-9 so far
+          p0 *= p1;
+          p2 *= p3;
+          p0 *= p2;  // >= 2^-36
+          p1 = p2 = p3 = 1.;
+          if (split_positive(p0, m, e)) { p0 = m; esum += e; }
+        }
+      }
+      for (; r < seg_end[0]; r += S) {
+        const double t0 = fma(mine[r * kClusterThreads], x, 1.0);
+        double m;
+        int e;
+        if (split_positive(t0, m, e)) { p0 *= m; esum += e; } else slow += log(t0);
+      }
+      prod = (p0 * p1) * (p2 * p3);  // >= 2^-40: normal
+      double m;
+      int e;
+      if (split_positive(prod, m, e)) { prod = m; esum += e; }
+    }
+#pragma unroll
+    for (int cls = 1; cls < 7; ++cls) {  // weights 2..7: (m 2^e)^w by squaring
+      const int wi = cls + 1;
+      for (int r = seg_begin[cls]; r < seg_end[cls]; r += S) {
+        const double tk = fma(mine[r * kClusterThreads], x, 1.0);
+        double m;
+        int e;
+        if (split_positive(tk, m, e)) {
+          const double m2 = m * m;
+          double mw = (wi & 1) ? m : 1.;
+          if (wi & 2) mw *= m2;
+          if (wi & 4) mw *= m2 * m2;
+          prod *= mw;
+          esum += e * wi;
+          if (split_positive(prod, m, e)) { prod = m; esum += e; }
+        } else {
+          slow += static_cast<double>(wi) * log(tk);
+        }
+      }
+    }
+    for (int r = seg_begin[7]; r < seg_end[7]; r += S) {  // general weights: explicit log
+      const double w = wperm[q0 + r * kClusterThreads + (threadIdx.x & (kClusterThreads - 1))];
+      if (w != 0.) slow += w * log(fma(mine[r * kClusterThreads], x, 1.0));
+    }
+    const double f = log(prod) + static_cast<double>(esum) * 0.6931471805599453094 + slow;
+    const double total = cluster_sum<T>(cluster, f, s_warp, s_slots, (round++) & 1);
+    if (threadIdx.x == 0) {
+      const double ll = total + s_state.ll_offset + edge_const +
+                        st.total_weight * c_model.group_lambda[0] * s_state.t_eval;
+      opt_advance(s_state, st, prm, ll, 0., 0.);
+      if (s_state.done && rank == 0)
+        atomicAdd(st.feval_total, static_cast<unsigned long long>(s_state.evals));
+    }
+    __syncthreads();
+    if (s_state.done) break;  // every block of the cluster leaves in the same round
+  }
+}
+
 // ---- utilities ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kTile)
     k_export_plv(DeviceState st, PlvRef src, double* __restrict__ out) {
@@ -1474,6 +1668,82 @@ void LaunchOptBlock(cudaStream_t s, const DeviceState& st, const OptOp* ops, int
     opted_in = smem;
   }
   k_opt_block<<<n_ops, kTile, smem, s>>>(st, ops, ctl);
+}
+// One cluster shape of the on-chip optimiser: `threads` per block (256 or 1024), `cluster_size`
+// blocks per edge. Fails when the edge's rho rows do not fit the cluster's shared memory or the
+// device cannot place such a cluster; active_clusters = edges resident on the device at once.
+template <int T>
+static bool PlanOptClusterT(int64_t rows_total, int c, OptClusterPlan* plan) {
+  static bool attrs_set = false;
+  if (!attrs_set) {
+    if (cudaFuncSetAttribute(k_opt_cluster<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(kOptClusterMaxSharedBytes)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_opt_cluster<T>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) !=
+            cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    attrs_set = true;
+  }
+  const int64_t rpb = (rows_total + c - 1) / c;
+  const size_t smem = static_cast<size_t>(rpb) * kClusterThreads * sizeof(double);
+  if (smem > kOptClusterMaxSharedBytes) return false;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(c) * 64u);
+  cfg.blockDim = dim3(T);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = static_cast<unsigned>(c);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, k_opt_cluster<T>, &cfg) != cudaSuccess || n < 1) {
+    cudaGetLastError();
+    return false;
+  }
+  plan->threads = T;
+  plan->cluster_size = c;
+  plan->rows_per_block = static_cast<int>(rpb);
+  plan->rows_total = static_cast<int>(rows_total);
+  plan->shared_bytes = smem;
+  plan->active_clusters = n;
+  return true;
+}
+bool PlanOptCluster(int64_t rows_total, int threads, int cluster_size, OptClusterPlan* plan) {
+  *plan = OptClusterPlan();
+  if (rows_total <= 0 || rows_total > (int64_t(1) << 30)) return false;
+  if (cluster_size < 1 || cluster_size > kMaxOptCluster || (cluster_size & (cluster_size - 1)))
+    return false;
+  if (threads == 256) return PlanOptClusterT<256>(rows_total, cluster_size, plan);
+  if (threads == 1024) return PlanOptClusterT<1024>(rows_total, cluster_size, plan);
+  return false;
+}
+cudaError_t LaunchOptCluster(cudaStream_t s, const DeviceState& st, const OptOp* ops, int n_ops,
+                             const OptControl* ctl, const int32_t* inv_perm, const double* wperm,
+                             const int32_t class_row_start[9], const OptClusterPlan& plan) {
+  if (n_ops == 0) return cudaSuccess;
+  OptClusterLayout lay;
+  for (int c = 0; c < 9; ++c) lay.class_row_start[c] = class_row_start[c];
+  lay.rows_total = plan.rows_total;
+  lay.rows_per_block = plan.rows_per_block;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(n_ops) * static_cast<unsigned>(plan.cluster_size));
+  cfg.blockDim = dim3(static_cast<unsigned>(plan.threads));
+  cfg.dynamicSmemBytes = plan.shared_bytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = static_cast<unsigned>(plan.cluster_size);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (plan.threads == 1024)
+    return cudaLaunchKernelEx(&cfg, k_opt_cluster<1024>, st, ops, ctl, inv_perm, wperm, lay);
+  return cudaLaunchKernelEx(&cfg, k_opt_cluster<256>, st, ops, ctl, inv_perm, wperm, lay);
 }
 int64_t OptPrepareTileGroups(int n_ops, int64_t P) {
   const int64_t tiles = TilesFor(P);

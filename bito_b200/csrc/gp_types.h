@@ -13,6 +13,9 @@ namespace bito_gp {
 constexpr int kTile = 256;          // patterns per thread block (one pattern per thread)
 constexpr int kItemChunk = 64;      // transition matrices staged in shared memory at a time
 constexpr int kMaxEigenGroups = 4;  // distinct eigenvalues of the substitution model
+constexpr int kClusterThreads = 256;  // k_opt_cluster block size = patterns per rho row
+constexpr int kMaxOptCluster = 16;     // largest (non-portable) thread-block cluster on sm_100
+constexpr size_t kOptClusterMaxSharedBytes = 200 * 1024;  // rho rows of one block of a cluster
 constexpr int kOptPatternsPerThread = 8;  // k_opt_eval_ratio: patterns one thread folds into one log
 
 // How a PLV operand is stored in HBM.
@@ -224,6 +227,22 @@ struct OptControl {
   OptParams prm;
   int32_t method;
   int32_t n_derivatives;
+};
+
+// k_opt_cluster: rho rows (kClusterThreads patterns each, one weight class per row) of an edge are
+// dealt to the blocks of its cluster, rows_per_block consecutive rows each.
+struct OptClusterLayout {
+  int32_t class_row_start[9];  // rows of class c: [class_row_start[c], class_row_start[c + 1])
+  int32_t rows_total;
+  int32_t rows_per_block;
+};
+struct OptClusterPlan {
+  int threads = 0;          // threads per block: 256 or 1024
+  int cluster_size = 0;     // blocks per cluster (0: the cluster path is not available)
+  int rows_per_block = 0;
+  int rows_total = 0;
+  size_t shared_bytes = 0;
+  int active_clusters = 0;  // edges resident on the chip at once (cudaOccupancyMaxActiveClusters)
 };
 
 }  // namespace bito_gp

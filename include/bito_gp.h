@@ -242,6 +242,14 @@ typedef struct bito_gp_stats {
   double algorithmic_bytes_last;/* SURVEY 8(d) bytes per local pattern x patterns, last program */
   double last_process_ms;       /* device time of the last process_operations (events)   */
   int64_t device_status_bits;   /* OR of assert violations seen so far (see gp_types.h)  */
+  /* How the most recent level of OptimizeBranchLength ops ran: 0 = one launch per objective round
+   * over all edges of the level (rho streamed from HBM), 1 = one thread block per edge, 2 = one
+   * thread-block cluster per edge (rho in distributed shared memory). The engine picks per level:
+   * on-chip searches for levels of few edges, streaming for thousands of edges at 1e5 patterns. */
+  int64_t optimizer_scheme;
+  int64_t optimizer_cluster_size;    /* blocks per cluster for scheme 2, else 0              */
+  int64_t optimizer_cluster_threads; /* threads per block for scheme 2, else 0               */
+  int64_t optimizer_edges_in_flight; /* clusters resident on the device at once, scheme 2   */
 } bito_gp_stats;
 BITO_GP_API int bito_gp_get_stats(bito_gp_engine* e, bito_gp_stats* out);
 

@@ -316,6 +316,130 @@ def test_weight_classes_general_weights_match_oracle(cuda_engine_lib):
         assert np.max(np.abs(gpu.get_branch_lengths() - cpu2.branch_lengths())) <= BL_ATOL
 
 
+@pytest.fixture
+def cluster_size(request, monkeypatch):
+    """BITO_GP_OPT_CLUSTER=N makes the engine use the cluster-resident optimiser (k_opt_cluster) with
+    clusters of exactly N thread blocks, even where a single block could hold the alignment; "NxT" also
+    fixes the threads per block (256: many edges resident; 1024: one edge spread wide, Gauss-Seidel levels)."""
+    c, _, t = str(request.param).partition("x")
+    monkeypatch.setenv("BITO_GP_OPT_CLUSTER", c)
+    if t:
+        monkeypatch.setenv("BITO_GP_OPT_CLUSTER_THREADS", t)
+    return request.param
+
+
+def _launches_of(engine, name):
+    return sum(k["launches"] for k in engine.kernel_profile() if k["name"] == name)
+
+
+@pytest.mark.parametrize("cluster_size", [1, 2, 8, 16, "1x1024", "16x1024"], indirect=True)
+@pytest.mark.parametrize("case", ALL_CASES)
+def test_cluster_optimizer_sweeps_match_reference(cuda_engine_lib, case, cluster_size):
+    """The one-cluster-per-edge Brent search (rho in distributed shared memory, one cluster barrier per
+    objective evaluation) against the reference's Gauss-Seidel sweeps, every cluster shape; with more
+    blocks than rho rows some blocks of the cluster own no pattern at all."""
+    fx = Fixture(case)
+    if "brent" not in fx.methods:
+        pytest.skip("fixture has no plain-Brent sweep")
+    for ti in range(len(fx.thresholds)):
+        with make_cuda(fx, ti) as e:
+            check_sweeps(e, fx, ti, "brent")
+            st = e.stats()
+        assert st["objective_evaluations"] > 0 and st["graph_launches"] > 0
+    # the kernel that ran really was the cluster one
+    with make_cuda(fx, 0) as e:
+        e.set_optimization_method("brent")
+        e.set_profiling(True)
+        e.process_operations(*fx.ops("populate_plvs"))
+        e.process_operations(*fx.ops("branch_length_optimization"))
+        assert _launches_of(e, "k_opt_cluster") > 0
+        assert _launches_of(e, "k_opt_block") == 0 and _launches_of(e, "k_opt_eval") == 0
+
+
+@pytest.mark.parametrize("cluster_size", [2, 16, "4x1024"], indirect=True)
+@pytest.mark.parametrize("taxa,patterns,thr", [(4, 1, 1e-40), (7, 255, 1e-40), (9, 256, 0.5), (12, 257, 0.9),
+                                                (30, 3001, 0.7), (64, 20000, 1e-40)])
+def test_cluster_optimizer_random_trees_match_oracle(cuda_engine_lib, taxa, patterns, thr, cluster_size):
+    """Ragged row edges (P = 1, 255, 256, 257, ...) and a batched optimisation of every edge at once
+    through the cluster path (Brent) - Newton on the same engine takes the per-block / round path."""
+    from oracle.port_engine import PortEngine
+    rng = np.random.default_rng(taxa * 1000 + patterns)
+    pb = _random_problem(rng, taxa, patterns)
+    site_count = int(pb["weights"].sum())
+    cpu = PortEngine(pb["symbols"], pb["weights"], site_count, pb["node_count"], pb["edge_count"],
+                     rescaling_threshold=thr)
+    _random_tree_case(pb, cpu, site_count, thr, 0)
+
+
+@pytest.mark.parametrize("cluster_size", [1, 4, 16, "2x1024", "16x1024"], indirect=True)
+def test_cluster_optimizer_weight_classes(cuda_engine_lib, cluster_size):
+    """Every weight class of the cluster layout (1..7 by squaring, general weights through log, padding
+    rows between classes) against the oracle, then new weights on the same engine."""
+    from bito_b200.gp_engine import GPEngine
+    from oracle.port_engine import PortEngine
+    rng = np.random.default_rng(12)
+    pb = _random_problem(rng, 10, 2500)
+    w = pb["weights"].copy()
+    w[::5] = rng.integers(2, 8, size=w[::5].size)         # classes 2..7
+    w[3::7] = rng.uniform(0.25, 3.5, size=w[3::7].size)   # non-integer
+    w[5::31] = rng.integers(8, 400, size=w[5::31].size)   # large multiplicities
+    site_count = int(round(w.sum()))
+    cpu = PortEngine(pb["symbols"], w, site_count, pb["node_count"], pb["edge_count"])
+    with GPEngine(pb["symbols"], w, site_count, pb["node_count"], pb["edge_count"]) as gpu:
+        gpu.set_profiling(True)
+        for e in (cpu, gpu):
+            e.set_branch_lengths(pb["branch_lengths"])
+            e.process_operations(*pb["populate"])
+            e.process_operations(*pb["likelihoods"])
+            e.process_operations(*pb["optimize"])
+        assert _launches_of(gpu, "k_opt_cluster") > 0
+        assert rel_err(gpu.get_per_gpcsp_log_likelihoods(), cpu.per_gpcsp_log_likelihoods()) <= LL_RTOL
+        assert np.max(np.abs(gpu.get_branch_lengths() - cpu.branch_lengths())) <= BL_ATOL
+        w2 = np.ones_like(w)
+        cpu2 = PortEngine(pb["symbols"], w2, int(w2.sum()), pb["node_count"], pb["edge_count"])
+        gpu.set_site_patterns(pb["symbols"], w2)
+        for e in (cpu2, gpu):
+            e.set_branch_lengths(pb["branch_lengths"])
+            e.reset_optimization_count()
+            e.process_operations(*pb["populate"])
+            e.process_operations(*pb["optimize"])
+        assert np.max(np.abs(gpu.get_branch_lengths() - cpu2.branch_lengths())) <= BL_ATOL
+
+
+def test_optimizer_scheme_is_chosen_per_level(cuda_engine_lib):
+    """Without any override the engine picks per level: DS1-sized alignments run one block per edge; at 20 000
+    patterns (too big for one block) a level of 126 edges runs one cluster per edge (latency per edge beats
+    streaming rho 16 times at this size) and still replays as a CUDA graph, and takes the oracle's branch lengths;
+    Newton has no cluster kernel and falls back to rounds."""
+    from bito_b200.gp_engine import GPEngine
+    from oracle.port_engine import PortEngine
+    rng = np.random.default_rng(64 * 1000 + 20000)
+    pb = _random_problem(rng, 64, 20000)
+    site_count = int(pb["weights"].sum())
+    cpu = PortEngine(pb["symbols"], pb["weights"], site_count, pb["node_count"], pb["edge_count"])
+    with GPEngine(pb["symbols"], pb["weights"], site_count, pb["node_count"], pb["edge_count"]) as gpu:
+        for e in (cpu, gpu):
+            e.set_branch_lengths(pb["branch_lengths"])
+            e.set_optimization_method("brent")
+            e.process_operations(*pb["populate"])
+            e.process_operations(*pb["optimize"])
+        st = gpu.stats()
+        assert st["optimizer_scheme"] == 2 and st["optimizer_cluster_size"] >= 1 and st["graph_launches"] >= 2
+        assert np.max(np.abs(gpu.get_branch_lengths() - cpu.branch_lengths())) <= BL_ATOL
+        gpu.set_optimization_method("newton")  # no cluster kernel for Newton: rounds, launched directly
+        gpu.process_operations(*pb["populate"])
+        before = gpu.stats()["graph_launches"]
+        gpu.process_operations(*pb["optimize"])
+        st = gpu.stats()
+        assert st["optimizer_scheme"] == 0 and st["graph_launches"] == before
+    fx = Fixture("ds1")
+    with make_cuda(fx, 0) as e:
+        e.set_optimization_method("brent")
+        e.process_operations(*fx.ops("populate_plvs"))
+        e.process_operations(*fx.ops("branch_length_optimization"))
+        assert e.stats()["optimizer_scheme"] == 1
+
+
 def test_bench_size_properties(cuda_engine_lib):
     """BASELINE.json configs[3] at full size (200 taxa x 100 000 patterns, 3474 nodes, 8369 edges),
     where the CPU oracle is too slow to be the checker: size-independent properties instead.
