@@ -343,10 +343,14 @@ def measure(args, name, rank, world, local_rank, extras=True):
 
     # ---- one branch-length optimisation sweep (reported beside the pass; not part of `value`) ----
     sweep = None
-    if not args.no_sweep:
-        blo = wl.ops("batched_branch_length_optimization")
-        n_edges_opt = blo[0].shape[0]
-        sweep_runs = []
+    sweep_reference_schedule = None
+    scheme_names = {0: "rounds: one launch per objective round over all edges of a level, rho (8 B/pattern) streamed from HBM",
+                    1: "on chip: one thread block per edge, coefficients in shared memory",
+                    2: "on chip: one thread-block cluster per edge, rho in distributed shared memory"}
+
+    def time_sweep(op_list, schedule):
+        n_edges_opt = int((op_list[0][:, 0] == 5).sum())  # gp_operation.OPTIMIZE_BRANCH_LENGTH
+        runs = []
         for _ in range(2):  # same starting point twice: the first run also compiles the list and allocates
             engine.set_branch_lengths(bl_pinned.numpy())
             engine.reset_optimization_count()
@@ -355,28 +359,35 @@ def measure(args, name, rank, world, local_rank, extras=True):
             f0 = engine.stats()["objective_evaluations"]
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record(stream)
-            engine.process_operations(*blo)
+            engine.process_operations(*op_list)
             ev1.record(stream)
             barrier()
-            sweep_runs.append((max_over_ranks(ev0.elapsed_time(ev1)), engine.stats()["objective_evaluations"] - f0))
-        sweep_ms, fevals = min(sweep_runs)
-        device_step()
+            runs.append((max_over_ranks(ev0.elapsed_time(ev1)), engine.stats()["objective_evaluations"] - f0))
+        ms, fevals = min(runs)
         st = engine.stats()
-        scheme = {0: "rounds: one launch per objective round over all edges, rho (8 B/pattern) streamed from HBM",
-                  1: "on chip: one thread block per edge, coefficients in shared memory",
-                  2: "on chip: one thread-block cluster per edge, rho in distributed shared memory"}[st["optimizer_scheme"]]
-        # HBM traffic as executed: the two PLVs of every edge once; the round scheme also writes rho once
-        # and re-reads it for every objective evaluation
+        device_step()
+        # HBM traffic as executed by the optimiser: the two PLVs of every edge once; the round scheme also
+        # writes rho once and re-reads it for every objective evaluation
         executed = 64.0 * n_edges_opt * P_local + (8.0 * (fevals + n_edges_opt) * P_local if st["optimizer_scheme"] == 0 else 0.0)
-        sweep = {"schedule": "batched (all edges in one level, Brent)", "optimizer": scheme,
-                 "cluster_size": st["optimizer_cluster_size"], "edges_in_flight": st["optimizer_edges_in_flight"],
-                 "ms": sweep_ms, "ms_first_call": sweep_runs[0][0],
-                 "edges": n_edges_opt, "objective_evaluations": fevals,
-                 "algorithmic_bytes": 64.0 * n_edges_opt * P_local,
-                 "frac_of_hbm_peak": 64.0 * n_edges_opt * P_local / (sweep_ms * 1e-3) / 1e9 / peak_gbs,
-                 "as_executed_bytes": executed,
-                 "as_executed_frac_of_hbm_peak": executed / (sweep_ms * 1e-3) / 1e9 / peak_gbs,
-                 "log_marginal_after": engine.get_log_marginal_likelihood()}
+        return {"schedule": schedule, "optimizer": scheme_names[st["optimizer_scheme"]],
+                "cluster_size": st["optimizer_cluster_size"], "cluster_threads": st["optimizer_cluster_threads"],
+                "edges_in_flight": st["optimizer_edges_in_flight"], "levels": st["levels_last"],
+                "ms": ms, "ms_first_call": runs[0][0], "edges": n_edges_opt, "objective_evaluations": fevals,
+                "algorithmic_bytes": 64.0 * n_edges_opt * P_local,
+                "frac_of_hbm_peak": 64.0 * n_edges_opt * P_local / (ms * 1e-3) / 1e9 / peak_gbs,
+                "as_executed_bytes": executed,
+                "as_executed_frac_of_hbm_peak": executed / (ms * 1e-3) / 1e9 / peak_gbs,
+                "log_marginal_after": engine.get_log_marginal_likelihood()}
+
+    if not args.no_sweep:
+        sweep = time_sweep(wl.ops("batched_branch_length_optimization"), "batched (all edges in one level, Brent)")
+        if world == 1:
+            # the reference's own schedule (GPDAG::BranchLengthOptimization, gp_dag.cpp:52-176): a depth-first
+            # Gauss-Seidel walk, one or two edges per dependency level, PLV updates between them - bound by
+            # latency per edge, not by HBM (its `frac_of_hbm_peak` counts the optimiser's PLV reads only)
+            sweep_reference_schedule = time_sweep(
+                wl.ops("branch_length_optimization"),
+                "GPDAG::BranchLengthOptimization (Gauss-Seidel; optimise + PLV updates interleaved, Brent)")
 
     # ---- CPU baseline: the reference's own engine on this box's host cores (rank 0, N = 1) -------
     cpu_baseline = None
@@ -408,6 +419,7 @@ def measure(args, name, rank, world, local_rank, extras=True):
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "sweep": sweep,
+            "sweep_reference_schedule": sweep_reference_schedule,
             "single_gpu_same_shard": standalone,
             "log_marginal": log_marginal,
             "full_pass_ms": ms_per_step,
@@ -446,7 +458,7 @@ def main():
         other = measure(args, SINGLE_B200_WORKLOAD, rank, world, local_rank, extras=False)
         if line is not None and other is not None:
             line["config3_single_b200"] = {k: other[k] for k in ("value", "unit", "ms_per_step", "e2e", "config",
-                                                                 "roofline", "sweep", "log_marginal")}
+                                                                 "roofline", "sweep", "sweep_reference_schedule", "log_marginal")}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

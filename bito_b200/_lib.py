@@ -82,6 +82,7 @@ SIGNATURES = {
     "bito_gp_set_null_prior": (_int, [_vp]),
     "bito_gp_process_operations": (_int, [_vp, _vp, _i64, _vp, _i64]),
     "bito_gp_set_branch_lengths": (_int, [_vp, _vp]),
+    "bito_gp_set_branch_lengths_range": (_int, [_vp, _i64, _i64, _vp]),
     "bito_gp_set_branch_lengths_to_constant": (_int, [_vp, _f64]),
     "bito_gp_set_branch_lengths_to_default": (_int, [_vp]),
     "bito_gp_get_branch_lengths": (_int, [_vp, _i64, _i64, _vp]),

@@ -88,6 +88,11 @@ int bito_gp_set_branch_lengths(bito_gp_engine* e, const double* branch_lengths) 
   ENGINE_OR_FAIL(e);
   return Guard([&] { e->impl.SetBranchLengths(branch_lengths); });
 }
+int bito_gp_set_branch_lengths_range(bito_gp_engine* e, int64_t start, int64_t length,
+                                     const double* branch_lengths) {
+  ENGINE_OR_FAIL(e);
+  return Guard([&] { e->impl.SetBranchLengthsRange(start, length, branch_lengths); });
+}
 int bito_gp_set_branch_lengths_to_constant(bito_gp_engine* e, double branch_length) {
   ENGINE_OR_FAIL(e);
   return Guard([&] { e->impl.SetBranchLengthsToConstant(branch_length); });

@@ -1431,8 +1431,7 @@ OptParams Engine::OptimizerParams(bool check_convergence) const {
 // (k_opt_cluster: plain Brent on a two-eigenvalue model), *plan = its shape.
 // The on-chip searches are bound by latency per edge (~16 dependent objective evaluations), the
 // round scheme by HBM bandwidth: few edges -> spread each over as many SMs as a cluster has; a level
-// with thousands of edges at 1e5 patterns -> stream. The constants below are B200 measurements
-// (profiles/r01f_*: 3-4 us per on-chip evaluation, 2.5 us per two-row load trip, 5.2 TB/s streamed).
+// with thousands of edges at 1e5 patterns -> stream.
 int Engine::OptScheme(int n_ops, const OptClusterPlan** plan) const {
   if (plan != nullptr) *plan = nullptr;
   if (n_ranks_ != 1 || P_ <= 0 || (cfg_.flags & BITO_GP_FLAG_NO_ONCHIP_OPTIMIZER)) return 0;
@@ -1442,23 +1441,30 @@ int Engine::OptScheme(int n_ops, const OptClusterPlan** plan) const {
   if (!(cluster_ok && forced) && OptBlockSharedBytes(P_, n_eigen_groups_) <= kOptBlockMaxSharedBytes)
     return 1;
   if (!cluster_ok) return 0;
-  const double n_evals = 16.;
+  // Cost model, microseconds, fitted to B200 timings (profiles/r01g_sweep_variants_*.log):
+  //  on chip, per edge: two-row load trips of ~2.5 us, then ~14.5 dependent objective evaluations of
+  //  2.4 us (reduction + cluster barrier + optimiser step) + 0.05 us per rho row a thread walks,
+  //  +0.5 us with 1024-thread blocks (wider barriers); x1.4 once edges queue for SMs (co-resident
+  //  clusters contend); streamed: 64 + 8 + 8 x evaluations bytes per pattern at 5.5 TB/s plus ~8 us
+  //  of launches per round and the host's look at the active-edge counter.
+  const double n_evals = 14.5;
   double best = 0.;
   const OptClusterPlan* best_plan = nullptr;
   for (const OptClusterPlan& c : cluster_plans_) {
     const int rows_per_thread = (c.rows_per_block * kClusterThreads + c.threads - 1) / c.threads;
     const double load_us = 1.0 + 2.5 * ((rows_per_thread + 1) / 2);
-    const double eval_us = 3.2 + 0.06 * rows_per_thread;
+    const double eval_us = 2.4 + 0.05 * rows_per_thread + (c.threads > 256 ? 0.5 : 0.);
     const double waves = std::ceil(static_cast<double>(n_ops) / c.active_clusters);
-    const double us = waves * (load_us + n_evals * eval_us);
+    const double us = waves * (load_us + n_evals * eval_us) * (waves > 1. ? 1.4 : 1.);
     if (best_plan == nullptr || us < best) {
       best = us;
       best_plan = &c;
     }
   }
   if (!forced) {
-    const double streamed_bytes = static_cast<double>(n_ops) * static_cast<double>(P_) * (64. + 8. + 8. * n_evals);
-    const double rounds_us = streamed_bytes / 5.2e6 + 26. * 10. + 60.;
+    const double streamed_bytes =
+        static_cast<double>(n_ops) * static_cast<double>(P_) * (64. + 8. + 8. * n_evals);
+    const double rounds_us = streamed_bytes / 5.5e6 + n_evals * 8. + 30.;
     if (rounds_us < best) return 0;
   }
   if (plan != nullptr) *plan = best_plan;
@@ -1702,6 +1708,14 @@ void Engine::ProcessOperations(const bito_gp_op* ops, int64_t n, const int64_t* 
 void Engine::SetBranchLengths(const double* bl) {
   Activate();
   GP_CUDA(cudaMemcpyAsync(d_bl_.ptr, bl, gpcsp_count_ * sizeof(double), cudaMemcpyHostToDevice,
+                          stream_));
+  GP_CUDA(cudaStreamSynchronize(stream_));
+}
+void Engine::SetBranchLengthsRange(int64_t start, int64_t length, const double* bl) {
+  Activate();
+  if (start < 0 || length < 0 || start + length > padded_gpcsp_count())
+    Fail("Requested range of BranchLengths is out-of-range.");
+  GP_CUDA(cudaMemcpyAsync(d_bl_.ptr + start, bl, length * sizeof(double), cudaMemcpyHostToDevice,
                           stream_));
   GP_CUDA(cudaStreamSynchronize(stream_));
 }

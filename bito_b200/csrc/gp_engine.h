@@ -141,6 +141,7 @@ class Engine {
   void ProcessOperations(const bito_gp_op* ops, int64_t n, const int64_t* vec, int64_t vec_len);
 
   void SetBranchLengths(const double* bl);
+  void SetBranchLengthsRange(int64_t start, int64_t length, const double* bl);
   void SetBranchLengthsToConstant(double v);
   void GetBranchLengths(int64_t start, int64_t length, double* out);
   void GetBranchLengthDifferences(double* out);

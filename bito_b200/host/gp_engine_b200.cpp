@@ -97,12 +97,12 @@ Self::BITO_B200_ENGINE_CLASS(SitePattern site_pattern, size_t node_count, size_t
       const auto s = patterns[t][p];
       symbols[t * P + p] = static_cast<uint8_t>(s > 4 ? 4 : s);
     }
-  Check(bito_gp_set_site_patterns(handle_, symbols.data(), site_pattern_.GetWeights().data()));
+  Check(bito_gp_set_site_patterns(H(), symbols.data(), site_pattern_.GetWeights().data()));
   // The reference moves the three vectors in whatever their size (gp_engine.hpp:382-393 builds an
   // engine with empty ones); only full-size priors are meaningful to upload.
   if (size_t(sbn_prior.size()) == gpcsp_count && size_t(inverted_sbn_prior.size()) == gpcsp_count &&
       size_t(unconditional_node_probabilities.size()) == node_count)
-    Check(bito_gp_initialize_priors(handle_, sbn_prior.data(),
+    Check(bito_gp_initialize_priors(H(), sbn_prior.data(),
                                     unconditional_node_probabilities.data(),
                                     inverted_sbn_prior.data()));
   transition_matrix_.setZero();
@@ -117,10 +117,10 @@ void Self::InitializePriors(EigenVectorXd sbn_prior, EigenVectorXd unconditional
   Assert(size_t(sbn_prior.size()) == GetGPCSPCount(), "sbn_prior is wrong size for GPEngine.");
   Assert(size_t(inverted_sbn_prior.size()) == GetGPCSPCount(),
          "inverted_sbn_prior is wrong size for GPEngine.");
-  Check(bito_gp_initialize_priors(handle_, sbn_prior.data(), unconditional_node_probabilities.data(),
+  Check(bito_gp_initialize_priors(H(), sbn_prior.data(), unconditional_node_probabilities.data(),
                                   inverted_sbn_prior.data()));
 }
-void Self::SetNullPrior() { Check(bito_gp_set_null_prior(handle_)); }
+void Self::SetNullPrior() { Check(bito_gp_set_null_prior(H())); }
 
 // ---- resize / reindex: gp_engine.cpp:64-209 ---------------------------------------------------
 void Self::GrowPLVs(const size_t node_count, std::optional<const Reindexer> node_reindexer,
@@ -128,7 +128,7 @@ void Self::GrowPLVs(const size_t node_count, std::optional<const Reindexer> node
   std::vector<int64_t> idx;
   if (node_reindexer.has_value())
     idx.assign(node_reindexer->GetData().begin(), node_reindexer->GetData().end());
-  Check(bito_gp_grow_plvs(handle_, I(node_count), node_reindexer.has_value() ? idx.data() : nullptr,
+  Check(bito_gp_grow_plvs(H(), I(node_count), node_reindexer.has_value() ? idx.data() : nullptr,
                           explicit_allocation.has_value() ? I(*explicit_allocation) : -1));
 }
 void Self::GrowGPCSPs(const size_t gpcsp_count, std::optional<const Reindexer> gpcsp_reindexer,
@@ -136,12 +136,16 @@ void Self::GrowGPCSPs(const size_t gpcsp_count, std::optional<const Reindexer> g
   std::vector<int64_t> idx;
   if (gpcsp_reindexer.has_value())
     idx.assign(gpcsp_reindexer->GetData().begin(), gpcsp_reindexer->GetData().end());
-  Check(bito_gp_grow_gpcsps(handle_, I(gpcsp_count),
+  Check(bito_gp_grow_gpcsps(H(), I(gpcsp_count),
                             gpcsp_reindexer.has_value() ? idx.data() : nullptr,
                             explicit_allocation.has_value() ? I(*explicit_allocation) : -1));
+  AfterBranchLengthChange();
 }
-void Self::GrowSparePLVs(const size_t n) { Check(bito_gp_grow_spare_plvs(handle_, I(n))); }
-void Self::GrowSpareGPCSPs(const size_t n) { Check(bito_gp_grow_spare_gpcsps(handle_, I(n))); }
+void Self::GrowSparePLVs(const size_t n) { Check(bito_gp_grow_spare_plvs(H(), I(n))); }
+void Self::GrowSpareGPCSPs(const size_t n) {
+  Check(bito_gp_grow_spare_gpcsps(H(), I(n)));
+  AfterBranchLengthChange();
+}
 
 // ---- the hot call: gp_engine.cpp:335-339 ------------------------------------------------------
 void Self::ProcessOperations(GPOperationVector operations) {
@@ -150,57 +154,110 @@ void Self::ProcessOperations(GPOperationVector operations) {
   ops.reserve(operations.size());
   Flatten flatten{ops, vec};
   for (const auto& op : operations) std::visit(flatten, op);
-  Check(bito_gp_process_operations(handle_, ops.data(), I(ops.size()), vec.data(), I(vec.size())));
+  Check(bito_gp_process_operations(H(), ops.data(), I(ops.size()), vec.data(), I(vec.size())));
+  AfterBranchLengthChange();
 }
 
 // ---- optimiser settings -----------------------------------------------------------------------
 void Self::SetOptimizationMethod(const OptimizationMethod method) {
-  Check(bito_gp_set_optimization_method(handle_, static_cast<int>(method)));
+  Check(bito_gp_set_optimization_method(H(), static_cast<int>(method)));
 }
 void Self::UseGradientOptimization(const bool use_gradients) {
-  Check(bito_gp_use_gradient_optimization(handle_, use_gradients ? 1 : 0));
+  Check(bito_gp_use_gradient_optimization(H(), use_gradients ? 1 : 0));
 }
 void Self::SetSignificantDigitsForOptimization(int significant_digits) {
-  Check(bito_gp_set_significant_digits_for_optimization(handle_, significant_digits));
+  Check(bito_gp_set_significant_digits_for_optimization(H(), significant_digits));
 }
 size_t Self::GetOptimizationCount() {
-  return static_cast<size_t>(bito_gp_get_optimization_count(handle_));
+  return static_cast<size_t>(bito_gp_get_optimization_count(H()));
 }
-void Self::ResetOptimizationCount() { Check(bito_gp_reset_optimization_count(handle_)); }
-void Self::IncrementOptimizationCount() { Check(bito_gp_increment_optimization_count(handle_)); }
+void Self::ResetOptimizationCount() {
+  Check(bito_gp_reset_optimization_count(H()));
+  AfterBranchLengthChange();
+}
+void Self::IncrementOptimizationCount() { Check(bito_gp_increment_optimization_count(H())); }
 
 void Self::SetTransitionMatrixToHaveBranchLength(double branch_length) {
   double m[16];
-  Check(bito_gp_get_transition_matrix(handle_, branch_length, m));
+  Check(bito_gp_get_transition_matrix(H(), branch_length, m));
   for (int i = 0; i < 4; ++i)
     for (int j = 0; j < 4; ++j) transition_matrix_(i, j) = m[4 * i + j];
 }
 void Self::SetBranchLengths(EigenVectorXd branch_lengths) {
   Assert(size_t(branch_lengths.size()) == GetGPCSPCount(),
          "Size mismatch in GPEngine::SetBranchLengths.");
-  Check(bito_gp_set_branch_lengths(handle_, branch_lengths.data()));
+  Check(bito_gp_set_branch_lengths(H(), branch_lengths.data()));
+  AfterBranchLengthChange();
 }
 void Self::SetBranchLengthsToConstant(double branch_length) {
-  Check(bito_gp_set_branch_lengths_to_constant(handle_, branch_length));
+  Check(bito_gp_set_branch_lengths_to_constant(H(), branch_length));
+  AfterBranchLengthChange();
 }
-void Self::SetBranchLengthsToDefault() { Check(bito_gp_set_branch_lengths_to_default(handle_)); }
+void Self::SetBranchLengthsToDefault() {
+  Check(bito_gp_set_branch_lengths_to_default(H()));
+  AfterBranchLengthChange();
+}
 void Self::ResetLogMarginalLikelihood() { (*this)(GPOperations::ResetMarginalLikelihood{}); }
 
 void Self::CopyNodeData(const NodeId src, const NodeId dest) {
-  Check(bito_gp_copy_node_data(handle_, I(src.value_), I(dest.value_)));
+  Check(bito_gp_copy_node_data(H(), I(src.value_), I(dest.value_)));
 }
 void Self::CopyPLVData(const size_t src, const size_t dest) {
-  Check(bito_gp_copy_plv_data(handle_, I(src), I(dest)));
+  Check(bito_gp_copy_plv_data(H(), I(src), I(dest)));
 }
 void Self::CopyGPCSPData(const EdgeId src, const EdgeId dest) {
-  Check(bito_gp_copy_gpcsp_data(handle_, I(src.value_), I(dest.value_)));
+  Check(bito_gp_copy_gpcsp_data(H(), I(src.value_), I(dest.value_)));
+  AfterBranchLengthChange();
+}
+
+// ---- the DAGBranchHandler mirror ---------------------------------------------------------------
+DAGBranchHandler& Self::GetBranchLengthHandler() {
+  if (mirror_live_) PushMirror();
+  PullMirror();
+  mirror_live_ = true;
+  return branch_mirror_;
+}
+const DAGBranchHandler& Self::GetBranchLengthHandler() const {
+  if (mirror_live_) PushMirror();
+  PullMirror();
+  mirror_live_ = true;
+  return branch_mirror_;
+}
+void Self::PullMirror() const {
+  const size_t count = static_cast<size_t>(bito_gp_get_gpcsp_count(handle_));
+  const size_t padded = static_cast<size_t>(bito_gp_get_padded_gpcsp_count(handle_));
+  if (branch_mirror_.GetBranchLengths().GetCount() != count ||
+      branch_mirror_.GetBranchLengths().GetSpareCount() != padded - count)
+    branch_mirror_.Resize(count, padded - count, std::nullopt, std::nullopt);
+  branch_mirror_.SetDefaultBranchLength(default_branch_length_);
+  EigenVectorXd& bl = branch_mirror_.GetBranchLengthData();
+  EigenVectorXd& diff = branch_mirror_.GetBranchDifferenceData();
+  Assert(size_t(bl.size()) >= padded && size_t(diff.size()) >= count,
+         "DAGBranchHandler mirror is smaller than the engine.");
+  Check(bito_gp_get_branch_lengths(handle_, 0, I(padded), bl.data()));
+  Check(bito_gp_get_branch_length_differences(handle_, diff.data()));
+  mirror_synced_ = bl.head(padded);
+}
+void Self::PushMirror() const {
+  const EigenVectorXd& bl = branch_mirror_.GetBranchLengthData();
+  const size_t padded = static_cast<size_t>(mirror_synced_.size());
+  if (size_t(bl.size()) < padded) return;  // the caller shrank it: nothing of ours left to compare
+  size_t lo = padded, hi = 0;
+  for (size_t i = 0; i < padded; ++i)
+    if (bl[i] != mirror_synced_[i]) {
+      lo = std::min(lo, i);
+      hi = i + 1;
+    }
+  if (hi == 0) return;
+  Check(bito_gp_set_branch_lengths_range(handle_, I(lo), I(hi - lo), bl.data() + lo));
+  mirror_synced_.segment(lo, hi - lo) = bl.segment(lo, hi - lo);
 }
 
 // ---- read-back: gp_engine.cpp:413-468 ---------------------------------------------------------
 EigenVectorXd Self::GetBranchLengths() const { return GetBranchLengths(0, GetGPCSPCount()); }
 EigenVectorXd Self::GetBranchLengths(const size_t start, const size_t length) const {
   EigenVectorXd out(length);
-  Check(bito_gp_get_branch_lengths(handle_, I(start), I(length), out.data()));
+  Check(bito_gp_get_branch_lengths(H(), I(start), I(length), out.data()));
   return out;
 }
 EigenVectorXd Self::GetSpareBranchLengths(const size_t start, const size_t length) const {
@@ -208,7 +265,7 @@ EigenVectorXd Self::GetSpareBranchLengths(const size_t start, const size_t lengt
 }
 EigenVectorXd Self::GetBranchLengthDifferences() const {
   EigenVectorXd out(GetGPCSPCount());
-  Check(bito_gp_get_branch_length_differences(handle_, out.data()));
+  Check(bito_gp_get_branch_length_differences(H(), out.data()));
   return out;
 }
 EigenVectorXd Self::GetPerGPCSPLogLikelihoods() const {
@@ -216,7 +273,7 @@ EigenVectorXd Self::GetPerGPCSPLogLikelihoods() const {
 }
 EigenVectorXd Self::GetPerGPCSPLogLikelihoods(const size_t start, const size_t length) const {
   EigenVectorXd out(length);
-  Check(bito_gp_get_per_gpcsp_log_likelihoods(handle_, I(start), I(length), out.data()));
+  Check(bito_gp_get_per_gpcsp_log_likelihoods(H(), I(start), I(length), out.data()));
   return out;
 }
 EigenVectorXd Self::GetSparePerGPCSPLogLikelihoods(const size_t start, const size_t length) const {
@@ -224,27 +281,27 @@ EigenVectorXd Self::GetSparePerGPCSPLogLikelihoods(const size_t start, const siz
 }
 EigenVectorXd Self::GetPerGPCSPComponentsOfFullLogMarginal() const {
   EigenVectorXd out(GetGPCSPCount());
-  Check(bito_gp_get_per_gpcsp_components_of_full_log_marginal(handle_, out.data()));
+  Check(bito_gp_get_per_gpcsp_components_of_full_log_marginal(H(), out.data()));
   return out;
 }
 EigenMatrixXd Self::GetLogLikelihoodMatrix() const {
   EigenMatrixXd out(GetGPCSPCount(), GetSitePatternCount());  // row-major (eigen_sugar.hpp:20-22)
-  Check(bito_gp_get_log_likelihood_matrix(handle_, out.data()));
+  Check(bito_gp_get_log_likelihood_matrix(H(), out.data()));
   return out;
 }
 EigenVectorXd Self::GetHybridMarginals() const {
   EigenVectorXd out(GetGPCSPCount());
-  Check(bito_gp_get_hybrid_marginals(handle_, out.data()));
+  Check(bito_gp_get_hybrid_marginals(H(), out.data()));
   return out;
 }
 EigenVectorXd Self::GetSBNParameters() const {
   EigenVectorXd out(GetGPCSPCount());
-  Check(bito_gp_get_sbn_parameters(handle_, out.data()));
+  Check(bito_gp_get_sbn_parameters(H(), out.data()));
   return out;
 }
 double Self::GetLogMarginalLikelihood() const {
   double v = 0.;
-  Check(bito_gp_get_log_marginal_likelihood(handle_, &v));
+  Check(bito_gp_get_log_marginal_likelihood(H(), &v));
   return v;
 }
 
@@ -252,12 +309,12 @@ double Self::GetLogMarginalLikelihood() const {
 // which is the C-ABI's layout, so the Eigen buffer is handed over as is.
 NucleotidePLV Self::GetPLV(const PVId plv_index) const {
   NucleotidePLV out(4, GetSitePatternCount());
-  Check(bito_gp_get_plv(handle_, I(plv_index.value_), out.data()));
+  Check(bito_gp_get_plv(H(), I(plv_index.value_), out.data()));
   return out;
 }
 void Self::SetPLV(const PVId plv_index, const NucleotidePLV& plv, int rescaling_count) {
   Assert(size_t(plv.cols()) == GetSitePatternCount(), "SetPLV: wrong pattern count.");
-  Check(bito_gp_set_plv(handle_, I(plv_index.value_), plv.data(), rescaling_count));
+  Check(bito_gp_set_plv(H(), I(plv_index.value_), plv.data(), rescaling_count));
 }
 PVId Self::GetSparePLVIndex(const PVId plv_index) const {  // pv_handler.hpp:227-232
   Assert(plv_index.value_ < GetSparePLVCount(),
@@ -267,7 +324,7 @@ PVId Self::GetSparePLVIndex(const PVId plv_index) const {  // pv_handler.hpp:227
 EigenVectorXi Self::GetRescalingCounts() const {
   static_assert(sizeof(int) == sizeof(int32_t), "EigenVectorXi must hold int32");
   EigenVectorXi out(GetPaddedPLVCount());
-  Check(bito_gp_get_rescaling_counts(handle_, out.data()));
+  Check(bito_gp_get_rescaling_counts(H(), out.data()));
   return out;
 }
 
@@ -277,7 +334,7 @@ EigenVectorXd Self::CalculateQuartetHybridLikelihoods(const QuartetHybridRequest
   std::vector<int32_t> counts;
   FlattenRequest(request, tips, counts);
   EigenVectorXd out(size_t(counts[0]) * counts[1] * counts[2] * counts[3]);
-  Check(bito_gp_calculate_quartet_hybrid_likelihoods(handle_, I(request.central_gpcsp_idx_),
+  Check(bito_gp_calculate_quartet_hybrid_likelihoods(H(), I(request.central_gpcsp_idx_),
                                                      tips.data(), counts.data(), out.data()));
   return out;
 }
@@ -292,7 +349,7 @@ void Self::ProcessQuartetHybridRequests(const std::vector<QuartetHybridRequest>&
     central.push_back(I(request.central_gpcsp_idx_));
     FlattenRequest(request, tips, counts);
   }
-  Check(bito_gp_process_quartet_hybrid_requests(handle_, I(central.size()), central.data(),
+  Check(bito_gp_process_quartet_hybrid_requests(H(), I(central.size()), central.data(),
                                                 counts.data(), tips.data()));
 }
 
@@ -351,7 +408,7 @@ DoublePair Self::LogLikelihoodAndDerivative(const GPOperations::OptimizeBranchLe
 DoublePair Self::LogLikelihoodAndDerivative(const size_t gpcsp, const size_t rootward,
                                             const size_t leafward) {
   double out[3];
-  Check(bito_gp_log_likelihood_and_derivatives(handle_, I(gpcsp), I(rootward), I(leafward), out));
+  Check(bito_gp_log_likelihood_and_derivatives(H(), I(gpcsp), I(rootward), I(leafward), out));
   return {out[0], out[1]};
 }
 std::tuple<double, double, double> Self::LogLikelihoodAndFirstTwoDerivatives(
@@ -361,7 +418,7 @@ std::tuple<double, double, double> Self::LogLikelihoodAndFirstTwoDerivatives(
 std::tuple<double, double, double> Self::LogLikelihoodAndFirstTwoDerivatives(
     const size_t gpcsp, const size_t rootward, const size_t leafward) {
   double out[3];
-  Check(bito_gp_log_likelihood_and_derivatives(handle_, I(gpcsp), I(rootward), I(leafward), out));
+  Check(bito_gp_log_likelihood_and_derivatives(H(), I(gpcsp), I(rootward), I(leafward), out));
   return {out[0], out[1], out[2]};
 }
 
@@ -388,12 +445,12 @@ std::string Self::LogLikelihoodMatrixToString() const {
 }
 
 // ---- counts -----------------------------------------------------------------------------------
-size_t Self::GetNodeCount() const { return size_t(bito_gp_get_node_count(handle_)); }
+size_t Self::GetNodeCount() const { return size_t(bito_gp_get_node_count(H())); }
 size_t Self::GetSpareNodeCount() const { return GetSparePLVCount() / 6; }
-size_t Self::GetPLVCount() const { return size_t(bito_gp_get_plv_count(handle_)); }
-size_t Self::GetPaddedPLVCount() const { return size_t(bito_gp_get_padded_plv_count(handle_)); }
-size_t Self::GetGPCSPCount() const { return size_t(bito_gp_get_gpcsp_count(handle_)); }
-size_t Self::GetPaddedGPCSPCount() const { return size_t(bito_gp_get_padded_gpcsp_count(handle_)); }
+size_t Self::GetPLVCount() const { return size_t(bito_gp_get_plv_count(H())); }
+size_t Self::GetPaddedPLVCount() const { return size_t(bito_gp_get_padded_plv_count(H())); }
+size_t Self::GetGPCSPCount() const { return size_t(bito_gp_get_gpcsp_count(H())); }
+size_t Self::GetPaddedGPCSPCount() const { return size_t(bito_gp_get_padded_gpcsp_count(H())); }
 size_t Self::GetSpareGPCSPIndex(const size_t gpcsp_offset) const {
   Assert(gpcsp_offset < GetSpareGPCSPCount(),
          "Requested gpcsp_offset outside of allocated scratch space.");
@@ -401,6 +458,6 @@ size_t Self::GetSpareGPCSPIndex(const size_t gpcsp_offset) const {
 }
 bito_gp_stats Self::Stats() const {
   bito_gp_stats s{};
-  Check(bito_gp_get_stats(handle_, &s));
+  Check(bito_gp_get_stats(H(), &s));
   return s;
 }

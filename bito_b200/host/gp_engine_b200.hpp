@@ -12,8 +12,14 @@
 // Differences from the reference surface, all forced by PLVs living in HBM:
 //  * GetPLV / GetSparePLV / GetLogLikelihoodMatrix / GetHybridMarginals / GetSBNParameters return
 //    copies, not Eigen::Ref into engine memory; writes go through SetPLV.
-//  * GetPLVHandler / GetBranchLengthHandler (raw handler objects) are not offered; the index
-//    arithmetic callers take from them is (GetSparePLVIndex, GetSpareGPCSPIndex, Get*Count).
+//  * GetPLVHandler() returns an index-only view (GetPVIndex / GetSparePVIndex / counts): PLV data
+//    is not host-addressable. That is all NNIEvalEngineViaGP takes from it
+//    (nni_evaluation_engine.cpp:233-421, 633, 813-923).
+//  * GetBranchLengthHandler() returns a genuine reference DAGBranchHandler that MIRRORS the
+//    device's branch lengths and differences: it is refreshed after every member that can change
+//    them, and whatever the caller wrote through it (branch_handler(edge) = x,
+//    nni_evaluation_engine.cpp:108, 187) is uploaded before the next member touches the device.
+//    Optimiser settings are NOT read from the mirror: set them through the engine's own members.
 //  * mmap_file_path is accepted and ignored.
 #pragma once
 
@@ -34,6 +40,7 @@
 #include "site_pattern.hpp"
 #include "subsplit_dag_storage.hpp"
 #include "pv_handler.hpp"
+#include "dag_branch_handler.hpp"
 
 #include "bito_gp.h"
 
@@ -118,6 +125,29 @@ class BITO_B200_ENGINE_CLASS {
   PVId GetSparePLVIndex(const PVId plv_index) const;
   EigenVectorXi GetRescalingCounts() const;  // rescaling_counts_ (private in the reference)
 
+  // ** Handlers (gp_engine.hpp:145-156)
+  // PLVNodeHandler's index arithmetic (pv_handler.hpp:26-33, 227-238, 487-490) without its storage.
+  class PLVIndexView {
+   public:
+    using PLVType = PLVNodeHandler::PLVType;
+    explicit PLVIndexView(const BITO_B200_ENGINE_CLASS& engine) : engine_(engine) {}
+    PVId GetPVIndex(const PLVType plv_type, const NodeId node_id) const {
+      return PLVNodeHandler::GetPVIndex(plv_type, node_id, engine_.GetNodeCount());
+    }
+    PVId GetSparePVIndex(const PVId pv_id) const { return engine_.GetSparePLVIndex(pv_id); }
+    size_t GetNodeCount() const { return engine_.GetNodeCount(); }
+    size_t GetSpareNodeCount() const { return engine_.GetSpareNodeCount(); }
+    size_t GetPVCount() const { return engine_.GetPLVCount(); }
+    size_t GetSparePVCount() const { return engine_.GetSparePLVCount(); }
+    size_t GetPaddedPVCount() const { return engine_.GetPaddedPLVCount(); }
+
+   private:
+    const BITO_B200_ENGINE_CLASS& engine_;
+  };
+  const PLVIndexView& GetPLVHandler() const { return plv_view_; }
+  DAGBranchHandler& GetBranchLengthHandler();
+  const DAGBranchHandler& GetBranchLengthHandler() const;
+
   // ** Other Operations (gp_engine.hpp:158-182)
   EigenVectorXd CalculateQuartetHybridLikelihoods(const QuartetHybridRequest& request);
   void ProcessQuartetHybridRequest(const QuartetHybridRequest& request);
@@ -166,8 +196,24 @@ class BITO_B200_ENGINE_CLASS {
   void SetBranchLengthsFromTotals(std::vector<double>& totals, const std::vector<int>& seen,
                                   bool mean);
 
+  // The device handle for a call. While a DAGBranchHandler mirror is out, first uploads what the
+  // caller changed through it.
+  bito_gp_engine* H() const {
+    if (mirror_live_) PushMirror();
+    return handle_;
+  }
+  void PullMirror() const;  // device -> mirror (sizes, branch lengths, differences)
+  void PushMirror() const;  // mirror -> device, if the caller wrote to it
+  void AfterBranchLengthChange() const {
+    if (mirror_live_) PullMirror();
+  }
+
   SitePattern site_pattern_;
   bito_gp_engine* handle_ = nullptr;
+  PLVIndexView plv_view_{*this};
+  mutable DAGBranchHandler branch_mirror_{0};
+  mutable EigenVectorXd mirror_synced_;  // branch lengths as last exchanged with the device
+  mutable bool mirror_live_ = false;
   Eigen::Matrix4d transition_matrix_;
   static constexpr double default_branch_length_ = 0.1;  // dag_branch_handler.hpp:266
 };

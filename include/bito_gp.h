@@ -136,6 +136,11 @@ BITO_GP_API int bito_gp_process_operations(bito_gp_engine* e, const bito_gp_op* 
 
 /* ---- branch lengths / optimiser: gp_engine.cpp:366-380, 656-674 --------------------- */
 BITO_GP_API int bito_gp_set_branch_lengths(bito_gp_engine* e, const double* branch_lengths /* gpcsp_count */);
+/* Writes [start, start + length) of the padded branch-length vector (spare edges included): what a
+ * caller does through the reference's mutable DAGBranchHandler reference, e.g.
+ * branch_handler(edge_id) = x in nni_evaluation_engine.cpp:108, 187. */
+BITO_GP_API int bito_gp_set_branch_lengths_range(bito_gp_engine* e, int64_t start, int64_t length,
+                                     const double* branch_lengths);
 BITO_GP_API int bito_gp_set_branch_lengths_to_constant(bito_gp_engine* e, double branch_length);
 BITO_GP_API int bito_gp_set_branch_lengths_to_default(bito_gp_engine* e);
 BITO_GP_API int bito_gp_get_branch_lengths(bito_gp_engine* e, int64_t start, int64_t length, double* out);

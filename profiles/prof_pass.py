@@ -10,6 +10,7 @@ name = sys.argv[1] if len(sys.argv) > 1 else "synthetic-1000taxa-1Mpat-5000trees
 patterns = int(sys.argv[2]) if len(sys.argv) > 2 else None
 passes = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 with_sweep = len(sys.argv) > 4 and sys.argv[4] == "sweep"
+with_gs = len(sys.argv) > 4 and sys.argv[4] == "gs"  # the reference's Gauss-Seidel sweep (on-chip optimiser kernels)
 wl = make_named_workload(name, pattern_count=patterns)
 dag = wl.dag
 eng = GPEngine(wl.symbols, wl.weights, wl.site_count, dag.node_count, dag.edge_count, sbn_prior=wl.sbn_prior,
@@ -20,4 +21,6 @@ for _ in range(passes):
     eng.process_operations(*wl.ops("compute_likelihoods"))
 if with_sweep:
     eng.process_operations(*wl.ops("batched_branch_length_optimization"))
+if with_gs:
+    eng.process_operations(*wl.ops("branch_length_optimization"))
 print("log marginal", eng.get_log_marginal_likelihood(), eng.stats())
