@@ -1179,7 +1179,7 @@ Program* Engine::Compile(const bito_gp_op* ops, int64_t n, const int64_t* vec, i
   std::vector<int32_t> f_lik_scatter, f_marg_scatter;
   const int64_t tiles = TilesFor(P_);
   const int32_t marg_slot = static_cast<int32_t>(d_ll_sum_.n - 1);
-  bool dirty_matrices = false;
+  bool dirty_matrices = false, after_opt = false;
   for (int lv = 0; lv < n_levels; ++lv) {
     Level& L = prog->levels[lv];
     L.zero_off = static_cast<int>(f_zero.size());
@@ -1248,7 +1248,9 @@ Program* Engine::Compile(const bito_gp_op* ops, int64_t n, const int64_t* vec, i
     // Transition matrices are (re)built before the first level and after any level that may have
     // changed branch lengths (OptimizeBranchLength) or q (UpdateSBNProbabilities).
     L.rebuild_matrices = (lv == 0) || dirty_matrices;
-    dirty_matrices = L.n_opt > 0;
+    L.rebuild_after_opt = after_opt && !L.rebuild_matrices;
+    after_opt = L.n_opt > 0;
+    dirty_matrices = false;
     for (int t = 0; t < L.n_scalar; ++t) dirty_matrices |= (f_scalar[L.scalar_off + t].kind == kScalarSbn);
     prog->launches += (L.n_zero > 0) + (L.n_scalar > 0) + (L.n_stat > 0) + (L.n_node > 0) +
                       (L.n_mult > 0) + 2 * (L.n_lik > 0) + 2 * L.has_marg + L.rebuild_matrices;
@@ -1261,6 +1263,22 @@ Program* Engine::Compile(const bito_gp_op* ops, int64_t n, const int64_t* vec, i
   prog->n_macro = static_cast<int64_t>(macros.size());
   prog->alg_bytes_per_pattern = alg_bytes;
   prog->alloc_version = alloc_version_;
+
+  // Each OptimizeBranchLength carries the transition-matrix slots that hold its edge, so that the
+  // on-chip optimisers refresh just those when they finish (see OptOp).
+  if (!f_opt.empty()) {
+    std::unordered_map<int32_t, std::vector<int32_t>> slots_of_edge;
+    for (size_t i = 0; i < h_items.size(); ++i)
+      slots_of_edge[h_items[i].edge].push_back(static_cast<int32_t>(2 * i));
+    for (size_t j = 0; j < f_lik.size(); ++j)
+      slots_of_edge[f_lik[j].edge].push_back(static_cast<int32_t>(2 * j + 1));
+    for (OptOp& o : f_opt) {
+      const std::vector<int32_t>& v = slots_of_edge[o.edge];
+      o.fix_off = static_cast<int32_t>(h_pool.size());
+      o.fix_n = static_cast<int32_t>(v.size());
+      h_pool.insert(h_pool.end(), v.begin(), v.end());
+    }
+  }
 
   // -- pass 4: one device arena for all tables -------------------------------------------------
   size_t off = 0;
@@ -1350,7 +1368,10 @@ void Engine::ExecuteLevels(Program& prog, size_t first, size_t last) {
       ProfScope ps(this, kProfStationary, 32. * L.n_stat * Pd);
       LaunchStationary(stream_, st, prog.d_stat + L.stat_off, L.n_stat);
     }
-    if (L.rebuild_matrices && (prog.n_items_total > 0 || prog.n_lik_total > 0)) {
+    const bool stale = L.rebuild_after_opt && matrices_stale_;
+    if (stale && !capturing_) stats_.kernel_launches++;  // not part of prog.launches
+    if ((L.rebuild_matrices || stale) && (prog.n_items_total > 0 || prog.n_lik_total > 0)) {
+      matrices_stale_ = false;
       ProfScope ps(this, kProfPrologue, 0.);
       LaunchBuildMatrices(stream_, st, prog.d_items, static_cast<int>(prog.n_items_total), prog.d_lik,
                           prog.n_lik_total, d_mtab_.ptr, d_mtab_lik_.ptr);
@@ -1422,6 +1443,8 @@ OptParams Engine::OptimizerParams(bool check_convergence) const {
   prm.step_size = kStepSizeForOptimization;
   prm.log_step_size = kStepSizeForLogSpaceOptimization;
   prm.diff_threshold = kBranchLengthDifferenceThreshold;
+  prm.brent_tolerance = std::ldexp(1.0, 1 - significant_digits_);
+  prm.decimal_tolerance = std::pow(10., static_cast<double>(-significant_digits_));
   return prm;
 }
 
@@ -1480,7 +1503,10 @@ bool Engine::ProgramOptimizesOnChip(const Program& prog) const {
 }
 
 void Engine::RunOptimizeLevel(Program& prog, const Level& L) {
+  opt_refresh_ = OptRefresh{prog.d_pool, d_mtab_.ptr, d_mtab_lik_.ptr};
   RunOptimizer(prog.d_opt + L.opt_off, L.n_opt, method_, optimization_count_ != 0);
+  // the round scheme leaves the matrix tables to a full rebuild before the next level
+  if (last_opt_scheme_ == 0) matrices_stale_ = true;
 }
 
 // Device-resident 1-D optimisers stepping every edge of the batch in lockstep: one objective
@@ -1503,14 +1529,14 @@ void Engine::RunOptimizer(const OptOp* d_ops, int n_ops, int method, bool check_
     // small alignment, single rank: every edge's whole search in one launch (k_opt_block); the
     // settings were written to d_opt_ctl_ by Execute, outside any captured graph
     ProfScope ps(this, kProfOptBlock, 64. * n_ops * static_cast<double>(P_));
-    LaunchOptBlock(stream_, st, d_ops, n_ops, d_opt_ctl_.ptr, G);
+    LaunchOptBlock(stream_, st, d_ops, n_ops, d_opt_ctl_.ptr, G, opt_refresh_);
     return;
   }
   if (on_chip == 2) {
     // large alignment, single rank, plain Brent: one thread-block cluster per edge (k_opt_cluster)
     ProfScope ps(this, kProfOptCluster, 64. * n_ops * static_cast<double>(P_));
     GP_CUDA(LaunchOptCluster(stream_, st, d_ops, n_ops, d_opt_ctl_.ptr, d_cluster_inv_perm_.ptr,
-                             d_cluster_wperm_.ptr, cluster_class_row_start_, *plan));
+                             d_cluster_wperm_.ptr, cluster_class_row_start_, *plan, opt_refresh_));
     return;
   }
   const OptParams prm = OptimizerParams(check_convergence);

@@ -70,7 +70,9 @@ struct Level {
   int marg_off = 0, n_marg = 0, marg_reset = 0, has_marg = 0, marg_scatter_off = 0;
   int opt_off = 0, n_opt = 0;
   double node_bytes_per_pattern = 0.;
-  bool rebuild_matrices = false;  // branch lengths / q may have changed since the tables were built
+  bool rebuild_matrices = false;  // first level, or q may have changed (UpdateSBNProbabilities) since the tables were built
+  bool rebuild_after_opt = false; // the previous level optimised branch lengths: a full rebuild only if it ran
+                                  // the round scheme (the on-chip optimisers refresh their own edges' slots)
 };
 
 struct Program {
@@ -268,6 +270,8 @@ class Engine {
   int last_opt_scheme_ = 0;           // scheme and shape of the most recent optimiser level
   OptClusterPlan last_opt_plan_;
   bool capturing_ = false;            // inside cudaStreamBeginCapture .. EndCapture
+  OptRefresh opt_refresh_{};          // where the on-chip optimisers refresh their edges' matrices
+  bool matrices_stale_ = false;       // a round-scheme optimiser level changed branch lengths
   bool coef_padding_zeroed_ = false;
   std::vector<double> host_weights_cache_;
   DeviceArray<OptOp> d_single_opt_;

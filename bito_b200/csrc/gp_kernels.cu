@@ -44,6 +44,18 @@ __device__ __forceinline__ void st256(double* p, const V4& v) {
                : "memory");
 }
 
+// Same store with the cache-streaming hint: a PLV written by a level is next read a whole level
+// (gigabytes of traffic) later, so it should not push the level's shared source tiles out of L2.
+__device__ __forceinline__ void st256cs(double* p, const V4& v) {
+  asm volatile("st.global.cs.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.a), "d"(v.b), "d"(v.c),
+               "d"(v.d)
+               : "memory");
+}
+template <bool kStream>
+__device__ __forceinline__ void st256p(double* p, const V4& v) {
+  if (kStream) st256cs(p, v); else st256(p, v);
+}
+
 __device__ __forceinline__ V4 load_plv(const PlvRef& r, int64_t p) {
   if (r.kind == kPlvDense) return ld256(static_cast<const double*>(r.ptr) + 4 * p);
   V4 v = {0., 0., 0., 0.};
@@ -193,7 +205,7 @@ __device__ __forceinline__ void accumulate_items(V4& acc, const double (*sM)[16]
 // (gp_engine.cpp:278-285), plus the per-PLV maximum for the rescale decision (:583-597).
 // Blocks are ordered tile-major (all macro-ops of one pattern tile are neighbours in the grid), so
 // a PLV tile read by several macro-ops of the level is served from L2 after its first use.
-template <int kMinBlocks>
+template <int kMinBlocks, bool kStream>
 __global__ void __launch_bounds__(kTile, kMinBlocks)
     k_node(DeviceState st, const NodeOp* __restrict__ nodes, const AccumItem* __restrict__ items,
            const int32_t* __restrict__ pool, const double* __restrict__ mtab, int n_nodes, int tiles,
@@ -341,15 +353,15 @@ __global__ void __launch_bounds__(kTile, kMinBlocks)
       }
     }
     if (live) {
-      if (ng > 0) st256(dest0 + 4 * p, acc0);
-      if (ng > 1) st256(dest1 + 4 * p, acc1);
+      if (ng > 0) st256p<kStream>(dest0 + 4 * p, acc0);
+      if (ng > 1) st256p<kStream>(dest1 + 4 * p, acc1);
       for (int mi = 0; mi < nm; ++mi) {
         const NodeMult* m = &nd->m[mi];
         const int g1 = m->s1_group, g2 = m->s2_group;
         const V4 x = g1 == 0 ? acc0 : (g1 == 1 ? acc1 : load_plv(m->s1, p));
         const V4 y = g2 == 0 ? acc0 : (g2 == 1 ? acc1 : load_plv(m->s2, p));
         const V4 v = {x.a * y.a, x.b * y.b, x.c * y.c, x.d * y.d};
-        st256(m->dest + 4 * p, v);
+        st256p<kStream>(m->dest + 4 * p, v);
         const double hi = fmax(fmax(v.a, v.b), fmax(v.c, v.d));
         const double lo = fmin(fmin(v.a, v.b), fmin(v.c, v.d));
         // AssertPLVIsFinite (:575-577), non-negativity (:585-586). fmax/fmin drop NaNs, so
@@ -644,9 +656,20 @@ enum OptPhase : int32_t {
 __device__ void opt_request(OptState& s, double x, bool log_space) {
   s.x_eval = x;
   s.t_eval = log_space ? exp(x) : x;
-  // diag(e^{lambda t}) once per edge and request, not once per pattern (gp_engine.cpp:341-344)
-  for (int g = 0; g < c_model.n_groups; ++g) s.e[g] = exp(c_model.group_lambda[g] * s.t_eval);
-  s.x_ratio = s.e[1] / s.e[0];  // two-eigenvalue ratio form, k_opt_eval_ratio
+  // diag(e^{lambda t}) once per edge and request, not once per pattern (gp_engine.cpp:341-344).
+  // This runs on ONE thread with every other thread of the block (cluster) waiting for it, so the
+  // exponentials are issued side by side (fully unrolled) and the zero eigenvalue every reversible
+  // model has costs nothing: exp(0 * t) and x / 1 are exact, so skipping them changes no bit.
+  double e[kMaxEigenGroups];
+#pragma unroll
+  for (int g = 0; g < kMaxEigenGroups; ++g) {
+    const double l = c_model.group_lambda[g];
+    e[g] = (g < c_model.n_groups && l != 0.) ? exp(l * s.t_eval) : 1.0;
+  }
+#pragma unroll
+  for (int g = 0; g < kMaxEigenGroups; ++g)
+    if (g < c_model.n_groups) s.e[g] = e[g];
+  s.x_ratio = e[0] == 1.0 ? e[1] : e[1] / e[0];  // two-eigenvalue ratio form, k_opt_eval_ratio
   s.evals++;
 }
 
@@ -705,7 +728,7 @@ __device__ void opt_finish_brent(OptState& s, const DeviceState& st) {
 
 // Top of the do-while body of BrentMinimize up to the objective call (optimization.hpp:95-148).
 __device__ void brent_next(OptState& s, const DeviceState& st, const OptParams& prm) {
-  const double tolerance = ldexp(1.0, 1 - prm.significant_digits);
+  const double tolerance = prm.brent_tolerance;  // 2^(1 - significant digits), optimization.hpp:84
   const double golden = 0.3819660f;
   const double mid = (s.min + s.max) / 2;
   const double fract1 = tolerance * fabs(s.x) + tolerance / 4;
@@ -812,7 +835,7 @@ __device__ void opt_advance(OptState& s, const DeviceState& st, const OptParams&
       break;
     }
     case kPhGradientAscent: {  // optimization.hpp:331-345 (min_x is the LOG bound, as there)
-      const double tolerance = pow(10., static_cast<double>(-prm.significant_digits));
+      const double tolerance = prm.decimal_tolerance;  // 10^-significant digits
       const double new_x = s.x + d1 * prm.step_size;
       s.x = fmax(new_x, prm.min_log_bl);
       if (fabs(d1) < fabs(ll) * tolerance || s.iter >= prm.max_iter) {
@@ -826,7 +849,7 @@ __device__ void opt_advance(OptState& s, const DeviceState& st, const OptParams&
       break;
     }
     case kPhLogSpaceGradientAscent: {  // optimization.hpp:347-365
-      const double tolerance = pow(10., static_cast<double>(-prm.significant_digits));
+      const double tolerance = prm.decimal_tolerance;  // 10^-significant digits
       const double y = log(s.x);
       const double log_space_grad = s.x * d1;
       const double new_x = exp(y + log_space_grad * prm.log_step_size);
@@ -842,7 +865,7 @@ __device__ void opt_advance(OptState& s, const DeviceState& st, const OptParams&
       break;
     }
     default: {  // Newton, optimization.hpp:367-402 on gp_engine.cpp:641-653
-      const double tolerance = pow(10., static_cast<double>(-prm.significant_digits));
+      const double tolerance = prm.decimal_tolerance;  // 10^-significant digits
       const double t = s.t_eval;
       const double f_prime_y = t * d1;
       const double f_double_prime_y = f_prime_y + (t * t) * d2;
@@ -1150,6 +1173,21 @@ __global__ void k_opt_step(DeviceState st, int n_ops, OptState* __restrict__ sta
   }
 }
 
+// After an on-chip search: rebuild the transition matrices of the program that hold this edge from
+// its new branch length (k_build_matrices does the whole table; this does the edge's few slots).
+__device__ __forceinline__ void refresh_edge_matrices(const DeviceState& st, const OptOp& op,
+                                                      const OptRefresh& rf, int tid, int n_threads) {
+  if (rf.pool == nullptr) return;
+  const double t = st.bl[op.edge], q = st.q[op.edge];
+  for (int k = tid; k < op.fix_n; k += n_threads) {
+    const int v = rf.pool[op.fix_off + k];
+    if (v & 1)
+      build_matrix(t, 0, 1., rf.mtab_lik + 16 * static_cast<int64_t>(v >> 1));
+    else
+      build_matrix(t, 0, q, rf.mtab + 16 * static_cast<int64_t>(v >> 1));
+  }
+}
+
 // ---- OptimizeBranchLength on chip (small alignments) -------------------------------------------
 // Real alignments have 1e2..1e4 site patterns: there the round-per-launch scheme above is bound by
 // launch and host-check latency, not by HBM. Here one block owns one edge for its whole 1-D search:
@@ -1159,7 +1197,8 @@ __global__ void k_opt_step(DeviceState st, int n_ops, OptState* __restrict__ sta
 // level of k independent edges is k blocks of ONE launch with no host round trip, so whole
 // Gauss-Seidel sweeps (GPDAG::BranchLengthOptimization) replay as a CUDA graph.
 __global__ void __launch_bounds__(kTile)
-    k_opt_block(DeviceState st, const OptOp* __restrict__ ops, const OptControl* __restrict__ ctl) {
+    k_opt_block(DeviceState st, const OptOp* __restrict__ ops, const OptControl* __restrict__ ctl,
+                OptRefresh refresh) {
   extern __shared__ __align__(16) double s_coef[];  // [G][P]
   __shared__ OptState s_state;
   const OptParams prm = ctl->prm;
@@ -1228,6 +1267,7 @@ __global__ void __launch_bounds__(kTile)
     }
     __syncthreads();
   }
+  refresh_edge_matrices(st, op, refresh, threadIdx.x, kTile);  // st.bl[edge] was written before the barrier
 }
 
 // ---- OptimizeBranchLength on chip (large alignments): one thread-block CLUSTER per edge -----------
@@ -1278,9 +1318,17 @@ __device__ __forceinline__ double cluster_sum(cg::cluster_group& cluster, double
       *cluster.map_shared_rank(&s_slots[parity][cluster.block_rank()], lane) = t;
   }
   cluster.sync();  // release/acquire: the remote stores above are visible to every block
-  double total = 0.;
-  for (unsigned k = 0; k < n_blocks; ++k) total += s_slots[parity][k];  // same order in every block
-  return total;
+  // fixed pairwise tree over the (at most 16) block sums: the same order in every block, and four
+  // dependent additions instead of sixteen on the path every thread of the cluster waits on
+  double v16[kMaxOptCluster];
+#pragma unroll
+  for (int k = 0; k < kMaxOptCluster; ++k)
+    v16[k] = k < static_cast<int>(n_blocks) ? s_slots[parity][k] : 0.;
+#pragma unroll
+  for (int w = kMaxOptCluster / 2; w > 0; w >>= 1)
+#pragma unroll
+    for (int k = 0; k < w; ++k) v16[k] += v16[k + w];
+  return v16[0];
 }
 
 // T = threads per block: 256 (several blocks per SM: many edges resident, for levels with many
@@ -1291,7 +1339,7 @@ template <int T>
 __global__ void __launch_bounds__(T, T == 256 ? 3 : 1)
     k_opt_cluster(DeviceState st, const OptOp* __restrict__ ops, const OptControl* __restrict__ ctl,
                   const int32_t* __restrict__ inv_perm, const double* __restrict__ wperm,
-                  OptClusterLayout lay) {
+                  OptClusterLayout lay, OptRefresh refresh) {
   constexpr int S = T / kClusterThreads;           // rows walked per step
   constexpr int kStep = S * kClusterThreads;       // = T positions
   extern __shared__ __align__(16) double s_rho[];  // rows_per_block x kClusterThreads
@@ -1418,6 +1466,8 @@ __global__ void __launch_bounds__(T, T == 256 ? 3 : 1)
     __syncthreads();
     if (s_state.done) break;  // every block of the cluster leaves in the same round
   }
+  // st.bl[edge] was written by this block's thread 0 before the barrier above
+  if (rank == 0) refresh_edge_matrices(st, op, refresh, threadIdx.x, T);
 }
 
 // ---- utilities ---------------------------------------------------------------------------------
@@ -1563,10 +1613,18 @@ void LaunchNodes(cudaStream_t s, const DeviceState& st, const NodeOp* nodes, con
   }();
   const unsigned grid = Grid(n_nodes, (tiles + tpb - 1) / tpb);
   unsigned long long* mx = reinterpret_cast<unsigned long long*>(level_max);
-  if (occ >= 4)
-    k_node<4><<<grid, kTile, 0, s>>>(st, nodes, items, pool, mtab, n_nodes, tiles, tpb, mx);
-  else
-    k_node<3><<<grid, kTile, 0, s>>>(st, nodes, items, pool, mtab, n_nodes, tiles, tpb, mx);
+  static const bool stream = [] {  // BITO_GP_NODE_STORE=cs: cache-streaming stores for the PLVs a level writes
+    const char* e = getenv("BITO_GP_NODE_STORE");
+    return e != nullptr && e[0] == 'c';
+  }();
+  if (occ >= 4) {
+    if (stream)
+      k_node<4, true><<<grid, kTile, 0, s>>>(st, nodes, items, pool, mtab, n_nodes, tiles, tpb, mx);
+    else
+      k_node<4, false><<<grid, kTile, 0, s>>>(st, nodes, items, pool, mtab, n_nodes, tiles, tpb, mx);
+  } else {
+    k_node<3, false><<<grid, kTile, 0, s>>>(st, nodes, items, pool, mtab, n_nodes, tiles, tpb, mx);
+  }
 }
 void LaunchRescale(cudaStream_t s, const DeviceState& st, const MultOp* ops, int n_ops,
                    const double* level_max) {
@@ -1659,7 +1717,7 @@ void LaunchSetOptControl(cudaStream_t s, OptControl* ctl, const OptControl& valu
   k_set_opt_control<<<1, 1, 0, s>>>(ctl, value);
 }
 void LaunchOptBlock(cudaStream_t s, const DeviceState& st, const OptOp* ops, int n_ops,
-                    const OptControl* ctl, int n_groups) {
+                    const OptControl* ctl, int n_groups, const OptRefresh& refresh) {
   if (n_ops == 0) return;
   const size_t smem = OptBlockSharedBytes(st.P, n_groups);
   static size_t opted_in = 0;
@@ -1667,7 +1725,7 @@ void LaunchOptBlock(cudaStream_t s, const DeviceState& st, const OptOp* ops, int
     cudaFuncSetAttribute(k_opt_block, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     opted_in = smem;
   }
-  k_opt_block<<<n_ops, kTile, smem, s>>>(st, ops, ctl);
+  k_opt_block<<<n_ops, kTile, smem, s>>>(st, ops, ctl, refresh);
 }
 // One cluster shape of the on-chip optimiser: `threads` per block (256 or 1024), `cluster_size`
 // blocks per edge. Fails when the edge's rho rows do not fit the cluster's shared memory or the
@@ -1723,7 +1781,8 @@ bool PlanOptCluster(int64_t rows_total, int threads, int cluster_size, OptCluste
 }
 cudaError_t LaunchOptCluster(cudaStream_t s, const DeviceState& st, const OptOp* ops, int n_ops,
                              const OptControl* ctl, const int32_t* inv_perm, const double* wperm,
-                             const int32_t class_row_start[9], const OptClusterPlan& plan) {
+                             const int32_t class_row_start[9], const OptClusterPlan& plan,
+                             const OptRefresh& refresh) {
   if (n_ops == 0) return cudaSuccess;
   OptClusterLayout lay;
   for (int c = 0; c < 9; ++c) lay.class_row_start[c] = class_row_start[c];
@@ -1742,8 +1801,8 @@ cudaError_t LaunchOptCluster(cudaStream_t s, const DeviceState& st, const OptOp*
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   if (plan.threads == 1024)
-    return cudaLaunchKernelEx(&cfg, k_opt_cluster<1024>, st, ops, ctl, inv_perm, wperm, lay);
-  return cudaLaunchKernelEx(&cfg, k_opt_cluster<256>, st, ops, ctl, inv_perm, wperm, lay);
+    return cudaLaunchKernelEx(&cfg, k_opt_cluster<1024>, st, ops, ctl, inv_perm, wperm, lay, refresh);
+  return cudaLaunchKernelEx(&cfg, k_opt_cluster<256>, st, ops, ctl, inv_perm, wperm, lay, refresh);
 }
 int64_t OptPrepareTileGroups(int n_ops, int64_t P) {
   const int64_t tiles = TilesFor(P);

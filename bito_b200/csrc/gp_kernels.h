@@ -72,7 +72,7 @@ size_t OptBlockSharedBytes(int64_t P, int n_groups);
 // before the program runs) so that a captured launch picks up the settings of each replay.
 void LaunchSetOptControl(cudaStream_t s, OptControl* ctl, const OptControl& value);
 void LaunchOptBlock(cudaStream_t s, const DeviceState& st, const OptOp* ops, int n_ops,
-                    const OptControl* ctl, int n_groups);
+                    const OptControl* ctl, int n_groups, const OptRefresh& refresh);
 // Large alignments (plain Brent, two-eigenvalue model, single rank): one thread-block cluster per
 // edge keeps rho in distributed shared memory and runs the whole search there (k_opt_cluster).
 // PlanOptCluster describes one cluster shape (threads per block 256 | 1024, cluster_size blocks) for
@@ -80,7 +80,8 @@ void LaunchOptBlock(cudaStream_t s, const DeviceState& st, const OptOp* ops, int
 bool PlanOptCluster(int64_t rows_total, int threads, int cluster_size, OptClusterPlan* plan);
 cudaError_t LaunchOptCluster(cudaStream_t s, const DeviceState& st, const OptOp* ops, int n_ops,
                              const OptControl* ctl, const int32_t* inv_perm, const double* wperm,
-                             const int32_t class_row_start[9], const OptClusterPlan& plan);
+                             const int32_t class_row_start[9], const OptClusterPlan& plan,
+                             const OptRefresh& refresh);
 int64_t OptPrepareTileGroups(int n_ops, int64_t P);
 int64_t OptRatioTileGroups(int64_t P);
 int64_t OptRatioPartials(int64_t P);  // partial sums per edge written by LaunchOptEvalRatio

@@ -174,6 +174,11 @@ struct ScalarOp {
 struct OptOp {
   PlvRef parent, child;  // rootward_ (r-PLV of the parent), leafward_ (p-PLV of the child)
   int32_t edge;
+  // pool[fix_off .. fix_off + fix_n): the program's transition-matrix slots that hold this edge
+  // (2 * accumulate item, or 2 * Likelihood op + 1). The on-chip optimisers refresh exactly those
+  // when they finish, instead of a rebuild of the whole table after every optimiser level.
+  int32_t fix_off;
+  int32_t fix_n;
   int32_t pad;
 };
 
@@ -218,6 +223,9 @@ struct OptParams {
   double denominator_tolerance;
   double step_size, log_step_size;
   double diff_threshold;
+  // derived on the host so that the optimiser's single-thread step does not spend time on them
+  double brent_tolerance;    // ldexp(1, 1 - significant_digits), optimization.hpp:84
+  double decimal_tolerance;  // pow(10, -significant_digits), optimization.hpp:336, 352, 372
 };
 
 // What a captured OptimizeBranchLength launch must not bake in: the optimiser settings can change
@@ -227,6 +235,13 @@ struct OptControl {
   OptParams prm;
   int32_t method;
   int32_t n_derivatives;
+};
+
+// The transition-matrix tables of the running program and the slot pool OptOp::fix_off indexes.
+struct OptRefresh {
+  const int32_t* pool;
+  double* mtab;      // 16 doubles per accumulate item: q[e] * M(t_e)
+  double* mtab_lik;  // 16 doubles per Likelihood op: M(t_e)
 };
 
 // k_opt_cluster: rho rows (kClusterThreads patterns each, one weight class per row) of an edge are

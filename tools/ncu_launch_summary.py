@@ -1,6 +1,7 @@
 """Aggregates an `ncu --csv --metrics gpu__time_duration.sum[,dram__bytes_read.sum,dram__bytes_write.sum]`
 launch list per kernel: launches, total time, share, DRAM bytes per launch.
-    python tools/ncu_launch_summary.py gpurun_out/launches.csv [--json out.json]"""
+    python tools/ncu_launch_summary.py gpurun_out/launches.csv [--json out.json]
+        [--traffic profiles/r01_traffic.json WORKLOAD "source note"]   # refresh bench.py's per-kernel DRAM-traffic table"""
 import collections
 import csv
 import json
@@ -56,6 +57,17 @@ if __name__ == "__main__":
         out[k] = dict(launches=d["launches"], total_ms=d["ns"] / 1e6,
                       dram_bytes_per_launch=(d["dram_read"] + d["dram_write"]) / d["launches"])
     print(f"\ntotal kernel time {total / 1e6:.2f} ms")
+    if "--traffic" in sys.argv:
+        i = sys.argv.index("--traffic")
+        path, workload, note = sys.argv[i + 1], sys.argv[i + 2], sys.argv[i + 3]
+        try:
+            table = json.load(open(path))
+        except FileNotFoundError:
+            table = {}
+        table[workload] = {k.split("<")[0]: dict(launches=v["launches"], dram_bytes_per_launch=v["dram_bytes_per_launch"],
+                                                  source=note) for k, v in out.items() if v["dram_bytes_per_launch"] > 0}
+        with open(path, "w") as f:
+            json.dump(table, f, indent=1)
     if "--json" in sys.argv:
         with open(sys.argv[sys.argv.index("--json") + 1], "w") as f:
             json.dump(out, f, indent=1)

@@ -13,7 +13,7 @@ from bito_b200.gp_engine import GPEngine  # noqa: E402
 from bito_b200.synthetic import make_named_workload  # noqa: E402
 
 name = sys.argv[1] if len(sys.argv) > 1 else "synthetic-1000taxa-1Mpat-5000trees"
-patterns = int(sys.argv[2]) if len(sys.argv) > 2 else None
+patterns = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2] != "-" else None
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
 wl = make_named_workload(name, pattern_count=patterns)
 dag = wl.dag
