@@ -58,6 +58,7 @@ class Stats(C.Structure):
         ("optimizer_cluster_size", C.c_int64),
         ("optimizer_cluster_threads", C.c_int64),
         ("optimizer_edges_in_flight", C.c_int64),
+        ("peer_collective_calls", C.c_int64),
     ]
 
 

@@ -74,6 +74,7 @@ struct NcclApi {
   int (*GetUniqueId)(NcclUniqueId*) = nullptr;
   int (*CommInitRank)(NcclComm*, int, NcclUniqueId, int) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, NcclComm, cudaStream_t) = nullptr;
   int (*CommDestroy)(NcclComm) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
   bool loaded = false;
@@ -88,6 +89,7 @@ NcclApi& Nccl() {
   api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
   api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
   api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(h, "ncclAllReduce"));
+  api.AllGather = reinterpret_cast<decltype(api.AllGather)>(dlsym(h, "ncclAllGather"));
   api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
   api.GetErrorString =
       reinterpret_cast<decltype(api.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
@@ -103,7 +105,7 @@ void NcclCheck(int rc, const char* what) {
          (api.GetErrorString ? api.GetErrorString(rc) : "?"));
   }
 }
-constexpr int kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2;
+constexpr int kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2, kNcclInt8 = 0;
 
 }  // namespace
 
@@ -266,6 +268,8 @@ Engine::~Engine() {
   cudaSetDevice(device_);
   cudaStreamSynchronize(stream_);
   for (auto& kv : programs_) FreeProgram(*kv.second);
+  ReleasePeerMemory();
+  d_peer_epoch_.Release();
   if (nccl_comm_ != nullptr) Nccl().CommDestroy(nccl_comm_);
   plv_pool_.Release();
   row_pool_.Release();
@@ -603,6 +607,13 @@ void Engine::DropGraphs() {
 
 void Engine::AllReduce(double* buf, int64_t n, bool max_op) {
   if (n_ranks_ <= 1 || n <= 0) return;
+  if (peer_ready_ && n <= kPeerCapacity) {  // a few scalars per edge: one kernel over NVLink peer memory
+    LaunchPeerAllReduce(stream_, peer_, buf, static_cast<int>(n), max_op);
+    stats_.collective_calls++;
+    stats_.peer_collective_calls++;
+    if (!capturing_) stats_.kernel_launches++;
+    return;
+  }
   NcclCheck(Nccl().AllReduce(buf, buf, static_cast<size_t>(n), kNcclFloat64,
                              max_op ? kNcclMax : kNcclSum, nccl_comm_, stream_),
             "ncclAllReduce");
@@ -621,6 +632,7 @@ void Engine::CommInit(int n_ranks, int rank, const uint8_t id[128]) {
   NcclComm comm = nullptr;
   NcclCheck(Nccl().CommInitRank(&comm, n_ranks, uid, rank), "ncclCommInitRank");
   nccl_comm_ = comm;
+  SetUpPeerMemory();
   if (have_patterns_) {  // total weight must now be global
     EnsureScratch(TilesFor(P_), 2);
     GP_CUDA(cudaMemcpyAsync(d_packed_.ptr, &total_weight_, sizeof(double), cudaMemcpyHostToDevice,
@@ -632,6 +644,81 @@ void Engine::CommInit(int n_ranks, int rank, const uint8_t id[128]) {
     total_weight_ = *static_cast<double*>(pinned_);
   }
   InvalidatePrograms();
+}
+
+// Exchange buffers for k_peer_allreduce: one cudaMalloc per rank, its IPC handle all-gathered over
+// the NCCL communicator that was just built, every peer's buffer mapped here (which also enables
+// peer access). Any failure (no IPC in this container, no P2P path, more than 8 ranks, or
+// BITO_GP_PEER_ALLREDUCE=0) leaves the engine on NCCL all-reduces: same results, more latency.
+// All ranks must agree, so the outcome is itself all-reduced (min) before anyone uses the buffers.
+void Engine::SetUpPeerMemory() {
+  peer_ready_ = false;
+  const char* env = getenv("BITO_GP_PEER_ALLREDUCE");
+  bool ok = !(env != nullptr && atoi(env) == 0) && n_ranks_ <= kMaxPeerRanks && Nccl().AllGather != nullptr;
+  const size_t bytes = PeerBufferBytes(n_ranks_);
+  std::vector<cudaIpcMemHandle_t> handles(static_cast<size_t>(n_ranks_));
+  if (ok) ok = cudaMalloc(&peer_local_, bytes) == cudaSuccess;
+  if (ok) ok = cudaMemsetAsync(peer_local_, 0, bytes, stream_) == cudaSuccess;
+  cudaIpcMemHandle_t mine{};
+  if (ok) ok = cudaIpcGetMemHandle(&mine, peer_local_) == cudaSuccess;
+  cudaGetLastError();
+  // the gather runs on every rank whatever happened above (a collective must not be skipped by some)
+  DeviceArray<uint8_t> d_handles;
+  d_handles.Resize(sizeof(cudaIpcMemHandle_t) * static_cast<size_t>(n_ranks_ + 1), false, stream_);
+  GP_CUDA(cudaMemcpyAsync(d_handles.ptr + sizeof(mine) * static_cast<size_t>(n_ranks_), &mine, sizeof(mine),
+                          cudaMemcpyHostToDevice, stream_));
+  if (Nccl().AllGather != nullptr) {
+    NcclCheck(Nccl().AllGather(d_handles.ptr + sizeof(mine) * static_cast<size_t>(n_ranks_), d_handles.ptr,
+                               sizeof(mine), kNcclInt8, nccl_comm_, stream_),
+              "ncclAllGather");
+    GP_CUDA(cudaMemcpyAsync(handles.data(), d_handles.ptr, sizeof(mine) * static_cast<size_t>(n_ranks_),
+                            cudaMemcpyDeviceToHost, stream_));
+  }
+  GP_CUDA(cudaStreamSynchronize(stream_));
+  d_handles.Release();
+  for (int r = 0; r < n_ranks_ && ok; ++r) {
+    if (r == rank_) {
+      peer_.base[r] = static_cast<double*>(peer_local_);
+      continue;
+    }
+    void* p = nullptr;
+    ok = cudaIpcOpenMemHandle(&p, handles[static_cast<size_t>(r)], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+    if (ok) {
+      peer_.base[r] = static_cast<double*>(p);
+      peer_opened_.push_back(p);
+    }
+  }
+  cudaGetLastError();
+  // agree: everyone or no one
+  EnsureScratch(TilesFor(P_), 2);
+  const double flag = ok ? 1. : 0.;
+  GP_CUDA(cudaMemcpyAsync(d_packed_.ptr, &flag, sizeof(double), cudaMemcpyHostToDevice, stream_));
+  NcclCheck(Nccl().AllReduce(d_packed_.ptr, d_packed_.ptr, 1, kNcclFloat64, /*ncclMin*/ 3, nccl_comm_, stream_),
+            "ncclAllReduce");
+  double all = 0.;
+  GP_CUDA(cudaMemcpyAsync(&all, d_packed_.ptr, sizeof(double), cudaMemcpyDeviceToHost, stream_));
+  GP_CUDA(cudaStreamSynchronize(stream_));
+  if (all != 1.) {
+    ReleasePeerMemory();
+    return;
+  }
+  if (d_peer_epoch_.n == 0) d_peer_epoch_.Resize(1, false, stream_);
+  GP_CUDA(cudaMemsetAsync(d_peer_epoch_.ptr, 0, sizeof(unsigned long long), stream_));
+  GP_CUDA(cudaStreamSynchronize(stream_));
+  peer_.epoch = d_peer_epoch_.ptr;
+  peer_.status = d_status_.ptr;
+  peer_.n_ranks = n_ranks_;
+  peer_.rank = rank_;
+  peer_ready_ = true;
+}
+
+void Engine::ReleasePeerMemory() {
+  peer_ready_ = false;
+  for (void* p : peer_opened_) cudaIpcCloseMemHandle(p);
+  peer_opened_.clear();
+  if (peer_local_ != nullptr) cudaFree(peer_local_);
+  peer_local_ = nullptr;
+  cudaGetLastError();
 }
 
 void Engine::SetStream(cudaStream_t s) {

@@ -284,6 +284,14 @@ class Engine {
   // NCCL (dlopen'ed)
   void* nccl_comm_ = nullptr;
   int n_ranks_ = 1, rank_ = 0;
+  // NVLink peer memory for the scalar all-reduces (k_peer_allreduce); NCCL remains the fallback
+  void SetUpPeerMemory();
+  void ReleasePeerMemory();
+  PeerComm peer_{};
+  void* peer_local_ = nullptr;       // this rank's exchange buffer (cudaMalloc + IPC handle)
+  std::vector<void*> peer_opened_;   // the other ranks' buffers as mapped here
+  DeviceArray<unsigned long long> d_peer_epoch_;
+  bool peer_ready_ = false;
 
   bito_gp_stats stats_{};
 

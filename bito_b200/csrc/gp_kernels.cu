@@ -1470,6 +1470,65 @@ __global__ void __launch_bounds__(T, T == 256 ? 3 : 1)
   if (rank == 0) refresh_edge_matrices(st, op, refresh, threadIdx.x, T);
 }
 
+// ---- all-reduce of per-edge scalars over NVLink peer memory --------------------------------------
+// The collectives of this path carry a few scalars per edge: latency, not bandwidth.
+// One block pushes its rank's n values into slot [parity][rank] of EVERY rank's exchange buffer
+// (plain stores through the IPC mappings: NVLink writes), publishes them with a release store of
+// the epoch number into the matching flag of every rank, waits until the flags of all ranks in its
+// own buffer show this epoch, and reduces the n_ranks slots in rank order - the same order on every
+// GPU, so all ranks get bitwise-identical sums and take identical optimiser / rescale decisions.
+// Buffers are double-buffered by epoch parity: a rank can be at most one all-reduce ahead of a peer
+// (it needs that peer's flag to finish its own), so the slot it writes is never one still being read.
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+constexpr int kPeerThreads = 256;
+__global__ void __launch_bounds__(kPeerThreads)
+    k_peer_allreduce(PeerComm pc, double* __restrict__ buf, int n, int max_op) {
+  __shared__ unsigned long long s_epoch;
+  if (threadIdx.x == 0) s_epoch = *pc.epoch + 1;
+  __syncthreads();
+  const unsigned long long epoch = s_epoch;
+  const int parity = static_cast<int>(epoch & 1), R = pc.n_ranks;
+  const int64_t slot = (static_cast<int64_t>(parity) * R + pc.rank) * kPeerCapacity;
+  for (int r = 0; r < R; ++r) {
+    double* dst = pc.base[r] + slot;
+    for (int i = threadIdx.x; i < n; i += kPeerThreads) dst[i] = buf[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < R) {
+    // flag[parity][source = me] of rank threadIdx.x, then wait for flag[parity][source = threadIdx.x] here
+    unsigned long long* their = reinterpret_cast<unsigned long long*>(pc.base[threadIdx.x] + 2 * R * kPeerCapacity);
+    st_release_sys(their + parity * R + pc.rank, epoch);
+    const unsigned long long* mine =
+        reinterpret_cast<const unsigned long long*>(pc.base[pc.rank] + 2 * R * kPeerCapacity) + parity * R +
+        threadIdx.x;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(mine) < epoch) {
+      if (clock64() - t0 > (1ll << 33)) {  // ~4 s: a peer died; fail the call instead of hanging
+        atomicOr(pc.status, kErrPeerTimeout);
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  const double* mine = pc.base[pc.rank] + static_cast<int64_t>(parity) * R * kPeerCapacity;
+  for (int i = threadIdx.x; i < n; i += kPeerThreads) {
+    double acc = __ldcg(mine + i);
+    for (int r = 1; r < R; ++r) {
+      const double v = __ldcg(mine + r * kPeerCapacity + i);
+      acc = max_op ? fmax(acc, v) : acc + v;
+    }
+    buf[i] = acc;
+  }
+  if (threadIdx.x == 0) *pc.epoch = epoch;
+}
 // ---- utilities ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kTile)
     k_export_plv(DeviceState st, PlvRef src, double* __restrict__ out) {
@@ -1843,6 +1902,11 @@ void LaunchOptEvalRatio(cudaStream_t s, const DeviceState& st, int n_ops, const 
   }();
   k_opt_eval_ratio<<<static_cast<unsigned>(items < cap ? items : cap), kTile, 0, s>>>(
       st, groups, states, rho, rho_stride, wperm, row_class, partials, active, active_capacity, parity);
+}
+
+void LaunchPeerAllReduce(cudaStream_t s, const PeerComm& pc, double* buf, int n, bool max_op) {
+  if (n <= 0) return;
+  k_peer_allreduce<<<1, kPeerThreads, 0, s>>>(pc, buf, n, max_op ? 1 : 0);
 }
 
 void LaunchExportPlv(cudaStream_t s, const DeviceState& st, PlvRef src, double* dense_out) {

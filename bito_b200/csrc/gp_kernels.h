@@ -100,6 +100,10 @@ void LaunchQuartet(cudaStream_t s, const DeviceState& st, const QuartetItem* ite
 void LaunchQuartetFinish(cudaStream_t s, const DeviceState& st, const QuartetItem* items, int n_items,
                          const double* sums, double* out);
 
+// In-place all-reduce (sum or max, fixed rank order) of n <= kPeerCapacity doubles across the ranks
+// of `pc` by peer-memory stores over NVLink: one launch, no NCCL call.
+void LaunchPeerAllReduce(cudaStream_t s, const PeerComm& pc, double* buf, int n, bool max_op);
+
 // Utilities.
 void LaunchExportPlv(cudaStream_t s, const DeviceState& st, PlvRef src, double* dense_out);
 void LaunchFill(cudaStream_t s, double* dst, int64_t n, double value);

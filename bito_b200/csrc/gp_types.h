@@ -38,7 +38,8 @@ enum StatusBits : uint32_t {
   kErrNegativePLV = 4u,          // gp_engine.cpp:585-586
   kErrRescaledStationary = 8u,   // gp_engine.cpp:256-257
   kErrEmptyPrep = 16u,           // gp_engine.cpp:325
-  kErrQuartetRescaled = 32u      // gp_engine.cpp:750-753
+  kErrQuartetRescaled = 32u,     // gp_engine.cpp:750-753
+  kErrPeerTimeout = 64u          // a peer GPU never delivered its share of an all-reduce
 };
 
 // Per-engine device pointers handed to every kernel by value.
@@ -236,6 +237,21 @@ struct OptControl {
   int32_t method;
   int32_t n_derivatives;
 };
+
+// Peer-memory all-reduce over NVLink (k_peer_allreduce): every rank owns one exchange buffer, mapped
+// into every other rank's address space through CUDA IPC. Layout of a buffer, in doubles:
+//   data[parity][source rank][capacity], then (as 64-bit words) flag[parity][source rank].
+constexpr int kMaxPeerRanks = 8;
+constexpr int64_t kPeerCapacity = 8192;  // doubles per all-reduce; larger ones go through NCCL
+struct PeerComm {
+  double* base[kMaxPeerRanks];  // base[r] = rank r's exchange buffer as mapped in THIS process
+  unsigned long long* epoch;    // all-reduces completed so far (device memory, so graphs replay)
+  uint32_t* status;             // DeviceState::status
+  int32_t n_ranks, rank;
+};
+inline size_t PeerBufferBytes(int n_ranks) {
+  return (size_t(2) * n_ranks * kPeerCapacity + size_t(2) * n_ranks) * sizeof(double);
+}
 
 // The transition-matrix tables of the running program and the slot pool OptOp::fix_off indexes.
 struct OptRefresh {

@@ -241,7 +241,7 @@ typedef struct bito_gp_stats {
   int64_t levels_last;          /* dependency levels of the last program                 */
   int64_t fused_ops_last;       /* macro-ops after fusion in the last program            */
   int64_t objective_evaluations;/* OptimizeBranchLength f-evals (all edges) so far       */
-  int64_t collective_calls;     /* NCCL all-reduces issued so far                        */
+  int64_t collective_calls;     /* all-reduces issued so far (NCCL or peer memory)       */
   int64_t device_bytes_in_use;  /* PLV slabs + rows + scalars                            */
   int64_t plvs_resident;        /* PLVs that own HBM (the rest are symbolic or zero)     */
   double algorithmic_bytes_last;/* SURVEY 8(d) bytes per local pattern x patterns, last program */
@@ -255,6 +255,7 @@ typedef struct bito_gp_stats {
   int64_t optimizer_cluster_size;    /* blocks per cluster for scheme 2, else 0              */
   int64_t optimizer_cluster_threads; /* threads per block for scheme 2, else 0               */
   int64_t optimizer_edges_in_flight; /* clusters resident on the device at once, scheme 2   */
+  int64_t peer_collective_calls;     /* of collective_calls: one-kernel all-reduces over NVLink peer memory */
 } bito_gp_stats;
 BITO_GP_API int bito_gp_get_stats(bito_gp_engine* e, bito_gp_stats* out);
 

@@ -20,6 +20,9 @@ timeout 300 python tools/profile_sweep.py $WL $PAT > $out/${tag}_profile_sweep.l
 # launch list: one pass + one batched sweep, graphs off
 timeout 500 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 6000 --csv \
   --log-file $out/${tag}_launches_pass.csv python profiles/prof_pass.py $WL $PAT 1 > $out/${tag}_prof_pass.log 2>&1; echo "ncu list rc=$?"
+# launch list of the reference's Gauss-Seidel sweep at 100k patterns (3000 launches from inside the sweep)
+timeout 500 ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 3000 --csv --log-file $out/${tag}_launches_gs.csv \
+  python profiles/prof_pass.py synthetic-200taxa-100kpat-1000trees 100000 1 gs > $out/${tag}_prof_gs.log 2>&1; echo "ncu gs list rc=$?"
 [ -n "$QUICK" ] && { ls -la $out; exit 0; }
 # full captures (at 40k / 20k patterns so that ncu's save/restore of device memory stays small): the two
 # largest k_node launches (first rootward levels), the likelihood kernel, the sweep objective
@@ -29,4 +32,6 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_li
   python profiles/prof_pass.py $WL 20000 1 > $out/${tag}_ncu_lik.log 2>&1; echo "ncu lik rc=$?"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_opt -s 4 -c 4 -f -o $out/${tag}_k_opt \
   python profiles/prof_pass.py $WL 40000 1 sweep > $out/${tag}_ncu_opt.log 2>&1; echo "ncu opt rc=$?"
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_opt_cluster -s 200 -c 2 -f -o $out/${tag}_k_opt_cluster \
+  python profiles/prof_pass.py synthetic-200taxa-100kpat-1000trees 100000 1 gs > $out/${tag}_ncu_cluster.log 2>&1; echo "ncu cluster rc=$?"
 ls -la $out
