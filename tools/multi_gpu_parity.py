@@ -24,6 +24,7 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 failures = []
+collectives = [0, 0]  # all-reduces issued, of which over NVLink peer memory (k_peer_allreduce)
 
 
 def check(name, ok):
@@ -75,11 +76,17 @@ for case, thresholds in (("ds1", (0, 2)), ("fluA", (0, 4)), ("five_taxon", (0, 1
         check(f"{case} thr#{ti} brent sweeps |dBL| {worst:.1e}", worst <= BL_ATOL)
         want = fx[skey + "_counts"]
         check(f"{case} thr#{ti} counts after sweeps", np.array_equal(e.rescaling_counts()[:want.size], want))
+        st = e.stats()
+        collectives[0] += st["collective_calls"]
+        collectives[1] += st["peer_collective_calls"]
+        check(f"{case} thr#{ti} no device-side assert / peer timeout", st["device_status_bits"] == 0)
         e.close()
 
 t = torch.tensor([len(failures)], device="cuda")
 dist.all_reduce(t)
 if rank == 0:
+    print(f"all-reduces: {collectives[0]}, of which over peer memory: {collectives[1]} "
+          f"(BITO_GP_PEER_ALLREDUCE={os.environ.get('BITO_GP_PEER_ALLREDUCE', 'unset')})", flush=True)
     print("MULTI-GPU PARITY", "PASSED" if t.item() == 0 else f"FAILED ({failures})", f"on {world} GPUs", flush=True)
 dist.destroy_process_group()
 sys.exit(0 if t.item() == 0 else 1)
