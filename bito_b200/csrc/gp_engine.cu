@@ -270,6 +270,8 @@ Engine::~Engine() {
   for (auto& kv : programs_) FreeProgram(*kv.second);
   ReleasePeerMemory();
   d_peer_epoch_.Release();
+  d_peer_seq_.Release();
+  d_peer_comm_.Release();
   if (nccl_comm_ != nullptr) Nccl().CommDestroy(nccl_comm_);
   plv_pool_.Release();
   row_pool_.Release();
@@ -407,6 +409,7 @@ void Engine::SetSitePatterns(const uint8_t* symbols, const double* weights, bool
   }
   have_patterns_ = true;
   BuildWeightClasses(on_device ? nullptr : weights);
+  AgreeOnClusterScheme();
   // Re-uploading an alignment of the same shape leaves every compiled program valid.
   if (slots_changed) InvalidatePrograms();
 }
@@ -502,14 +505,14 @@ void Engine::BuildWeightClasses(const double* host_weights) {
     const size_t had = cluster_plans_.size();
     const int had_rows = had > 0 ? cluster_plans_[0].rows_total : -1;
     cluster_plans_.clear();
-    if (opt_cluster_env_ != 0 && P_ > 0) {
+    if (opt_cluster_env_ != 0) {  // an empty shard (P = 0) plans one all-padding row: it still takes part in the exchange
       for (int threads : {256, 1024}) {
         if (opt_cluster_threads_env_ > 0 && threads != opt_cluster_threads_env_) continue;
         if (opt_cluster_env_ > 0 && opt_cluster_threads_env_ <= 0 && threads != 256) continue;
         for (int c = 1; c <= kMaxOptCluster; c *= 2) {
           if (opt_cluster_env_ > 0 && c != opt_cluster_env_) continue;
           OptClusterPlan plan;
-          if (PlanOptCluster(cpos / row, threads, c, &plan)) cluster_plans_.push_back(plan);
+          if (PlanOptCluster(std::max<int64_t>(cpos / row, 1), threads, c, &plan)) cluster_plans_.push_back(plan);
         }
       }
     }
@@ -642,8 +645,30 @@ void Engine::CommInit(int n_ranks, int rank, const uint8_t id[128]) {
                             stream_));
     GP_CUDA(cudaStreamSynchronize(stream_));
     total_weight_ = *static_cast<double*>(pinned_);
+    AgreeOnClusterScheme();
   }
   InvalidatePrograms();
+}
+
+// Several ranks: whether a level's searches run in clusters must be the same decision everywhere
+// (the clusters of one edge on different GPUs wait for each other). Each rank knows how many
+// clusters its device keeps resident for its shard; the minimum over ranks bounds the edges of a
+// level that may take the cluster path. Collective: called by every rank at the same points.
+void Engine::AgreeOnClusterScheme() {
+  multi_rank_cluster_ops_ = 0;
+  if (n_ranks_ <= 1) return;
+  int local = 0;
+  for (const OptClusterPlan& c : cluster_plans_) local = std::max(local, c.active_clusters);
+  if (!peer_ready_ || n_eigen_groups_ != 2) local = 0;
+  EnsureScratch(TilesFor(P_), 2);
+  const double neg = -static_cast<double>(local);
+  GP_CUDA(cudaMemcpyAsync(d_packed_.ptr, &neg, sizeof(double), cudaMemcpyHostToDevice, stream_));
+  AllReduce(d_packed_.ptr, 1, true);  // max of the negatives = minus the minimum
+  double out = 0.;
+  GP_CUDA(cudaMemcpyAsync(&out, d_packed_.ptr, sizeof(double), cudaMemcpyDeviceToHost, stream_));
+  GP_CUDA(cudaStreamSynchronize(stream_));
+  multi_rank_cluster_ops_ = std::min<int>(static_cast<int>(-out), kPeerEdgeSlots);
+  DropGraphs();
 }
 
 // Exchange buffers for k_peer_allreduce: one cudaMalloc per rank, its IPC handle all-gathered over
@@ -704,12 +729,27 @@ void Engine::SetUpPeerMemory() {
   }
   if (d_peer_epoch_.n == 0) d_peer_epoch_.Resize(1, false, stream_);
   GP_CUDA(cudaMemsetAsync(d_peer_epoch_.ptr, 0, sizeof(unsigned long long), stream_));
+  if (d_peer_seq_.n == 0) d_peer_seq_.Resize(kPeerEdgeSlots, false, stream_);
+  GP_CUDA(cudaMemsetAsync(d_peer_seq_.ptr, 0, kPeerEdgeSlots * sizeof(unsigned long long), stream_));
   GP_CUDA(cudaStreamSynchronize(stream_));
   peer_.epoch = d_peer_epoch_.ptr;
   peer_.status = d_status_.ptr;
   peer_.n_ranks = n_ranks_;
   peer_.rank = rank_;
+  if (d_peer_comm_.n == 0) d_peer_comm_.Resize(1, false, stream_);
+  GP_CUDA(cudaMemcpyAsync(d_peer_comm_.ptr, &peer_, sizeof(PeerComm), cudaMemcpyHostToDevice, stream_));
+  GP_CUDA(cudaStreamSynchronize(stream_));
   peer_ready_ = true;
+}
+
+PeerEdge Engine::PeerEdgeContext() const {
+  PeerEdge px{};
+  if (n_ranks_ > 1 && peer_ready_) {
+    px.pc = d_peer_comm_.ptr;
+    px.seq = d_peer_seq_.ptr;
+    px.enabled = 1;
+  }
+  return px;
 }
 
 void Engine::ReleasePeerMemory() {
@@ -746,6 +786,14 @@ void Engine::CheckStatus() {
   if (bits == 0) return;
   GP_CUDA(cudaMemsetAsync(d_status_.ptr, 0, sizeof(uint32_t), stream_));
   stats_.device_status_bits |= bits;
+  if (bits & kErrPeerTimeout) {
+    // not an assert of the reference: a peer rank never delivered its share of an exchange. The bit
+    // stays set on the device (kernels stop waiting for peers) and every call fails from here on.
+    const uint32_t keep = kErrPeerTimeout;
+    GP_CUDA(cudaMemcpyAsync(d_status_.ptr, &keep, sizeof(uint32_t), cudaMemcpyHostToDevice, stream_));
+    GP_CUDA(cudaStreamSynchronize(stream_));
+    Fail("a peer GPU did not answer a peer-memory exchange within ~4 s (rank died or ranks issued different calls)");
+  }
   if (!(cfg_.flags & BITO_GP_FLAG_STRICT_ASSERTS)) return;  // Release-build semantics
   std::string msg;
   if (bits & kErrRescalingDifference)
@@ -1544,7 +1592,29 @@ OptParams Engine::OptimizerParams(bool check_convergence) const {
 // with thousands of edges at 1e5 patterns -> stream.
 int Engine::OptScheme(int n_ops, const OptClusterPlan** plan) const {
   if (plan != nullptr) *plan = nullptr;
-  if (n_ranks_ != 1 || P_ <= 0 || (cfg_.flags & BITO_GP_FLAG_NO_ONCHIP_OPTIMIZER)) return 0;
+  if (cfg_.flags & BITO_GP_FLAG_NO_ONCHIP_OPTIMIZER) return 0;
+  if (n_ranks_ > 1) {
+    // one cluster per edge on every GPU, their per-evaluation sums exchanged over NVLink inside the
+    // kernel (peer_edge_sum): only when every cluster of the level is resident at once on every rank
+    // (they wait for each other), which is the reference's Gauss-Seidel schedule; else rounds + all-reduce
+    if (method_ != BITO_GP_BRENT_OPTIMIZATION || n_ops > multi_rank_cluster_ops_) return 0;
+    const OptClusterPlan* best_plan = nullptr;
+    double best = 0.;
+    for (const OptClusterPlan& c : cluster_plans_) {
+      if (c.active_clusters < n_ops) continue;
+      const int rows_per_thread = (c.rows_per_block * kClusterThreads + c.threads - 1) / c.threads;
+      const double us = 1.0 + 2.5 * ((rows_per_thread + 1) / 2) +
+                        14.5 * (2.4 + 0.05 * rows_per_thread + (c.threads > 256 ? 0.5 : 0.));
+      if (best_plan == nullptr || us < best) {
+        best = us;
+        best_plan = &c;
+      }
+    }
+    if (best_plan == nullptr) return 0;  // cannot happen: multi_rank_cluster_ops_ <= this rank's maximum
+    if (plan != nullptr) *plan = best_plan;
+    return 2;
+  }
+  if (P_ <= 0) return 0;
   const bool cluster_ok = !cluster_plans_.empty() && n_eigen_groups_ == 2 &&
                           method_ == BITO_GP_BRENT_OPTIMIZATION;
   const bool forced = opt_cluster_env_ > 0;
@@ -1623,7 +1693,8 @@ void Engine::RunOptimizer(const OptOp* d_ops, int n_ops, int method, bool check_
     // large alignment, single rank, plain Brent: one thread-block cluster per edge (k_opt_cluster)
     ProfScope ps(this, kProfOptCluster, 64. * n_ops * static_cast<double>(P_));
     GP_CUDA(LaunchOptCluster(stream_, st, d_ops, n_ops, d_opt_ctl_.ptr, d_cluster_inv_perm_.ptr,
-                             d_cluster_wperm_.ptr, cluster_class_row_start_, *plan, opt_refresh_));
+                             d_cluster_wperm_.ptr, cluster_class_row_start_, *plan, opt_refresh_,
+                             PeerEdgeContext()));
     return;
   }
   const OptParams prm = OptimizerParams(check_convergence);

@@ -290,7 +290,11 @@ class Engine {
   PeerComm peer_{};
   void* peer_local_ = nullptr;       // this rank's exchange buffer (cudaMalloc + IPC handle)
   std::vector<void*> peer_opened_;   // the other ranks' buffers as mapped here
-  DeviceArray<unsigned long long> d_peer_epoch_;
+  DeviceArray<unsigned long long> d_peer_epoch_, d_peer_seq_;
+  DeviceArray<PeerComm> d_peer_comm_;  // peer_ for kernels whose lanes index base[] by rank
+  PeerEdge PeerEdgeContext() const;
+  void AgreeOnClusterScheme();
+  int multi_rank_cluster_ops_ = 0;   // largest level (edges) that may take the cluster path, agreed by all ranks
   bool peer_ready_ = false;
 
   bito_gp_stats stats_{};

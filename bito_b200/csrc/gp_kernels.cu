@@ -1298,11 +1298,57 @@ __device__ __forceinline__ void ratio_coefficients(const V4& r, const V4& c, dou
   c0_out = c0;
 }
 
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// One value per rank summed across GPUs, for the edge that owns record slot `slot`: warp 0 of the
+// cluster's block 0 stores (value, then tag with release) into every rank's record
+// [slot][parity][my rank] over NVLink, waits for the tags of all ranks in its own buffer, and adds
+// the values in rank order (the same on every GPU). Called by a full warp; returns the sum in
+// every lane. `tag` grows with every exchange of this slot, so a stale record is never taken.
+__device__ __forceinline__ double peer_edge_sum(const PeerEdge& px, int slot, int parity,
+                                                unsigned long long tag, double v) {
+  const PeerComm* pc = px.pc;
+  const int R = pc->n_ranks, me = pc->rank, lane = threadIdx.x & 31;
+  // bank = (search parity, round parity); tag = search number << 20 | round + 1
+  const size_t bank = ((tag >> 20) & 1) * 2 + parity;
+  const size_t rec0 = PeerEdgeOffsetDoubles(R) + (static_cast<size_t>(slot) * 4 + bank) * R * 2;
+  double got = 0.;
+  if (lane < R) {
+    double* theirs = pc->base[lane] + rec0 + 2 * me;
+    *reinterpret_cast<volatile double*>(theirs) = v;
+    st_release_sys(reinterpret_cast<unsigned long long*>(theirs + 1), tag);
+    const double* mine = pc->base[me] + rec0 + 2 * lane;
+    const long long t0 = clock64();
+    // ~4 s without an answer: a peer died. Fail the call instead of hanging, and once that has
+    // happened never wait again (every later exchange of this engine would time out too).
+    const bool dead = (*reinterpret_cast<volatile uint32_t*>(pc->status) & kErrPeerTimeout) != 0;
+    while (!dead && ld_acquire_sys(reinterpret_cast<const unsigned long long*>(mine + 1)) != tag) {
+      if (clock64() - t0 > (1ll << 33)) {
+        atomicOr(pc->status, kErrPeerTimeout);
+        break;
+      }
+    }
+    got = *reinterpret_cast<const volatile double*>(mine);
+  }
+  double acc = __shfl_sync(0xffffffffu, got, 0);
+  for (int r = 1; r < R; ++r) acc += __shfl_sync(0xffffffffu, got, r);
+  return acc;
+}
+
 // Sum of `v` over every thread of every block of the cluster, returned to all threads. s_slots is
 // double-buffered by `parity`: a block can only be one barrier ahead of its peers.
 template <int T>
 __device__ __forceinline__ double cluster_sum(cg::cluster_group& cluster, double v, double* s_warp,
-                                              double (*s_slots)[kMaxOptCluster], int parity) {
+                                              double (*s_slots)[kMaxOptCluster], int parity,
+                                              const PeerEdge& px, int slot, unsigned long long tag,
+                                              double* s_global) {
 #pragma unroll
   for (int sh = 16; sh > 0; sh >>= 1) v += __shfl_down_sync(0xffffffffu, v, sh);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1328,7 +1374,14 @@ __device__ __forceinline__ double cluster_sum(cg::cluster_group& cluster, double
   for (int w = kMaxOptCluster / 2; w > 0; w >>= 1)
 #pragma unroll
     for (int k = 0; k < w; ++k) v16[k] += v16[k + w];
-  return v16[0];
+  if (!px.enabled) return v16[0];
+  // several GPUs: this GPU's total goes through NVLink, the global one comes back to every block
+  if (cluster.block_rank() == 0 && warp == 0) {
+    const double g = peer_edge_sum(px, slot, parity, tag, v16[0]);
+    if (lane < static_cast<int>(n_blocks)) *cluster.map_shared_rank(&s_global[parity], lane) = g;
+  }
+  cluster.sync();
+  return s_global[parity];
 }
 
 // T = threads per block: 256 (several blocks per SM: many edges resident, for levels with many
@@ -1339,16 +1392,20 @@ template <int T>
 __global__ void __launch_bounds__(T, T == 256 ? 3 : 1)
     k_opt_cluster(DeviceState st, const OptOp* __restrict__ ops, const OptControl* __restrict__ ctl,
                   const int32_t* __restrict__ inv_perm, const double* __restrict__ wperm,
-                  OptClusterLayout lay, OptRefresh refresh) {
+                  OptClusterLayout lay, OptRefresh refresh, PeerEdge px) {
   constexpr int S = T / kClusterThreads;           // rows walked per step
   constexpr int kStep = S * kClusterThreads;       // = T positions
   extern __shared__ __align__(16) double s_rho[];  // rows_per_block x kClusterThreads
   __shared__ OptState s_state;
   __shared__ double s_warp[T / 32];
   __shared__ double s_slots[2][kMaxOptCluster];
+  __shared__ double s_global[2];
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = static_cast<int>(cluster.block_rank());
   const int o = blockIdx.x / cluster.num_blocks();
+  // several GPUs: edge o of the level owns exchange slot o (the engine only takes this path when the
+  // level has at most kPeerEdgeSlots edges and all its clusters are resident at once)
+  const unsigned long long tag0 = px.enabled ? (px.seq[o] << 20) : 0ull;
   const OptOp op = ops[o];
   const OptParams prm = ctl->prm;
   if (threadIdx.x == 0) opt_init(s_state, st, prm, ctl->method, op);
@@ -1360,17 +1417,18 @@ __global__ void __launch_bounds__(T, T == 256 ? 3 : 1)
   const int64_t q0 = static_cast<int64_t>(row0) * kClusterThreads;
   const int sub = threadIdx.x / kClusterThreads;  // this thread's rows: sub, sub + S, sub + 2 S, ...
   // the edge's PLVs, once: rho into shared memory, K_e = sum_p w_p log c0_p. Two rows per trip
-  // with all four 256-bit loads issued before the first use (padding reads pattern 0 and is masked).
+  // with all four 256-bit loads issued before the first use (padding positions load nothing).
   double k_part = 0.;
   for (int r = sub; r < n_rows; r += 2 * S) {
     const int i0 = r * kClusterThreads + (threadIdx.x & (kClusterThreads - 1)), i1 = i0 + kStep;
     const bool two = r + S < n_rows;
     const int32_t pa = inv_perm[q0 + i0];
     const int32_t pb = two ? inv_perm[q0 + i1] : -1;
-    const V4 ra = load_plv(op.parent, max(pa, 0));
-    const V4 ca = load_plv(op.child, max(pa, 0));
-    const V4 rb = load_plv(op.parent, max(pb, 0));
-    const V4 cb = load_plv(op.child, max(pb, 0));
+    V4 ra = {1., 1., 1., 1.}, ca = ra, rb = ra, cb = ra;  // padding: any finite value, masked below
+    if (pa >= 0) ra = load_plv(op.parent, pa);
+    if (pa >= 0) ca = load_plv(op.child, pa);
+    if (pb >= 0) rb = load_plv(op.parent, pb);
+    if (pb >= 0) cb = load_plv(op.child, pb);
     double rho, c0;
     ratio_coefficients(ra, ca, rho, c0);
     if (pa >= 0) k_part += wperm[q0 + i0] * log(c0);
@@ -1382,7 +1440,9 @@ __global__ void __launch_bounds__(T, T == 256 ? 3 : 1)
     }
   }
   int round = 0;
-  const double edge_const = cluster_sum<T>(cluster, k_part, s_warp, s_slots, (round++) & 1);
+  const double edge_const =
+      cluster_sum<T>(cluster, k_part, s_warp, s_slots, round & 1, px, o, tag0 + round + 1, s_global);
+  ++round;
   // this thread's rows by weight class: first row >= the class's first row that is = sub (mod S)
   int seg_begin[8], seg_end[8];
 #pragma unroll
@@ -1455,7 +1515,9 @@ __global__ void __launch_bounds__(T, T == 256 ? 3 : 1)
       if (w != 0.) slow += w * log(fma(mine[r * kClusterThreads], x, 1.0));
     }
     const double f = log(prod) + static_cast<double>(esum) * 0.6931471805599453094 + slow;
-    const double total = cluster_sum<T>(cluster, f, s_warp, s_slots, (round++) & 1);
+    const double total =
+        cluster_sum<T>(cluster, f, s_warp, s_slots, round & 1, px, o, tag0 + round + 1, s_global);
+    ++round;
     if (threadIdx.x == 0) {
       const double ll = total + s_state.ll_offset + edge_const +
                         st.total_weight * c_model.group_lambda[0] * s_state.t_eval;
@@ -1467,7 +1529,10 @@ __global__ void __launch_bounds__(T, T == 256 ? 3 : 1)
     if (s_state.done) break;  // every block of the cluster leaves in the same round
   }
   // st.bl[edge] was written by this block's thread 0 before the barrier above
-  if (rank == 0) refresh_edge_matrices(st, op, refresh, threadIdx.x, T);
+  if (rank == 0) {
+    refresh_edge_matrices(st, op, refresh, threadIdx.x, T);
+    if (px.enabled && threadIdx.x == 0) px.seq[o] += 1;  // the next search of this slot uses fresh tags
+  }
 }
 
 // ---- all-reduce of per-edge scalars over NVLink peer memory --------------------------------------
@@ -1479,14 +1544,6 @@ __global__ void __launch_bounds__(T, T == 256 ? 3 : 1)
 // GPU, so all ranks get bitwise-identical sums and take identical optimiser / rescale decisions.
 // Buffers are double-buffered by epoch parity: a rank can be at most one all-reduce ahead of a peer
 // (it needs that peer's flag to finish its own), so the slot it writes is never one still being read.
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
 constexpr int kPeerThreads = 256;
 __global__ void __launch_bounds__(kPeerThreads)
     k_peer_allreduce(PeerComm pc, double* __restrict__ buf, int n, int max_op) {
@@ -1510,8 +1567,10 @@ __global__ void __launch_bounds__(kPeerThreads)
         reinterpret_cast<const unsigned long long*>(pc.base[pc.rank] + 2 * R * kPeerCapacity) + parity * R +
         threadIdx.x;
     const long long t0 = clock64();
-    while (ld_acquire_sys(mine) < epoch) {
-      if (clock64() - t0 > (1ll << 33)) {  // ~4 s: a peer died; fail the call instead of hanging
+    // ~4 s without an answer: a peer died; fail the call instead of hanging, and never wait again
+    const bool dead = (*reinterpret_cast<volatile uint32_t*>(pc.status) & kErrPeerTimeout) != 0;
+    while (!dead && ld_acquire_sys(mine) < epoch) {
+      if (clock64() - t0 > (1ll << 33)) {
         atomicOr(pc.status, kErrPeerTimeout);
         break;
       }
@@ -1841,7 +1900,7 @@ bool PlanOptCluster(int64_t rows_total, int threads, int cluster_size, OptCluste
 cudaError_t LaunchOptCluster(cudaStream_t s, const DeviceState& st, const OptOp* ops, int n_ops,
                              const OptControl* ctl, const int32_t* inv_perm, const double* wperm,
                              const int32_t class_row_start[9], const OptClusterPlan& plan,
-                             const OptRefresh& refresh) {
+                             const OptRefresh& refresh, const PeerEdge& peer) {
   if (n_ops == 0) return cudaSuccess;
   OptClusterLayout lay;
   for (int c = 0; c < 9; ++c) lay.class_row_start[c] = class_row_start[c];
@@ -1860,8 +1919,8 @@ cudaError_t LaunchOptCluster(cudaStream_t s, const DeviceState& st, const OptOp*
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   if (plan.threads == 1024)
-    return cudaLaunchKernelEx(&cfg, k_opt_cluster<1024>, st, ops, ctl, inv_perm, wperm, lay, refresh);
-  return cudaLaunchKernelEx(&cfg, k_opt_cluster<256>, st, ops, ctl, inv_perm, wperm, lay, refresh);
+    return cudaLaunchKernelEx(&cfg, k_opt_cluster<1024>, st, ops, ctl, inv_perm, wperm, lay, refresh, peer);
+  return cudaLaunchKernelEx(&cfg, k_opt_cluster<256>, st, ops, ctl, inv_perm, wperm, lay, refresh, peer);
 }
 int64_t OptPrepareTileGroups(int n_ops, int64_t P) {
   const int64_t tiles = TilesFor(P);

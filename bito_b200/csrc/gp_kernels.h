@@ -81,7 +81,7 @@ bool PlanOptCluster(int64_t rows_total, int threads, int cluster_size, OptCluste
 cudaError_t LaunchOptCluster(cudaStream_t s, const DeviceState& st, const OptOp* ops, int n_ops,
                              const OptControl* ctl, const int32_t* inv_perm, const double* wperm,
                              const int32_t class_row_start[9], const OptClusterPlan& plan,
-                             const OptRefresh& refresh);
+                             const OptRefresh& refresh, const PeerEdge& peer);
 int64_t OptPrepareTileGroups(int n_ops, int64_t P);
 int64_t OptRatioTileGroups(int64_t P);
 int64_t OptRatioPartials(int64_t P);  // partial sums per edge written by LaunchOptEvalRatio

@@ -249,9 +249,25 @@ struct PeerComm {
   uint32_t* status;             // DeviceState::status
   int32_t n_ranks, rank;
 };
-inline size_t PeerBufferBytes(int n_ranks) {
-  return (size_t(2) * n_ranks * kPeerCapacity + size_t(2) * n_ranks) * sizeof(double);
+// ... then, for the cluster-resident optimiser on several GPUs (k_opt_cluster), kPeerEdgeSlots edge
+// records [slot][parity][source rank] of {value, tag} (16 bytes): the per-evaluation sums of one edge.
+constexpr int kPeerEdgeSlots = 64;
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline size_t PeerEdgeOffsetDoubles(int n_ranks) {
+  return size_t(2) * n_ranks * kPeerCapacity + size_t(2) * n_ranks;
 }
+inline size_t PeerBufferBytes(int n_ranks) {
+  return (PeerEdgeOffsetDoubles(n_ranks) + size_t(kPeerEdgeSlots) * 4 * n_ranks * 2) * sizeof(double);
+}
+// Cross-GPU part of k_opt_cluster's sums: enabled = 0 on a single rank.
+struct PeerEdge {
+  const PeerComm* pc;       // in device memory: lanes index base[] by rank
+  unsigned long long* seq;  // [kPeerEdgeSlots] searches run so far per edge slot (device memory)
+  int32_t enabled;
+  int32_t pad;
+};
 
 // The transition-matrix tables of the running program and the slot pool OptOp::fix_off indexes.
 struct OptRefresh {
