@@ -792,7 +792,7 @@ void Engine::CheckStatus() {
     const uint32_t keep = kErrPeerTimeout;
     GP_CUDA(cudaMemcpyAsync(d_status_.ptr, &keep, sizeof(uint32_t), cudaMemcpyHostToDevice, stream_));
     GP_CUDA(cudaStreamSynchronize(stream_));
-    Fail("a peer GPU did not answer a peer-memory exchange within ~4 s (rank died or ranks issued different calls)");
+    Fail("a peer GPU did not answer a peer-memory exchange within ~35 s (rank died or ranks issued different calls)");
   }
   if (!(cfg_.flags & BITO_GP_FLAG_STRICT_ASSERTS)) return;  // Release-build semantics
   std::string msg;

@@ -1298,6 +1298,11 @@ __device__ __forceinline__ void ratio_coefficients(const V4& r, const V4& c, dou
   c0_out = c0;
 }
 
+// How long a kernel waits for a peer GPU before it gives up (clock64 ticks: ~35 s at 1.97 GHz). Ranks
+// reach an exchange at slightly different times - one may still be compiling an op list on its
+// host - so this is generous; it only exists so that a dead rank fails the others instead of
+// hanging them.
+constexpr long long kPeerTimeoutCycles = 1ll << 36;
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -1326,11 +1331,11 @@ __device__ __forceinline__ double peer_edge_sum(const PeerEdge& px, int slot, in
     st_release_sys(reinterpret_cast<unsigned long long*>(theirs + 1), tag);
     const double* mine = pc->base[me] + rec0 + 2 * lane;
     const long long t0 = clock64();
-    // ~4 s without an answer: a peer died. Fail the call instead of hanging, and once that has
+    // ~35 s without an answer: a peer died. Fail the call instead of hanging, and once that has
     // happened never wait again (every later exchange of this engine would time out too).
     const bool dead = (*reinterpret_cast<volatile uint32_t*>(pc->status) & kErrPeerTimeout) != 0;
     while (!dead && ld_acquire_sys(reinterpret_cast<const unsigned long long*>(mine + 1)) != tag) {
-      if (clock64() - t0 > (1ll << 33)) {
+      if (clock64() - t0 > kPeerTimeoutCycles) {
         atomicOr(pc->status, kErrPeerTimeout);
         break;
       }
@@ -1567,10 +1572,10 @@ __global__ void __launch_bounds__(kPeerThreads)
         reinterpret_cast<const unsigned long long*>(pc.base[pc.rank] + 2 * R * kPeerCapacity) + parity * R +
         threadIdx.x;
     const long long t0 = clock64();
-    // ~4 s without an answer: a peer died; fail the call instead of hanging, and never wait again
+    // ~35 s without an answer: a peer died; fail the call instead of hanging, and never wait again
     const bool dead = (*reinterpret_cast<volatile uint32_t*>(pc.status) & kErrPeerTimeout) != 0;
     while (!dead && ld_acquire_sys(mine) < epoch) {
-      if (clock64() - t0 > (1ll << 33)) {
+      if (clock64() - t0 > kPeerTimeoutCycles) {
         atomicOr(pc.status, kErrPeerTimeout);
         break;
       }
