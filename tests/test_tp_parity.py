@@ -1,0 +1,46 @@
+"""The top-pruning (TP) likelihood evaluator as GP op lists.
+
+oracle/_ref/tp_parity (tests/cpp/tp_parity.cpp, built by `make -C oracle tpparity`) holds the reference's unmodified
+TPEngine, turns its TPChoiceMap into GPOperationVectors with bito_b200/host/tp_likelihood_plan.hpp and compares the
+per-edge top-tree log-likelihoods (TPEngine::GetTopTreeLikelihoods) with the op lists' per-GPCSP log-likelihoods
+ * on CPU: through the reference CPU GPEngine (the plan itself; runs in the build container and on the GPU box),
+ * on GPU (`--gpu`): through GPEngineB200, i.e. the CUDA kernels, twice with different branch lengths.
+1e-9 relative; inputs are generated here (the reference's data directory does not travel)."""
+import os
+import subprocess
+
+import pytest
+
+from test_host_shim_gpu import _write_case
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BINARY = os.path.join(ROOT, "oracle", "_ref", "tp_parity")
+CASES = [(5, 300, 3, 1), (8, 800, 6, 2), (16, 2000, 12, 2), (30, 3000, 40, 2)]
+
+
+def _run(tmp_path, taxa, sites, trees, moves, *flags):
+    fasta, newick = _write_case(tmp_path, taxa, sites, trees, moves, seed=taxa * 313 + trees)
+    run = subprocess.run([BINARY, fasta, newick, *flags], capture_output=True, text=True, timeout=600)
+    print(run.stdout[-3000:])
+    print(run.stderr[-2000:])
+    assert run.returncode == 0, run.stdout[-2000:] + run.stderr[-2000:]
+    lines = run.stdout.splitlines()
+    assert lines[-1] == "TP PARITY PASS"
+    return lines
+
+
+@pytest.mark.skipif(not os.path.exists(BINARY), reason="oracle/_ref/tp_parity not built (make -C oracle tpparity)")
+@pytest.mark.parametrize("taxa,sites,trees,moves", CASES)
+def test_tp_plan_matches_reference_tp_engine_on_cpu(tmp_path, taxa, sites, trees, moves):
+    lines = _run(tmp_path, taxa, sites, trees, moves)
+    assert sum(line.startswith("ok  ") for line in lines) == 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("taxa,sites,trees,moves", CASES)
+def test_tp_plan_through_the_cuda_engine_matches_reference_tp_engine(cuda_engine_lib, tmp_path, taxa, sites, trees, moves):
+    if not os.path.exists(BINARY):
+        pytest.fail(f"{BINARY} is missing: run `make -C oracle tpparity` in the build container "
+                    "(needs /root/reference); the binary travels with the snapshot")
+    lines = _run(tmp_path, taxa, sites, trees, moves, "--gpu")
+    assert sum(line.startswith("ok  ") for line in lines) == 3
