@@ -18,6 +18,10 @@
 // After ProcessOperations(InitializeOps()) and ProcessOperations(ComputeScoresOps()),
 // GetPerGPCSPLogLikelihoods() holds what TPEngine::GetTopTreeLikelihoods() holds
 // (tp_evaluation_engine.cpp:921-935): the log-likelihood of the best tree through every edge.
+//
+// ProposedNNIOps() does the same for GetTopTreeScoreWithProposedNNI (:466-641): the score of an NNI
+// that is NOT in the DAG, computed in spare PVs / spare edges from the PVs of its pre-NNI, with the
+// five edges around it optionally optimised (OptimizeBranchLength ops) for a few rounds.
 #pragma once
 
 #include <vector>
@@ -26,6 +30,7 @@
 #include "gp_operation.hpp"
 #include "pv_handler.hpp"
 #include "tp_choice_map.hpp"
+#include "tp_evaluation_engine.hpp"
 
 class TPLikelihoodPlan {
  public:
@@ -83,6 +88,112 @@ class TPLikelihoodPlan {
       ops.push_back(Likelihood{edge_id.value_, PV(PLVType::P, edge_id), parent_pv});
     }
     return ops;
+  }
+
+  // TP PV id (PLVEdgeHandler numbering, pv_handler.hpp:487-490, 227-238: type * E + edge, spare j at
+  // 6 E + j) -> engine PLV id (spare j -> the engine's spare PLV j).
+  size_t EnginePV(const PVId tp_pv) const {
+    const size_t v = tp_pv.value_;
+    if (v >= 6 * edge_count_) return 6 * EngineNodeCount() + (v - 6 * edge_count_);
+    return PV(static_cast<PLVType>(v / edge_count_), EdgeId(v % edge_count_));
+  }
+
+  // The three op lists of one proposed NNI, and which of its five edges get optimised.
+  struct ProposedNNI {
+    GPOperationVector initialize;  // RootwardPass + LeafwardPass (:501-537)
+    GPOperationVector iteration;   // one round of OptimizeLeftChild .. OptimizeParent + both passes (:615-630)
+    GPOperationVector score;       // ComputeLikelihood of the focal edge (:634-636)
+    size_t focal_gpcsp;            // row that then holds the score: GetPerGPCSPLogLikelihoods(focal_gpcsp, 1)
+    NNIAdjBools do_optimize_edge;
+  };
+  // `info` = TPEvalEngineViaLikelihood::GetProposedNNIInfo(post_nni, pre_nni, spare_offset) (:643-721);
+  // the two flags are the evaluator's do_init_proposed_branch_lengths_with_dag_ /
+  // do_fix_proposed_branch_lengths_from_dag_ (both true by default, tp_evaluation_engine.hpp:437-439).
+  // Run: ResetOptimizationCount; initialize; [iteration; IncrementOptimizationCount] x max_iter; score.
+  ProposedNNI ProposedNNIOps(const ProposedNNIInfo& info, const bool init_with_dag = true,
+                             const bool fix_from_dag = true) const {
+    using namespace GPOperations;
+    using Adj = NNIAdjacent;
+    ProposedNNI out;
+    const auto& t = info.temp_pv_ids;
+    const auto& r = info.ref_pv_ids;
+    const auto& te = info.temp_edge_ids;
+    out.focal_gpcsp = te.focal.value_;
+    out.do_optimize_edge = info.do_optimize_edge;
+    for (auto adj : NNIAdjacentEnum::Iterator())  // :480-497
+      if (init_with_dag && info.adj_edge_ids[adj] != NoId && fix_from_dag) out.do_optimize_edge[adj] = false;
+    // parent_rhat: evolved down from the grandparent, or - below the DAG root - the reference PV itself
+    // (TakePVValue, :524-529; the temp copy is only ever read, so the plan reads the original)
+    const bool has_grandparent = r.grandparent_rfocal_ != NoId;
+    const size_t parent_rhat = has_grandparent ? EnginePV(t.parent_rhat_) : EnginePV(r.parent_rhat_);
+    auto rootward_pass = [&](GPOperationVector& ops) {  // :501-515
+      Evolve(ops, EnginePV(t.child_phatleft_), te.left_child, EnginePV(r.leftchild_p_));
+      Evolve(ops, EnginePV(t.child_phatright_), te.right_child, EnginePV(r.rightchild_p_));
+      ops.push_back(Multiply{EnginePV(t.child_p_), EnginePV(t.child_phatleft_), EnginePV(t.child_phatright_)});
+      Evolve(ops, EnginePV(t.parent_phatsister_), te.sister, EnginePV(r.sister_p_));
+      Evolve(ops, EnginePV(t.parent_phatfocal_), te.focal, EnginePV(t.child_p_));
+      ops.push_back(Multiply{EnginePV(t.parent_p_), EnginePV(t.parent_phatfocal_), EnginePV(t.parent_phatsister_)});
+    };
+    auto leafward_pass = [&](GPOperationVector& ops) {  // :516-537
+      if (has_grandparent) Evolve(ops, parent_rhat, te.parent, EnginePV(r.grandparent_rfocal_));
+      ops.push_back(Multiply{EnginePV(t.parent_rfocal_), parent_rhat, EnginePV(t.parent_phatsister_)});
+      ops.push_back(Multiply{EnginePV(t.parent_rsister_), parent_rhat, EnginePV(t.parent_phatfocal_)});
+      Evolve(ops, EnginePV(t.child_rhat_), te.focal, EnginePV(t.parent_rfocal_));
+      ops.push_back(Multiply{EnginePV(t.child_rleft_), EnginePV(t.child_rhat_), EnginePV(t.child_phatright_)});
+      ops.push_back(Multiply{EnginePV(t.child_rright_), EnginePV(t.child_rhat_), EnginePV(t.child_phatleft_)});
+    };
+    // OptimizeEdge (:540-569); PV arguments already as engine ids, kNone where the reference passes NoId
+    constexpr size_t kNone = static_cast<size_t>(-1);
+    auto optimize_edge = [&](GPOperationVector& ops, EdgeId edge, size_t parent_p, size_t parent_phatfocal,
+                             size_t parent_phatsister, size_t prhat, size_t parent_rfocal, size_t child_p,
+                             size_t child_phatleft, size_t child_phatright, bool update, bool not_child_edge,
+                             bool not_parent_edge) {
+      if (not_child_edge) ops.push_back(Multiply{child_p, child_phatleft, child_phatright});
+      if (not_parent_edge) ops.push_back(Multiply{parent_rfocal, prhat, parent_phatsister});
+      if (update) ops.push_back(OptimizeBranchLength{child_p, parent_rfocal, edge.value_});
+      if (not_parent_edge) {
+        Evolve(ops, parent_phatfocal, edge, child_p);
+        ops.push_back(Multiply{parent_p, parent_phatfocal, parent_phatsister});
+      }
+    };
+    rootward_pass(out.initialize);
+    leafward_pass(out.initialize);
+    auto& it = out.iteration;
+    const auto& opt = out.do_optimize_edge;
+    optimize_edge(it, te.left_child, EnginePV(t.child_p_), EnginePV(t.child_phatleft_), EnginePV(t.child_phatright_),
+                  EnginePV(t.child_rhat_), EnginePV(t.child_rleft_), EnginePV(r.leftchild_p_), kNone, kNone,
+                  opt[Adj::LeftChild], false, true);  // :571-578
+    optimize_edge(it, te.right_child, EnginePV(t.child_p_), EnginePV(t.child_phatright_), EnginePV(t.child_phatleft_),
+                  EnginePV(t.child_rhat_), EnginePV(t.child_rright_), EnginePV(r.rightchild_p_), kNone, kNone,
+                  opt[Adj::RightChild], false, true);  // :579-586
+    optimize_edge(it, te.sister, EnginePV(t.parent_p_), EnginePV(t.parent_phatsister_), EnginePV(t.parent_phatfocal_),
+                  parent_rhat, EnginePV(t.parent_rsister_), EnginePV(r.sister_p_), kNone, kNone, opt[Adj::Sister],
+                  false, true);  // :587-594
+    optimize_edge(it, te.focal, EnginePV(t.parent_p_), EnginePV(t.parent_phatfocal_), EnginePV(t.parent_phatsister_),
+                  parent_rhat, EnginePV(t.parent_rfocal_), EnginePV(t.child_p_), EnginePV(t.child_phatleft_),
+                  EnginePV(t.child_phatright_), opt[Adj::Focal], true, true);  // :595-603
+    if (!info.post_nni.GetParent().SubsplitIsRootsplit() && te.parent != NoId && has_grandparent)
+      optimize_edge(it, te.parent, kNone, kNone, kNone, kNone, EnginePV(r.grandparent_rfocal_), EnginePV(t.parent_p_),
+                    EnginePV(t.parent_phatfocal_), EnginePV(t.parent_phatsister_), opt[Adj::Parent], true,
+                    false);  // :604-612, 621-625
+    rootward_pass(it);
+    leafward_pass(it);
+    out.score.push_back(Likelihood{te.focal.value_, EnginePV(t.child_p_), EnginePV(t.parent_rfocal_)});
+    return out;
+  }
+  // Branch lengths the reference gives the five temp edges before it scores (:480-497): the default,
+  // or the pre-NNI's (reference) edge, or - when the edge already exists in the DAG - that edge's.
+  template <typename BranchHandler>
+  static void InitializeTempBranchLengths(BranchHandler& handler, const ProposedNNIInfo& info,
+                                          const double default_branch_length, const bool init_with_dag = true) {
+    for (auto adj : NNIAdjacentEnum::Iterator()) {
+      double value = default_branch_length;
+      if (init_with_dag) {
+        value = handler(info.ref_edge_ids[adj]);
+        if (info.adj_edge_ids[adj] != NoId) value = handler(info.adj_edge_ids[adj]);
+      }
+      handler(info.temp_edge_ids[adj]) = value;
+    }
   }
 
  private:

@@ -7,9 +7,14 @@
 //   (cpu) through the unmodified reference CPU GPEngine — this checks the plan itself, no GPU needed;
 //   (gpu) with `--gpu`, through GPEngineB200 (the host class over libbito_gp_b200.so).
 // Per-edge top-tree log-likelihoods must agree to 1e-9 relative.
+// Then the NNIs adjacent to the DAG are scored as PROPOSED NNIs (GetTopTreeScoreWithProposedNNI, :466-641:
+// spare PVs and edges, branch lengths taken over from the pre-NNI, optionally five rounds of
+// OptimizeBranchLength on the new edges) by the reference and by TPLikelihoodPlan::ProposedNNIOps on the
+// same engines: scores to 1e-9 with fixed branch lengths, 1e-7 with optimised ones (optimised lengths 1e-6).
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <unistd.h>
 
@@ -18,6 +23,7 @@
 #include "gp_dag.hpp"
 #include "gp_engine.hpp"
 #include "gp_engine_b200.hpp"
+#include "nni_engine.hpp"
 #include "rooted_tree_collection.hpp"
 #include "site_pattern.hpp"
 #include "tp_engine.hpp"
@@ -37,6 +43,27 @@ void Report(const char* what, double err, double tol) {
   std::printf("%s %-58s err %.3e (tol %.1e)\n", ok ? "ok  " : "FAIL", what, err, tol);
   if (!ok) ++g_failures;
 }
+// Scores `info`'s NNI on `engine` (whose DAG-edge PVs and branch lengths are in place).
+template <typename Engine>
+double ScoreProposedNNI(Engine& engine, const TPLikelihoodPlan& plan, const ProposedNNIInfo& info,
+                        const NNIAdjDoubles& temp_branch_lengths, const bool optimize, const size_t max_iter,
+                        NNIAdjDoubles* optimised) {
+  const auto ops = plan.ProposedNNIOps(info);
+  auto& handler = engine.GetBranchLengthHandler();
+  for (auto adj : NNIAdjacentEnum::Iterator()) handler(info.temp_edge_ids[adj]) = temp_branch_lengths[adj];
+  engine.ResetOptimizationCount();
+  engine.ProcessOperations(ops.initialize);
+  if (optimize)
+    for (size_t iter = 0; iter < max_iter; ++iter) {
+      engine.ProcessOperations(ops.iteration);
+      engine.IncrementOptimizationCount();
+    }
+  engine.ProcessOperations(ops.score);
+  const EigenVectorXd all = engine.GetBranchLengths(0, engine.GetPaddedGPCSPCount());
+  for (auto adj : NNIAdjacentEnum::Iterator()) (*optimised)[adj] = all[info.temp_edge_ids[adj].value_];
+  return engine.GetPerGPCSPLogLikelihoods(ops.focal_gpcsp, 1)[0];
+}
+
 template <typename Engine>
 EigenVectorXd RunPlan(Engine& engine, const TPLikelihoodPlan& plan, const EigenVectorXd& branch_lengths) {
   engine.SetNullPrior();
@@ -101,6 +128,86 @@ int main(int argc, char** argv) {
       tp.GetLikelihoodEvalEngine().ComputeScores();
       Report("second evaluation, new branch lengths (CUDA) vs TPEngine",
              RelErr(RunPlan(gpu, plan, other), tp.GetTopTreeLikelihoods().head(E)), 1e-9);
+    }
+    // ---- proposed NNIs -------------------------------------------------------------------------
+    {
+      padded.head(E) = branch_lengths;
+      tp.SetBranchLengths(padded);
+      tp.SelectLikelihoodEvalEngine();
+      auto& eval = tp.GetLikelihoodEvalEngine();
+      eval.Initialize();
+      eval.ComputeScores();
+      tp.GrowSpareNodeData(tp.GetSpareNodesPerNNI());  // NNIEvalEngineViaTP::GrowEngineForAdjacentNNIs,
+      tp.GrowSpareEdgeData(tp.GetSpareEdgesPerNNI());  // nni_evaluation_engine.cpp:1050-1065
+      NNIEngine nni_engine(dag, nullptr, nullptr);
+      nni_engine.SyncAdjacentNNIsWithDAG();
+      GPEngine cpu(SitePattern(alignment, trees.TagTaxonMap()), N, G, tag + ".gp", 1e-40, ones_g, ones_n, ones_g,
+                   false);
+      cpu.GrowSpareGPCSPs(8);
+      RunPlan(cpu, plan, branch_lengths);
+      std::unique_ptr<GPEngineB200> gpu;
+      if (with_gpu) {
+        gpu = std::make_unique<GPEngineB200>(SitePattern(alignment, trees.TagTaxonMap()), N, G, tag + ".gp", 1e-40,
+                                             ones_g, ones_n, ones_g, false);
+        gpu->GrowSpareGPCSPs(8);
+        RunPlan(*gpu, plan, branch_lengths);
+      }
+      double worst[2][3] = {{0., 0., 0.}, {0., 0., 0.}};  // [optimize][cpu score, gpu score, gpu lengths]
+      double worst_cpu_bl = 0., moved = 0.;  // moved: how far the reference's optimiser took a new edge
+      size_t n_scored = 0;
+      for (const auto& post_nni : nni_engine.GetAdjacentNNIs()) {
+        if (n_scored >= 8) break;
+        const auto pre_nni = dag.FindNNINeighborInDAG(post_nni);
+        for (const bool optimize : {false, true}) {
+          eval.SetOptimizeNewEdges(optimize);
+          const ProposedNNIInfo info = eval.GetProposedNNIInfo(post_nni, pre_nni, 0, std::nullopt);
+          // the lengths the reference starts from: the same rule, read from ITS handler before it scores
+          NNIAdjDoubles start;
+          {
+            auto& handler = eval.GetDAGBranchHandler();
+            TPLikelihoodPlan::InitializeTempBranchLengths(handler, info, handler.GetDefaultBranchLength());
+            for (auto adj : NNIAdjacentEnum::Iterator()) start[adj] = handler(info.temp_edge_ids[adj]);
+          }
+          const double want_score = tp.GetTopTreeScoreWithProposedNNI(post_nni, pre_nni, 0, std::nullopt);
+          NNIAdjDoubles want_bl;
+          for (auto adj : NNIAdjacentEnum::Iterator())
+            want_bl[adj] = eval.GetDAGBranchHandler()(info.temp_edge_ids[adj]);
+          if (optimize)
+            for (auto adj : NNIAdjacentEnum::Iterator())
+              moved = std::max(moved, std::abs(want_bl[adj] - start[adj]));
+          NNIAdjDoubles got_bl;
+          const double cpu_score =
+              ScoreProposedNNI(cpu, plan, info, start, optimize, eval.GetOptimizationMaxIteration(), &got_bl);
+          worst[optimize][0] = std::max(worst[optimize][0], std::abs(cpu_score - want_score) / std::abs(want_score));
+          for (auto adj : NNIAdjacentEnum::Iterator())
+            worst_cpu_bl = std::max(worst_cpu_bl, std::abs(got_bl[adj] - want_bl[adj]));
+          if (with_gpu) {
+            const double gpu_score =
+                ScoreProposedNNI(*gpu, plan, info, start, optimize, eval.GetOptimizationMaxIteration(), &got_bl);
+            worst[optimize][1] =
+                std::max(worst[optimize][1], std::abs(gpu_score - want_score) / std::abs(want_score));
+            for (auto adj : NNIAdjacentEnum::Iterator())
+              worst[optimize][2] = std::max(worst[optimize][2], std::abs(got_bl[adj] - want_bl[adj]));
+          }
+        }
+        ++n_scored;
+      }
+      std::printf("proposed NNIs scored: %zu (the reference's optimiser moved a new edge by up to %.3e)\n", n_scored,
+                  moved);
+      if (n_scored > 0 && !(moved > 1e-4)) {
+        std::printf("FAIL the optimised case did not optimise anything\n");
+        ++g_failures;
+      }
+      if (n_scored > 0) {
+        Report("proposed NNIs, fixed lengths: plan on CPU GPEngine vs TPEngine", worst[0][0], 1e-9);
+        Report("proposed NNIs, optimised: plan on CPU GPEngine vs TPEngine", worst[1][0], 1e-9);
+        Report("proposed NNIs, optimised branch lengths on CPU GPEngine", worst_cpu_bl, 1e-9);
+        if (with_gpu) {
+          Report("proposed NNIs, fixed lengths: plan on CUDA vs TPEngine", worst[0][1], 1e-9);
+          Report("proposed NNIs, optimised: plan on CUDA vs TPEngine", worst[1][1], 1e-7);
+          Report("proposed NNIs, optimised branch lengths on CUDA", worst[1][2], 1e-6);
+        }
+      }
     }
     for (const char* suffix : {".tp_lik", ".tp_pars", ".gp"}) unlink((tag + suffix).c_str());
   } catch (const std::exception& e) {
