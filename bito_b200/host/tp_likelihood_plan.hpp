@@ -90,6 +90,28 @@ class TPLikelihoodPlan {
     return ops;
   }
 
+  // One round of TPEvalEngineViaLikelihood::BranchLengthOptimization (:988-1022) over every edge below a
+  // rootsplit edge, rootward order: refresh the PVs around the edge, optimise it, push the result down.
+  // The reference decides ONCE per call whether converged edges are skipped (check_branch_convergence =
+  // !IsFirstOptimization() before its loop of GetOptimizationMaxIteration() rounds), so run this list
+  // that many times and only then call IncrementOptimizationCount() as many times.
+  GPOperationVector BranchLengthOptimizationOps() const {
+    using namespace GPOperations;
+    GPOperationVector ops;
+    for (const auto edge_id : dag_.RootwardEdgeTraversalTrace(false)) {
+      const auto& choices = choice_map_.GetEdgeChoice(edge_id);
+      if (choices.parent == NoId) continue;
+      RootwardForEdge(ops, edge_id);
+      RootwardForEdge(ops, choices.parent);
+      LeafwardForEdge(ops, choices.parent);
+      ops.push_back(OptimizeBranchLength{PV(PLVType::P, edge_id),
+                                         PV(PLVTypeEnum::RPLVType(dag_.GetFocalClade(edge_id)), choices.parent),
+                                         edge_id.value_});
+      LeafwardForEdge(ops, edge_id);
+    }
+    return ops;
+  }
+
   // TP PV id (PLVEdgeHandler numbering, pv_handler.hpp:487-490, 227-238: type * E + edge, spare j at
   // 6 E + j) -> engine PLV id (spare j -> the engine's spare PLV j).
   size_t EnginePV(const PVId tp_pv) const {

@@ -7,7 +7,8 @@ per-edge top-tree log-likelihoods (TPEngine::GetTopTreeLikelihoods) with the op 
  * on GPU (`--gpu`): through GPEngineB200, i.e. the CUDA kernels, twice with different branch lengths.
 Then up to eight NNIs adjacent to the DAG are scored as PROPOSED NNIs (GetTopTreeScoreWithProposedNNI: spare PVs and
 edges, lengths from the pre-NNI, with and without five rounds of OptimizeBranchLength on the new edges) by the reference
-and by TPLikelihoodPlan::ProposedNNIOps. 1e-9 relative (through the CPU GPEngine the plan is bit-exact; CUDA with
+and by TPLikelihoodPlan::ProposedNNIOps, and the whole-DAG BranchLengthOptimization (two calls of five rounds) by
+BranchLengthOptimizationOps. 1e-9 relative (through the CPU GPEngine the plan is bit-exact; CUDA with
 optimisation: scores 1e-7, lengths 1e-6); inputs are generated here (the reference's data directory does not travel)."""
 import os
 import subprocess
@@ -36,8 +37,9 @@ def _run(tmp_path, taxa, sites, trees, moves, *flags):
 @pytest.mark.parametrize("taxa,sites,trees,moves", CASES)
 def test_tp_plan_matches_reference_tp_engine_on_cpu(tmp_path, taxa, sites, trees, moves):
     lines = _run(tmp_path, taxa, sites, trees, moves)
-    # the per-edge pass, then proposed NNIs: scores with fixed lengths, scores and lengths after optimisation
-    assert sum(line.startswith("ok  ") for line in lines) == 4
+    # the per-edge pass; proposed NNIs: scores with fixed lengths, scores and lengths after optimisation; the
+    # whole-DAG branch-length optimisation
+    assert sum(line.startswith("ok  ") for line in lines) == 5
 
 
 @pytest.mark.gpu
@@ -47,5 +49,6 @@ def test_tp_plan_through_the_cuda_engine_matches_reference_tp_engine(cuda_engine
         pytest.fail(f"{BINARY} is missing: run `make -C oracle tpparity` in the build container "
                     "(needs /root/reference); the binary travels with the snapshot")
     lines = _run(tmp_path, taxa, sites, trees, moves, "--gpu")
-    # CPU checks as above (4) + CUDA: two per-edge passes, proposed NNIs fixed / optimised / optimised lengths
-    assert sum(line.startswith("ok  ") for line in lines) == 9
+    # CPU checks as above (5) + CUDA: two per-edge passes, proposed NNIs fixed / optimised / optimised lengths,
+    # whole-DAG optimisation
+    assert sum(line.startswith("ok  ") for line in lines) == 11
