@@ -284,18 +284,21 @@ EigenVectorXd Self::GetPerGPCSPComponentsOfFullLogMarginal() const {
   Check(bito_gp_get_per_gpcsp_components_of_full_log_marginal(H(), out.data()));
   return out;
 }
-EigenMatrixXd Self::GetLogLikelihoodMatrix() const {
-  EigenMatrixXd out(GetGPCSPCount(), GetSitePatternCount());  // row-major (eigen_sugar.hpp:20-22)
+const EigenMatrixXd& Self::GetLogLikelihoodMatrix() const {
+  EigenMatrixXd& out = log_likelihood_matrix_copy_;
+  out.resize(GetGPCSPCount(), GetSitePatternCount());  // row-major (eigen_sugar.hpp:20-22)
   Check(bito_gp_get_log_likelihood_matrix(H(), out.data()));
   return out;
 }
-EigenVectorXd Self::GetHybridMarginals() const {
-  EigenVectorXd out(GetGPCSPCount());
+const EigenVectorXd& Self::GetHybridMarginals() const {
+  EigenVectorXd& out = hybrid_marginals_copy_;
+  out.resize(GetGPCSPCount());
   Check(bito_gp_get_hybrid_marginals(H(), out.data()));
   return out;
 }
-EigenVectorXd Self::GetSBNParameters() const {
-  EigenVectorXd out(GetGPCSPCount());
+const EigenVectorXd& Self::GetSBNParameters() const {
+  EigenVectorXd& out = sbn_parameters_copy_;
+  out.resize(GetGPCSPCount());
   Check(bito_gp_get_sbn_parameters(H(), out.data()));
   return out;
 }

@@ -10,8 +10,9 @@
 // parity program tests/cpp/host_parity.cpp hold the reference GPEngine and this class side by side.
 //
 // Differences from the reference surface, all forced by PLVs living in HBM:
-//  * GetPLV / GetSparePLV / GetLogLikelihoodMatrix / GetHybridMarginals / GetSBNParameters return
-//    copies, not Eigen::Ref into engine memory; writes go through SetPLV.
+//  * GetPLV / GetSparePLV return copies, not Eigen::Ref into engine memory; writes go through SetPLV.
+//    GetLogLikelihoodMatrix / GetHybridMarginals / GetSBNParameters return references to host copies
+//    this object holds (valid until the next call of the same getter).
 //  * GetPLVHandler() returns an index-only view (GetPVIndex / GetSparePVIndex / counts): PLV data
 //    is not host-addressable. That is all NNIEvalEngineViaGP takes from it
 //    (nni_evaluation_engine.cpp:233-421, 633, 813-923).
@@ -114,9 +115,12 @@ class BITO_B200_ENGINE_CLASS {
   EigenVectorXd GetPerGPCSPLogLikelihoods(const size_t start, const size_t length = 1) const;
   EigenVectorXd GetSparePerGPCSPLogLikelihoods(const size_t start, const size_t length = 1) const;
   EigenVectorXd GetPerGPCSPComponentsOfFullLogMarginal() const;
-  EigenMatrixXd GetLogLikelihoodMatrix() const;
-  EigenVectorXd GetHybridMarginals() const;
-  EigenVectorXd GetSBNParameters() const;
+  // The reference returns Eigen::Ref views into engine memory here (gp_engine.hpp:136-138) and callers bind
+  // them (GPInstance::GetSBNParameters returns such a Ref, gp_instance.cpp:419-421): these three return
+  // references to host copies held by this object, refreshed by each call, so a bound Ref stays valid.
+  const EigenMatrixXd& GetLogLikelihoodMatrix() const;
+  const EigenVectorXd& GetHybridMarginals() const;
+  const EigenVectorXd& GetSBNParameters() const;
   double GetLogMarginalLikelihood() const;
 
   NucleotidePLV GetPLV(const PVId plv_index) const;
@@ -140,6 +144,8 @@ class BITO_B200_ENGINE_CLASS {
     size_t GetPVCount() const { return engine_.GetPLVCount(); }
     size_t GetSparePVCount() const { return engine_.GetSparePLVCount(); }
     size_t GetPaddedPVCount() const { return engine_.GetPaddedPLVCount(); }
+    // GPInstance::PrintStatus (gp_instance.cpp:33-36) reports the PLV memory: here HBM actually held, in bytes
+    double GetByteCount() const { return static_cast<double>(engine_.Stats().device_bytes_in_use); }
 
    private:
     const BITO_B200_ENGINE_CLASS& engine_;
@@ -211,6 +217,8 @@ class BITO_B200_ENGINE_CLASS {
   SitePattern site_pattern_;
   bito_gp_engine* handle_ = nullptr;
   PLVIndexView plv_view_{*this};
+  mutable EigenMatrixXd log_likelihood_matrix_copy_;
+  mutable EigenVectorXd hybrid_marginals_copy_, sbn_parameters_copy_;
   mutable DAGBranchHandler branch_mirror_{0};
   mutable EigenVectorXd mirror_synced_;  // branch lengths as last exchanged with the device
   mutable bool mirror_live_ = false;
