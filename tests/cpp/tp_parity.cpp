@@ -248,6 +248,73 @@ int main(int argc, char** argv) {
       Report("BranchLengthOptimization: plan on CPU GPEngine vs TPEngine, |dBL|", worst_cpu, 1e-9);
       if (with_gpu) Report("BranchLengthOptimization: plan on CUDA vs TPEngine, |dBL|", worst_gpu, 1e-6);
     }
+    // ---- the reference's NNI search in TP mode grows the DAG (nni_search.py:624-642: top-1 filter, new edges
+    // optimised); after every iteration the plan is rebuilt for the grown DAG and must reproduce what the
+    // reference gets when it re-evaluates that DAG from scratch (Initialize + ComputeScores) with the branch
+    // lengths the search has left behind, and the next round of proposed NNIs --------------------------------
+    {
+      auto& eval = tp.GetLikelihoodEvalEngine();
+      eval.SetOptimizeNewEdges(true);
+      NNIEngine search(dag, nullptr, &tp);
+      search.SetTPLikelihoodCutoffFilteringScheme(0.0);
+      search.SetTopKScoreFilteringScheme(1);
+      search.RunInit(true);
+      double worst_cpu = 0., worst_gpu = 0., worst_nni_cpu = 0., worst_nni_gpu = 0.;
+      size_t iterations = 0, grown_edges = E;
+      for (; iterations < 3 && search.GetAdjacentNNICount() > 0; ++iterations) {
+        search.RunMainLoop(true);
+        search.RunPostLoop(true);
+        const size_t E2 = dag.EdgeCountWithLeafSubsplits();
+        grown_edges = E2;
+        const EigenVectorXd bl2 = eval.GetDAGBranchHandler().GetBranchLengthData().head(E2);
+        eval.Initialize();
+        eval.ComputeScores();
+        const EigenVectorXd want2 = tp.GetTopTreeLikelihoods().head(E2);
+        const TPLikelihoodPlan plan2(dag, tp.GetChoiceMap());
+        const size_t N2 = plan2.EngineNodeCount(), G2 = plan2.EngineGPCSPCount();
+        const EigenVectorXd ones_g2 = EigenVectorXd::Ones(G2), ones_n2 = EigenVectorXd::Ones(N2);
+        GPEngine cpu(SitePattern(alignment, trees.TagTaxonMap()), N2, G2, tag + ".gp", 1e-40, ones_g2, ones_n2,
+                     ones_g2, false);
+        cpu.GrowSpareGPCSPs(8);
+        worst_cpu = std::max(worst_cpu, RelErr(RunPlan(cpu, plan2, bl2), want2));
+        std::unique_ptr<GPEngineB200> gpu;
+        if (with_gpu) {
+          gpu = std::make_unique<GPEngineB200>(SitePattern(alignment, trees.TagTaxonMap()), N2, G2, tag + ".gp",
+                                               1e-40, ones_g2, ones_n2, ones_g2, false);
+          gpu->GrowSpareGPCSPs(8);
+          worst_gpu = std::max(worst_gpu, RelErr(RunPlan(*gpu, plan2, bl2), want2));
+        }
+        // the NNIs the search will score next, on the grown DAG
+        size_t n = 0;
+        for (const auto& post_nni : search.GetAdjacentNNIs()) {
+          if (n++ >= 4) break;
+          const auto pre_nni = dag.FindNNINeighborInDAG(post_nni);
+          const ProposedNNIInfo info = eval.GetProposedNNIInfo(post_nni, pre_nni, 0, std::nullopt);
+          NNIAdjDoubles start, unused;
+          auto& handler = eval.GetDAGBranchHandler();
+          TPLikelihoodPlan::InitializeTempBranchLengths(handler, info, handler.GetDefaultBranchLength());
+          for (auto adj : NNIAdjacentEnum::Iterator()) start[adj] = handler(info.temp_edge_ids[adj]);
+          const double want_score = tp.GetTopTreeScoreWithProposedNNI(post_nni, pre_nni, 0, std::nullopt);
+          const double cpu_score =
+              ScoreProposedNNI(cpu, plan2, info, start, true, eval.GetOptimizationMaxIteration(), &unused);
+          worst_nni_cpu = std::max(worst_nni_cpu, std::abs(cpu_score - want_score) / std::abs(want_score));
+          if (with_gpu) {
+            const double gpu_score =
+                ScoreProposedNNI(*gpu, plan2, info, start, true, eval.GetOptimizationMaxIteration(), &unused);
+            worst_nni_gpu = std::max(worst_nni_gpu, std::abs(gpu_score - want_score) / std::abs(want_score));
+          }
+        }
+      }
+      std::printf("TP-mode NNI search: %zu iterations, DAG grew from %zu to %zu edges\n", iterations, E, grown_edges);
+      if (iterations > 0) {
+        Report("grown DAG: plan on CPU GPEngine vs TPEngine", worst_cpu, 1e-9);
+        Report("grown DAG, next proposed NNIs (optimised): plan on CPU GPEngine", worst_nni_cpu, 1e-9);
+        if (with_gpu) {
+          Report("grown DAG: plan on CUDA vs TPEngine", worst_gpu, 1e-9);
+          Report("grown DAG, next proposed NNIs (optimised): plan on CUDA", worst_nni_gpu, 1e-7);
+        }
+      }
+    }
     for (const char* suffix : {".tp_lik", ".tp_pars", ".gp"}) unlink((tag + suffix).c_str());
   } catch (const std::exception& e) {
     std::fprintf(stderr, "tp_parity: %s\n", e.what());

@@ -8,7 +8,9 @@ per-edge top-tree log-likelihoods (TPEngine::GetTopTreeLikelihoods) with the op 
 Then up to eight NNIs adjacent to the DAG are scored as PROPOSED NNIs (GetTopTreeScoreWithProposedNNI: spare PVs and
 edges, lengths from the pre-NNI, with and without five rounds of OptimizeBranchLength on the new edges) by the reference
 and by TPLikelihoodPlan::ProposedNNIOps, and the whole-DAG BranchLengthOptimization (two calls of five rounds) by
-BranchLengthOptimizationOps. 1e-9 relative (through the CPU GPEngine the plan is bit-exact; CUDA with
+BranchLengthOptimizationOps. Finally the reference's NNI search runs three iterations in TP mode (top-1 filter, new
+edges optimised, nni_search.py:624-642) and the plan, rebuilt for the grown DAG, must reproduce the reference's
+re-evaluation of it and the next round of proposed NNIs. 1e-9 relative (through the CPU GPEngine the plan is bit-exact; CUDA with
 optimisation: scores 1e-7, lengths 1e-6); inputs are generated here (the reference's data directory does not travel)."""
 import os
 import subprocess
@@ -38,8 +40,9 @@ def _run(tmp_path, taxa, sites, trees, moves, *flags):
 def test_tp_plan_matches_reference_tp_engine_on_cpu(tmp_path, taxa, sites, trees, moves):
     lines = _run(tmp_path, taxa, sites, trees, moves)
     # the per-edge pass; proposed NNIs: scores with fixed lengths, scores and lengths after optimisation; the
-    # whole-DAG branch-length optimisation
-    assert sum(line.startswith("ok  ") for line in lines) == 5
+    # whole-DAG branch-length optimisation; the DAG grown by three iterations of the reference's TP-mode NNI search
+    # (re-evaluated from scratch + its next proposed NNIs)
+    assert sum(line.startswith("ok  ") for line in lines) == 7
 
 
 @pytest.mark.gpu
@@ -50,5 +53,5 @@ def test_tp_plan_through_the_cuda_engine_matches_reference_tp_engine(cuda_engine
                     "(needs /root/reference); the binary travels with the snapshot")
     lines = _run(tmp_path, taxa, sites, trees, moves, "--gpu")
     # CPU checks as above (5) + CUDA: two per-edge passes, proposed NNIs fixed / optimised / optimised lengths,
-    # whole-DAG optimisation
-    assert sum(line.startswith("ok  ") for line in lines) == 11
+    # whole-DAG optimisation, grown DAG + its next proposed NNIs
+    assert sum(line.startswith("ok  ") for line in lines) == 15
