@@ -114,11 +114,23 @@ class TPLikelihoodPlan {
 
   // TP PV id (PLVEdgeHandler numbering, pv_handler.hpp:487-490, 227-238: type * E + edge, spare j at
   // 6 E + j) -> engine PLV id (spare j -> the engine's spare PLV j).
-  size_t EnginePV(const PVId tp_pv) const {
+  size_t EnginePV(const PVId tp_pv) const { return EnginePV(tp_pv, 0, 0); }
+  // Same, for the `slot`-th NNI of a batch whose info was built with spare offset `tp_spare_offset`: the
+  // reference hands NNI i the temp PVs [12 i, 12 i + 18) (GetTempLocalPVIdsForProposedNNIs, :742-776:
+  // 18 ids at a stride of spare_nodes_per_nni_ = 12, so neighbours overlap - harmless there, one NNI is scored
+  // at a time); a batch needs them disjoint, so temp j of NNI `slot` becomes engine spare PLV 18 slot + j.
+  static constexpr size_t kTempPVsPerNNI = 18, kReferenceTempStride = 12;
+  size_t EnginePV(const PVId tp_pv, const size_t tp_spare_offset, const size_t slot) const {
     const size_t v = tp_pv.value_;
-    if (v >= 6 * edge_count_) return 6 * EngineNodeCount() + (v - 6 * edge_count_);
+    if (v >= 6 * edge_count_) {
+      const size_t j = (v - 6 * edge_count_) - kReferenceTempStride * tp_spare_offset;
+      return 6 * EngineNodeCount() + kTempPVsPerNNI * slot + j;
+    }
     return PV(static_cast<PLVType>(v / edge_count_), EdgeId(v % edge_count_));
   }
+  // Spare PLVs (in engine "nodes" of six PLVs) and spare GPCSPs an engine needs to score n NNIs in one batch.
+  static size_t SpareNodesForBatch(const size_t n) { return (kTempPVsPerNNI * n + 5) / 6; }
+  static size_t SpareGPCSPsForBatch(const size_t n) { return 5 * n; }
 
   // The three op lists of one proposed NNI, and which of its five edges get optimised.
   struct ProposedNNI {
@@ -133,10 +145,14 @@ class TPLikelihoodPlan {
   // do_fix_proposed_branch_lengths_from_dag_ (both true by default, tp_evaluation_engine.hpp:437-439).
   // Run: ResetOptimizationCount; initialize; [iteration; IncrementOptimizationCount] x max_iter; score.
   ProposedNNI ProposedNNIOps(const ProposedNNIInfo& info, const bool init_with_dag = true,
-                             const bool fix_from_dag = true) const {
+                             const bool fix_from_dag = true, const size_t tp_spare_offset = 0,
+                             const size_t slot = 0) const {
     using namespace GPOperations;
     using Adj = NNIAdjacent;
     ProposedNNI out;
+    auto EnginePV = [this, tp_spare_offset, slot](const PVId id) {  // temps of this NNI's slot
+      return this->EnginePV(id, tp_spare_offset, slot);
+    };
     const auto& t = info.temp_pv_ids;
     const auto& r = info.ref_pv_ids;
     const auto& te = info.temp_edge_ids;
@@ -203,19 +219,50 @@ class TPLikelihoodPlan {
     out.score.push_back(Likelihood{te.focal.value_, EnginePV(t.child_p_), EnginePV(t.parent_rfocal_)});
     return out;
   }
+  // All the NNIs adjacent to the DAG in ONE set of lists (what NNIEvalEngineViaTP::ScoreAdjacentNNIs,
+  // nni_evaluation_engine.cpp:1075-1086, does one NNI at a time): the NNIs are independent - each works in
+  // its own temp PVs and temp edges - so the engine's level scheduler runs the k-th step of every NNI as one
+  // batch of kernels, and a whole round of scoring costs the launches of a single NNI.
+  // infos[i] = GetProposedNNIInfo(post_i, pre_i, i) (spare offset i: disjoint temp EDGES, 5 per NNI).
+  // Run as for one NNI; the score of NNI i is then GetPerGPCSPLogLikelihoods(focal_gpcsp[i], 1).
+  struct ProposedNNIBatch {
+    GPOperationVector initialize, iteration, score;
+    std::vector<size_t> focal_gpcsp;
+  };
+  ProposedNNIBatch BatchedProposedNNIOps(const std::vector<ProposedNNIInfo>& infos, const bool init_with_dag = true,
+                                         const bool fix_from_dag = true) const {
+    ProposedNNIBatch batch;
+    for (size_t i = 0; i < infos.size(); ++i) {
+      const ProposedNNI one = ProposedNNIOps(infos[i], init_with_dag, fix_from_dag, i, i);
+      batch.initialize.insert(batch.initialize.end(), one.initialize.begin(), one.initialize.end());
+      batch.iteration.insert(batch.iteration.end(), one.iteration.begin(), one.iteration.end());
+      batch.score.insert(batch.score.end(), one.score.begin(), one.score.end());
+      batch.focal_gpcsp.push_back(one.focal_gpcsp);
+    }
+    return batch;
+  }
+
   // Branch lengths the reference gives the five temp edges before it scores (:480-497): the default,
   // or the pre-NNI's (reference) edge, or - when the edge already exists in the DAG - that edge's.
   template <typename BranchHandler>
-  static void InitializeTempBranchLengths(BranchHandler& handler, const ProposedNNIInfo& info,
-                                          const double default_branch_length, const bool init_with_dag = true) {
+  static NNIAdjDoubles TempBranchLengths(const BranchHandler& handler, const ProposedNNIInfo& info,
+                                         const double default_branch_length, const bool init_with_dag = true) {
+    NNIAdjDoubles out;
     for (auto adj : NNIAdjacentEnum::Iterator()) {
       double value = default_branch_length;
       if (init_with_dag) {
-        value = handler(info.ref_edge_ids[adj]);
+        if (info.ref_edge_ids[adj] != NoId) value = handler(info.ref_edge_ids[adj]);
         if (info.adj_edge_ids[adj] != NoId) value = handler(info.adj_edge_ids[adj]);
       }
-      handler(info.temp_edge_ids[adj]) = value;
+      out[adj] = value;
     }
+    return out;
+  }
+  template <typename BranchHandler>
+  static void InitializeTempBranchLengths(BranchHandler& handler, const ProposedNNIInfo& info,
+                                          const double default_branch_length, const bool init_with_dag = true) {
+    const NNIAdjDoubles values = TempBranchLengths(handler, info, default_branch_length, init_with_dag);
+    for (auto adj : NNIAdjacentEnum::Iterator()) handler(info.temp_edge_ids[adj]) = values[adj];
   }
 
  private:

@@ -80,6 +80,9 @@ int main(int argc, char** argv) {
     return 2;
   }
   const bool with_gpu = argc > 3 && std::strcmp(argv[3], "--gpu") == 0;
+  // --gpu-batched: additionally run the batched proposed-NNI lists on the CUDA engine (not part of the committed
+  // GPU tests yet: verified on the CPU engine only this round)
+  const bool gpu_batched = argc > 3 && std::strcmp(argv[3], "--gpu-batched") == 0;
   try {
     Alignment alignment = Alignment::ReadFasta(argv[1]);
     Driver driver;
@@ -206,6 +209,77 @@ int main(int argc, char** argv) {
           Report("proposed NNIs, fixed lengths: plan on CUDA vs TPEngine", worst[0][1], 1e-9);
           Report("proposed NNIs, optimised: plan on CUDA vs TPEngine", worst[1][1], 1e-7);
           Report("proposed NNIs, optimised branch lengths on CUDA", worst[1][2], 1e-6);
+        }
+      }
+    }
+    // ---- every adjacent NNI in ONE batch of lists (TPLikelihoodPlan::BatchedProposedNNIOps) against the
+    // reference scoring them one at a time -----------------------------------------------------------
+    {
+      padded = tp.GetBranchLengths();
+      padded.head(E) = branch_lengths;
+      tp.SetBranchLengths(padded);
+      auto& eval = tp.GetLikelihoodEvalEngine();
+      eval.SetOptimizeNewEdges(true);
+      eval.Initialize();
+      eval.ComputeScores();
+      NNIEngine nni_engine(dag, nullptr, nullptr);
+      nni_engine.SyncAdjacentNNIsWithDAG();
+      std::vector<NNIOperation> posts;
+      for (const auto& nni : nni_engine.GetAdjacentNNIs())
+        if (posts.size() < 12) posts.push_back(nni);
+      const size_t n = posts.size();
+      // the reference scores them one after the other in the same temp slot (spare offset 0,
+      // nni_evaluation_engine.cpp:1081-1085); the batch gives NNI i the ids of spare offset i
+      std::vector<ProposedNNIInfo> infos;
+      std::vector<NNIAdjDoubles> starts(n);
+      std::vector<double> want(n);
+      for (size_t i = 0; i < n; ++i) {
+        const auto pre_nni = dag.FindNNINeighborInDAG(posts[i]);
+        infos.push_back(eval.GetProposedNNIInfo(posts[i], pre_nni, i, std::nullopt));
+        const auto& handler = eval.GetDAGBranchHandler();
+        starts[i] = TPLikelihoodPlan::TempBranchLengths(handler, infos[i], handler.GetDefaultBranchLength());
+        want[i] = tp.GetTopTreeScoreWithProposedNNI(posts[i], pre_nni, 0, std::nullopt);
+      }
+      const auto batch = plan.BatchedProposedNNIOps(infos);
+      auto run_batch = [&](auto& engine) {
+        engine.GrowSparePLVs(TPLikelihoodPlan::SpareNodesForBatch(n));
+        // The reference engine only rebuilds its PV index map when it reallocates (pv_handler.hpp:173-177 looks
+        // every PV up through pv_reindexer_, sized at the last Resize): ask for an explicit allocation so that
+        // the new spare PLVs are addressable there too. A no-op for the CUDA engine's slot table.
+        engine.GrowPLVs(engine.GetNodeCount(), std::nullopt, engine.GetNodeCount());
+        engine.GrowSpareGPCSPs(TPLikelihoodPlan::SpareGPCSPsForBatch(n) + n);
+        RunPlan(engine, plan, branch_lengths);
+        auto& handler = engine.GetBranchLengthHandler();
+        for (size_t i = 0; i < n; ++i)
+          for (auto adj : NNIAdjacentEnum::Iterator()) handler(infos[i].temp_edge_ids[adj]) = starts[i][adj];
+        engine.ResetOptimizationCount();
+        engine.ProcessOperations(batch.initialize);
+        for (size_t iter = 0; iter < eval.GetOptimizationMaxIteration(); ++iter) {
+          engine.ProcessOperations(batch.iteration);
+          engine.IncrementOptimizationCount();
+        }
+        engine.ProcessOperations(batch.score);
+        double worst = 0.;
+        for (size_t i = 0; i < n; ++i) {
+          const double got = engine.GetPerGPCSPLogLikelihoods(batch.focal_gpcsp[i], 1)[0];
+          if (getenv("TP_PARITY_DEBUG")) std::printf("  nni %zu focal %zu got %.12g want %.12g\n", i, batch.focal_gpcsp[i], got, want[i]);
+          worst = std::max(worst, std::abs(got - want[i]) / std::abs(want[i]));
+        }
+        return worst;
+      };
+      if (n > 0) {
+        GPEngine cpu(SitePattern(alignment, trees.TagTaxonMap()), N, G, tag + ".gp", 1e-40, ones_g, ones_n, ones_g,
+                     false);
+        std::printf("batched proposed NNIs: %zu NNIs, %zu + %zu x %zu + %zu ops\n", n, batch.initialize.size(),
+                    size_t(eval.GetOptimizationMaxIteration()), batch.iteration.size(), batch.score.size());
+        Report("batched proposed NNIs (optimised): plan on CPU GPEngine vs TPEngine", run_batch(cpu), 1e-9);
+        if (gpu_batched) {
+          GPEngineB200 gpu(SitePattern(alignment, trees.TagTaxonMap()), N, G, tag + ".gp", 1e-40, ones_g, ones_n,
+                           ones_g, false);
+          Report("batched proposed NNIs (optimised): plan on CUDA vs TPEngine", run_batch(gpu), 1e-7);
+          const bito_gp_stats st = gpu.Stats();
+          std::printf("CUDA engine: %lld kernel launches, %lld levels in the last list\n",
+                      static_cast<long long>(st.kernel_launches), static_cast<long long>(st.levels_last));
         }
       }
     }

@@ -10,7 +10,9 @@ edges, lengths from the pre-NNI, with and without five rounds of OptimizeBranchL
 and by TPLikelihoodPlan::ProposedNNIOps, and the whole-DAG BranchLengthOptimization (two calls of five rounds) by
 BranchLengthOptimizationOps. Finally the reference's NNI search runs three iterations in TP mode (top-1 filter, new
 edges optimised, nni_search.py:624-642) and the plan, rebuilt for the grown DAG, must reproduce the reference's
-re-evaluation of it and the next round of proposed NNIs. 1e-9 relative (through the CPU GPEngine the plan is bit-exact; CUDA with
+re-evaluation of it and the next round of proposed NNIs. BatchedProposedNNIOps scores all adjacent NNIs in one set of
+lists (disjoint temps per NNI, so the engine batches the k-th step of every NNI into one level) against the reference
+scoring them one at a time - on the CPU engine so far. 1e-9 relative (through the CPU GPEngine the plan is bit-exact; CUDA with
 optimisation: scores 1e-7, lengths 1e-6); inputs are generated here (the reference's data directory does not travel)."""
 import os
 import subprocess
@@ -42,7 +44,8 @@ def test_tp_plan_matches_reference_tp_engine_on_cpu(tmp_path, taxa, sites, trees
     # the per-edge pass; proposed NNIs: scores with fixed lengths, scores and lengths after optimisation; the
     # whole-DAG branch-length optimisation; the DAG grown by three iterations of the reference's TP-mode NNI search
     # (re-evaluated from scratch + its next proposed NNIs)
-    assert sum(line.startswith("ok  ") for line in lines) == 7
+    # ... and every adjacent NNI scored in ONE batch of lists (BatchedProposedNNIOps)
+    assert sum(line.startswith("ok  ") for line in lines) == 8
 
 
 @pytest.mark.gpu
@@ -54,4 +57,5 @@ def test_tp_plan_through_the_cuda_engine_matches_reference_tp_engine(cuda_engine
     lines = _run(tmp_path, taxa, sites, trees, moves, "--gpu")
     # CPU checks as above (5) + CUDA: two per-edge passes, proposed NNIs fixed / optimised / optimised lengths,
     # whole-DAG optimisation, grown DAG + its next proposed NNIs
-    assert sum(line.startswith("ok  ") for line in lines) == 15
+    # (the batched lists are checked on the CPU engine only so far: 8 CPU + 8 CUDA checks)
+    assert sum(line.startswith("ok  ") for line in lines) == 16
