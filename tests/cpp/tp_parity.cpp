@@ -333,7 +333,7 @@ int main(int argc, char** argv) {
       search.SetTPLikelihoodCutoffFilteringScheme(0.0);
       search.SetTopKScoreFilteringScheme(1);
       search.RunInit(true);
-      double worst_cpu = 0., worst_gpu = 0., worst_nni_cpu = 0., worst_nni_gpu = 0.;
+      double worst_cpu = 0., worst_gpu = 0., worst_nni_cpu = 0., worst_nni_gpu = 0., stale = 0.;
       size_t iterations = 0, grown_edges = E;
       for (; iterations < 3 && search.GetAdjacentNNICount() > 0; ++iterations) {
         search.RunMainLoop(true);
@@ -341,9 +341,11 @@ int main(int argc, char** argv) {
         const size_t E2 = dag.EdgeCountWithLeafSubsplits();
         grown_edges = E2;
         const EigenVectorXd bl2 = eval.GetDAGBranchHandler().GetBranchLengthData().head(E2);
+        const EigenVectorXd incremental = tp.GetTopTreeLikelihoods().head(E2);  // what the search itself holds
         eval.Initialize();
         eval.ComputeScores();
         const EigenVectorXd want2 = tp.GetTopTreeLikelihoods().head(E2);
+        stale = std::max(stale, RelErr(incremental, want2));
         const TPLikelihoodPlan plan2(dag, tp.GetChoiceMap());
         const size_t N2 = plan2.EngineNodeCount(), G2 = plan2.EngineGPCSPCount();
         const EigenVectorXd ones_g2 = EigenVectorXd::Ones(G2), ones_n2 = EigenVectorXd::Ones(N2);
@@ -379,7 +381,9 @@ int main(int argc, char** argv) {
           }
         }
       }
-      std::printf("TP-mode NNI search: %zu iterations, DAG grew from %zu to %zu edges\n", iterations, E, grown_edges);
+      std::printf("TP-mode NNI search: %zu iterations, DAG grew from %zu to %zu edges; the reference's incrementally "
+                  "updated scores differ from its own re-evaluation by up to %.3e (relative)\n",
+                  iterations, E, grown_edges, stale);
       if (iterations > 0) {
         Report("grown DAG: plan on CPU GPEngine vs TPEngine", worst_cpu, 1e-9);
         Report("grown DAG, next proposed NNIs (optimised): plan on CPU GPEngine", worst_nni_cpu, 1e-9);
