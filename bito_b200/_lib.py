@@ -59,6 +59,8 @@ class Stats(C.Structure):
         ("optimizer_cluster_threads", C.c_int64),
         ("optimizer_edges_in_flight", C.c_int64),
         ("peer_collective_calls", C.c_int64),
+        ("programs_evicted", C.c_int64),
+        ("programs_cached", C.c_int64),
     ]
 
 

@@ -99,7 +99,7 @@ int bito_gp_set_branch_lengths_to_constant(bito_gp_engine* e, double branch_leng
 }
 int bito_gp_set_branch_lengths_to_default(bito_gp_engine* e) {
   ENGINE_OR_FAIL(e);
-  return Guard([&] { e->impl.SetBranchLengthsToConstant(0.1); });
+  return Guard([&] { e->impl.SetBranchLengthsToDefault(); });
 }
 int bito_gp_get_branch_lengths(bito_gp_engine* e, int64_t start, int64_t length, double* out) {
   ENGINE_OR_FAIL(e);

@@ -46,16 +46,20 @@ constexpr double kBranchLengthDifferenceThreshold = 1e-15;
 // k_opt_block keeps G doubles per pattern in shared memory: up to 10240 patterns under JC69 (G = 2)
 constexpr size_t kOptBlockMaxSharedBytes = 160 * 1024;
 
-uint64_t HashOps(const bito_gp_op* ops, int64_t n, const int64_t* vec, int64_t vec_len) {
-  uint64_t h = 1469598103934665603ull;
-  auto mix = [&h](const void* data, size_t bytes) {
+// Two independent 64-bit hashes of an op list: `seed` 0 keys the program cache, `seed` 1 is kept in
+// the Program and compared on every hit, so a collision of the key alone cannot run another list.
+uint64_t HashOps(const bito_gp_op* ops, int64_t n, const int64_t* vec, int64_t vec_len, int seed = 0) {
+  uint64_t h = seed == 0 ? 1469598103934665603ull : 0x9e3779b97f4a7c15ull;
+  const uint64_t mul = seed == 0 ? 1099511628211ull : 0xff51afd7ed558ccdull;
+  const int shift = seed == 0 ? 29 : 33;
+  auto mix = [&h, mul, shift](const void* data, size_t bytes) {
     const unsigned char* p = static_cast<const unsigned char*>(data);
     // FNV-1a over 8-byte words (inputs are int64 tables).
     for (size_t i = 0; i + 8 <= bytes; i += 8) {
       uint64_t w;
       std::memcpy(&w, p + i, 8);
-      h = (h ^ w) * 1099511628211ull;
-      h ^= h >> 29;
+      h = (h ^ w) * mul;
+      h ^= h >> shift;
     }
   };
   mix(&n, sizeof n);
@@ -182,7 +186,8 @@ Engine::Engine(const bito_gp_config& cfg) : cfg_(cfg) {
   GP_CUDA(cudaSetDevice(device_));
   cudaDeviceProp prop;
   GP_CUDA(cudaGetDeviceProperties(&prop, device_));
-  if (prop.major < 10)
+  // the library carries sm_100a SASS only (no PTX): any other device would fail at its first launch
+  if (prop.major != 10 || prop.minor != 0)
     Fail("bito_gp_create: kernels are built for sm_100a (B200) only; found sm_" +
          std::to_string(prop.major) + std::to_string(prop.minor));
   GP_CUDA(cudaStreamCreateWithFlags(&own_stream_, cudaStreamNonBlocking));
@@ -240,6 +245,16 @@ Engine::Engine(const bito_gp_config& cfg) : cfg_(cfg) {
   if (const char* env = getenv("BITO_GP_OPT_CLUSTER")) opt_cluster_env_ = atoi(env);
   // BITO_GP_OPT_CLUSTER_THREADS: 256 | 1024 = only that block size (with a forced cluster size: tests)
   if (const char* env = getenv("BITO_GP_OPT_CLUSTER_THREADS")) opt_cluster_threads_env_ = atoi(env);
+  // BITO_GP_OPT_SCHEME: 0 = rounds, 2 = one cluster per edge reading the PLVs, 3 = pipelined clusters
+  // (a streaming producer writes rho, clusters run the searches); unset = the engine's own choice
+  if (const char* env = getenv("BITO_GP_OPT_SCHEME")) opt_scheme_env_ = atoi(env);
+  if (const char* env = getenv("BITO_GP_OPT_RING_EDGES")) opt_ring_edges_env_ = atoi(env);
+  GP_CUDA(cudaStreamCreateWithFlags(&prep_stream_, cudaStreamNonBlocking));
+  GP_CUDA(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
+  for (int b = 0; b < 2; ++b) {
+    GP_CUDA(cudaEventCreateWithFlags(&ev_ready_[b], cudaEventDisableTiming));
+    GP_CUDA(cudaEventCreateWithFlags(&ev_free_[b], cudaEventDisableTiming));
+  }
   GP_CUDA(UploadModel(m));
 
   // PLV slabs: ~256 MiB chunks (or one PLV, whichever is larger).
@@ -280,6 +295,13 @@ Engine::~Engine() {
   d_inverted_.Release(); d_uncond_.Release(); d_status_.Release(); d_feval_total_.Release();
   d_partials_.Release(); d_packed_.Release(); d_level_max_.Release(); d_coef_.Release(); d_opt_ctl_.Release();
   d_dense_tmp_.Release(); d_mtab_.Release(); d_mtab_lik_.Release(); d_opt_states_.Release(); d_opt_const_.Release(); d_opt_active_.Release(); d_perm_.Release(); d_wperm_.Release(); d_row_class_.Release(); d_active_.Release(); d_single_opt_.Release(); d_cluster_inv_perm_.Release(); d_cluster_wperm_.Release(); d_quartet_items_.Release(); d_quartet_mats_.Release();
+  d_cluster_pos_.Release(); d_rho_ring_.Release(); d_ring_const_.Release(); d_ring_partials_.Release();
+  if (prep_stream_) cudaStreamDestroy(prep_stream_);
+  if (ev_fork_) cudaEventDestroy(ev_fork_);
+  for (int b = 0; b < 2; ++b) {
+    if (ev_ready_[b]) cudaEventDestroy(ev_ready_[b]);
+    if (ev_free_[b]) cudaEventDestroy(ev_free_[b]);
+  }
   if (pinned_ != nullptr) cudaFreeHost(pinned_);
   if (ev_begin_) cudaEventDestroy(ev_begin_);
   if (ev_end_) cudaEventDestroy(ev_end_);
@@ -357,28 +379,15 @@ void Engine::InvalidatePrograms() { alloc_version_++; }
 void Engine::SetSitePatterns(const uint8_t* symbols, const double* weights, bool on_device) {
   Activate();
   const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-  if (P_ == 0) {  // empty shard: nothing to upload
-    bool slots_changed = false;
-    for (int64_t t = 0; t < taxon_count_; ++t) {
-      PlvSlot& s = plvs_[static_cast<size_t>(t)];
-      void* want = d_symbols_.ptr + t * P_stride_;
-      if (s.kind == kPlvSymbols && s.ptr == want) continue;
-      if (s.kind == kPlvDense) plv_pool_.Free(s.ptr);
-      s.ptr = want;
-      s.kind = kPlvSymbols;
-      slots_changed = true;
-    }
-    total_weight_ = 0.;
-    have_patterns_ = true;
-    BuildWeightClasses(weights);
-    if (slots_changed) InvalidatePrograms();
-    return;
+  // An empty shard (P_ == 0: a rank of a multi-GPU run that owns no pattern) uploads nothing but
+  // runs every collective below with a zero contribution, so that all ranks issue the same sequence.
+  if (P_ > 0) {
+    GP_CUDA(cudaMemcpy2DAsync(d_symbols_.ptr, static_cast<size_t>(P_stride_), symbols,
+                              static_cast<size_t>(P_), static_cast<size_t>(P_),
+                              static_cast<size_t>(taxon_count_), kind, stream_));
+    GP_CUDA(cudaMemcpyAsync(d_weights_.ptr, weights, static_cast<size_t>(P_) * sizeof(double), kind,
+                            stream_));
   }
-  GP_CUDA(cudaMemcpy2DAsync(d_symbols_.ptr, static_cast<size_t>(P_stride_), symbols,
-                            static_cast<size_t>(P_), static_cast<size_t>(P_),
-                            static_cast<size_t>(taxon_count_), kind, stream_));
-  GP_CUDA(cudaMemcpyAsync(d_weights_.ptr, weights, static_cast<size_t>(P_) * sizeof(double), kind,
-                          stream_));
   // Leaf P-PLVs (ids [0, taxa)) stay symbolic: 1 byte per pattern instead of 32.
   bool slots_changed = false;
   for (int64_t t = 0; t < taxon_count_; ++t) {
@@ -394,7 +403,7 @@ void Engine::SetSitePatterns(const uint8_t* symbols, const double* weights, bool
   const int64_t tiles = TilesFor(P_);
   EnsureScratch(tiles, 2);
   LaunchFill(stream_, d_dense_tmp_.ptr, P_stride_, 1.0);
-  LaunchWeightedSum(stream_, State(), d_dense_tmp_.ptr, d_partials_.ptr);
+  LaunchWeightedSum(stream_, State(), d_dense_tmp_.ptr, d_partials_.ptr);  // P_ == 0: one tile, sum 0
   LaunchReducePartials(stream_, d_partials_.ptr, 1, tiles, d_packed_.ptr, nullptr, nullptr);
   AllReduce(d_packed_.ptr, 1, false);
   // The symbols are validated where they now live (a host-side scan of taxa x P bytes costs more
@@ -402,13 +411,16 @@ void Engine::SetSitePatterns(const uint8_t* symbols, const double* weights, bool
   LaunchMaxSymbol(stream_, d_symbols_.ptr, taxon_count_, P_, P_stride_, d_packed_.ptr + 1);
   GP_CUDA(cudaMemcpyAsync(pinned_, d_packed_.ptr, 2 * sizeof(double), cudaMemcpyDeviceToHost, stream_));
   GP_CUDA(cudaStreamSynchronize(stream_));
-  total_weight_ = static_cast<double*>(pinned_)[0];
+  const double new_total = static_cast<double*>(pinned_)[0];
   if (static_cast<double*>(pinned_)[1] > 4.) {
     have_patterns_ = false;
     Fail("bito_gp_set_site_patterns: symbol outside 0..4");
   }
+  // captured kernels take DeviceState (total_weight) by value
+  if (new_total != total_weight_) DropGraphs();
+  total_weight_ = new_total;
   have_patterns_ = true;
-  BuildWeightClasses(on_device ? nullptr : weights);
+  BuildWeightClasses(on_device && P_ > 0 ? nullptr : weights);
   AgreeOnClusterScheme();
   // Re-uploading an alignment of the same shape leaves every compiled program valid.
   if (slots_changed) InvalidatePrograms();
@@ -432,6 +444,8 @@ void Engine::BuildWeightClasses(const double* host_weights) {
   }
   if (w == host_weights_cache_ && P_perm_ > 0 && P_ > 0) return;  // same weights: layout is current
   host_weights_cache_ = w;
+  DropGraphs();  // captured optimiser launches bake the class boundaries (OptClusterLayout) in by value
+  layout_version_++;
   auto cls = [](double x) {
     const int wi = static_cast<int>(x);
     return (x == static_cast<double>(wi) && wi >= 1 && wi <= 7) ? wi - 1 : 7;
@@ -495,6 +509,12 @@ void Engine::BuildWeightClasses(const double* host_weights) {
       inv[static_cast<size_t>(cnext[c])] = static_cast<int32_t>(p);
       cw[static_cast<size_t>(cnext[c]++)] = w[static_cast<size_t>(p)];
     }
+    std::vector<int32_t> pos_of(static_cast<size_t>(std::max<int64_t>(P_, 1)), 0);
+    for (size_t q = 0; q < inv.size(); ++q)
+      if (inv[q] >= 0) pos_of[static_cast<size_t>(inv[q])] = static_cast<int32_t>(q);
+    d_cluster_pos_.Resize(pos_of.size(), false, stream_);
+    GP_CUDA(cudaMemcpyAsync(d_cluster_pos_.ptr, pos_of.data(), pos_of.size() * sizeof(int32_t),
+                            cudaMemcpyHostToDevice, stream_));
     d_cluster_inv_perm_.Resize(inv.size(), false, stream_);
     d_cluster_wperm_.Resize(cw.size(), false, stream_);
     GP_CUDA(cudaMemcpyAsync(d_cluster_inv_perm_.ptr, inv.data(), inv.size() * sizeof(int32_t),
@@ -506,10 +526,10 @@ void Engine::BuildWeightClasses(const double* host_weights) {
     const int had_rows = had > 0 ? cluster_plans_[0].rows_total : -1;
     cluster_plans_.clear();
     if (opt_cluster_env_ != 0) {  // an empty shard (P = 0) plans one all-padding row: it still takes part in the exchange
-      for (int threads : {256, 1024}) {
+      for (int threads : {256, 512, 1024}) {
         if (opt_cluster_threads_env_ > 0 && threads != opt_cluster_threads_env_) continue;
         if (opt_cluster_env_ > 0 && opt_cluster_threads_env_ <= 0 && threads != 256) continue;
-        for (int c = 1; c <= kMaxOptCluster; c *= 2) {
+        for (int c = 1; c <= kMaxOptCluster; ++c) {
           if (opt_cluster_env_ > 0 && c != opt_cluster_env_) continue;
           OptClusterPlan plan;
           if (PlanOptCluster(std::max<int64_t>(cpos / row, 1), threads, c, &plan)) cluster_plans_.push_back(plan);
@@ -828,6 +848,42 @@ Program* Engine::Compile(const bito_gp_op* ops, int64_t n, const int64_t* vec, i
   const int64_t n_plv = padded_plv_count();
   const int64_t n_edge = padded_gpcsp_count();
 
+  // -- pass 0a: which PLVs hold (or will hold) data once this list has run. A Multiply whose
+  // destination owns no memory and one of whose operands is identically zero *for the whole list*
+  // stays a count-only op; any other Multiply makes its destination dense. The decision must not
+  // depend on the order in which later ops make an operand dense, so it is a fixpoint over the
+  // whole list, taken before anything is allocated; pass 0 and pass 1 both read `elide`.
+  std::vector<char> elide(static_cast<size_t>(n), 0);
+  {
+    std::vector<char> nonzero(static_cast<size_t>(n_plv), 0);
+    for (int64_t k = 0; k < n_plv; ++k) nonzero[k] = plvs_[k].kind != kPlvZero;
+    auto in_range = [&](int64_t id) { return id >= 0 && id < n_plv; };
+    for (int64_t i = 0; i < n; ++i) {
+      const bito_gp_op& op = ops[i];
+      if ((op.kind == BITO_GP_SET_TO_STATIONARY_DISTRIBUTION ||
+           op.kind == BITO_GP_INCREMENT_WITH_WEIGHTED_EVOLVED_PLV) && in_range(op.a))
+        nonzero[op.a] = 1;
+    }
+    bool changed = fuse;
+    while (changed) {
+      changed = false;
+      for (int64_t i = 0; i < n; ++i) {
+        const bito_gp_op& op = ops[i];
+        if (op.kind != BITO_GP_MULTIPLY || !in_range(op.a) || !in_range(op.b) || !in_range(op.c)) continue;
+        if (!nonzero[op.a] && nonzero[op.b] && nonzero[op.c]) {
+          nonzero[op.a] = 1;
+          changed = true;
+        }
+      }
+    }
+    if (fuse)
+      for (int64_t i = 0; i < n; ++i) {
+        const bito_gp_op& op = ops[i];
+        if (op.kind == BITO_GP_MULTIPLY && in_range(op.a) && in_range(op.b) && in_range(op.c))
+          elide[i] = !nonzero[op.a] && (!nonzero[op.b] || !nonzero[op.c]);
+      }
+  }
+
   // -- pass 0: validate and make every written PLV / row resident ------------------------
   for (int64_t i = 0; i < n; ++i) {
     const bito_gp_op& op = ops[i];
@@ -854,9 +910,7 @@ Program* Engine::Compile(const bito_gp_op* ops, int64_t n, const int64_t* vec, i
         // A product with a PLV that is (and stays) identically zero is zero: if the
         // destination owns no memory either it stays that way (e.g. the r-PLVs of leaves,
         // RHat o PHat with PHat never written).
-        if (!(fuse && plvs_[op.a].kind == kPlvZero &&
-              (plvs_[op.b].kind == kPlvZero || plvs_[op.c].kind == kPlvZero)))
-          EnsureDense(op.a);
+        if (!elide[i]) EnsureDense(op.a);
         break;
       case BITO_GP_LIKELIHOOD:
         CheckEdge(op.a, "Likelihood");
@@ -1049,10 +1103,9 @@ Program* Engine::Compile(const bito_gp_op* ops, int64_t n, const int64_t* vec, i
         if (op.c != op.a) before_read(op.c);
         if (op.b == op.a || op.c == op.a) before_read(op.a);
         pending_zero[op.a] = 0;
-        if (fuse && plvs_[op.a].kind == kPlvZero &&
-            (plvs_[op.b].kind == kPlvZero || plvs_[op.c].kind == kPlvZero)) {
-          // Kinds are final here (pass 0 made every really-written PLV dense): the product is
-          // identically zero and the destination keeps owning no memory. Only the count moves.
+        if (elide[i]) {
+          // Decided in pass 0a for the list as a whole: the product is identically zero and the
+          // destination keeps owning no memory. Only the count moves.
           Macro z;
           z.kind = kMkScalar;
           z.idx = static_cast<int>(h_scalar.size());
@@ -1471,10 +1524,42 @@ Program* Engine::Compile(const bito_gp_op* ops, int64_t n, const int64_t* vec, i
   stats_.programs_compiled++;
   Program* raw = prog.get();
   const uint64_t key = HashOps(ops, n, vec, vec_len);
+  prog->check_hash = HashOps(ops, n, vec, vec_len, 1);
+  prog->n_ops = n;
+  prog->vec_len = vec_len;
+  prog->last_used = ++program_clock_;
   auto it = programs_.find(key);
   if (it != programs_.end()) FreeProgram(*it->second);
   programs_[key] = std::move(prog);
+  EvictPrograms(raw);
   return raw;
+}
+
+// Programs compiled against an older PLV / edge allocation can never run again (ProcessOperations
+// recompiles on a version mismatch), and an NNI search issues a new, larger list after every DAG
+// growth plus one list per proposed NNI: free the dead ones now, and keep the live ones bounded
+// (least recently used first). `keep` is the program that is about to run.
+void Engine::EvictPrograms(const Program* keep) {
+  for (auto it = programs_.begin(); it != programs_.end();) {
+    Program* p = it->second.get();
+    if (p != keep && p->alloc_version != alloc_version_) {
+      FreeProgram(*p);
+      it = programs_.erase(it);
+      stats_.programs_evicted++;
+    } else {
+      ++it;
+    }
+  }
+  while (programs_.size() > kMaxCachedPrograms) {
+    auto victim = programs_.end();
+    for (auto it = programs_.begin(); it != programs_.end(); ++it)
+      if (it->second.get() != keep && (victim == programs_.end() || it->second->last_used < victim->second->last_used))
+        victim = it;
+    if (victim == programs_.end()) break;
+    FreeProgram(*victim->second);
+    programs_.erase(victim);
+    stats_.programs_evicted++;
+  }
 }
 
 void Engine::FreeProgram(Program& p) {
@@ -1618,9 +1703,28 @@ int Engine::OptScheme(int n_ops, const OptClusterPlan** plan) const {
   const bool cluster_ok = !cluster_plans_.empty() && n_eigen_groups_ == 2 &&
                           method_ == BITO_GP_BRENT_OPTIMIZATION;
   const bool forced = opt_cluster_env_ > 0;
-  if (!(cluster_ok && forced) && OptBlockSharedBytes(P_, n_eigen_groups_) <= kOptBlockMaxSharedBytes)
+  if (opt_scheme_env_ == 0) return 0;
+  if (!(cluster_ok && (forced || opt_scheme_env_ >= 2)) &&
+      OptBlockSharedBytes(P_, n_eigen_groups_) <= kOptBlockMaxSharedBytes)
     return 1;
   if (!cluster_ok) return 0;
+  // Scheme 3, pipelined clusters: for levels with many more edges than the chip keeps resident. A
+  // streaming producer (HBM-bound) turns the PLVs of the next chunk of edges into rho while the
+  // clusters (latency-bound, shared memory) run the searches of the current chunk, so shared memory
+  // only ever holds edges whose search is running. Shape: as many edges in flight as possible.
+  {
+    const OptClusterPlan* widest = nullptr;
+    for (const OptClusterPlan& c : cluster_plans_) {
+      if (widest == nullptr || c.active_clusters > widest->active_clusters ||
+          (c.active_clusters == widest->active_clusters && c.threads < widest->threads))
+        widest = &c;
+    }
+    const bool many = n_ops >= 4 * widest->active_clusters;
+    if (opt_scheme_env_ == 3 || (opt_scheme_env_ < 0 && !forced && many)) {
+      if (plan != nullptr) *plan = widest;
+      return 3;
+    }
+  }
   // Cost model, microseconds, fitted to B200 timings (profiles/r01g_sweep_variants_*.log):
   //  on chip, per edge: two-row load trips of ~2.5 us, then ~14.5 dependent objective evaluations of
   //  2.4 us (reduction + cluster barrier + optimiser step) + 0.05 us per rho row a thread walks,
@@ -1681,12 +1785,18 @@ void Engine::RunOptimizer(const OptOp* d_ops, int n_ops, int method, bool check_
   const int on_chip = OptScheme(n_ops, &plan);
   last_opt_scheme_ = on_chip;
   last_opt_plan_ = plan != nullptr ? *plan : OptClusterPlan();
-  if (on_chip != 0 && !capturing_) stats_.kernel_launches++;
+  if (on_chip == 1 || on_chip == 2) {
+    if (capturing_) capture_opt_launches_++; else stats_.kernel_launches++;
+  }
   if (on_chip == 1) {
     // small alignment, single rank: every edge's whole search in one launch (k_opt_block); the
     // settings were written to d_opt_ctl_ by Execute, outside any captured graph
     ProfScope ps(this, kProfOptBlock, 64. * n_ops * static_cast<double>(P_));
     LaunchOptBlock(stream_, st, d_ops, n_ops, d_opt_ctl_.ptr, G, opt_refresh_);
+    return;
+  }
+  if (on_chip == 3) {
+    RunOptimizerPipelined(d_ops, n_ops, *plan);
     return;
   }
   if (on_chip == 2) {
@@ -1790,6 +1900,99 @@ void Engine::RunOptimizer(const OptOp* d_ops, int n_ops, int method, bool check_
   }
 }
 
+// Scheme 3. Two streams, two chunk buffers:
+//   producer (prep_stream_): k_opt_prepare_cluster(chunk i) -> rho ring half i&1, K_e partials ->
+//                            k_reduce_partials -> K_e                      [HBM-bound: 64 B / pattern / edge]
+//   consumer (stream_):      k_opt_cluster<T, true>(chunk i): one cluster per edge copies its rho rows
+//                            to shared memory and runs the whole Brent search there [latency-bound]
+// chunk i + 1 is produced while chunk i is searched; events hand the halves back and forth. No
+// host round trip, so the level is capturable (the producer stream joins the capture through the
+// fork event and rejoins through the last `ready` event).
+int Engine::EnsurePipelineBuffers(int n_ops, const OptClusterPlan& plan) {
+  const int64_t rho_stride = static_cast<int64_t>(plan.rows_total) * kClusterThreads;
+  // chunk: several waves of resident clusters (so that the tail of a launch, where its last searches
+  // finish alone, stays small) within ~128 MiB of rho per half
+  int chunk = opt_ring_edges_env_ > 0 ? opt_ring_edges_env_
+                                      : std::max(6 * plan.active_clusters,
+                                                 static_cast<int>((int64_t(128) << 20) / (8 * rho_stride)));
+  chunk = std::max(1, std::min(chunk, n_ops));
+  // the producer's tile-group count depends on the op count (TilesPerBlock): size for the worst case
+  const int64_t max_groups = TilesFor(P_);
+  const size_t ring_doubles = static_cast<size_t>(2) * chunk * rho_stride;
+  if (d_rho_ring_.n < ring_doubles || ring_rho_stride_ != rho_stride) {
+    if (capturing_) Fail("internal: pipelined optimiser buffers must exist before graph capture");
+    GP_CUDA(cudaStreamSynchronize(stream_));
+    GP_CUDA(cudaStreamSynchronize(prep_stream_));
+    if (d_rho_ring_.n < ring_doubles) {
+      d_rho_ring_.Release();
+      d_rho_ring_.Resize(ring_doubles, false, stream_);
+      DropGraphs();
+    }
+    // padding positions of the class layout hold rho = 0 (a factor of exactly 1) and are never
+    // written by the producer; a new layout (other weights, other shape) moves them
+    GP_CUDA(cudaMemsetAsync(d_rho_ring_.ptr, 0, d_rho_ring_.n * sizeof(double), stream_));
+    ring_rho_stride_ = rho_stride;
+    ring_layout_version_ = layout_version_;
+  } else if (ring_layout_version_ != layout_version_) {
+    if (capturing_) Fail("internal: pipelined optimiser buffers must exist before graph capture");
+    GP_CUDA(cudaStreamSynchronize(prep_stream_));
+    GP_CUDA(cudaMemsetAsync(d_rho_ring_.ptr, 0, d_rho_ring_.n * sizeof(double), stream_));
+    ring_layout_version_ = layout_version_;
+  }
+  if (d_ring_const_.n < static_cast<size_t>(2 * chunk) ||
+      d_ring_partials_.n < static_cast<size_t>(2 * chunk * max_groups)) {
+    if (capturing_) Fail("internal: pipelined optimiser buffers must exist before graph capture");
+    GP_CUDA(cudaStreamSynchronize(stream_));
+    GP_CUDA(cudaStreamSynchronize(prep_stream_));
+    d_ring_const_.Resize(static_cast<size_t>(2 * chunk), false, stream_);
+    d_ring_partials_.Resize(static_cast<size_t>(2 * chunk * max_groups), false, stream_);
+    DropGraphs();
+  }
+  return chunk;
+}
+
+void Engine::RunOptimizerPipelined(const OptOp* d_ops, int n_ops, const OptClusterPlan& plan) {
+  const DeviceState st = State();
+  const int64_t rho_stride = static_cast<int64_t>(plan.rows_total) * kClusterThreads;
+  const int chunk = EnsurePipelineBuffers(n_ops, plan);
+  const int64_t max_groups = TilesFor(P_);
+  // with per-kernel profiling on, everything runs on the engine's stream (serialised, but timed)
+  cudaStream_t ps = profiling_ ? stream_ : prep_stream_;
+  if (ps != stream_) {
+    GP_CUDA(cudaEventRecord(ev_fork_, stream_));
+    GP_CUDA(cudaStreamWaitEvent(ps, ev_fork_, 0));
+  }
+  int i = 0;
+  for (int c0 = 0; c0 < n_ops; c0 += chunk, ++i) {
+    const int m = std::min(chunk, n_ops - c0);
+    const int b = i & 1;
+    double* rho = d_rho_ring_.ptr + static_cast<size_t>(b) * chunk * rho_stride;
+    double* consts = d_ring_const_.ptr + static_cast<size_t>(b) * chunk;
+    double* parts = d_ring_partials_.ptr + static_cast<size_t>(b) * chunk * max_groups;
+    if (ps != stream_ && i >= 2) GP_CUDA(cudaStreamWaitEvent(ps, ev_free_[b], 0));
+    {
+      ProfScope scope(this, kProfOptPrepare, 64. * m * static_cast<double>(P_));
+      LaunchOptPrepareCluster(ps, st, d_ops + c0, m, rho, d_cluster_pos_.ptr, rho_stride, parts);
+    }
+    {
+      ProfScope scope(this, kProfReduce, 0.);
+      LaunchReducePartials(ps, parts, m, OptPrepareTileGroups(m, P_), consts, nullptr, nullptr);
+    }
+    if (ps != stream_) {
+      GP_CUDA(cudaEventRecord(ev_ready_[b], ps));
+      GP_CUDA(cudaStreamWaitEvent(stream_, ev_ready_[b], 0));
+    }
+    {
+      ProfScope scope(this, kProfOptCluster, 0.);
+      GP_CUDA(LaunchOptCluster(stream_, st, d_ops + c0, m, d_opt_ctl_.ptr, d_cluster_inv_perm_.ptr,
+                               d_cluster_wperm_.ptr, cluster_class_row_start_, plan, opt_refresh_,
+                               PeerEdgeContext(), rho, rho_stride, consts));
+    }
+    if (ps != stream_) GP_CUDA(cudaEventRecord(ev_free_[b], stream_));
+    if (capturing_) capture_opt_launches_ += 3; else stats_.kernel_launches += 3;
+  }
+}
+
 void Engine::Execute(Program& prog) {
   EnsureScratch(prog.max_partials, prog.max_packed);
   {
@@ -1812,7 +2015,12 @@ void Engine::Execute(Program& prog) {
   // optimiser launches are counted where they are issued (RunOptimizer), except inside a graph
   // replay, where every OptimizeBranchLength level is exactly one on-chip launch
   const int64_t launches = prog.launches;
-  const int64_t graph_launches = prog.launches + (opt_on_chip ? prog.n_opt_levels : 0);
+  if (opt_on_chip) {  // the pipelined scheme's buffers cannot be (re)allocated inside a capture
+    for (const Level& L : prog.levels) {
+      const OptClusterPlan* plan = nullptr;
+      if (L.n_opt > 0 && OptScheme(L.n_opt, &plan) == 3) EnsurePipelineBuffers(L.n_opt, *plan);
+    }
+  }
   if (prog.n_opt_total > 0) {  // read by k_opt_block / k_opt_cluster, whichever levels use them
     OptControl ctl{};
     ctl.prm = OptimizerParams(optimization_count_ != 0);
@@ -1833,6 +2041,7 @@ void Engine::Execute(Program& prog) {
       cudaGraph_t graph = nullptr;
       GP_CUDA(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
       capturing_ = true;
+      capture_opt_launches_ = 0;
       try {
         body();
       } catch (...) {
@@ -1842,6 +2051,7 @@ void Engine::Execute(Program& prog) {
         throw;
       }
       capturing_ = false;
+      prog.graph_opt_launches = capture_opt_launches_;
       GP_CUDA(cudaStreamEndCapture(stream_, &graph));
       cudaError_t err = cudaGraphInstantiate(&prog.graph, graph, 0);
       cudaGraphDestroy(graph);
@@ -1853,7 +2063,7 @@ void Engine::Execute(Program& prog) {
     if (prog.graph != nullptr) {
       GP_CUDA(cudaGraphLaunch(prog.graph, stream_));
       stats_.graph_launches++;
-      stats_.kernel_launches += graph_launches;
+      stats_.kernel_launches += prog.launches + prog.graph_opt_launches;
       return;
     }
   }
@@ -1870,8 +2080,10 @@ void Engine::ProcessOperations(const bito_gp_op* ops, int64_t n, const int64_t* 
   const uint64_t key = HashOps(ops, n, vec, vec_len);
   Program* prog = nullptr;
   auto it = programs_.find(key);
-  if (it != programs_.end() && it->second->alloc_version == alloc_version_) {
+  if (it != programs_.end() && it->second->alloc_version == alloc_version_ && it->second->n_ops == n &&
+      it->second->vec_len == vec_len && it->second->check_hash == HashOps(ops, n, vec, vec_len, 1)) {
     prog = it->second.get();
+    prog->last_used = ++program_clock_;
   } else {
     prog = Compile(ops, n, vec, vec_len);
     // Compile may itself have made PLVs resident (bumping the version) before building the
@@ -1907,6 +2119,7 @@ void Engine::SetBranchLengthsToConstant(double v) {
   Activate();
   LaunchFill(stream_, d_bl_.ptr, static_cast<int64_t>(d_bl_.n), v);
 }
+void Engine::SetBranchLengthsToDefault() { SetBranchLengthsToConstant(kDefaultBranchLength); }
 void Engine::GetBranchLengths(int64_t start, int64_t length, double* out) {
   Activate();
   if (start < 0 || length < 0 || start + length > padded_gpcsp_count())
@@ -2278,6 +2491,7 @@ void Engine::GrowGpcsps(int64_t new_count, const int64_t* reindexer, int64_t exp
   for (int64_t j = 0; j < spare_gpcsps_; ++j) {
     const int64_t src = old_count + j, dst = new_count + j;
     nq[dst] = q[src]; ninv[dst] = inv[src]; nbl[dst] = bl[src]; ndiff[dst] = diff[src];
+    nhyb[dst] = hyb[src];
     nlls[dst] = lls[src];
     nrows[dst] = rows_[src];
     moved[src] = 1;
@@ -2483,6 +2697,7 @@ void Engine::GetStats(bito_gp_stats* out) {
   stats_.optimizer_cluster_size = last_opt_scheme_ == 2 ? last_opt_plan_.cluster_size : 0;
   stats_.optimizer_cluster_threads = last_opt_scheme_ == 2 ? last_opt_plan_.threads : 0;
   stats_.optimizer_edges_in_flight = last_opt_scheme_ == 2 ? last_opt_plan_.active_clusters : 0;
+  stats_.programs_cached = static_cast<int64_t>(programs_.size());
   *out = stats_;
 }
 

@@ -77,6 +77,9 @@ struct Level {
 
 struct Program {
   uint64_t alloc_version = 0;
+  uint64_t check_hash = 0;  // second hash of the op list, compared on every cache hit
+  int64_t n_ops = 0, vec_len = 0;
+  uint64_t last_used = 0;
   std::vector<Level> levels;
   // device tables (one arena)
   char* arena = nullptr;
@@ -103,6 +106,7 @@ struct Program {
   int64_t n_macro = 0;
   int64_t launches = 0;      // kernels per execution (without optimiser rounds)
   double alg_bytes_per_pattern = 0.;
+  int64_t graph_opt_launches = 0;  // optimiser kernels inside the captured graph
   cudaGraphExec_t graph = nullptr;
   bool graph_tried = false;
 };
@@ -145,6 +149,7 @@ class Engine {
   void SetBranchLengths(const double* bl);
   void SetBranchLengthsRange(int64_t start, int64_t length, const double* bl);
   void SetBranchLengthsToConstant(double v);
+  void SetBranchLengthsToDefault();  // dag_branch_handler.hpp:266 default_branch_length_
   void GetBranchLengths(int64_t start, int64_t length, double* out);
   void GetBranchLengthDifferences(double* out);
   void SetOptimizationMethod(int m);
@@ -216,7 +221,15 @@ class Engine {
   bool ProgramOptimizesOnChip(const Program& prog) const;
   OptParams OptimizerParams(bool check_convergence) const;
   void RunOptimizer(const OptOp* d_ops, int n_ops, int method, bool check_convergence);
+  void RunOptimizerPipelined(const OptOp* d_ops, int n_ops, const OptClusterPlan& plan);
+  int EnsurePipelineBuffers(int n_ops, const OptClusterPlan& plan);  // returns the chunk size (edges)
+  int64_t ring_rho_stride_ = 0;
+  uint64_t layout_version_ = 0, ring_layout_version_ = 0;
+  int64_t capture_opt_launches_ = 0;
   void FreeProgram(Program& p);
+  void EvictPrograms(const Program* keep);
+  static constexpr size_t kMaxCachedPrograms = 48;
+  uint64_t program_clock_ = 0;
   void EnsureScratch(int64_t partial_doubles, int64_t packed_doubles);
   void BuildWeightClasses(const double* host_weights);
   void DropGraphs();
@@ -262,6 +275,14 @@ class Engine {
   int64_t P_perm_ = 0;  // patterns in weight-class order, classes padded to 256-pattern rows
   // k_opt_cluster's layout: position -> pattern (-1 = padding), weights by position, class rows
   DeviceArray<int32_t> d_cluster_inv_perm_;
+  DeviceArray<int32_t> d_cluster_pos_;  // pattern -> position (the inverse of d_cluster_inv_perm_)
+  // Pipelined cluster scheme (RunOptimizerPipelined): rho of two chunks of edges, their K_e and the
+  // producer's tile partials, double-buffered between the producer stream and the engine's stream
+  DeviceArray<double> d_rho_ring_, d_ring_const_, d_ring_partials_;
+  cudaStream_t prep_stream_ = nullptr;
+  cudaEvent_t ev_fork_ = nullptr, ev_ready_[2] = {nullptr, nullptr}, ev_free_[2] = {nullptr, nullptr};
+  int opt_scheme_env_ = -1;       // BITO_GP_OPT_SCHEME (-1: automatic)
+  int opt_ring_edges_env_ = 0;    // BITO_GP_OPT_RING_EDGES (0: automatic)
   DeviceArray<double> d_cluster_wperm_;
   int32_t cluster_class_row_start_[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   std::vector<OptClusterPlan> cluster_plans_;  // every shape this device runs for this alignment

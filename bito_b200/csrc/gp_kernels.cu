@@ -1040,6 +1040,77 @@ __global__ void __launch_bounds__(kTile)
   if (threadIdx.x == 0) partials[static_cast<int64_t>(o) * n_groups + tile_group] = k_part;
 }
 
+// c0, c1 = the two eigen-group coefficients of L_p(t) for one pattern (see k_opt_prepare_ratio);
+// rho = c1 / c0.
+__device__ __forceinline__ void ratio_coefficients(const V4& r, const V4& c, double& rho, double& c0_out) {
+  double c0 = 0., c1 = 0.;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const double rv = r.a * c_model.V[k] + r.b * c_model.V[4 + k] + r.c * c_model.V[8 + k] +
+                      r.d * c_model.V[12 + k];
+    const double vp = c_model.Vinv[4 * k] * c.a + c_model.Vinv[4 * k + 1] * c.b +
+                      c_model.Vinv[4 * k + 2] * c.c + c_model.Vinv[4 * k + 3] * c.d;
+    const double term = rv * vp;
+    if (c_model.group[k] == 0) c0 += term; else c1 += term;
+  }
+  rho = c0 != 0. ? c1 / c0 : 0.;
+  c0_out = c0;
+}
+
+// The same pass for the pipelined cluster scheme (Engine::RunOptimizerPipelined): rho goes to the
+// CLUSTER weight-class layout (classes padded to rows of kClusterThreads patterns, position
+// cpos[p]) of a chunk buffer that the consumer kernel k_opt_cluster<T, true> copies into shared
+// memory; optimiser states are initialised by the consumer. partials: K_e tile-group sums.
+__global__ void __launch_bounds__(kTile, 4)
+    k_opt_prepare_cluster(DeviceState st, const OptOp* __restrict__ ops, int n_ops, int tiles,
+                          int tiles_per_block, double* __restrict__ rho,
+                          const int32_t* __restrict__ cpos, int64_t rho_stride,
+                          double* __restrict__ partials) {
+  const int n_groups = gridDim.x / n_ops;
+  const int tile_group = blockIdx.x / n_ops;
+  const int o = blockIdx.x - tile_group * n_ops;
+  const OptOp op = ops[o];
+  double k_part = 0.;
+  const int tile_begin = tile_group * tiles_per_block;
+  const int tile_end = min(tiles, tile_begin + tiles_per_block);
+  double* const rho_o = rho + static_cast<int64_t>(o) * rho_stride;
+  // two pattern tiles per trip: four 256-bit loads in flight before the first divide / log
+  int tile = tile_begin;
+  for (; tile + 2 <= tile_end; tile += 2) {
+    const int64_t p0 = static_cast<int64_t>(tile) * kTile + threadIdx.x, p1 = p0 + kTile;
+    const bool live0 = p0 < st.P, live1 = p1 < st.P;
+    V4 r0 = {1., 1., 1., 1.}, c0v = r0, r1 = r0, c1v = r0;
+    int32_t q0 = 0, q1 = 0;
+    double w0 = 0., w1 = 0.;
+    if (live0) { r0 = load_plv(op.parent, p0); c0v = load_plv(op.child, p0); q0 = cpos[p0]; w0 = st.weights[p0]; }
+    if (live1) { r1 = load_plv(op.parent, p1); c1v = load_plv(op.child, p1); q1 = cpos[p1]; w1 = st.weights[p1]; }
+    double rr, cc;
+    if (live0) {
+      ratio_coefficients(r0, c0v, rr, cc);
+      rho_o[q0] = rr;
+      k_part += w0 * log(cc);
+    }
+    if (live1) {
+      ratio_coefficients(r1, c1v, rr, cc);
+      rho_o[q1] = rr;
+      k_part += w1 * log(cc);
+    }
+  }
+  for (; tile < tile_end; ++tile) {
+    const int64_t p = static_cast<int64_t>(tile) * kTile + threadIdx.x;
+    if (p < st.P) {
+      const V4 r = load_plv(op.parent, p);
+      const V4 c = load_plv(op.child, p);
+      double rr, cc;
+      ratio_coefficients(r, c, rr, cc);
+      rho_o[cpos[p]] = rr;
+      k_part += st.weights[p] * log(cc);
+    }
+  }
+  k_part = block_reduce(k_part, SumOp(), 0.);
+  if (threadIdx.x == 0) partials[static_cast<int64_t>(o) * n_groups + tile_group] = k_part;
+}
+
 // Splits t > 0 (finite, normal) into m * 2^e with m in [0.5, 1).
 __device__ __forceinline__ bool split_positive(double t, double& m, int& e) {
   const int hi = __double2hiint(t);
@@ -1281,23 +1352,6 @@ __global__ void __launch_bounds__(kTile)
 // re-streams rho from HBM for each of the ~16 evaluations instead.
 // Pattern order: the cluster weight-class layout of Engine::BuildWeightClasses (classes padded to
 // rows of kClusterThreads patterns; padding has inv_perm = -1 and contributes rho = 0).
-// c0, c1 = the two eigen-group coefficients of L_p(t) for one pattern (see k_opt_prepare_ratio);
-// rho = c1 / c0.
-__device__ __forceinline__ void ratio_coefficients(const V4& r, const V4& c, double& rho, double& c0_out) {
-  double c0 = 0., c1 = 0.;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const double rv = r.a * c_model.V[k] + r.b * c_model.V[4 + k] + r.c * c_model.V[8 + k] +
-                      r.d * c_model.V[12 + k];
-    const double vp = c_model.Vinv[4 * k] * c.a + c_model.Vinv[4 * k + 1] * c.b +
-                      c_model.Vinv[4 * k + 2] * c.c + c_model.Vinv[4 * k + 3] * c.d;
-    const double term = rv * vp;
-    if (c_model.group[k] == 0) c0 += term; else c1 += term;
-  }
-  rho = c0 != 0. ? c1 / c0 : 0.;
-  c0_out = c0;
-}
-
 // How long a kernel waits for a peer GPU before it gives up (clock64 ticks: ~35 s at 1.97 GHz). Ranks
 // reach an exchange at slightly different times - one may still be compiling an op list on its
 // host - so this is generous; it only exists so that a dead rank fails the others instead of
@@ -1393,11 +1447,20 @@ __device__ __forceinline__ double cluster_sum(cg::cluster_group& cluster, double
 // edges) or 1024 (one edge spread over as many threads as a cluster has: the shortest time per
 // edge, for the one-or-two-edge levels of a Gauss-Seidel sweep). Rows are kClusterThreads = 256
 // patterns whatever T is; a block of T threads walks T / 256 rows at a time.
-template <int T>
-__global__ void __launch_bounds__(T, T == 256 ? 3 : 1)
+// kFromRho: the pipelined scheme. rho and K_e of this edge were produced by k_opt_prepare_cluster
+// (rho_in: chunk buffer in the cluster layout, rho_stride doubles per edge; edge_const_in[o] = K_e),
+// so the cluster copies its rows into shared memory (sequential 16-byte loads, served from L2 when
+// the chunk is still resident) instead of reading the PLVs, and its shared memory is only ever
+// occupied by an edge whose search is running.
+template <int T, bool kFromRho>
+// (pipelined variant: at most 64 registers, so that three resident blocks leave a quarter of the
+// register file to the producer kernel's blocks that share the SM)
+__global__ void __launch_bounds__(T, T == 256 ? (kFromRho ? 4 : 3) : (T == 512 ? 2 : 1))
     k_opt_cluster(DeviceState st, const OptOp* __restrict__ ops, const OptControl* __restrict__ ctl,
                   const int32_t* __restrict__ inv_perm, const double* __restrict__ wperm,
-                  OptClusterLayout lay, OptRefresh refresh, PeerEdge px) {
+                  OptClusterLayout lay, OptRefresh refresh, PeerEdge px,
+                  const double* __restrict__ rho_in, int64_t rho_stride,
+                  const double* __restrict__ edge_const_in) {
   constexpr int S = T / kClusterThreads;           // rows walked per step
   constexpr int kStep = S * kClusterThreads;       // = T positions
   extern __shared__ __align__(16) double s_rho[];  // rows_per_block x kClusterThreads
@@ -1424,7 +1487,19 @@ __global__ void __launch_bounds__(T, T == 256 ? 3 : 1)
   // the edge's PLVs, once: rho into shared memory, K_e = sum_p w_p log c0_p. Two rows per trip
   // with all four 256-bit loads issued before the first use (padding positions load nothing).
   double k_part = 0.;
-  for (int r = sub; r < n_rows; r += 2 * S) {
+  if (kFromRho) {
+    const double2* src = reinterpret_cast<const double2*>(rho_in + static_cast<int64_t>(o) * rho_stride + q0);
+    double2* dst = reinterpret_cast<double2*>(s_rho);
+    const int n2 = n_rows * (kClusterThreads / 2);
+    int i = threadIdx.x;
+    for (; i + 3 * T < n2; i += 4 * T) {  // four independent 16-byte loads in flight per thread
+      const double2 a = __ldcg(src + i), b = __ldcg(src + i + T), c = __ldcg(src + i + 2 * T),
+                    d = __ldcg(src + i + 3 * T);
+      dst[i] = a; dst[i + T] = b; dst[i + 2 * T] = c; dst[i + 3 * T] = d;
+    }
+    for (; i < n2; i += T) dst[i] = __ldcg(src + i);
+  }
+  for (int r = sub; !kFromRho && r < n_rows; r += 2 * S) {
     const int i0 = r * kClusterThreads + (threadIdx.x & (kClusterThreads - 1)), i1 = i0 + kStep;
     const bool two = r + S < n_rows;
     const int32_t pa = inv_perm[q0 + i0];
@@ -1445,9 +1520,17 @@ __global__ void __launch_bounds__(T, T == 256 ? 3 : 1)
     }
   }
   int round = 0;
-  const double edge_const =
-      cluster_sum<T>(cluster, k_part, s_warp, s_slots, round & 1, px, o, tag0 + round + 1, s_global);
-  ++round;
+  double edge_const;
+  if (kFromRho && !px.enabled) {
+    edge_const = edge_const_in[o];
+    __syncthreads();  // s_rho is complete before the first pass over it
+  } else {
+    // several GPUs: edge_const_in holds this rank's share of K_e; one exchange makes it global
+    if (kFromRho) k_part = (rank == 0 && threadIdx.x == 0) ? edge_const_in[o] : 0.;
+    edge_const =
+        cluster_sum<T>(cluster, k_part, s_warp, s_slots, round & 1, px, o, tag0 + round + 1, s_global);
+    ++round;
+  }
   // this thread's rows by weight class: first row >= the class's first row that is = sub (mod S)
   int seg_begin[8], seg_end[8];
 #pragma unroll
@@ -1857,9 +1940,13 @@ template <int T>
 static bool PlanOptClusterT(int64_t rows_total, int c, OptClusterPlan* plan) {
   static bool attrs_set = false;
   if (!attrs_set) {
-    if (cudaFuncSetAttribute(k_opt_cluster<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(k_opt_cluster<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              static_cast<int>(kOptClusterMaxSharedBytes)) != cudaSuccess ||
-        cudaFuncSetAttribute(k_opt_cluster<T>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) !=
+        cudaFuncSetAttribute(k_opt_cluster<T, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) !=
+            cudaSuccess ||
+        cudaFuncSetAttribute(k_opt_cluster<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(kOptClusterMaxSharedBytes)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_opt_cluster<T, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) !=
             cudaSuccess) {
       cudaGetLastError();
       return false;
@@ -1881,7 +1968,8 @@ static bool PlanOptClusterT(int64_t rows_total, int c, OptClusterPlan* plan) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, k_opt_cluster<T>, &cfg) != cudaSuccess || n < 1) {
+  // the pipelined variant has the same footprint (same shared memory, fewer registers)
+  if (cudaOccupancyMaxActiveClusters(&n, k_opt_cluster<T, false>, &cfg) != cudaSuccess || n < 1) {
     cudaGetLastError();
     return false;
   }
@@ -1896,16 +1984,17 @@ static bool PlanOptClusterT(int64_t rows_total, int c, OptClusterPlan* plan) {
 bool PlanOptCluster(int64_t rows_total, int threads, int cluster_size, OptClusterPlan* plan) {
   *plan = OptClusterPlan();
   if (rows_total <= 0 || rows_total > (int64_t(1) << 30)) return false;
-  if (cluster_size < 1 || cluster_size > kMaxOptCluster || (cluster_size & (cluster_size - 1)))
-    return false;
+  if (cluster_size < 1 || cluster_size > kMaxOptCluster) return false;  // any size, not only powers of two
   if (threads == 256) return PlanOptClusterT<256>(rows_total, cluster_size, plan);
+  if (threads == 512) return PlanOptClusterT<512>(rows_total, cluster_size, plan);
   if (threads == 1024) return PlanOptClusterT<1024>(rows_total, cluster_size, plan);
   return false;
 }
 cudaError_t LaunchOptCluster(cudaStream_t s, const DeviceState& st, const OptOp* ops, int n_ops,
                              const OptControl* ctl, const int32_t* inv_perm, const double* wperm,
                              const int32_t class_row_start[9], const OptClusterPlan& plan,
-                             const OptRefresh& refresh, const PeerEdge& peer) {
+                             const OptRefresh& refresh, const PeerEdge& peer, const double* rho_in,
+                             int64_t rho_stride, const double* edge_const_in) {
   if (n_ops == 0) return cudaSuccess;
   OptClusterLayout lay;
   for (int c = 0; c < 9; ++c) lay.class_row_start[c] = class_row_start[c];
@@ -1923,9 +2012,26 @@ cudaError_t LaunchOptCluster(cudaStream_t s, const DeviceState& st, const OptOp*
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (plan.threads == 1024)
-    return cudaLaunchKernelEx(&cfg, k_opt_cluster<1024>, st, ops, ctl, inv_perm, wperm, lay, refresh, peer);
-  return cudaLaunchKernelEx(&cfg, k_opt_cluster<256>, st, ops, ctl, inv_perm, wperm, lay, refresh, peer);
+#define GP_LAUNCH_CLUSTER(T, R)                                                                          \
+  return cudaLaunchKernelEx(&cfg, k_opt_cluster<T, R>, st, ops, ctl, inv_perm, wperm, lay, refresh, peer, \
+                            rho_in, rho_stride, edge_const_in)
+  if (rho_in != nullptr) {
+    if (plan.threads == 1024) GP_LAUNCH_CLUSTER(1024, true);
+    if (plan.threads == 512) GP_LAUNCH_CLUSTER(512, true);
+    GP_LAUNCH_CLUSTER(256, true);
+  }
+  if (plan.threads == 1024) GP_LAUNCH_CLUSTER(1024, false);
+  if (plan.threads == 512) GP_LAUNCH_CLUSTER(512, false);
+  GP_LAUNCH_CLUSTER(256, false);
+#undef GP_LAUNCH_CLUSTER
+}
+void LaunchOptPrepareCluster(cudaStream_t s, const DeviceState& st, const OptOp* ops, int n_ops, double* rho,
+                             const int32_t* cpos, int64_t rho_stride, double* partials) {
+  if (n_ops == 0) return;
+  const int tiles = static_cast<int>(TilesFor(st.P));
+  const int tpb = TilesPerBlock(n_ops, tiles, "BITO_GP_OPT_TILES_PER_BLOCK", 32);
+  k_opt_prepare_cluster<<<Grid(n_ops, (tiles + tpb - 1) / tpb), kTile, 0, s>>>(st, ops, n_ops, tiles, tpb, rho,
+                                                                               cpos, rho_stride, partials);
 }
 int64_t OptPrepareTileGroups(int n_ops, int64_t P) {
   const int64_t tiles = TilesFor(P);

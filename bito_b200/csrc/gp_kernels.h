@@ -81,7 +81,12 @@ bool PlanOptCluster(int64_t rows_total, int threads, int cluster_size, OptCluste
 cudaError_t LaunchOptCluster(cudaStream_t s, const DeviceState& st, const OptOp* ops, int n_ops,
                              const OptControl* ctl, const int32_t* inv_perm, const double* wperm,
                              const int32_t class_row_start[9], const OptClusterPlan& plan,
-                             const OptRefresh& refresh, const PeerEdge& peer);
+                             const OptRefresh& refresh, const PeerEdge& peer, const double* rho_in = nullptr,
+                             int64_t rho_stride = 0, const double* edge_const_in = nullptr);
+// Pipelined cluster scheme: rho (cluster layout, position cpos[p]) and K_e tile-group partials
+// (n_ops x OptPrepareTileGroups) of a chunk of edges, written for k_opt_cluster<T, true>.
+void LaunchOptPrepareCluster(cudaStream_t s, const DeviceState& st, const OptOp* ops, int n_ops, double* rho,
+                             const int32_t* cpos, int64_t rho_stride, double* partials);
 int64_t OptPrepareTileGroups(int n_ops, int64_t P);
 int64_t OptRatioTileGroups(int64_t P);
 int64_t OptRatioPartials(int64_t P);  // partial sums per edge written by LaunchOptEvalRatio

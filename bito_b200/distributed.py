@@ -69,6 +69,19 @@ def max_over_ranks(x: float) -> float:
     return float(t.item())
 
 
+def max_over_ranks_array(values) -> np.ndarray:
+    """Element-wise MAX over ranks (with the MAX of the negated array it tells whether every rank holds the
+    same values: the rank-agreement checks of bench.py)."""
+    a = np.atleast_1d(np.asarray(values, dtype=np.float64)).copy()
+    if world_size() == 1:
+        return a
+    import torch
+    import torch.distributed as dist
+    t = torch.from_numpy(a).to(_device())
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.cpu().numpy()
+
+
 def sum_over_ranks(values) -> np.ndarray:
     a = np.atleast_1d(np.asarray(values, dtype=np.float64)).copy()
     if world_size() == 1:

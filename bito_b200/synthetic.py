@@ -50,6 +50,28 @@ def simulate_alignment(tree: RootedTree, site_count: int, rng: np.random.Generat
     return out
 
 
+def distinct_patterns(symbols: np.ndarray, weights: np.ndarray, refill) -> Tuple[np.ndarray, np.ndarray]:
+    """Site-pattern compression as SitePattern::Compress does it (site_pattern.cpp:67-115): identical
+    columns become ONE pattern whose weight is the sum of theirs. `refill(n)` draws n more columns (and
+    weights) so that the caller still gets the pattern count it asked for; the result has no duplicate
+    column. The first occurrence keeps its place, so a shard without duplicates is returned unchanged."""
+    want = symbols.shape[1]
+    for _ in range(64):
+        cols = np.ascontiguousarray(symbols.T)
+        key = cols.view(np.dtype((np.void, cols.shape[1]))).ravel()
+        _, first, inverse = np.unique(key, return_index=True, return_inverse=True)
+        if first.size == symbols.shape[1] and symbols.shape[1] == want:
+            return symbols, weights
+        merged = np.zeros(first.size)
+        np.add.at(merged, inverse.ravel(), weights)
+        order = np.argsort(first)  # keep first-occurrence order
+        symbols, weights = symbols[:, first[order]], merged[order]
+        if symbols.shape[1] < want:
+            more_s, more_w = refill(want - symbols.shape[1])
+            symbols, weights = np.concatenate([symbols, more_s], axis=1), np.concatenate([weights, more_w])
+    raise RuntimeError("distinct_patterns: could not reach the requested number of distinct columns")
+
+
 class _MutableTree:
     def __init__(self, tree: RootedTree):
         self.n = tree.taxon_count
@@ -194,11 +216,15 @@ def make_workload(name: str, taxon_count: int, pattern_count: int, tree_count: i
     tree = random_tree(taxon_count, topo_rng, mean_bl)
     dag = nni_neighbourhood_dag(tree, tree_count, moves_per_tree, np.random.default_rng(seed + 1), walk)
     col_rng = np.random.default_rng([seed + 2, rank])
-    symbols = simulate_alignment(tree, pattern_count, col_rng, gap_rate)
-    # multiplicities as site-pattern compression would give them: mostly 1
-    weights = np.where(col_rng.random(pattern_count) < 0.85, 1.0,
-                       col_rng.integers(2, 6, size=pattern_count).astype(np.float64))
-    return Workload(name, dag, symbols, weights, int(weights.sum()), tree)
+    def draw(n):
+        s = simulate_alignment(tree, n, col_rng, gap_rate)
+        # multiplicities as site-pattern compression would give them: mostly 1
+        w = np.where(col_rng.random(n) < 0.85, 1.0, col_rng.integers(2, 6, size=n).astype(np.float64))
+        return s, w
+
+    # `pattern_count` DISTINCT columns, weights = multiplicities (duplicates of the draw are merged)
+    symbols, weights = distinct_patterns(*draw(pattern_count), draw)
+    return Workload(name, dag, np.ascontiguousarray(symbols), weights, int(weights.sum()), tree)
 
 
 # The synthetic configurations of BASELINE.json (configs[3] and configs[4]).

@@ -256,6 +256,8 @@ typedef struct bito_gp_stats {
   int64_t optimizer_cluster_threads; /* threads per block for scheme 2, else 0               */
   int64_t optimizer_edges_in_flight; /* clusters resident on the device at once, scheme 2   */
   int64_t peer_collective_calls;     /* of collective_calls: one-kernel all-reduces over NVLink peer memory */
+  int64_t programs_evicted;          /* compiled programs freed: stale after a resize, or least recently used */
+  int64_t programs_cached;           /* compiled programs alive now                                          */
 } bito_gp_stats;
 BITO_GP_API int bito_gp_get_stats(bito_gp_engine* e, bito_gp_stats* out);
 

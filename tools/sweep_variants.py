@@ -1,8 +1,9 @@
 """Times one branch-length sweep of a bench workload under each optimiser scheme and checks that they agree:
     python tools/sweep_variants.py [workload] [patterns] [gauss_seidel]
-Schemes (BITO_GP_OPT_CLUSTER, read when an engine is created): 0 = rounds (rho streamed from HBM every
-objective evaluation), C or CxT = one thread-block cluster of C blocks of T (256 | 1024) threads per edge, auto = the
-engine's own per-level choice.
+Schemes (environment read when an engine is created): 0 = rounds (rho streamed from HBM every objective
+evaluation), C or CxT = one thread-block cluster of C blocks of T (256 | 512 | 1024) threads per edge reading the PLVs,
+p / pC / pCxT / pCxT/R = the pipelined cluster scheme (streaming producer + clusters reading rho; R edges per ring
+half), auto = the engine's own per-level choice.
 The workload is built once; each engine is destroyed before the next is created (they fill the HBM)."""
 import os
 import sys
@@ -32,10 +33,18 @@ print("| variant | scheme | cluster | threads | edges in flight | sweep ms (best
 print("|---|---|---|---|---|---|---|---|---|")
 first_bl = None
 for v in variants:
-    os.environ.pop("BITO_GP_OPT_CLUSTER", None)
-    os.environ.pop("BITO_GP_OPT_CLUSTER_THREADS", None)
-    if v != "auto":  # "C" or "CxT": cluster size, threads per block
-        c, _, t = v.partition("x")
+    for k in ("BITO_GP_OPT_CLUSTER", "BITO_GP_OPT_CLUSTER_THREADS", "BITO_GP_OPT_SCHEME", "BITO_GP_OPT_RING_EDGES"):
+        os.environ.pop(k, None)
+    shape = v
+    if v.startswith("p"):  # pipelined cluster scheme: "p", "pC", "pCxT", "pCxT/R" (R = edges per ring half)
+        os.environ["BITO_GP_OPT_SCHEME"] = "3"
+        shape, _, ring = v[1:].partition("/")
+        if ring:
+            os.environ["BITO_GP_OPT_RING_EDGES"] = ring
+    if shape == "0":
+        os.environ["BITO_GP_OPT_SCHEME"] = "0"
+    elif shape not in ("auto", ""):  # "C" or "CxT": cluster size, threads per block
+        c, _, t = shape.partition("x")
         os.environ["BITO_GP_OPT_CLUSTER"] = c
         if t:
             os.environ["BITO_GP_OPT_CLUSTER_THREADS"] = t
