@@ -249,7 +249,17 @@ Engine::Engine(const bito_gp_config& cfg) : cfg_(cfg) {
   // (a streaming producer writes rho, clusters run the searches); unset = the engine's own choice
   if (const char* env = getenv("BITO_GP_OPT_SCHEME")) opt_scheme_env_ = atoi(env);
   if (const char* env = getenv("BITO_GP_OPT_RING_EDGES")) opt_ring_edges_env_ = atoi(env);
-  GP_CUDA(cudaStreamCreateWithFlags(&prep_stream_, cudaStreamNonBlocking));
+  if (const char* env = getenv("BITO_GP_PREP_BLOCKS_PER_SM")) prep_blocks_per_sm_ = atoi(env);
+  if (const char* env = getenv("BITO_GP_OPT_PRIORITY")) opt_priority_env_ = atoi(env);
+  {
+    // the producer runs at the lowest stream priority and the consumer clusters at the highest, so that a
+    // cluster whose edge is ready is placed before more producer blocks are
+    int least = 0, greatest = 0;
+    GP_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    GP_CUDA(cudaStreamCreateWithPriority(&prep_stream_, cudaStreamNonBlocking, least));
+    GP_CUDA(cudaStreamCreateWithPriority(&cons_stream_, cudaStreamNonBlocking, greatest));
+  }
+  GP_CUDA(cudaEventCreateWithFlags(&ev_join_, cudaEventDisableTiming));
   GP_CUDA(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
   for (int b = 0; b < 2; ++b) {
     GP_CUDA(cudaEventCreateWithFlags(&ev_ready_[b], cudaEventDisableTiming));
@@ -297,6 +307,8 @@ Engine::~Engine() {
   d_dense_tmp_.Release(); d_mtab_.Release(); d_mtab_lik_.Release(); d_opt_states_.Release(); d_opt_const_.Release(); d_opt_active_.Release(); d_perm_.Release(); d_wperm_.Release(); d_row_class_.Release(); d_active_.Release(); d_single_opt_.Release(); d_cluster_inv_perm_.Release(); d_cluster_wperm_.Release(); d_quartet_items_.Release(); d_quartet_mats_.Release();
   d_cluster_pos_.Release(); d_rho_ring_.Release(); d_ring_const_.Release(); d_ring_partials_.Release();
   if (prep_stream_) cudaStreamDestroy(prep_stream_);
+  if (cons_stream_) cudaStreamDestroy(cons_stream_);
+  if (ev_join_) cudaEventDestroy(ev_join_);
   if (ev_fork_) cudaEventDestroy(ev_fork_);
   for (int b = 0; b < 2; ++b) {
     if (ev_ready_[b]) cudaEventDestroy(ev_ready_[b]);
@@ -535,6 +547,11 @@ void Engine::BuildWeightClasses(const double* host_weights) {
           if (PlanOptCluster(std::max<int64_t>(cpos / row, 1), threads, c, &plan)) cluster_plans_.push_back(plan);
         }
       }
+    }
+    if (getenv("BITO_GP_DEBUG_PLANS") != nullptr) {
+      for (const OptClusterPlan& c : cluster_plans_)
+        std::fprintf(stderr, "bito_gp plan: %2d blocks x %4d threads, %3d rows/block, %6zu B smem, %3d clusters resident\n",
+                     c.cluster_size, c.threads, c.rows_per_block, c.shared_bytes, c.active_clusters);
     }
     if (had != cluster_plans_.size() ||
         (had > 0 && had_rows != cluster_plans_[0].rows_total))
@@ -1958,10 +1975,15 @@ void Engine::RunOptimizerPipelined(const OptOp* d_ops, int n_ops, const OptClust
   const int64_t max_groups = TilesFor(P_);
   // with per-kernel profiling on, everything runs on the engine's stream (serialised, but timed)
   cudaStream_t ps = profiling_ ? stream_ : prep_stream_;
+  cudaStream_t cs = (profiling_ || opt_priority_env_ == 0) ? stream_ : cons_stream_;
   if (ps != stream_) {
     GP_CUDA(cudaEventRecord(ev_fork_, stream_));
     GP_CUDA(cudaStreamWaitEvent(ps, ev_fork_, 0));
+    if (cs != stream_) GP_CUDA(cudaStreamWaitEvent(cs, ev_fork_, 0));
   }
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device_);
+  const int prep_max_blocks = (profiling_ || prep_blocks_per_sm_ <= 0) ? 0 : prep_blocks_per_sm_ * sms;
   int i = 0;
   for (int c0 = 0; c0 < n_ops; c0 += chunk, ++i) {
     const int m = std::min(chunk, n_ops - c0);
@@ -1972,7 +1994,7 @@ void Engine::RunOptimizerPipelined(const OptOp* d_ops, int n_ops, const OptClust
     if (ps != stream_ && i >= 2) GP_CUDA(cudaStreamWaitEvent(ps, ev_free_[b], 0));
     {
       ProfScope scope(this, kProfOptPrepare, 64. * m * static_cast<double>(P_));
-      LaunchOptPrepareCluster(ps, st, d_ops + c0, m, rho, d_cluster_pos_.ptr, rho_stride, parts);
+      LaunchOptPrepareCluster(ps, st, d_ops + c0, m, rho, d_cluster_pos_.ptr, rho_stride, parts, prep_max_blocks);
     }
     {
       ProfScope scope(this, kProfReduce, 0.);
@@ -1980,16 +2002,20 @@ void Engine::RunOptimizerPipelined(const OptOp* d_ops, int n_ops, const OptClust
     }
     if (ps != stream_) {
       GP_CUDA(cudaEventRecord(ev_ready_[b], ps));
-      GP_CUDA(cudaStreamWaitEvent(stream_, ev_ready_[b], 0));
+      GP_CUDA(cudaStreamWaitEvent(cs, ev_ready_[b], 0));
     }
     {
       ProfScope scope(this, kProfOptCluster, 0.);
-      GP_CUDA(LaunchOptCluster(stream_, st, d_ops + c0, m, d_opt_ctl_.ptr, d_cluster_inv_perm_.ptr,
+      GP_CUDA(LaunchOptCluster(cs, st, d_ops + c0, m, d_opt_ctl_.ptr, d_cluster_inv_perm_.ptr,
                                d_cluster_wperm_.ptr, cluster_class_row_start_, plan, opt_refresh_,
                                PeerEdgeContext(), rho, rho_stride, consts));
     }
-    if (ps != stream_) GP_CUDA(cudaEventRecord(ev_free_[b], stream_));
+    if (ps != stream_) GP_CUDA(cudaEventRecord(ev_free_[b], cs));
     if (capturing_) capture_opt_launches_ += 3; else stats_.kernel_launches += 3;
+  }
+  if (cs != stream_) {  // the engine's stream continues after the last search
+    GP_CUDA(cudaEventRecord(ev_join_, cs));
+    GP_CUDA(cudaStreamWaitEvent(stream_, ev_join_, 0));
   }
 }
 
@@ -2694,9 +2720,9 @@ void Engine::GetStats(bito_gp_stats* out) {
   for (const PlvSlot& s : plvs_) resident += (s.kind == kPlvDense);
   stats_.plvs_resident = resident;
   stats_.optimizer_scheme = last_opt_scheme_;
-  stats_.optimizer_cluster_size = last_opt_scheme_ == 2 ? last_opt_plan_.cluster_size : 0;
-  stats_.optimizer_cluster_threads = last_opt_scheme_ == 2 ? last_opt_plan_.threads : 0;
-  stats_.optimizer_edges_in_flight = last_opt_scheme_ == 2 ? last_opt_plan_.active_clusters : 0;
+  stats_.optimizer_cluster_size = last_opt_scheme_ >= 2 ? last_opt_plan_.cluster_size : 0;
+  stats_.optimizer_cluster_threads = last_opt_scheme_ >= 2 ? last_opt_plan_.threads : 0;
+  stats_.optimizer_edges_in_flight = last_opt_scheme_ >= 2 ? last_opt_plan_.active_clusters : 0;
   stats_.programs_cached = static_cast<int64_t>(programs_.size());
   *out = stats_;
 }

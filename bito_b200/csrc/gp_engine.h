@@ -279,7 +279,10 @@ class Engine {
   // Pipelined cluster scheme (RunOptimizerPipelined): rho of two chunks of edges, their K_e and the
   // producer's tile partials, double-buffered between the producer stream and the engine's stream
   DeviceArray<double> d_rho_ring_, d_ring_const_, d_ring_partials_;
-  cudaStream_t prep_stream_ = nullptr;
+  cudaStream_t prep_stream_ = nullptr, cons_stream_ = nullptr;
+  cudaEvent_t ev_join_ = nullptr;
+  int prep_blocks_per_sm_ = 0;    // BITO_GP_PREP_BLOCKS_PER_SM: fixed producer grid (0: one block per item)
+  int opt_priority_env_ = 1;      // BITO_GP_OPT_PRIORITY=0: consumer on the engine's stream (no priority)
   cudaEvent_t ev_fork_ = nullptr, ev_ready_[2] = {nullptr, nullptr}, ev_free_[2] = {nullptr, nullptr};
   int opt_scheme_env_ = -1;       // BITO_GP_OPT_SCHEME (-1: automatic)
   int opt_ring_edges_env_ = 0;    // BITO_GP_OPT_RING_EDGES (0: automatic)

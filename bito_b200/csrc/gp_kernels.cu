@@ -1063,12 +1063,15 @@ __device__ __forceinline__ void ratio_coefficients(const V4& r, const V4& c, dou
 // memory; optimiser states are initialised by the consumer. partials: K_e tile-group sums.
 __global__ void __launch_bounds__(kTile, 4)
     k_opt_prepare_cluster(DeviceState st, const OptOp* __restrict__ ops, int n_ops, int tiles,
-                          int tiles_per_block, double* __restrict__ rho,
+                          int tiles_per_block, int n_groups, double* __restrict__ rho,
                           const int32_t* __restrict__ cpos, int64_t rho_stride,
                           double* __restrict__ partials) {
-  const int n_groups = gridDim.x / n_ops;
-  const int tile_group = blockIdx.x / n_ops;
-  const int o = blockIdx.x - tile_group * n_ops;
+  // fixed grid walking the (edge, tile group) items edge-major within a tile group (a PLV tile shared by
+  // several edges of the chunk is then served from L2): the producer never occupies more of an SM than
+  // the launch asks for, so the consumer's clusters always find room next to it
+  for (int item = blockIdx.x; item < n_ops * n_groups; item += gridDim.x) {
+  const int tile_group = item / n_ops;
+  const int o = item - tile_group * n_ops;
   const OptOp op = ops[o];
   double k_part = 0.;
   const int tile_begin = tile_group * tiles_per_block;
@@ -1109,6 +1112,7 @@ __global__ void __launch_bounds__(kTile, 4)
   }
   k_part = block_reduce(k_part, SumOp(), 0.);
   if (threadIdx.x == 0) partials[static_cast<int64_t>(o) * n_groups + tile_group] = k_part;
+  }
 }
 
 // Splits t > 0 (finite, normal) into m * 2^e with m in [0.5, 1).
@@ -1544,59 +1548,59 @@ __global__ void __launch_bounds__(T, T == 256 ? (kFromRho ? 4 : 3) : (T == 512 ?
     const double x = s_state.x_ratio;
     double prod = 1., slow = 0.;
     int esum = 0;
-    // weight 1: the bulk of any alignment; four independent chains, renormalised as they go
+    // Every factor t = 1 + rho x is either 0 or lies in [2^-53, 4] (L_p(t) >= 0 at t = 0 gives rho >= -1,
+    // JC69 has rho <= 3, and 0 <= x <= 1), so a chain of up to 10 raw factors stays a normal double
+    // (>= 2^-530, <= 2^20) and the product of two such chains too:
+    // the chains multiply the factors as they are, and only every 32nd factor pays for the exponent
+    // split (the mantissa bits are those of the product of mantissas: scaling by 2^e is exact).
+    auto fold = [&](double q) {  // q = a partial product: its log goes into (prod, esum) or, if q <= 0, slow
+      double m;
+      int e;
+      if (split_positive(q, m, e)) {
+        prod *= m;  // >= 1/4
+        esum += e;
+        if (split_positive(prod, m, e)) { prod = m; esum += e; }
+      } else {
+        slow += log(q);  // log(0) = -inf as the reference's log of a zero likelihood; negative: NaN
+      }
+    };
+    // weight 1: the bulk of any alignment; four independent chains
     {
       double p0 = 1., p1 = 1., p2 = 1., p3 = 1.;
       int r = seg_begin[0], trip = 0;
       for (; r + 3 * S < seg_end[0]; r += 4 * S, ++trip) {
-        const double t0 = fma(mine[(r + 0 * S) * kClusterThreads], x, 1.0);
-        const double t1 = fma(mine[(r + 1 * S) * kClusterThreads], x, 1.0);
-        const double t2 = fma(mine[(r + 2 * S) * kClusterThreads], x, 1.0);
-        const double t3 = fma(mine[(r + 3 * S) * kClusterThreads], x, 1.0);
-        double m;
-        int e;
-        if (split_positive(t0, m, e)) { p0 *= m; esum += e; } else slow += log(t0);
-        if (split_positive(t1, m, e)) { p1 *= m; esum += e; } else slow += log(t1);
-        if (split_positive(t2, m, e)) { p2 *= m; esum += e; } else slow += log(t2);
-        if (split_positive(t3, m, e)) { p3 *= m; esum += e; } else slow += log(t3);
-        if ((trip & 7) == 7) {  // every 8th trip: each chain >= 2^-9 so far
-          p0 *= p1;
-          p2 *= p3;
-          p0 *= p2;  // >= 2^-36
-          p1 = p2 = p3 = 1.;
-          if (split_positive(p0, m, e)) { p0 = m; esum += e; }
+        p0 *= fma(mine[(r + 0 * S) * kClusterThreads], x, 1.0);
+        p1 *= fma(mine[(r + 1 * S) * kClusterThreads], x, 1.0);
+        p2 *= fma(mine[(r + 2 * S) * kClusterThreads], x, 1.0);
+        p3 *= fma(mine[(r + 3 * S) * kClusterThreads], x, 1.0);
+        if ((trip & 7) == 7) {  // 8 factors per chain: each >= 2^-424
+          fold(p0 * p1);
+          fold(p2 * p3);
+          p0 = p1 = p2 = p3 = 1.;
         }
       }
-      for (; r < seg_end[0]; r += S) {
-        const double t0 = fma(mine[r * kClusterThreads], x, 1.0);
-        double m;
-        int e;
-        if (split_positive(t0, m, e)) { p0 *= m; esum += e; } else slow += log(t0);
-      }
-      prod = (p0 * p1) * (p2 * p3);  // >= 2^-40: normal
-      double m;
-      int e;
-      if (split_positive(prod, m, e)) { prod = m; esum += e; }
+      for (; r < seg_end[0]; r += S) p0 *= fma(mine[r * kClusterThreads], x, 1.0);  // at most 3 more on chain 0
+      fold(p0 * p1);
+      fold(p2 * p3);
     }
 #pragma unroll
-    for (int cls = 1; cls < 7; ++cls) {  // weights 2..7: (m 2^e)^w by squaring
+    for (int cls = 1; cls < 7; ++cls) {  // weights 2..7: t^w by squaring (>= 2^-371), folded two at a time
       const int wi = cls + 1;
-      for (int r = seg_begin[cls]; r < seg_end[cls]; r += S) {
+      double c = 1.;
+      int k = 0;
+      for (int r = seg_begin[cls]; r < seg_end[cls]; r += S, ++k) {
         const double tk = fma(mine[r * kClusterThreads], x, 1.0);
-        double m;
-        int e;
-        if (split_positive(tk, m, e)) {
-          const double m2 = m * m;
-          double mw = (wi & 1) ? m : 1.;
-          if (wi & 2) mw *= m2;
-          if (wi & 4) mw *= m2 * m2;
-          prod *= mw;
-          esum += e * wi;
-          if (split_positive(prod, m, e)) { prod = m; esum += e; }
-        } else {
-          slow += static_cast<double>(wi) * log(tk);
+        const double t2 = tk * tk;
+        double tw = (wi & 1) ? tk : 1.;
+        if (wi & 2) tw *= t2;
+        if (wi & 4) tw *= t2 * t2;
+        c *= tw;
+        if (k & 1) {
+          fold(c);
+          c = 1.;
         }
       }
+      fold(c);
     }
     for (int r = seg_begin[7]; r < seg_end[7]; r += S) {  // general weights: explicit log
       const double w = wperm[q0 + r * kClusterThreads + (threadIdx.x & (kClusterThreads - 1))];
@@ -2026,12 +2030,15 @@ cudaError_t LaunchOptCluster(cudaStream_t s, const DeviceState& st, const OptOp*
 #undef GP_LAUNCH_CLUSTER
 }
 void LaunchOptPrepareCluster(cudaStream_t s, const DeviceState& st, const OptOp* ops, int n_ops, double* rho,
-                             const int32_t* cpos, int64_t rho_stride, double* partials) {
+                             const int32_t* cpos, int64_t rho_stride, double* partials, int max_blocks) {
   if (n_ops == 0) return;
   const int tiles = static_cast<int>(TilesFor(st.P));
   const int tpb = TilesPerBlock(n_ops, tiles, "BITO_GP_OPT_TILES_PER_BLOCK", 32);
-  k_opt_prepare_cluster<<<Grid(n_ops, (tiles + tpb - 1) / tpb), kTile, 0, s>>>(st, ops, n_ops, tiles, tpb, rho,
-                                                                               cpos, rho_stride, partials);
+  const int n_groups = (tiles + tpb - 1) / tpb;
+  const int64_t items = static_cast<int64_t>(n_ops) * n_groups;
+  const int64_t cap = max_blocks > 0 ? max_blocks : items;
+  k_opt_prepare_cluster<<<static_cast<unsigned>(items < cap ? items : cap), kTile, 0, s>>>(
+      st, ops, n_ops, tiles, tpb, n_groups, rho, cpos, rho_stride, partials);
 }
 int64_t OptPrepareTileGroups(int n_ops, int64_t P) {
   const int64_t tiles = TilesFor(P);

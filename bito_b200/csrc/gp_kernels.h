@@ -85,8 +85,9 @@ cudaError_t LaunchOptCluster(cudaStream_t s, const DeviceState& st, const OptOp*
                              int64_t rho_stride = 0, const double* edge_const_in = nullptr);
 // Pipelined cluster scheme: rho (cluster layout, position cpos[p]) and K_e tile-group partials
 // (n_ops x OptPrepareTileGroups) of a chunk of edges, written for k_opt_cluster<T, true>.
+// max_blocks > 0: a fixed grid of that many blocks walks the (edge, tile group) items.
 void LaunchOptPrepareCluster(cudaStream_t s, const DeviceState& st, const OptOp* ops, int n_ops, double* rho,
-                             const int32_t* cpos, int64_t rho_stride, double* partials);
+                             const int32_t* cpos, int64_t rho_stride, double* partials, int max_blocks);
 int64_t OptPrepareTileGroups(int n_ops, int64_t P);
 int64_t OptRatioTileGroups(int64_t P);
 int64_t OptRatioPartials(int64_t P);  // partial sums per edge written by LaunchOptEvalRatio

@@ -1,0 +1,84 @@
+"""north_star: "keeps the GPInstance/GPEngine/GPOperation API and the pybito bindings". bito_b200/host/pybito_gp.cpp
+is the GP part of the reference's pybito.cpp (gp_instance :614-776, dag :780-837, gp_engine :866-870 and the value
+types their signatures mention), compiled twice by `make -C oracle pybito`:
+    oracle/_ref/pybito_b200/bito*.so : the reference's unchanged gp_instance.cpp over the host class -> CUDA engine
+    oracle/_ref/pybito_ref/bito*.so  : the same binding TU over the reference CPU GPEngine (the checker)
+tests/pybito_walk.py drives `import bito` the way /root/reference/test/test_bito.py:166-184 (test_gp_instance) and
+test/nni_search.py do; each build runs in its own subprocess. Tolerances: log-likelihoods 1e-9 relative at fixed
+branch lengths (1e-7 after optimisation), branch lengths 1e-6, SBN parameters 1e-6, everything discrete identical."""
+import glob
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from test_host_shim_gpu import _write_case
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+WALK = os.path.join(ROOT, "tests", "pybito_walk.py")
+
+
+def _module_dir(which):
+    d = os.path.join(ROOT, "oracle", "_ref", f"pybito_{which}")
+    return d if glob.glob(os.path.join(d, "bito*.so")) else None
+
+
+def _walk(which, fasta, newick, workdir, threshold="1e-40"):
+    d = _module_dir(which)
+    if d is None:
+        pytest.fail(f"oracle/_ref/pybito_{which}/bito*.so is missing: run `make -C oracle pybito` in the build "
+                    "container (needs /root/reference); the modules travel with the snapshot")
+    env = dict(os.environ, PYTHONPATH=d)
+    run = subprocess.run([sys.executable, WALK, fasta, newick, str(workdir), threshold], capture_output=True, text=True,
+                         timeout=900, env=env)
+    assert run.returncode == 0, (run.stdout[-2000:], run.stderr[-3000:])
+    line = [ln for ln in run.stdout.splitlines() if ln.startswith("PYBITO_WALK ")][-1]
+    return json.loads(line[len("PYBITO_WALK "):])
+
+
+@pytest.mark.skipif(_module_dir("ref") is None, reason="oracle/_ref/pybito_ref not built")
+def test_binding_tu_over_the_reference_engine(tmp_path):
+    """CPU: the binding TU itself (names, defaults, ownership) with the reference engine behind it."""
+    fasta, newick = _write_case(tmp_path, 6, 300, 3, 1, seed=61)
+    out = _walk("ref", fasta, newick, tmp_path)
+    assert out["backend"] == "reference CPU GPEngine"
+    assert out["dag"][2] == 6 and out["engine"][2] == out["dag"][1] and out["engine"][1] == 6 * out["engine"][0]
+    assert all(bl == 0.1 for bl in out["init_branch_lengths"])
+    assert out["pcsp_roundtrip"] and out["edge_id_roundtrip"] and out["beagle"] == "RuntimeError"
+    assert np.isfinite(out["converged_log_marginal"]) and np.all(np.isfinite(out["estimated_per_pcsp_llh"]))
+    assert len(out["edge_pcsps"]) == out["dag"][1] and len(out["sbn_parameters"]) >= out["dag"][1]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("taxa,sites,trees,moves,threshold", [
+    (6, 400, 3, 1, "1e-40"),
+    (12, 1200, 10, 2, "1e-40"),
+    (12, 1200, 10, 2, "0.5"),
+])
+def test_import_bito_runs_gp_instance_on_the_cuda_engine(cuda_engine_lib, tmp_path, taxa, sites, trees, moves, threshold):
+    fasta, newick = _write_case(tmp_path, taxa, sites, trees, moves, seed=taxa * 77 + trees)
+    (tmp_path / "ref").mkdir()
+    (tmp_path / "b200").mkdir()
+    want = _walk("ref", fasta, newick, tmp_path / "ref", threshold)
+    got = _walk("b200", fasta, newick, tmp_path / "b200", threshold)
+    assert got["backend"].startswith("bito_b200") and want["backend"] == "reference CPU GPEngine"
+    for key in ("dag", "engine", "edge_pcsps", "node_bitsets", "first_tree", "pcsp_roundtrip", "edge_id_roundtrip",
+                "beagle", "init_branch_lengths"):
+        assert got[key] == want[key], key
+
+    def close(key, rtol=0.0, atol=0.0):
+        g, w = np.atleast_1d(np.asarray(got[key], dtype=float)), np.atleast_1d(np.asarray(want[key], dtype=float))
+        n = min(g.size, w.size)
+        return bool(np.all(np.abs(g[:n] - w[:n]) <= atol + rtol * np.maximum(1.0, np.abs(w[:n]))))
+
+    assert close("pass_per_pcsp_llh", rtol=1e-9)
+    assert close("hot_start_branch_lengths", atol=1e-12)
+    assert close("estimated_branch_lengths", atol=1e-6)
+    assert close("first_tree_branch_lengths", atol=1e-6)
+    assert close("estimated_per_pcsp_llh", rtol=1e-7)
+    assert close("log_marginal", rtol=1e-7)
+    assert close("sbn_parameters", atol=1e-6)
+    assert close("converged_log_marginal", rtol=1e-6)

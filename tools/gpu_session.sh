@@ -11,7 +11,7 @@ for s in $steps; do
     tests)
       timeout 1500 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" >> $out/${tag}_pytest.log ;;
     tests_new)
-      timeout 1200 python -m pytest tests/test_round2_gpu.py -m gpu -q > $out/${tag}_pytest_new.log 2>&1; echo "pytest rc=$?" >> $out/${tag}_pytest_new.log ;;
+      timeout 1200 python -m pytest tests/test_round2_gpu.py tests/test_pybito_gpu.py -m gpu -q > $out/${tag}_pytest_new.log 2>&1; echo "pytest rc=$?" >> $out/${tag}_pytest_new.log ;;
     bench)
       timeout 900 python bench.py --steps 10 --warmup 3 > $out/${tag}_bench.json 2> $out/${tag}_bench.err; echo "bench rc=$?" >> $out/${tag}_bench.err ;;
     bench_ref)
@@ -23,6 +23,11 @@ for s in $steps; do
     ncu_sweep)
       BITO_GP_OPT_SCHEME=3 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_opt_cluster|k_opt_prepare_cluster" -s 2 -c 4 \
         -o $out/${tag}_k_opt_pipelined -f python profiles/prof_pass.py synthetic-1000taxa-1Mpat-5000trees 40000 1 sweep > $out/${tag}_ncu_sweep.log 2>&1 ;;
+    ncu_small)
+      BITO_GP_OPT_SCHEME=3 BITO_GP_OPT_CLUSTER=16 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_opt_cluster|k_opt_prepare_cluster" -c 2 \
+        -o $out/${tag}_k_opt_pipelined -f python profiles/prof_pass.py synthetic-small 125000 1 sweep > $out/${tag}_ncu_small.log 2>&1
+      BITO_GP_OPT_SCHEME=3 BITO_GP_OPT_CLUSTER=16 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum,sm__throughput.avg.pct_of_peak_sustained_elapsed --clock-control none --csv \
+        --log-file $out/${tag}_launches_small.csv python profiles/prof_pass.py synthetic-small 125000 1 sweep > $out/${tag}_launches_small.log 2>&1 ;;
     ncu_pass)
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_node" -s 40 -c 2 \
         -o $out/${tag}_k_node -f python profiles/prof_pass.py synthetic-1000taxa-1Mpat-5000trees 40000 1 > $out/${tag}_ncu_pass.log 2>&1 ;;

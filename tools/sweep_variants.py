@@ -35,6 +35,13 @@ first_bl = None
 for v in variants:
     for k in ("BITO_GP_OPT_CLUSTER", "BITO_GP_OPT_CLUSTER_THREADS", "BITO_GP_OPT_SCHEME", "BITO_GP_OPT_RING_EDGES"):
         os.environ.pop(k, None)
+    for k in [k for k in os.environ if k.startswith("BITO_GP_")]:
+        os.environ.pop(k)
+    v, *extra = v.split("@")  # "...@KEY=VAL": also set BITO_GP_KEY=VAL for this variant
+    for kv in extra:
+        k, _, val = kv.partition("=")
+        os.environ["BITO_GP_" + k] = val
+    label = "@".join([v] + extra)
     shape = v
     if v.startswith("p"):  # pipelined cluster scheme: "p", "pC", "pCxT", "pCxT/R" (R = edges per ring half)
         os.environ["BITO_GP_OPT_SCHEME"] = "3"
@@ -72,6 +79,6 @@ for v in variants:
         st = eng.stats()
         if first_bl is None:
             first_bl = bl
-        print(f"| {v} | {st['optimizer_scheme']} | {st['optimizer_cluster_size']} | {st['optimizer_cluster_threads']} | {st['optimizer_edges_in_flight']} | "
+        print(f"| {label} | {st['optimizer_scheme']} | {st['optimizer_cluster_size']} | {st['optimizer_cluster_threads']} | {st['optimizer_edges_in_flight']} | "
               f"{best:.3f} | {evals} | {np.max(np.abs(bl - first_bl)):.3e} | {eng.get_log_marginal_likelihood():.6f} |",
               flush=True)
