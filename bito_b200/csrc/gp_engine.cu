@@ -237,6 +237,14 @@ Engine::Engine(const bito_gp_config& cfg) : cfg_(cfg) {
     }
     m.group[k] = g;
   }
+  {
+    int count[kMaxEigenGroups] = {0, 0, 0, 0};
+    for (int k = 0; k < 4; ++k) count[m.group[k]]++;
+    m.small_group = (m.n_groups == 2 && count[1] < count[0]) ? 1 : 0;
+    m.small_count = 0;
+    for (int k = 0; k < 4; ++k)
+      if (m.group[k] == m.small_group) m.small_idx[m.small_count++] = k;
+  }
   n_eigen_groups_ = m.n_groups;
   for (int g = 0; g < m.n_groups; ++g) group_lambda_[g] = m.group_lambda[g];
   if (const char* env = getenv("BITO_GP_OPT_CHUNK_MB")) opt_chunk_bytes_ = int64_t(atoll(env)) << 20;

@@ -982,13 +982,78 @@ __global__ void __launch_bounds__(kTile)
   }
 }
 
+// c0, c1 = the two eigen-group coefficients of L_p(t) for one pattern (see k_opt_prepare_ratio);
+// rho = c1 / c0.
+// Splits t > 0 (finite, normal) into m * 2^e with m in [0.5, 1).
+__device__ __forceinline__ bool split_positive(double t, double& m, int& e) {
+  const int hi = __double2hiint(t);
+  // biased exponent in [1, 2046] and sign bit clear
+  if (static_cast<unsigned>(hi - 0x00100000) >= 0x7fe00000u) return false;
+  e = (hi >> 20) - 1022;
+  m = __hiloint2double((hi & 0x000fffff) | 0x3fe00000, __double2loint(t));
+  return true;
+}
+
+__device__ __forceinline__ double pow_small(double t, int wi) {  // t^wi, 1 <= wi <= 7
+  const double t2 = t * t;
+  double r = (wi & 1) ? t : 1.;
+  if (wi & 2) r *= t2;
+  if (wi & 4) r *= t2 * t2;
+  return r;
+}
+
+// Two-group models: sum_k (V^T r)_k (V^-1 p)_k = r.p, so only the smaller group (one eigenvalue for JC69:
+// 8 multiply-adds) is summed explicitly and the other coefficient is r.p minus it.
+__device__ __forceinline__ void ratio_coefficients(const V4& r, const V4& c, double& rho, double& c0_out) {
+  double cs = 0.;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {  // a two-group model has at most 2 eigenvalues in its smaller group... or 1 + 3
+    if (j < c_model.small_count) {
+      const int k = c_model.small_idx[j];
+      const double rv = r.a * c_model.V[k] + r.b * c_model.V[4 + k] + r.c * c_model.V[8 + k] +
+                        r.d * c_model.V[12 + k];
+      const double vp = c_model.Vinv[4 * k] * c.a + c_model.Vinv[4 * k + 1] * c.b +
+                        c_model.Vinv[4 * k + 2] * c.c + c_model.Vinv[4 * k + 3] * c.d;
+      cs += rv * vp;
+    }
+  }
+  const double total = r.a * c.a + r.b * c.b + r.c * c.c + r.d * c.d;
+  const double co = total - cs;
+  const double c0 = c_model.small_group == 0 ? cs : co;
+  const double c1 = c_model.small_group == 0 ? co : cs;
+  rho = c0 != 0. ? c1 / c0 : 0.;
+  c0_out = c0;
+}
+// sum += w log c, through (mantissa product, exponent sum) for w = 1..7, so that a thread pays one log per
+// item instead of one per pattern. c may be as small as thr^2 (1e-80): the exponent is split off BEFORE the
+// power is taken. Everything else (c <= 0, other weights) goes through an explicit log.
+struct LogSum {
+  double prod = 1., slow = 0.;
+  int esum = 0;
+  __device__ __forceinline__ void add(double c, double w) {
+    double m;
+    int e;
+    const int wi = static_cast<int>(w);
+    if (w == static_cast<double>(wi) && wi >= 1 && wi <= 7 && split_positive(c, m, e)) {
+      prod *= pow_small(m, wi);  // >= 2^-7
+      esum += e * wi;
+      if (split_positive(prod, m, e)) { prod = m; esum += e; }
+    } else if (w != 0.) {
+      slow += w * log(c);
+    }
+  }
+  __device__ __forceinline__ double value() const {
+    return log(prod) + static_cast<double>(esum) * 0.6931471805599453094 + slow;
+  }
+};
+
 // ---- Brent objective for two-eigenvalue models (JC69): ratio form -----------------------------
 // L_p(t) = c0_p e^{l0 t} + c1_p e^{l1 t} = c0_p e^{l0 t} (1 + rho_p x),  rho_p = c1_p / c0_p,
 // x = e^{(l1 - l0) t}. Hence  sum_p w_p log L_p = K + W l0 t + sum_p w_p log(1 + rho_p x)  with
 // K = sum_p w_p log c0_p computed once per edge. Only rho (8 B per pattern) is kept, and the last
 // sum is evaluated as the log of a running product with the binary exponents split off, so a
 // thread pays one log() per kOptPatternsPerThread patterns instead of one per pattern.
-__global__ void __launch_bounds__(kTile)
+__global__ void __launch_bounds__(kTile, 4)
     k_opt_prepare_ratio(DeviceState st, const OptOp* __restrict__ ops, int n_ops, int tiles,
                         int tiles_per_block, OptState* __restrict__ states, OptParams prm, int method,
                         double* __restrict__ rho, const int32_t* __restrict__ perm,
@@ -1013,48 +1078,45 @@ __global__ void __launch_bounds__(kTile)
     }
   }
   (void)active_capacity;
-  double k_part = 0.;
+  LogSum k_sum;  // K_e = sum_p w_p log c0_p: one log per thread, not one per pattern
   const int tile_begin = tile_group * tiles_per_block;
   const int tile_end = min(tiles, tile_begin + tiles_per_block);
   double* const rho_o = rho + static_cast<int64_t>(o) * rho_stride;
-  for (int tile = tile_begin; tile < tile_end; ++tile) {
+  // two pattern tiles per trip: four 256-bit loads in flight before the first divide
+  int tile = tile_begin;
+  for (; tile + 2 <= tile_end; tile += 2) {
+    const int64_t p0 = static_cast<int64_t>(tile) * kTile + threadIdx.x, p1 = p0 + kTile;
+    const bool live0 = p0 < st.P, live1 = p1 < st.P;
+    V4 r0 = {1., 1., 1., 1.}, c0v = r0, r1 = r0, c1v = r0;
+    int32_t q0 = 0, q1 = 0;
+    double w0 = 0., w1 = 0.;
+    if (live0) { r0 = load_plv(op.parent, p0); c0v = load_plv(op.child, p0); q0 = perm[p0]; w0 = st.weights[p0]; }
+    if (live1) { r1 = load_plv(op.parent, p1); c1v = load_plv(op.child, p1); q1 = perm[p1]; w1 = st.weights[p1]; }
+    double rr, cc;
+    if (live0) {
+      ratio_coefficients(r0, c0v, rr, cc);
+      rho_o[q0] = rr;
+      k_sum.add(cc, w0);
+    }
+    if (live1) {
+      ratio_coefficients(r1, c1v, rr, cc);
+      rho_o[q1] = rr;
+      k_sum.add(cc, w1);
+    }
+  }
+  for (; tile < tile_end; ++tile) {
     const int64_t p = static_cast<int64_t>(tile) * kTile + threadIdx.x;
     if (p < st.P) {
       const V4 r = load_plv(op.parent, p);
       const V4 c = load_plv(op.child, p);
-      double c0 = 0., c1 = 0.;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const double rv = r.a * c_model.V[k] + r.b * c_model.V[4 + k] + r.c * c_model.V[8 + k] +
-                          r.d * c_model.V[12 + k];
-        const double vp = c_model.Vinv[4 * k] * c.a + c_model.Vinv[4 * k + 1] * c.b +
-                          c_model.Vinv[4 * k + 2] * c.c + c_model.Vinv[4 * k + 3] * c.d;
-        const double term = rv * vp;
-        if (c_model.group[k] == 0) c0 += term; else c1 += term;
-      }
-      rho_o[perm[p]] = c0 != 0. ? c1 / c0 : 0.;
-      k_part += st.weights[p] * log(c0);
+      double rr, cc;
+      ratio_coefficients(r, c, rr, cc);
+      rho_o[perm[p]] = rr;
+      k_sum.add(cc, st.weights[p]);
     }
   }
-  k_part = block_reduce(k_part, SumOp(), 0.);
+  const double k_part = block_reduce(k_sum.value(), SumOp(), 0.);
   if (threadIdx.x == 0) partials[static_cast<int64_t>(o) * n_groups + tile_group] = k_part;
-}
-
-// c0, c1 = the two eigen-group coefficients of L_p(t) for one pattern (see k_opt_prepare_ratio);
-// rho = c1 / c0.
-__device__ __forceinline__ void ratio_coefficients(const V4& r, const V4& c, double& rho, double& c0_out) {
-  double c0 = 0., c1 = 0.;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const double rv = r.a * c_model.V[k] + r.b * c_model.V[4 + k] + r.c * c_model.V[8 + k] +
-                      r.d * c_model.V[12 + k];
-    const double vp = c_model.Vinv[4 * k] * c.a + c_model.Vinv[4 * k + 1] * c.b +
-                      c_model.Vinv[4 * k + 2] * c.c + c_model.Vinv[4 * k + 3] * c.d;
-    const double term = rv * vp;
-    if (c_model.group[k] == 0) c0 += term; else c1 += term;
-  }
-  rho = c0 != 0. ? c1 / c0 : 0.;
-  c0_out = c0;
 }
 
 // The same pass for the pipelined cluster scheme (Engine::RunOptimizerPipelined): rho goes to the
@@ -1073,11 +1135,11 @@ __global__ void __launch_bounds__(kTile, 4)
   const int tile_group = item / n_ops;
   const int o = item - tile_group * n_ops;
   const OptOp op = ops[o];
-  double k_part = 0.;
+  LogSum k_sum;
   const int tile_begin = tile_group * tiles_per_block;
   const int tile_end = min(tiles, tile_begin + tiles_per_block);
   double* const rho_o = rho + static_cast<int64_t>(o) * rho_stride;
-  // two pattern tiles per trip: four 256-bit loads in flight before the first divide / log
+  // two pattern tiles per trip: four 256-bit loads in flight before the first divide
   int tile = tile_begin;
   for (; tile + 2 <= tile_end; tile += 2) {
     const int64_t p0 = static_cast<int64_t>(tile) * kTile + threadIdx.x, p1 = p0 + kTile;
@@ -1091,12 +1153,12 @@ __global__ void __launch_bounds__(kTile, 4)
     if (live0) {
       ratio_coefficients(r0, c0v, rr, cc);
       rho_o[q0] = rr;
-      k_part += w0 * log(cc);
+      k_sum.add(cc, w0);
     }
     if (live1) {
       ratio_coefficients(r1, c1v, rr, cc);
       rho_o[q1] = rr;
-      k_part += w1 * log(cc);
+      k_sum.add(cc, w1);
     }
   }
   for (; tile < tile_end; ++tile) {
@@ -1107,25 +1169,31 @@ __global__ void __launch_bounds__(kTile, 4)
       double rr, cc;
       ratio_coefficients(r, c, rr, cc);
       rho_o[cpos[p]] = rr;
-      k_part += st.weights[p] * log(cc);
+      k_sum.add(cc, st.weights[p]);
     }
   }
-  k_part = block_reduce(k_part, SumOp(), 0.);
+  const double k_part = block_reduce(k_sum.value(), SumOp(), 0.);
   if (threadIdx.x == 0) partials[static_cast<int64_t>(o) * n_groups + tile_group] = k_part;
   }
 }
 
-// Splits t > 0 (finite, normal) into m * 2^e with m in [0.5, 1).
-__device__ __forceinline__ bool split_positive(double t, double& m, int& e) {
-  const int hi = __double2hiint(t);
-  // biased exponent in [1, 2046] and sign bit clear
-  if (static_cast<unsigned>(hi - 0x00100000) >= 0x7fe00000u) return false;
-  e = (hi >> 20) - 1022;
-  m = __hiloint2double((hi & 0x000fffff) | 0x3fe00000, __double2loint(t));
-  return true;
-}
 
-__global__ void __launch_bounds__(kTile)
+// One item = one tile group (kTile * kOptPatternsPerThread = 2048 positions, all of one weight class) of
+// one still-active edge. A thread owns 8 positions of the item as two 256-bit loads, and the loads of its
+// NEXT item are issued before the current one is evaluated, so 128 B per thread stay in flight while the
+// arithmetic runs (the kernel is bound by HBM: 8 B per pattern and evaluation, nothing is written but one
+// partial per warp). Every factor t = 1 + rho x is 0 or lies in [2^-53, 4] (see k_opt_cluster), so the
+// eight factors of a thread multiply up as they are: one log per 8 patterns and no exponent bookkeeping.
+struct Rho8 {
+  V4 lo, hi;
+};
+__device__ __forceinline__ Rho8 load_rho8(const double* item_base) {
+  Rho8 r;
+  r.lo = ld256(item_base + 4 * threadIdx.x);
+  r.hi = ld256(item_base + 4 * kTile + 4 * threadIdx.x);
+  return r;
+}
+__global__ void __launch_bounds__(kTile, 4)
     k_opt_eval_ratio(DeviceState st, int tile_groups, const OptState* __restrict__ states,
                      const double* __restrict__ rho, int64_t rho_stride,
                      const double* __restrict__ wperm, const uint8_t* __restrict__ group_class,
@@ -1137,64 +1205,58 @@ __global__ void __launch_bounds__(kTile)
   const int32_t* list = active + 4 + parity * active_capacity;
   if (blockIdx.x == 0 && threadIdx.x == 0) active[parity ^ 1] = 0;  // filled by this round's step
   const int n_items = n_active * tile_groups;  // < 2^31: the batch's rho buffer is at most a few GiB
-  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+  constexpr int64_t kItem = static_cast<int64_t>(kTile) * kOptPatternsPerThread;
+  auto item_base = [&](int item, int& o, int& tg) {
     const int a = item / tile_groups;
-    const int tg = item - a * tile_groups;
-    const int o = list[a];
+    tg = item - a * tile_groups;
+    o = list[a];
+    return rho + static_cast<int64_t>(o) * rho_stride + static_cast<int64_t>(tg) * kItem;
+  };
+  int item = blockIdx.x;
+  if (item >= n_items) return;
+  int o, tg;
+  Rho8 cur = load_rho8(item_base(item, o, tg));
+  for (;;) {
+    const int next = item + gridDim.x;
+    int o_next = 0, tg_next = 0;
+    Rho8 nxt = cur;
+    if (next < n_items) nxt = load_rho8(item_base(next, o_next, tg_next));  // in flight during the arithmetic below
     const double x = states[o].x_ratio;
     const int cls = group_class[tg];  // block-uniform: weight - 1, or 7 = general weights
-    const int64_t pos0 = static_cast<int64_t>(tg) * (kTile * kOptPatternsPerThread) + threadIdx.x;
-    const double* base = rho + static_cast<int64_t>(o) * rho_stride + pos0;
-    double t[kOptPatternsPerThread];
-#pragma unroll
-    for (int k = 0; k < kOptPatternsPerThread; ++k) t[k] = base[k * kTile];  // all loads first
-    double prod = 1., slow = 0.;
-    int esum = 0;
+    const double t0 = fma(cur.lo.a, x, 1.0), t1 = fma(cur.lo.b, x, 1.0), t2 = fma(cur.lo.c, x, 1.0),
+                 t3 = fma(cur.lo.d, x, 1.0), t4 = fma(cur.hi.a, x, 1.0), t5 = fma(cur.hi.b, x, 1.0),
+                 t6 = fma(cur.hi.c, x, 1.0), t7 = fma(cur.hi.d, x, 1.0);
+    double f;
     if (cls == 0) {  // weight 1: the bulk of any alignment
-#pragma unroll
-      for (int k = 0; k < kOptPatternsPerThread; ++k) {
-        const double tk = fma(t[k], x, 1.0);
-        double m;
-        int e;
-        if (split_positive(tk, m, e)) {
-          prod *= m;  // >= 2^-kOptPatternsPerThread
-          esum += e;
-        } else {
-          slow += log(tk);
-        }
-      }
-    } else if (cls < 7) {  // weights 2..7: (m 2^e)^w by squaring
+      f = log(((t0 * t1) * (t2 * t3)) * ((t4 * t5) * (t6 * t7)));
+    } else if (cls < 7) {  // weights 2..7: t^w >= 2^-371, two factors per log
       const int wi = cls + 1;
-#pragma unroll
-      for (int k = 0; k < kOptPatternsPerThread; ++k) {
-        const double tk = fma(t[k], x, 1.0);
-        double m;
-        int e;
-        if (split_positive(tk, m, e)) {
-          const double m2 = m * m;
-          double mw = (wi & 1) ? m : 1.;
-          if (wi & 2) mw *= m2;
-          if (wi & 4) mw *= m2 * m2;
-          prod *= mw;  // >= 2^-(7 * kOptPatternsPerThread): no underflow
-          esum += e * wi;
-        } else {
-          slow += static_cast<double>(wi) * log(tk);
-        }
-      }
-    } else {  // general weights: explicit log
-#pragma unroll
-      for (int k = 0; k < kOptPatternsPerThread; ++k) {
-        const double w = wperm[pos0 + k * kTile];
-        if (w != 0.) slow += w * log(fma(t[k], x, 1.0));
-      }
+      f = log(pow_small(t0, wi) * pow_small(t1, wi)) + log(pow_small(t2, wi) * pow_small(t3, wi)) +
+          log(pow_small(t4, wi) * pow_small(t5, wi)) + log(pow_small(t6, wi) * pow_small(t7, wi));
+    } else {  // general weights: explicit log (padding has weight 0 and rho 0)
+      const double* wp = wperm + static_cast<int64_t>(tg) * kItem;
+      const V4 wl = ld256(wp + 4 * threadIdx.x), wh = ld256(wp + 4 * kTile + 4 * threadIdx.x);
+      f = 0.;
+      if (wl.a != 0.) f += wl.a * log(t0);
+      if (wl.b != 0.) f += wl.b * log(t1);
+      if (wl.c != 0.) f += wl.c * log(t2);
+      if (wl.d != 0.) f += wl.d * log(t3);
+      if (wh.a != 0.) f += wh.a * log(t4);
+      if (wh.b != 0.) f += wh.b * log(t5);
+      if (wh.c != 0.) f += wh.c * log(t6);
+      if (wh.d != 0.) f += wh.d * log(t7);
     }
-    double f = log(prod) + static_cast<double>(esum) * 0.6931471805599453094 + slow;
     // One partial per warp (fixed shuffle tree) and no block barrier: warps of a block run ahead
     // independently into the next item; k_opt_step sums the kTile/32 * tile_groups partials.
 #pragma unroll
     for (int sh = 16; sh > 0; sh >>= 1) f += __shfl_down_sync(0xffffffffu, f, sh);
     if ((threadIdx.x & 31) == 0)
       partials[(static_cast<int64_t>(o) * tile_groups + tg) * (kTile / 32) + (threadIdx.x >> 5)] = f;
+    if (next >= n_items) break;
+    item = next;
+    o = o_next;
+    tg = tg_next;
+    cur = nxt;
   }
 }
 
