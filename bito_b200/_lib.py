@@ -98,6 +98,7 @@ SIGNATURES = {
     "bito_gp_increment_optimization_count": (_int, [_vp]),
     "bito_gp_log_likelihood_and_derivatives": (_int, [_vp, _i64, _i64, _i64, _vp]),
     "bito_gp_get_transition_matrix": (_int, [_vp, _f64, _vp]),
+    "bito_gp_set_substitution_model": (_int, [_vp, _vp, _vp, _vp, _vp]),
     "bito_gp_get_log_marginal_likelihood": (_int, [_vp, C.POINTER(_f64)]),
     "bito_gp_get_per_gpcsp_log_likelihoods": (_int, [_vp, _i64, _i64, _vp]),
     "bito_gp_get_per_gpcsp_components_of_full_log_marginal": (_int, [_vp, _vp]),

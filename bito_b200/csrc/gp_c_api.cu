@@ -145,6 +145,13 @@ int bito_gp_get_transition_matrix(bito_gp_engine* e, double branch_length, doubl
   return Guard([&] { e->impl.GetTransitionMatrix(branch_length, out); });
 }
 
+int bito_gp_set_substitution_model(bito_gp_engine* e, const double eigenvectors[16],
+                                   const double inverse_eigenvectors[16], const double eigenvalues[4],
+                                   const double frequencies[4]) {
+  ENGINE_OR_FAIL(e);
+  return Guard([&] { e->impl.SetSubstitutionModel(eigenvectors, inverse_eigenvectors, eigenvalues, frequencies); });
+}
+
 int bito_gp_get_log_marginal_likelihood(bito_gp_engine* e, double* out) {
   ENGINE_OR_FAIL(e);
   return Guard([&] { *out = e->impl.GetLogMarginalLikelihood(); });

@@ -5,6 +5,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -215,38 +216,16 @@ Engine::Engine(const bito_gp_config& cfg) : cfg_(cfg) {
                                                : static_cast<int64_t>(free_b * 0.9);
 
   // JC69 eigensystem, substitution_model.cpp:20-26.
-  ModelConst m{};
-  const double V[16] = {1.0, 2.0, 0.0, 0.5, 1.0, -2.0, 0.5, 0.0,
-                        1.0, 2.0, 0.0, -0.5, 1.0, -2.0, -0.5, 0.0};
-  const double Vinv[16] = {0.25, 0.25, 0.25, 0.25, 0.125, -0.125, 0.125, -0.125,
-                           0.0, 1.0, 0.0, -1.0, 1.0, 0.0, -1.0, 0.0};
-  const double lambda[4] = {0.0, -1.3333333333333333, -1.3333333333333333,
-                            -1.3333333333333333};
-  std::memcpy(m.V, V, sizeof V);
-  std::memcpy(m.Vinv, Vinv, sizeof Vinv);
-  std::memcpy(m.lambda, lambda, sizeof lambda);
-  for (int i = 0; i < 4; ++i) m.pi[i] = 0.25;
-  m.n_groups = 0;
-  for (int k = 0; k < 4; ++k) {
-    int g = -1;
-    for (int j = 0; j < m.n_groups; ++j)
-      if (m.group_lambda[j] == lambda[k]) g = j;
-    if (g < 0) {
-      g = m.n_groups++;
-      m.group_lambda[g] = lambda[k];
-    }
-    m.group[k] = g;
-  }
   {
-    int count[kMaxEigenGroups] = {0, 0, 0, 0};
-    for (int k = 0; k < 4; ++k) count[m.group[k]]++;
-    m.small_group = (m.n_groups == 2 && count[1] < count[0]) ? 1 : 0;
-    m.small_count = 0;
-    for (int k = 0; k < 4; ++k)
-      if (m.group[k] == m.small_group) m.small_idx[m.small_count++] = k;
+    const double V[16] = {1.0, 2.0, 0.0, 0.5, 1.0, -2.0, 0.5, 0.0,
+                          1.0, 2.0, 0.0, -0.5, 1.0, -2.0, -0.5, 0.0};
+    const double Vinv[16] = {0.25, 0.25, 0.25, 0.25, 0.125, -0.125, 0.125, -0.125,
+                             0.0, 1.0, 0.0, -1.0, 1.0, 0.0, -1.0, 0.0};
+    const double lambda[4] = {0.0, -1.3333333333333333, -1.3333333333333333,
+                              -1.3333333333333333};
+    const double pi[4] = {0.25, 0.25, 0.25, 0.25};
+    InstallModel(V, Vinv, lambda, pi);
   }
-  n_eigen_groups_ = m.n_groups;
-  for (int g = 0; g < m.n_groups; ++g) group_lambda_[g] = m.group_lambda[g];
   if (const char* env = getenv("BITO_GP_OPT_CHUNK_MB")) opt_chunk_bytes_ = int64_t(atoll(env)) << 20;
   // BITO_GP_OPT_CLUSTER: 0 = never use the cluster-resident optimiser; N > 0 = use it with clusters
   // of exactly N blocks even where one block would do (tests); unset = automatic
@@ -273,7 +252,6 @@ Engine::Engine(const bito_gp_config& cfg) : cfg_(cfg) {
     GP_CUDA(cudaEventCreateWithFlags(&ev_ready_[b], cudaEventDisableTiming));
     GP_CUDA(cudaEventCreateWithFlags(&ev_free_[b], cudaEventDisableTiming));
   }
-  GP_CUDA(UploadModel(m));
 
   // PLV slabs: ~256 MiB chunks (or one PLV, whichever is larger).
   plv_pool_.Init(static_cast<size_t>(32 * P_stride_), size_t(256) << 20);
@@ -394,6 +372,68 @@ void Engine::CheckEdge(int64_t id, const char* what) const {
 }
 
 void Engine::InvalidatePrograms() { alloc_version_++; }
+
+// ---- substitution model ---------------------------------------------------------------------------
+namespace {
+std::atomic<uint64_t> g_next_model_id{1};
+// which engine's eigensystem the constant-memory copy of each device holds
+uint64_t g_bound_model[64] = {0};
+}  // namespace
+
+void Engine::InstallModel(const double* v, const double* vinv, const double* lambda, const double* pi) {
+  ModelConst m{};
+  std::memcpy(m.V, v, sizeof m.V);
+  std::memcpy(m.Vinv, vinv, sizeof m.Vinv);
+  std::memcpy(m.lambda, lambda, sizeof m.lambda);
+  std::memcpy(m.pi, pi, sizeof m.pi);
+  m.n_groups = 0;
+  for (int k = 0; k < 4; ++k) {  // bit-equal eigenvalues share one exponential of the objective
+    int g = -1;
+    for (int j = 0; j < m.n_groups; ++j)
+      if (m.group_lambda[j] == lambda[k]) g = j;
+    if (g < 0) {
+      g = m.n_groups++;
+      m.group_lambda[g] = lambda[k];
+    }
+    m.group[k] = g;
+  }
+  {
+    int count[kMaxEigenGroups] = {0, 0, 0, 0};
+    for (int k = 0; k < 4; ++k) count[m.group[k]]++;
+    m.small_group = (m.n_groups == 2 && count[1] < count[0]) ? 1 : 0;
+    m.small_count = 0;
+    for (int k = 0; k < 4; ++k)
+      if (m.group[k] == m.small_group) m.small_idx[m.small_count++] = k;
+  }
+  model_ = m;
+  model_id_ = g_next_model_id++;
+  n_eigen_groups_ = m.n_groups;
+  for (int g = 0; g < kMaxEigenGroups; ++g) group_lambda_[g] = g < m.n_groups ? m.group_lambda[g] : 0.;
+}
+
+void Engine::BindModel() {
+  if (device_ < 64 && g_bound_model[device_] == model_id_) return;
+  GP_CUDA(cudaStreamSynchronize(stream_));  // nothing of this engine is in flight while the symbol changes
+  GP_CUDA(UploadModel(model_));
+  if (device_ < 64) g_bound_model[device_] = model_id_;
+}
+
+void Engine::SetSubstitutionModel(const double* v, const double* vinv, const double* lambda, const double* pi) {
+  Activate();
+  for (int k = 0; k < 16; ++k)
+    if (!std::isfinite(v[k]) || !std::isfinite(vinv[k])) Fail("bito_gp_set_substitution_model: eigenvectors must be finite");
+  double sum = 0.;
+  for (int k = 0; k < 4; ++k) {
+    if (!std::isfinite(lambda[k]) || !(pi[k] > 0.))
+      Fail("bito_gp_set_substitution_model: eigenvalues must be finite and frequencies positive");
+    sum += pi[k];
+  }
+  if (std::fabs(sum - 1.) >= 1e-3) Fail("bito_gp_set_substitution_model: frequencies do not sum to 1 +/- 0.001");
+  GP_CUDA(cudaStreamSynchronize(stream_));
+  InstallModel(v, vinv, lambda, pi);
+  DropGraphs();  // which optimiser kernels a captured level launches depends on the number of eigenvalue groups
+  AgreeOnClusterScheme();
+}
 
 // ---- site patterns: gp_engine.cpp:22-26, 544-562 -----------------------------------------
 void Engine::SetSitePatterns(const uint8_t* symbols, const double* weights, bool on_device) {
@@ -1733,22 +1773,23 @@ int Engine::OptScheme(int n_ops, const OptClusterPlan** plan) const {
       OptBlockSharedBytes(P_, n_eigen_groups_) <= kOptBlockMaxSharedBytes)
     return 1;
   if (!cluster_ok) return 0;
-  // Scheme 3, pipelined clusters: for levels with many more edges than the chip keeps resident. A
-  // streaming producer (HBM-bound) turns the PLVs of the next chunk of edges into rho while the
-  // clusters (latency-bound, shared memory) run the searches of the current chunk, so shared memory
-  // only ever holds edges whose search is running. Shape: as many edges in flight as possible.
-  {
+  // Scheme 3, pipelined clusters (BITO_GP_OPT_SCHEME=3 only): a streaming producer (HBM-bound) turns the
+  // PLVs of the next chunk of edges into rho while the clusters run the searches of the current chunk
+  // from shared memory, so shared memory only ever holds edges whose search is running. Measured on
+  // B200 (profiles/r02_sweep_ab.md): the searches are bound by latency per edge - 21-30 edges fit the
+  // chip's shared memory at 1e5 patterns and each takes ~70 us (~16 dependent objective evaluations,
+  // each a cluster barrier plus a serial FP64 optimiser step; warps wait at barriers 47 % of the time)
+  // - i.e. 45 ms for 11 139 edges whatever the producer does, against 46 ms for the WHOLE sweep with the
+  // streaming scheme below. It stays available (and tested) but is never chosen automatically.
+  if (opt_scheme_env_ == 3) {
     const OptClusterPlan* widest = nullptr;
     for (const OptClusterPlan& c : cluster_plans_) {
       if (widest == nullptr || c.active_clusters > widest->active_clusters ||
           (c.active_clusters == widest->active_clusters && c.threads < widest->threads))
         widest = &c;
     }
-    const bool many = n_ops >= 4 * widest->active_clusters;
-    if (opt_scheme_env_ == 3 || (opt_scheme_env_ < 0 && !forced && many)) {
-      if (plan != nullptr) *plan = widest;
-      return 3;
-    }
+    if (plan != nullptr) *plan = widest;
+    return 3;
   }
   // Cost model, microseconds, fitted to B200 timings (profiles/r01g_sweep_variants_*.log):
   //  on chip, per edge: two-row load trips of ~2.5 us, then ~14.5 dependent objective evaluations of
@@ -2109,6 +2150,7 @@ void Engine::ProcessOperations(const bito_gp_op* ops, int64_t n, const int64_t* 
                                int64_t vec_len) {
   Activate();
   if (!have_patterns_) Fail("ProcessOperations: call bito_gp_set_site_patterns first");
+  BindModel();
   stats_.process_calls++;
   if (n == 0) return;
   const uint64_t key = HashOps(ops, n, vec, vec_len);
@@ -2182,6 +2224,7 @@ void Engine::ResetOptimizationCount() {  // dag_branch_handler.hpp:49-52
 void Engine::LogLikelihoodAndDerivatives(int64_t gpcsp, int64_t rootward, int64_t leafward,
                                          double out[3]) {
   Activate();
+  BindModel();
   CheckEdge(gpcsp, "LogLikelihoodAndDerivative");
   CheckPlv(rootward, "LogLikelihoodAndDerivative");
   CheckPlv(leafward, "LogLikelihoodAndDerivative");
@@ -2239,6 +2282,7 @@ void Engine::QuartetHybrid(int64_t n_requests, const int64_t* central, const int
                            const bito_gp_quartet_tip* tips, double* likelihoods, bool store) {
   Activate();
   if (n_requests < 0) Fail("QuartetHybrid: negative request count");
+  BindModel();
   std::vector<QuartetItem> items;
   std::vector<int64_t> first_item(static_cast<size_t>(n_requests) + 1, 0);
   int64_t tip_off = 0;
@@ -2328,6 +2372,7 @@ void Engine::GetHybridMarginals(double* out) {
 
 void Engine::GetTransitionMatrix(double t, double out[16]) {
   Activate();
+  BindModel();
   EnsureScratch(16, 16);
   LaunchTransitionMatrix(stream_, t, d_packed_.ptr);
   GP_CUDA(cudaMemcpyAsync(out, d_packed_.ptr, 16 * sizeof(double), cudaMemcpyDeviceToHost, stream_));

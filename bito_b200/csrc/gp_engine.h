@@ -160,6 +160,7 @@ class Engine {
   void LogLikelihoodAndDerivatives(int64_t gpcsp, int64_t rootward, int64_t leafward,
                                    double out[3]);
   void GetTransitionMatrix(double t, double out[16]);
+  void SetSubstitutionModel(const double* v, const double* vinv, const double* lambda, const double* pi);
 
   double GetLogMarginalLikelihood();
   void GetPerGpcspLogLikelihoods(int64_t start, int64_t length, double* out);
@@ -202,6 +203,10 @@ class Engine {
  private:
   // state helpers
   void Activate() const;
+  void InstallModel(const double* v, const double* vinv, const double* lambda, const double* pi);
+  void BindModel();  // makes the constant-memory eigensystem this engine's before it launches anything
+  ModelConst model_{};
+  uint64_t model_id_ = 0;
   DeviceState State() const;
   void AllocEdgeArrays(int64_t padded);
   void EnsureDense(int64_t plv_id);  // allocate (zero-filled / expanded) HBM for a PLV

@@ -195,6 +195,15 @@ class GPEngine:
                                                                      int(leafward), _ptr(out)))
         return tuple(out)
 
+    def set_substitution_model(self, eigenvectors, inverse_eigenvectors, eigenvalues, frequencies):
+        """SubstitutionModel::GetEigenvectors / GetInverseEigenvectors (4x4) / GetEigenvalues / GetFrequencies of
+        any reversible nucleotide model (substitution_model.hpp:24-30); the engine starts with JC69."""
+        v = _f64(eigenvectors, 16, "eigenvectors")
+        vinv = _f64(inverse_eigenvectors, 16, "inverse_eigenvectors")
+        lam = _f64(eigenvalues, 4, "eigenvalues")
+        pi = _f64(frequencies, 4, "frequencies")
+        self._check(self._lib.bito_gp_set_substitution_model(self._h, _ptr(v), _ptr(vinv), _ptr(lam), _ptr(pi)))
+
     def get_transition_matrix(self, branch_length):
         out = np.zeros((4, 4))
         self._check(self._lib.bito_gp_get_transition_matrix(self._h, float(branch_length), _ptr(out)))

@@ -177,6 +177,19 @@ void Self::ResetOptimizationCount() {
 }
 void Self::IncrementOptimizationCount() { Check(bito_gp_increment_optimization_count(H())); }
 
+void Self::SetSubstitutionModel(const SubstitutionModel& model) {
+  Assert(model.GetStateCount() == 4, "GPEngine::SetSubstitutionModel needs a nucleotide model.");
+  double v[16], vinv[16], lambda[4], pi[4];
+  for (int i = 0; i < 4; ++i) {
+    for (int j = 0; j < 4; ++j) {
+      v[4 * i + j] = model.GetEigenvectors()(i, j);
+      vinv[4 * i + j] = model.GetInverseEigenvectors()(i, j);
+    }
+    lambda[i] = model.GetEigenvalues()[i];
+    pi[i] = model.GetFrequencies()[i];
+  }
+  Check(bito_gp_set_substitution_model(H(), v, vinv, lambda, pi));
+}
 void Self::SetTransitionMatrixToHaveBranchLength(double branch_length) {
   double m[16];
   Check(bito_gp_get_transition_matrix(H(), branch_length, m));

@@ -39,6 +39,7 @@
 #include "rooted_tree_collection.hpp"
 #include "sbn_maps.hpp"
 #include "site_pattern.hpp"
+#include "substitution_model.hpp"
 #include "subsplit_dag_storage.hpp"
 #include "pv_handler.hpp"
 #include "dag_branch_handler.hpp"
@@ -95,6 +96,10 @@ class BITO_B200_ENGINE_CLASS {
   void IncrementOptimizationCount();
   bool IsFirstOptimization() { return GetOptimizationCount() == 0; }
 
+  // Extension: the reference engine hard-wires `JC69Model substitution_model_`
+  // (gp_engine.hpp:366) although it only reads the four generic getters; any SubstitutionModel
+  // (GTRModel, HKYModel: substitution_model.hpp:80-111) can be installed here.
+  void SetSubstitutionModel(const SubstitutionModel& model);
   void SetTransitionMatrixToHaveBranchLength(double branch_length);
   const Eigen::Matrix4d& GetTransitionMatrix() const { return transition_matrix_; }
   void SetBranchLengths(EigenVectorXd branch_lengths);

@@ -158,6 +158,18 @@ BITO_GP_API int bito_gp_log_likelihood_and_derivatives(bito_gp_engine* e, int64_
 /* GPEngine::SetTransitionMatrixToHaveBranchLength + GetTransitionMatrix
  * (gp_engine.cpp:341-344), row-major 4x4, computed on the device. */
 BITO_GP_API int bito_gp_get_transition_matrix(bito_gp_engine* e, double branch_length, double out[16]);
+/* The substitution model as the engine uses it: the four getters of SubstitutionModel that GPEngine reads
+ * (/root/reference/src/gp_engine.hpp:366-376, substitution_model.hpp:24-30): GetEigenvectors() and
+ * GetInverseEigenvectors() as row-major 4x4, GetEigenvalues(), GetFrequencies(). The reference engine
+ * hard-wires JC69Model, and so does bito_gp_create; this call installs any other reversible nucleotide
+ * model - the reference's GTRModel / HKYModel eigendecompositions (substitution_model.cpp:79-186) are
+ * what tests/test_models_gpu.py passes in. P(t) = V diag(exp(eigenvalues t)) V^-1. Eigenvalues that are
+ * bit-equal share one exponential in the branch-length objective; with other than two distinct
+ * eigenvalues the optimiser uses its general per-eigenvalue coefficient kernels. Engines of one process
+ * that hold different models must not run concurrently (the eigensystem lives in constant memory). */
+BITO_GP_API int bito_gp_set_substitution_model(bito_gp_engine* e, const double eigenvectors[16],
+                                   const double inverse_eigenvectors[16], const double eigenvalues[4],
+                                   const double frequencies[4]);
 
 /* ---- read-back: gp_engine.cpp:413-468 ------------------------------------------------ */
 BITO_GP_API int bito_gp_get_log_marginal_likelihood(bito_gp_engine* e, double* out);

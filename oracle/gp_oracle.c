@@ -25,15 +25,39 @@
 #define SPARE_EDGES 3  /* gp_engine.hpp:306 */
 
 /* JC69 eigensystem, substitution_model.cpp:20-26 (row-major literals). */
-static const double kV[4][4] = {
+static const double kJcV[4][4] = {
     {1.0, 2.0, 0.0, 0.5}, {1.0, -2.0, 0.5, 0.0}, {1.0, 2.0, 0.0, -0.5}, {1.0, -2.0, -0.5, 0.0}};
-static const double kVinv[4][4] = {{0.25, 0.25, 0.25, 0.25},
-                                   {0.125, -0.125, 0.125, -0.125},
-                                   {0.0, 1.0, 0.0, -1.0},
-                                   {1.0, 0.0, -1.0, 0.0}};
-static const double kLambda[4] = {0.0, -1.3333333333333333, -1.3333333333333333,
-                                  -1.3333333333333333};
-static const double kPi[4] = {0.25, 0.25, 0.25, 0.25};
+static const double kJcVinv[4][4] = {{0.25, 0.25, 0.25, 0.25},
+                                     {0.125, -0.125, 0.125, -0.125},
+                                     {0.0, 1.0, 0.0, -1.0},
+                                     {1.0, 0.0, -1.0, 0.0}};
+static const double kJcLambda[4] = {0.0, -1.3333333333333333, -1.3333333333333333,
+                                    -1.3333333333333333};
+static const double kJcPi[4] = {0.25, 0.25, 0.25, 0.25};
+/* The model in use (process-wide, like the reference's one model per engine build): JC69 unless
+ * gpo_set_model installed another eigensystem - GTR / HKY as the reference's GTRModel / HKYModel compute
+ * them (substitution_model.cpp:79-186), taken from tests/golden/model_*.npz. */
+static double kV[4][4] = {
+    {1.0, 2.0, 0.0, 0.5}, {1.0, -2.0, 0.5, 0.0}, {1.0, 2.0, 0.0, -0.5}, {1.0, -2.0, -0.5, 0.0}};
+static double kVinv[4][4] = {{0.25, 0.25, 0.25, 0.25},
+                             {0.125, -0.125, 0.125, -0.125},
+                             {0.0, 1.0, 0.0, -1.0},
+                             {1.0, 0.0, -1.0, 0.0}};
+static double kLambda[4] = {0.0, -1.3333333333333333, -1.3333333333333333, -1.3333333333333333};
+static double kPi[4] = {0.25, 0.25, 0.25, 0.25};
+void gpo_set_model(const double* v, const double* vinv, const double* lambda, const double* pi) {
+  if (v == NULL) { /* back to JC69 */
+    memcpy(kV, kJcV, sizeof kV);
+    memcpy(kVinv, kJcVinv, sizeof kVinv);
+    memcpy(kLambda, kJcLambda, sizeof kLambda);
+    memcpy(kPi, kJcPi, sizeof kPi);
+    return;
+  }
+  memcpy(kV, v, sizeof kV);
+  memcpy(kVinv, vinv, sizeof kVinv);
+  memcpy(kLambda, lambda, sizeof kLambda);
+  memcpy(kPi, pi, sizeof kPi);
+}
 
 /* dag_branch_handler.hpp:266-295 */
 static const double kDefaultBranchLength = 0.1;

@@ -58,6 +58,8 @@ void gpo_set_null_prior(gpo* g);
 void gpo_loglik_and_derivatives(gpo* g, int64_t gpcsp, int64_t rootward, int64_t leafward,
                                 double* out);
 void gpo_transition_matrix(double t, double* out /* 4x4 row-major */);
+/* Process-wide substitution model: V, V^-1 (4x4 row-major), eigenvalues, frequencies; v == NULL restores JC69. */
+void gpo_set_model(const double* v, const double* vinv, const double* lambda, const double* pi);
 /* Quartet hybrid marginals (gp_engine.cpp:748-816); tips = (tip_node_id, plv_idx, gpcsp_idx)
  * triples, counts[4] = rootward, sister, rotated, sorted. */
 int gpo_quartet_likelihoods(gpo* g, int64_t central, const int32_t* counts, const int64_t* tips,

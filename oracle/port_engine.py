@@ -104,6 +104,19 @@ def brent_minimize(f, guess, lo, hi, significant_digits, max_iter):
     return x.value, fx.value
 
 
+def set_model(eigenvectors=None, inverse_eigenvectors=None, eigenvalues=None, frequencies=None):
+    """Installs a substitution model for every PortEngine of this process (None: back to JC69)."""
+    lib = _load()
+    lib.gpo_set_model.argtypes = [C.c_void_p] * 4
+    if eigenvectors is None:
+        lib.gpo_set_model(None, None, None, None)
+        return
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (eigenvectors, inverse_eigenvectors, eigenvalues,
+                                                                  frequencies)]
+    assert [a.size for a in arrs] == [16, 16, 4, 4]
+    lib.gpo_set_model(*[_ptr(a) for a in arrs])
+
+
 def transition_matrix(t):
     out = np.zeros((4, 4))
     _load().gpo_transition_matrix(float(t), _ptr(out))

@@ -515,6 +515,21 @@ int ref_loglik_and_derivatives(void* h, int64_t gpcsp, int64_t rootward, int64_t
 }
 
 // JC69 transition matrix at branch length t (gp_engine.cpp:341-344), row-major 4x4.
+// The eigensystem the engine was built with (JC69 in the stock build; whatever BITO_REF_MODEL selected in the
+// `refmodel` build): V and V^-1 row-major, eigenvalues, stationary frequencies (gp_engine.hpp:366-376).
+void ref_model_eigensystem(void* h, double* eigenvectors, double* inverse_eigenvectors, double* eigenvalues,
+                           double* frequencies) {
+  const GPEngine& e = *static_cast<RefInst*>(h)->engine;
+  for (int i = 0; i < 4; ++i) {
+    for (int j = 0; j < 4; ++j) {
+      eigenvectors[4 * i + j] = e.eigenmatrix_(i, j);
+      inverse_eigenvectors[4 * i + j] = e.inverse_eigenmatrix_(i, j);
+    }
+    eigenvalues[i] = e.eigenvalues_[i];
+    frequencies[i] = e.stationary_distribution_[i];
+  }
+}
+
 void ref_transition_matrix(void* h, double t, double* out) {
   auto& e = *static_cast<RefInst*>(h)->engine;
   e.SetTransitionMatrixToHaveBranchLength(t);

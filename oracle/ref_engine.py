@@ -14,7 +14,11 @@ import tempfile
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_ref", "libbito_gp_ref.so")
+# BITO_REF_LIB selects another build of the same driver: `make -C oracle refmodel` (libbito_gp_ref_model.so, the
+# reference GPEngine over its own GTR / HKY models, chosen by BITO_REF_MODEL when an engine is constructed) or
+# `make -C oracle refvar` (other floating-point code generation).
+LIB_PATH = os.environ.get("BITO_REF_LIB") or os.path.join(_HERE, "_ref", "libbito_gp_ref.so")
+MODEL_LIB_PATH = os.path.join(_HERE, "_ref", "libbito_gp_ref_model.so")
 
 OPLISTS = {
     "populate_plvs": 0,
@@ -103,6 +107,8 @@ def _load():
     lib.ref_quartet_likelihoods.argtypes = [vp, i64, vp, vp, vp]
     lib.ref_process_quartet_requests.argtypes = [vp, i64, vp, vp, vp]
     lib.ref_get_hybrid_marginals.argtypes = [vp, vp]
+    if hasattr(lib, "ref_model_eigensystem"):
+        lib.ref_model_eigensystem.argtypes = [vp, vp, vp, vp, vp]
     _lib = lib
     return lib
 
@@ -328,6 +334,12 @@ class RefEngine:
         self._check(_load().ref_loglik_and_derivatives(self._h, int(gpcsp), int(rootward),
                                                        int(leafward), int(two), _ptr(out)))
         return tuple(out[:3 if two else 2])
+
+    def model_eigensystem(self):
+        """(V, V^-1, eigenvalues, frequencies) of the substitution model the engine was built with."""
+        v, vinv, lam, pi = np.zeros((4, 4)), np.zeros((4, 4)), np.zeros(4), np.zeros(4)
+        _load().ref_model_eigensystem(self._h, _ptr(v), _ptr(vinv), _ptr(lam), _ptr(pi))
+        return v, vinv, lam, pi
 
     def transition_matrix(self, t):
         out = np.zeros((4, 4))

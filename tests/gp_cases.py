@@ -125,7 +125,9 @@ def check_sweeps(engine, fx: Fixture, ti, method, atol=BL_ATOL):
         engine.process_operations(*fx.ops("branch_length_optimization"))
         engine.process_operations(*fx.ops("populate_plvs"))
         engine.process_operations(*fx.ops("marginal_likelihood"))
-        assert np.max(np.abs(engine.branch_lengths() - want_bl[s])) <= atol, f"sweep {s}"
+        err = np.abs(engine.branch_lengths() - want_bl[s])
+        assert np.max(err) <= atol, (f"sweep {s}: edge {int(np.argmax(err))} off by {float(np.max(err)):.3e} "
+                                     f"(got {engine.branch_lengths()[np.argmax(err)]!r}, want {want_bl[s][np.argmax(err)]!r})")
         assert np.max(np.abs(engine.branch_length_differences() - want_diff[s])) <= atol, f"sweep {s}"
         assert rel_err(engine.log_marginal_likelihood(), want_marg[s]) <= 1e-7, f"sweep {s}"
         engine.increment_optimization_count()

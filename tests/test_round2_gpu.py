@@ -311,13 +311,14 @@ def test_stale_programs_are_evicted(cuda_engine_lib):
         e.grow_spare_plvs(24)          # invalidates every program
         e.process_operations(*pop)      # recompiled; the two stale ones are freed
         st = e.stats()
-        assert st["programs_cached"] == 1 and st["programs_evicted"] == 3
+        # (the recompiled list replaces its own stale entry in place; the other stale program is evicted)
+        assert st["programs_cached"] == 1 and st["programs_evicted"] == 2
         # many distinct lists: the cache is bounded (least recently used go first)
         for k in range(60):
             ops = np.array([[0, fx["node_count"] + 1 + (k % 3), 0, 0, 0, 0]] * (k + 1), dtype=np.int64)
             e.process_operations(ops)
         st = e.stats()
-        assert st["programs_cached"] <= 48 and st["programs_evicted"] >= 3 + 61 - 48
+        assert st["programs_cached"] <= 48 and st["programs_evicted"] >= 2 + 61 - 48
         e.process_operations(*pop)
         e.process_operations(*lik)
         assert rel_err(e.get_log_marginal_likelihood(), fx["t0_pass_log_marginal"]) <= LL_RTOL
