@@ -246,7 +246,7 @@ struct OptControl {
 // into every other rank's address space through CUDA IPC. Layout of a buffer, in doubles:
 //   data[parity][source rank][capacity], then (as 64-bit words) flag[parity][source rank].
 constexpr int kMaxPeerRanks = 8;
-constexpr int64_t kPeerCapacity = 8192;  // doubles per all-reduce; larger ones go through NCCL
+constexpr int64_t kPeerCapacity = 16384;  // doubles per all-reduce (the batched sweep of the bench DAG sums 11 139 per round); larger ones go through NCCL
 struct PeerComm {
   double* base[kMaxPeerRanks];  // base[r] = rank r's exchange buffer as mapped in THIS process
   unsigned long long* epoch;    // all-reduces completed so far (device memory, so graphs replay)

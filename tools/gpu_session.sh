@@ -24,8 +24,8 @@ for s in $steps; do
       BITO_GP_OPT_SCHEME=3 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_opt_cluster|k_opt_prepare_cluster" -s 2 -c 4 \
         -o $out/${tag}_k_opt_pipelined -f python profiles/prof_pass.py synthetic-1000taxa-1Mpat-5000trees 40000 1 sweep > $out/${tag}_ncu_sweep.log 2>&1 ;;
     node_variants)
-      for v in "X=0" "BITO_GP_TILES_PER_BLOCK=4" "BITO_GP_TILES_PER_BLOCK=16" "BITO_GP_TILES_PER_BLOCK=32" "BITO_GP_NODE_OCC=3" "BITO_GP_NODE_OCC=3 BITO_GP_TILES_PER_BLOCK=16"; do
-        env $v timeout 300 python tools/time_pass.py synthetic-1000taxa-1Mpat-5000trees - 5 >> $out/${tag}_time_pass.log 2>&1
+      for v in ${NODE_VARIANTS:-X=0 BITO_GP_NODE_PREFETCH=1 BITO_GP_NODE_PREFETCH=2 BITO_GP_NODE_PREFETCH=4 BITO_GP_PREP_PREFETCH=1 BITO_GP_PREP_PREFETCH=2}; do
+        env $v timeout 300 python tools/time_pass.py synthetic-1000taxa-1Mpat-5000trees - 5 sweep >> $out/${tag}_time_pass.log 2>&1
       done ;;
     ncu_small)
       BITO_GP_OPT_SCHEME=3 BITO_GP_OPT_CLUSTER=16 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_opt_cluster|k_opt_prepare_cluster" -c 2 \
