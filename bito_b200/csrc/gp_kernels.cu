@@ -205,14 +205,11 @@ __device__ __forceinline__ void accumulate_items(V4& acc, const double (*sM)[16]
 // (gp_engine.cpp:278-285), plus the per-PLV maximum for the rescale decision (:583-597).
 // Blocks are ordered tile-major (all macro-ops of one pattern tile are neighbours in the grid), so
 // a PLV tile read by several macro-ops of the level is served from L2 after its first use.
-__device__ __forceinline__ void prefetch_l2(const void* p) {
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
 template <int kMinBlocks, bool kStream>
 __global__ void __launch_bounds__(kTile, kMinBlocks)
     k_node(DeviceState st, const NodeOp* __restrict__ nodes, const AccumItem* __restrict__ items,
            const int32_t* __restrict__ pool, const double* __restrict__ mtab, int n_nodes, int tiles,
-           int tiles_per_block, unsigned long long* __restrict__ level_max, int prefetch_tiles) {
+           int tiles_per_block, unsigned long long* __restrict__ level_max) {
   const int tile_group = blockIdx.x / n_nodes;
   const int o = blockIdx.x - tile_group * n_nodes;
   const NodeOp* nd = nodes + o;
@@ -330,23 +327,6 @@ __global__ void __launch_bounds__(kTile, kMinBlocks)
   for (int tile = tile_begin; tile < tile_end; ++tile) {
     const int64_t p = static_cast<int64_t>(tile) * kTile + threadIdx.x;
     const bool live = p < st.P;
-    // The loads of a tile are as many 32-byte requests per thread as the node has sources: too few in
-    // flight to cover the HBM latency. Ask L2 for the sources of the tile `prefetch_tiles` ahead now (no
-    // register is tied up), so that their loads hit L2 when the loop gets there.
-    if (prefetch_tiles > 0 && single_chunk && tile + prefetch_tiles < tile_end) {
-      const int64_t pn = p + static_cast<int64_t>(prefetch_tiles) * kTile;
-      if (pn < st.P) {
-        for (int i = 0; i < n_tot; ++i)
-          if (s_kind[i] == kPlvDense) prefetch_l2(static_cast<const double*>(s_ptr[i]) + 4 * pn);
-        if (keep0) prefetch_l2(dest0 + 4 * pn);
-        if (keep1) prefetch_l2(dest1 + 4 * pn);
-        for (int mi = 0; mi < nm; ++mi) {
-          const NodeMult* m = &nd->m[mi];
-          if (m->s1_group < 0 && m->s1.kind == kPlvDense) prefetch_l2(static_cast<const double*>(m->s1.ptr) + 4 * pn);
-          if (m->s2_group < 0 && m->s2.kind == kPlvDense) prefetch_l2(static_cast<const double*>(m->s2.ptr) + 4 * pn);
-        }
-      }
-    }
     V4 acc0 = {0., 0., 0., 0.}, acc1 = {0., 0., 0., 0.};
     if (live && keep0) acc0 = ld256(dest0 + 4 * p);
     if (live && keep1) acc1 = ld256(dest1 + 4 * p);
@@ -1022,25 +1002,21 @@ __device__ __forceinline__ double pow_small(double t, int wi) {  // t^wi, 1 <= w
   return r;
 }
 
-// Two-group models: sum_k (V^T r)_k (V^-1 p)_k = r.p, so only the smaller group (one eigenvalue for JC69:
-// 8 multiply-adds) is summed explicitly and the other coefficient is r.p minus it.
+// Each coefficient is the sum of its group's eigen terms in eigenvalue order. (A cheaper form - only the
+// smaller group summed, the other taken as r.p minus it, 14 instead of 36 flops - was measured and dropped:
+// it moves rho by an ulp, which is enough to move a Brent termination decision of the `hello` fixture off
+// the reference's side, tests/test_gp_engine_gpu.py; the prepare kernels are bound by HBM either way.)
 __device__ __forceinline__ void ratio_coefficients(const V4& r, const V4& c, double& rho, double& c0_out) {
-  double cs = 0.;
+  double c0 = 0., c1 = 0.;
 #pragma unroll
-  for (int j = 0; j < 3; ++j) {  // a two-group model has at most 2 eigenvalues in its smaller group... or 1 + 3
-    if (j < c_model.small_count) {
-      const int k = c_model.small_idx[j];
-      const double rv = r.a * c_model.V[k] + r.b * c_model.V[4 + k] + r.c * c_model.V[8 + k] +
-                        r.d * c_model.V[12 + k];
-      const double vp = c_model.Vinv[4 * k] * c.a + c_model.Vinv[4 * k + 1] * c.b +
-                        c_model.Vinv[4 * k + 2] * c.c + c_model.Vinv[4 * k + 3] * c.d;
-      cs += rv * vp;
-    }
+  for (int k = 0; k < 4; ++k) {
+    const double rv = r.a * c_model.V[k] + r.b * c_model.V[4 + k] + r.c * c_model.V[8 + k] +
+                      r.d * c_model.V[12 + k];
+    const double vp = c_model.Vinv[4 * k] * c.a + c_model.Vinv[4 * k + 1] * c.b +
+                      c_model.Vinv[4 * k + 2] * c.c + c_model.Vinv[4 * k + 3] * c.d;
+    const double term = rv * vp;
+    if (c_model.group[k] == 0) c0 += term; else c1 += term;
   }
-  const double total = r.a * c.a + r.b * c.b + r.c * c.c + r.d * c.d;
-  const double co = total - cs;
-  const double c0 = c_model.small_group == 0 ? cs : co;
-  const double c1 = c_model.small_group == 0 ? co : cs;
   rho = c0 != 0. ? c1 / c0 : 0.;
   c0_out = c0;
 }
@@ -1078,7 +1054,7 @@ __global__ void __launch_bounds__(kTile, 4)
                         int tiles_per_block, OptState* __restrict__ states, OptParams prm, int method,
                         double* __restrict__ rho, const int32_t* __restrict__ perm,
                         int64_t rho_stride, double* __restrict__ partials,
-                        int32_t* __restrict__ active, int active_capacity, int prefetch_trips) {
+                        int32_t* __restrict__ active, int active_capacity) {
   // tile-major: the edges of one pattern tile group are neighbours in the grid, so a parent r-PLV
   // or child p-PLV tile shared by several edges is read from HBM once and from L2 afterwards
   const int n_groups = gridDim.x / n_ops;
@@ -1107,19 +1083,6 @@ __global__ void __launch_bounds__(kTile, 4)
   for (; tile + 2 <= tile_end; tile += 2) {
     const int64_t p0 = static_cast<int64_t>(tile) * kTile + threadIdx.x, p1 = p0 + kTile;
     const bool live0 = p0 < st.P, live1 = p1 < st.P;
-    if (prefetch_trips > 0 && tile + 2 * prefetch_trips + 2 <= tile_end) {  // the trip after next, into L2
-      const int64_t pn = p0 + static_cast<int64_t>(2 * prefetch_trips) * kTile;
-      if (pn + kTile < st.P) {
-        if (op.parent.kind == kPlvDense) {
-          prefetch_l2(static_cast<const double*>(op.parent.ptr) + 4 * pn);
-          prefetch_l2(static_cast<const double*>(op.parent.ptr) + 4 * (pn + kTile));
-        }
-        if (op.child.kind == kPlvDense) {
-          prefetch_l2(static_cast<const double*>(op.child.ptr) + 4 * pn);
-          prefetch_l2(static_cast<const double*>(op.child.ptr) + 4 * (pn + kTile));
-        }
-      }
-    }
     V4 r0 = {1., 1., 1., 1.}, c0v = r0, r1 = r0, c1v = r0;
     int32_t q0 = 0, q1 = 0;
     double w0 = 0., w1 = 0.;
@@ -1922,17 +1885,13 @@ void LaunchNodes(cudaStream_t s, const DeviceState& st, const NodeOp* nodes, con
     const char* e = getenv("BITO_GP_NODE_STORE");
     return e != nullptr && e[0] == 'c';
   }();
-  static const int prefetch = [] {  // BITO_GP_NODE_PREFETCH: tiles ahead that are prefetched into L2 (0 = off)
-    const char* e = getenv("BITO_GP_NODE_PREFETCH");
-    return e != nullptr ? atoi(e) : 0;
-  }();
   if (occ >= 4) {
     if (stream)
-      k_node<4, true><<<grid, kTile, 0, s>>>(st, nodes, items, pool, mtab, n_nodes, tiles, tpb, mx, prefetch);
+      k_node<4, true><<<grid, kTile, 0, s>>>(st, nodes, items, pool, mtab, n_nodes, tiles, tpb, mx);
     else
-      k_node<4, false><<<grid, kTile, 0, s>>>(st, nodes, items, pool, mtab, n_nodes, tiles, tpb, mx, prefetch);
+      k_node<4, false><<<grid, kTile, 0, s>>>(st, nodes, items, pool, mtab, n_nodes, tiles, tpb, mx);
   } else {
-    k_node<3, false><<<grid, kTile, 0, s>>>(st, nodes, items, pool, mtab, n_nodes, tiles, tpb, mx, prefetch);
+    k_node<3, false><<<grid, kTile, 0, s>>>(st, nodes, items, pool, mtab, n_nodes, tiles, tpb, mx);
   }
 }
 void LaunchRescale(cudaStream_t s, const DeviceState& st, const MultOp* ops, int n_ops,
@@ -2151,13 +2110,9 @@ void LaunchOptPrepareRatio(cudaStream_t s, const DeviceState& st, const OptOp* o
   if (n_ops == 0) return;
   const int tiles = static_cast<int>(TilesFor(st.P));
   const int tpb = TilesPerBlock(n_ops, tiles, "BITO_GP_OPT_TILES_PER_BLOCK", 32);
-  static const int prefetch = [] {  // BITO_GP_PREP_PREFETCH: trips (of two tiles) ahead prefetched into L2
-    const char* e = getenv("BITO_GP_PREP_PREFETCH");
-    return e != nullptr ? atoi(e) : 0;
-  }();
   k_opt_prepare_ratio<<<Grid(n_ops, (tiles + tpb - 1) / tpb), kTile, 0, s>>>(
       st, ops, n_ops, tiles, tpb, states, params, method, rho, perm, rho_stride, partials, active,
-      active_capacity, prefetch);
+      active_capacity);
 }
 int64_t OptRatioTileGroups(int64_t P) {
   const int64_t per_block = static_cast<int64_t>(kTile) * kOptPatternsPerThread;

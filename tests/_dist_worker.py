@@ -26,6 +26,12 @@ assert got == bytes(range(128)), "broadcast_bytes"
 assert D.max_over_ranks(10.0 + rank) == 10.0 + world - 1
 assert np.allclose(D.sum_over_ranks([1.0, rank]), [world, world * (world - 1) / 2])
 
+# 2b. rank agreement as bench.py checks it: MAX of v and of -v agree exactly iff every rank holds the same values
+same = np.array([0.125, 3.0, -7.5])
+assert np.array_equal(D.max_over_ranks_array(same), -D.max_over_ranks_array(-same))
+differ = np.array([0.125, 3.0 + rank, -7.5])
+assert not np.array_equal(D.max_over_ranks_array(differ), -D.max_over_ranks_array(-differ))
+
 # 3. shards tile [0, P) exactly, ragged P included
 for P in (1, 2, 7, 934, 100_000, 1_000_003):
     lo, hi = D.my_shard(P)

@@ -26,14 +26,14 @@ def _module_dir(which):
     return d if glob.glob(os.path.join(d, "bito*.so")) else None
 
 
-def _walk(which, fasta, newick, workdir, threshold="1e-40"):
+def _walk(which, fasta, newick, workdir, threshold="1e-40", *extra):
     d = _module_dir(which)
     if d is None:
         pytest.fail(f"oracle/_ref/pybito_{which}/bito*.so is missing: run `make -C oracle pybito` in the build "
                     "container (needs /root/reference); the modules travel with the snapshot")
     env = dict(os.environ, PYTHONPATH=d)
-    run = subprocess.run([sys.executable, WALK, fasta, newick, str(workdir), threshold], capture_output=True, text=True,
-                         timeout=900, env=env)
+    run = subprocess.run([sys.executable, WALK, fasta, newick, str(workdir), threshold, *extra], capture_output=True,
+                         text=True, timeout=1500, env=env)
     assert run.returncode == 0, (run.stdout[-2000:], run.stderr[-3000:])
     line = [ln for ln in run.stdout.splitlines() if ln.startswith("PYBITO_WALK ")][-1]
     return json.loads(line[len("PYBITO_WALK "):])
@@ -93,3 +93,31 @@ def test_import_bito_runs_gp_instance_on_the_cuda_engine(cuda_engine_lib, tmp_pa
     assert close("log_marginal", rtol=1e-7 if off.sum() == 0 else 1e-6)
     assert close("sbn_parameters", atol=1e-6)
     assert close("converged_log_marginal", rtol=1e-6)
+
+
+@pytest.mark.gpu
+def test_gp_instance_plans_and_runs_a_bench_sized_dag(cuda_engine_lib, tmp_path):
+    """SURVEY 8f row 3 (host planner at scale): the reference's OWN C++ host path - newick parser, SubsplitDAG /
+    TidySubsplitDAG construction, GPDAG op-list planner, GPInstance - unchanged, driving the CUDA engine through
+    `import bito` on a DAG of BASELINE.json configs[3]'s shape (200 taxa, 1000 NNI-walk trees: ~3.5k nodes, ~8.4k
+    edges), against the same module over the reference CPU engine. Measured in the build container (reference
+    engine, 16 host cores; profiles/r02_host_planner.md): make_dag 3.5 s here and 224 s on a 9 935-node / 22 490-edge
+    DAG (1000 taxa, 5000 trees) - DAG construction, out of scope - while planning + running the first pass takes
+    1.7 s / 3.6 s: the dense N x N matrices of TidySubsplitDAG (2 x 12 MB / 2 x 99 MB) are not what limits the
+    host at these sizes, so the reference planner is used as it is and no replacement is linked in."""
+    fasta, newick = _write_case(tmp_path, 200, 1500, 1000, 2, seed=2003)
+    (tmp_path / "ref").mkdir()
+    (tmp_path / "b200").mkdir()
+    want = _walk("ref", fasta, newick, tmp_path / "ref", "1e-40", "light")
+    got = _walk("b200", fasta, newick, tmp_path / "b200", "1e-40", "light")
+    assert got["dag"] == want["dag"] and got["dag"][0] > 3000 and got["dag"][1] > 8000
+    assert got["edge_pcsps"] == want["edge_pcsps"] and got["node_bitsets"] == want["node_bitsets"]
+    g, w = np.asarray(got["pass_per_pcsp_llh"]), np.asarray(want["pass_per_pcsp_llh"])
+    assert np.max(np.abs(g - w) / np.maximum(1.0, np.abs(w))) <= 1e-9
+    g, w = np.asarray(got["estimated_branch_lengths"]), np.asarray(want["estimated_branch_lengths"])
+    off = np.abs(g - w) > 1e-6
+    tol = 2.0 ** -9
+    assert off.sum() <= 0.01 * w.size, int(off.sum())
+    assert np.all(np.abs(np.log(g[off]) - np.log(w[off])) <= 4 * (tol * np.abs(np.log(w[off])) + tol / 4))
+    assert abs(got["log_marginal"] - want["log_marginal"]) <= 1e-7 * abs(want["log_marginal"])
+    print("host seconds (CUDA engine):", got["seconds"], "(reference engine):", want["seconds"])
