@@ -397,6 +397,14 @@ void Engine::InstallModel(const double* v, const double* vinv, const double* lam
     }
     m.group[k] = g;
   }
+  {
+    int count[kMaxEigenGroups] = {0, 0, 0, 0};
+    for (int k = 0; k < 4; ++k) count[m.group[k]]++;
+    m.small_group = (m.n_groups == 2 && count[1] < count[0]) ? 1 : 0;
+    m.small_count = 0;
+    for (int k = 0; k < 4; ++k)
+      if (m.group[k] == m.small_group) m.small_idx[m.small_count++] = k;
+  }
   model_ = m;
   model_id_ = g_next_model_id++;
   n_eigen_groups_ = m.n_groups;

@@ -1002,21 +1002,25 @@ __device__ __forceinline__ double pow_small(double t, int wi) {  // t^wi, 1 <= w
   return r;
 }
 
-// Each coefficient is the sum of its group's eigen terms in eigenvalue order. (A cheaper form - only the
-// smaller group summed, the other taken as r.p minus it, 14 instead of 36 flops - was measured and dropped:
-// it moves rho by an ulp, which is enough to move a Brent termination decision of the `hello` fixture off
-// the reference's side, tests/test_gp_engine_gpu.py; the prepare kernels are bound by HBM either way.)
+// Two-group models: sum_k (V^T r)_k (V^-1 p)_k = r.p, so only the smaller group (one eigenvalue for JC69:
+// 8 multiply-adds) is summed explicitly and the other coefficient is r.p minus it.
 __device__ __forceinline__ void ratio_coefficients(const V4& r, const V4& c, double& rho, double& c0_out) {
-  double c0 = 0., c1 = 0.;
+  double cs = 0.;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const double rv = r.a * c_model.V[k] + r.b * c_model.V[4 + k] + r.c * c_model.V[8 + k] +
-                      r.d * c_model.V[12 + k];
-    const double vp = c_model.Vinv[4 * k] * c.a + c_model.Vinv[4 * k + 1] * c.b +
-                      c_model.Vinv[4 * k + 2] * c.c + c_model.Vinv[4 * k + 3] * c.d;
-    const double term = rv * vp;
-    if (c_model.group[k] == 0) c0 += term; else c1 += term;
+  for (int j = 0; j < 3; ++j) {  // a two-group model has at most 2 eigenvalues in its smaller group... or 1 + 3
+    if (j < c_model.small_count) {
+      const int k = c_model.small_idx[j];
+      const double rv = r.a * c_model.V[k] + r.b * c_model.V[4 + k] + r.c * c_model.V[8 + k] +
+                        r.d * c_model.V[12 + k];
+      const double vp = c_model.Vinv[4 * k] * c.a + c_model.Vinv[4 * k + 1] * c.b +
+                        c_model.Vinv[4 * k + 2] * c.c + c_model.Vinv[4 * k + 3] * c.d;
+      cs += rv * vp;
+    }
   }
+  const double total = r.a * c.a + r.b * c.b + r.c * c.c + r.d * c.d;
+  const double co = total - cs;
+  const double c0 = c_model.small_group == 0 ? cs : co;
+  const double c1 = c_model.small_group == 0 ? co : cs;
   rho = c0 != 0. ? c1 / c0 : 0.;
   c0_out = c0;
 }

@@ -10,6 +10,8 @@ for s in $steps; do
   case $s in
     tests)
       timeout 1500 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" >> $out/${tag}_pytest.log ;;
+    tests_all)
+      timeout 1800 python -m pytest tests -m gpu -q > $out/${tag}_pytest_all.log 2>&1; echo "pytest rc=$?" >> $out/${tag}_pytest_all.log ;;
     tests_new)
       timeout 1200 python -m pytest tests/test_round2_gpu.py tests/test_pybito_gpu.py -m gpu -q > $out/${tag}_pytest_new.log 2>&1; echo "pytest rc=$?" >> $out/${tag}_pytest_new.log ;;
     bench)
