@@ -398,12 +398,11 @@ void Engine::InstallModel(const double* v, const double* vinv, const double* lam
     m.group[k] = g;
   }
   {
-    int count[kMaxEigenGroups] = {0, 0, 0, 0};
-    for (int k = 0; k < 4; ++k) count[m.group[k]]++;
-    m.small_group = (m.n_groups == 2 && count[1] < count[0]) ? 1 : 0;
-    m.small_count = 0;
-    for (int k = 0; k < 4; ++k)
-      if (m.group[k] == m.small_group) m.small_idx[m.small_count++] = k;
+    const double jc_v[16] = {1.0, 2.0, 0.0, 0.5, 1.0, -2.0, 0.5, 0.0, 1.0, 2.0, 0.0, -0.5, 1.0, -2.0, -0.5, 0.0};
+    const double jc_vinv[16] = {0.25, 0.25, 0.25, 0.25, 0.125, -0.125, 0.125, -0.125,
+                                0.0, 1.0, 0.0, -1.0, 1.0, 0.0, -1.0, 0.0};
+    m.is_jc69 = std::memcmp(m.V, jc_v, sizeof jc_v) == 0 && std::memcmp(m.Vinv, jc_vinv, sizeof jc_vinv) == 0 &&
+                m.n_groups == 2 && m.group[0] == 0 && m.group[1] == 1 && m.group[2] == 1 && m.group[3] == 1;
   }
   model_ = m;
   model_id_ = g_next_model_id++;

@@ -1002,25 +1002,36 @@ __device__ __forceinline__ double pow_small(double t, int wi) {  // t^wi, 1 <= w
   return r;
 }
 
-// Two-group models: sum_k (V^T r)_k (V^-1 p)_k = r.p, so only the smaller group (one eigenvalue for JC69:
-// 8 multiply-adds) is summed explicitly and the other coefficient is r.p minus it.
+// Each coefficient is the sum of its group's eigen terms, in eigenvalue order: c_g = sum_{k in g} (V^T r)_k
+// (V^-1 p)_k. JC69 - the model the reference engine instantiates (gp_engine.hpp:366) - takes a branch that
+// produces the SAME BITS with 24 instead of 38 FP64 instructions: its eigenvector entries are 0, +-1/2, +-1,
+// +-2, 1/4, 1/8 (substitution_model.cpp:20-26), products with those are exact and adding an exact zero
+// changes nothing, so factoring the powers of two out of the general expression is not a re-association.
+// (A cheaper form for any two-group model - only the smaller group summed, the other taken as r.p minus it -
+// was measured and dropped: it moves rho by an ulp, which is enough to move a Brent termination decision of
+// the `hello` fixture off the reference's side; profiles/r02_sweep_ab.md.)
 __device__ __forceinline__ void ratio_coefficients(const V4& r, const V4& c, double& rho, double& c0_out) {
-  double cs = 0.;
+  double c0, c1;
+  if (c_model.is_jc69) {
+    const double sr = ((r.a + r.b) + r.c) + r.d, sp = ((c.a + c.b) + c.c) + c.d;  // k = 0: V[:,0] = 1, Vinv[0,:] = 1/4
+    const double ar = ((r.a - r.b) + r.c) - r.d, ap = ((c.a - c.b) + c.c) - c.d;  // k = 1: +-2, +-1/8
+    const double p2 = (r.b - r.d) * (c.b - c.d);                                   // k = 2: +-1/2 on (C, T); +-1
+    const double p3 = (r.a - r.c) * (c.a - c.c);                                   // k = 3: +-1/2 on (A, G); +-1
+    c0 = 0.25 * (sr * sp);
+    c1 = fma(0.5, p3, fma(0.5, p2, 0.25 * (ar * ap)));
+  } else {
+    c0 = 0.;
+    c1 = 0.;
 #pragma unroll
-  for (int j = 0; j < 3; ++j) {  // a two-group model has at most 2 eigenvalues in its smaller group... or 1 + 3
-    if (j < c_model.small_count) {
-      const int k = c_model.small_idx[j];
+    for (int k = 0; k < 4; ++k) {
       const double rv = r.a * c_model.V[k] + r.b * c_model.V[4 + k] + r.c * c_model.V[8 + k] +
                         r.d * c_model.V[12 + k];
       const double vp = c_model.Vinv[4 * k] * c.a + c_model.Vinv[4 * k + 1] * c.b +
                         c_model.Vinv[4 * k + 2] * c.c + c_model.Vinv[4 * k + 3] * c.d;
-      cs += rv * vp;
+      const double term = rv * vp;
+      if (c_model.group[k] == 0) c0 += term; else c1 += term;
     }
   }
-  const double total = r.a * c.a + r.b * c.b + r.c * c.c + r.d * c.d;
-  const double co = total - cs;
-  const double c0 = c_model.small_group == 0 ? cs : co;
-  const double c1 = c_model.small_group == 0 ? co : cs;
   rho = c0 != 0. ? c1 / c0 : 0.;
   c0_out = c0;
 }

@@ -75,10 +75,8 @@ struct ModelConst {
   int32_t group[4];
   int32_t n_groups;
   double group_lambda[kMaxEigenGroups];
-  // two-group models: the group with fewer eigenvalues (its coefficient is summed explicitly, the other
-  // one is r.p minus it, because V V^-1 = I), its size and its eigenvalue indices
-  int32_t small_group, small_count;
-  int32_t small_idx[4];
+  int32_t is_jc69;  // the eigensystem is bit for bit JC69Model's literals: ratio_coefficients takes its exact short form
+  int32_t pad;
 };
 
 // ---- macro-ops ---------------------------------------------------------------------
