@@ -61,6 +61,7 @@ class Stats(C.Structure):
         ("peer_collective_calls", C.c_int64),
         ("programs_evicted", C.c_int64),
         ("programs_cached", C.c_int64),
+        ("objective_passes", C.c_int64),
     ]
 
 

@@ -235,6 +235,8 @@ Engine::Engine(const bito_gp_config& cfg) : cfg_(cfg) {
   // BITO_GP_OPT_SCHEME: 0 = rounds, 2 = one cluster per edge reading the PLVs, 3 = pipelined clusters
   // (a streaming producer writes rho, clusters run the searches); unset = the engine's own choice
   if (const char* env = getenv("BITO_GP_OPT_SCHEME")) opt_scheme_env_ = atoi(env);
+  if (const char* env = getenv("BITO_GP_OPT_MODEL")) opt_model_env_ = atoi(env);
+  if (const char* env = getenv("BITO_GP_OPT_FIRST_CHECK")) opt_model_first_check_ = std::max(1, atoi(env));
   if (const char* env = getenv("BITO_GP_OPT_RING_EDGES")) opt_ring_edges_env_ = atoi(env);
   if (const char* env = getenv("BITO_GP_PREP_BLOCKS_PER_SM")) prep_blocks_per_sm_ = atoi(env);
   if (const char* env = getenv("BITO_GP_OPT_PRIORITY")) opt_priority_env_ = atoi(env);
@@ -268,8 +270,8 @@ Engine::Engine(const bito_gp_config& cfg) : cfg_(cfg) {
   LaunchFill(stream_, d_log_marg_.ptr, P_stride_, -std::numeric_limits<double>::infinity());
   d_status_.Resize(1, false, stream_);
   GP_CUDA(cudaMemsetAsync(d_status_.ptr, 0, sizeof(uint32_t), stream_));
-  d_feval_total_.Resize(1, false, stream_);
-  GP_CUDA(cudaMemsetAsync(d_feval_total_.ptr, 0, sizeof(unsigned long long), stream_));
+  d_feval_total_.Resize(2, false, stream_);  // [0] objective evaluations, [1] streamed passes over rho
+  GP_CUDA(cudaMemsetAsync(d_feval_total_.ptr, 0, 2 * sizeof(unsigned long long), stream_));
   d_active_.Resize(1, false, stream_);
   AllocEdgeArrays(padded_gpcsp_count());
   GP_CUDA(cudaStreamSynchronize(stream_));
@@ -290,7 +292,7 @@ Engine::~Engine() {
   d_q_.Release(); d_bl_.Release(); d_diff_.Release(); d_hybrid_.Release(); d_ll_sum_.Release();
   d_inverted_.Release(); d_uncond_.Release(); d_status_.Release(); d_feval_total_.Release();
   d_partials_.Release(); d_packed_.Release(); d_level_max_.Release(); d_coef_.Release(); d_opt_ctl_.Release();
-  d_dense_tmp_.Release(); d_mtab_.Release(); d_mtab_lik_.Release(); d_opt_states_.Release(); d_opt_const_.Release(); d_opt_active_.Release(); d_perm_.Release(); d_wperm_.Release(); d_row_class_.Release(); d_active_.Release(); d_single_opt_.Release(); d_cluster_inv_perm_.Release(); d_cluster_wperm_.Release(); d_quartet_items_.Release(); d_quartet_mats_.Release();
+  d_dense_tmp_.Release(); d_mtab_.Release(); d_mtab_lik_.Release(); d_opt_states_.Release(); d_opt_pass_.Release(); d_opt_req_.Release(); d_opt_const_.Release(); d_opt_active_.Release(); d_perm_.Release(); d_pos_w_.Release(); d_wperm_.Release(); d_row_class_.Release(); d_active_.Release(); d_single_opt_.Release(); d_cluster_inv_perm_.Release(); d_cluster_wperm_.Release(); d_quartet_items_.Release(); d_quartet_mats_.Release();
   d_cluster_pos_.Release(); d_rho_ring_.Release(); d_ring_const_.Release(); d_ring_partials_.Release();
   if (prep_stream_) cudaStreamDestroy(prep_stream_);
   if (cons_stream_) cudaStreamDestroy(cons_stream_);
@@ -501,6 +503,11 @@ void Engine::BuildWeightClasses(const double* host_weights) {
                             stream_));
     GP_CUDA(cudaStreamSynchronize(stream_));
   }
+  // smallest positive weight: bounds max |z| from the top power sum of the Taylor-model optimiser
+  local_min_weight_ = std::numeric_limits<double>::infinity();
+  for (double x : w)
+    if (x > 0. && x < local_min_weight_) local_min_weight_ = x;
+  if (n_ranks_ <= 1) min_weight_ = std::isfinite(local_min_weight_) ? local_min_weight_ : 1.;
   if (w == host_weights_cache_ && P_perm_ > 0 && P_ > 0) return;  // same weights: layout is current
   host_weights_cache_ = w;
   DropGraphs();  // captured optimiser launches bake the class boundaries (OptClusterLayout) in by value
@@ -520,6 +527,8 @@ void Engine::BuildWeightClasses(const double* host_weights) {
     pos += RoundUp(n_in[c], group);
   }
   P_perm_ = std::max<int64_t>(pos, group);
+  for (int c = 0; c < 8; ++c) opt_class_starts_.start[c] = static_cast<int32_t>(start[c] / group);
+  opt_class_starts_.start[8] = static_cast<int32_t>(P_perm_ / group);
   std::vector<int32_t> perm(static_cast<size_t>(P_));
   std::vector<double> wperm(static_cast<size_t>(P_perm_), 0.);
   std::vector<uint8_t> row_class(static_cast<size_t>(P_perm_ / group), 0);
@@ -534,7 +543,18 @@ void Engine::BuildWeightClasses(const double* host_weights) {
     perm[static_cast<size_t>(p)] = static_cast<int32_t>(next[c]);
     wperm[static_cast<size_t>(next[c]++)] = w[static_cast<size_t>(p)];
   }
+  // one word per pattern for k_opt_prepare_ratio: rho position and weight (1..7, else 0 = read weights[])
+  std::vector<int32_t> pos_w(static_cast<size_t>(P_));
+  const bool packable = P_perm_ < (int64_t(1) << 28);
+  for (int64_t p = 0; p < P_ && packable; ++p) {
+    const int c = cls(w[static_cast<size_t>(p)]);
+    pos_w[static_cast<size_t>(p)] = (perm[static_cast<size_t>(p)] << 3) | (c < 7 ? c + 1 : 0);
+  }
   GP_CUDA(cudaStreamSynchronize(stream_));
+  d_pos_w_.Resize(packable ? pos_w.size() : 0, false, stream_);
+  if (packable && P_ > 0)
+    GP_CUDA(cudaMemcpyAsync(d_pos_w_.ptr, pos_w.data(), pos_w.size() * sizeof(int32_t), cudaMemcpyHostToDevice,
+                            stream_));
   d_perm_.Resize(perm.size(), false, stream_);
   d_wperm_.Resize(wperm.size(), false, stream_);
   d_row_class_.Resize(row_class.size(), false, stream_);
@@ -745,13 +765,15 @@ void Engine::AgreeOnClusterScheme() {
   for (const OptClusterPlan& c : cluster_plans_) local = std::max(local, c.active_clusters);
   if (!peer_ready_ || n_eigen_groups_ != 2) local = 0;
   EnsureScratch(TilesFor(P_), 2);
-  const double neg = -static_cast<double>(local);
-  GP_CUDA(cudaMemcpyAsync(d_packed_.ptr, &neg, sizeof(double), cudaMemcpyHostToDevice, stream_));
-  AllReduce(d_packed_.ptr, 1, true);  // max of the negatives = minus the minimum
-  double out = 0.;
-  GP_CUDA(cudaMemcpyAsync(&out, d_packed_.ptr, sizeof(double), cudaMemcpyDeviceToHost, stream_));
+  // the smallest positive pattern weight of ANY rank rides along (Taylor-model optimiser)
+  const double neg[2] = {-static_cast<double>(local), -std::min(local_min_weight_, 1e300)};
+  GP_CUDA(cudaMemcpyAsync(d_packed_.ptr, neg, sizeof neg, cudaMemcpyHostToDevice, stream_));
+  AllReduce(d_packed_.ptr, 2, true);  // max of the negatives = minus the minimum
+  double out[2] = {0., 0.};
+  GP_CUDA(cudaMemcpyAsync(out, d_packed_.ptr, sizeof out, cudaMemcpyDeviceToHost, stream_));
   GP_CUDA(cudaStreamSynchronize(stream_));
-  multi_rank_cluster_ops_ = std::min<int>(static_cast<int>(-out), kPeerEdgeSlots);
+  multi_rank_cluster_ops_ = std::min<int>(static_cast<int>(-out[0]), kPeerEdgeSlots);
+  min_weight_ = (-out[1] > 0. && -out[1] < 1e300) ? -out[1] : 1.;
   DropGraphs();
 }
 
@@ -1890,10 +1912,19 @@ void Engine::RunOptimizer(const OptOp* d_ops, int n_ops, int method, bool check_
   d_opt_states_.Resize(static_cast<size_t>(chunk), false, stream_);
   d_opt_const_.Resize(static_cast<size_t>(chunk), false, stream_);
   d_opt_active_.Resize(static_cast<size_t>(4 + 2 * chunk), false, stream_);
-  const int64_t groups = ratio ? OptRatioPartials(P_perm_) : tiles;
-  const int n_values = nd + 1, value_stride = ratio ? 1 : 3;
+  // Taylor-model Brent (gp_types.h, OptPass): a pass yields kOptPassValues sums per edge and answers
+  // several of the optimiser's requests; BITO_GP_OPT_MODEL=0 keeps one pass per objective evaluation.
+  const bool model = ratio && opt_model_env_ != 0;
+  int seg_len = 1, n_seg = 1;
+  if (model) OptModelSegments(P_perm_, &seg_len, &n_seg);
+  const int64_t groups = model ? n_seg : (ratio ? OptRatioPartials(P_perm_) : tiles);
+  const int n_values = nd + 1, value_stride = model ? kOptPassValues : (ratio ? 1 : 3);
   EnsureScratch(static_cast<int64_t>(chunk) * std::max<int64_t>(value_stride * groups, tiles),
-                static_cast<int64_t>(chunk) * 3);
+                static_cast<int64_t>(chunk) * std::max(3, value_stride));
+  if (model) {
+    d_opt_pass_.Resize(static_cast<size_t>(chunk), false, stream_);
+    d_opt_req_.Resize(static_cast<size_t>(2 * chunk), false, stream_);
+  }
 
   const int64_t max_rounds = 3 * kMaxIterForOptimization + 8;
   int32_t* h_active = static_cast<int32_t*>(pinned_);
@@ -1904,7 +1935,7 @@ void Engine::RunOptimizer(const OptOp* d_ops, int n_ops, int method, bool check_
       {
         ProfScope ps(this, kProfOptPrepare, 64. * m * static_cast<double>(P_));
         LaunchOptPrepareRatio(stream_, st, d_ops + c0, m, d_opt_states_.ptr, prm, method, d_coef_.ptr,
-                              d_perm_.ptr, P_perm_, d_partials_.ptr, d_opt_active_.ptr, chunk);
+                              d_perm_.ptr, d_pos_w_.n > 0 ? d_pos_w_.ptr : nullptr, P_perm_, d_partials_.ptr, d_opt_active_.ptr, chunk);
       }
       ProfScope ps(this, kProfReduce, 0.);
       LaunchReducePartials(stream_, d_partials_.ptr, m, OptPrepareTileGroups(m, P_), d_opt_const_.ptr,
@@ -1917,8 +1948,46 @@ void Engine::RunOptimizer(const OptOp* d_ops, int n_ops, int method, bool check_
       stats_.kernel_launches++;
     }
     int64_t rounds = 0;
-    int batch = method <= BITO_GP_BRENT_OPTIMIZATION_WITH_GRADIENTS ? 12 : 6;
     int32_t* act = ratio ? d_opt_active_.ptr : nullptr;
+    if (model) {
+      LaunchOptPlan(stream_, st, m, d_opt_states_.ptr, prm, d_opt_pass_.ptr, d_opt_req_.ptr, act);
+      stats_.kernel_launches++;
+      int batch = opt_model_first_check_;  // most searches need 1..8 passes
+      for (;;) {
+        for (int r = 0; r < batch; ++r) {
+          const int parity = static_cast<int>((rounds + r) & 1);
+          {
+            ProfScope ps(this, kProfOptEval, 0.);
+            LaunchOptEvalModel(stream_, m, rounds + r == 0 ? kOptPoints : 1,
+                               d_opt_req_.ptr + static_cast<size_t>(parity) * chunk, d_coef_.ptr, P_perm_,
+                               d_wperm_.ptr, opt_class_starts_, d_partials_.ptr, act, parity);
+          }
+          const double* sums = nullptr;
+          const double* parts = d_partials_.ptr;
+          if (n_ranks_ > 1) {
+            ProfScope ps(this, kProfReduce, 0.);
+            LaunchReducePartials(stream_, d_partials_.ptr, kOptPassValues * m, n_seg, d_packed_.ptr, nullptr,
+                                 nullptr);
+            AllReduce(d_packed_.ptr, static_cast<int64_t>(kOptPassValues) * m, false);
+            sums = d_packed_.ptr;
+            parts = nullptr;
+            stats_.kernel_launches++;
+          }
+          ProfScope ps(this, kProfOptStep, 0.);
+          LaunchOptStepModel(stream_, st, m, d_opt_states_.ptr, d_opt_pass_.ptr, d_opt_req_.ptr, prm, sums, parts,
+                             n_seg, d_opt_const_.ptr, min_weight_, act, chunk, parity);
+          stats_.kernel_launches += 2;
+        }
+        rounds += batch;
+        GP_CUDA(cudaMemcpyAsync(h_active, act + (rounds & 1), sizeof(int32_t), cudaMemcpyDeviceToHost, stream_));
+        GP_CUDA(cudaStreamSynchronize(stream_));
+        if (*h_active == 0) break;
+        if (rounds > max_rounds) Fail("OptimizeBranchLength: optimiser did not terminate");
+        batch = 2;
+      }
+      continue;
+    }
+    int batch = method <= BITO_GP_BRENT_OPTIMIZATION_WITH_GRADIENTS ? 12 : 6;
     for (;;) {
       int32_t* counter = nullptr;
       for (int r = 0; r < batch; ++r) {
@@ -2763,9 +2832,10 @@ void Engine::GetStats(bito_gp_stats* out) {
     if (cudaEventElapsedTime(&ms, ev_begin_, ev_end_) == cudaSuccess) stats_.last_process_ms = ms;
     timing_pending_ = false;
   }
-  unsigned long long fevals = 0;
-  GP_CUDA(cudaMemcpy(&fevals, d_feval_total_.ptr, sizeof fevals, cudaMemcpyDeviceToHost));
-  stats_.objective_evaluations = static_cast<int64_t>(fevals);
+  unsigned long long fevals[2] = {0, 0};
+  GP_CUDA(cudaMemcpy(fevals, d_feval_total_.ptr, sizeof fevals, cudaMemcpyDeviceToHost));
+  stats_.objective_evaluations = static_cast<int64_t>(fevals[0]);
+  stats_.objective_passes = static_cast<int64_t>(fevals[1]);
   stats_.device_bytes_in_use =
       static_cast<int64_t>(plv_pool_.BytesReserved() + row_pool_.BytesReserved());
   int64_t resident = 0;

@@ -273,8 +273,11 @@ class Engine {
   // scratch
   DeviceArray<double> d_partials_, d_packed_, d_level_max_, d_coef_, d_dense_tmp_, d_mtab_, d_mtab_lik_;
   DeviceArray<OptState> d_opt_states_;
+  DeviceArray<OptPass> d_opt_pass_;  // Taylor-model Brent: per-edge pass request, cache and model
+  DeviceArray<OptReq> d_opt_req_;    // the pass lists of the current and the next round
+  OptClassStarts opt_class_starts_ = {};
   DeviceArray<double> d_opt_const_;
-  DeviceArray<int32_t> d_active_, d_opt_active_, d_perm_;
+  DeviceArray<int32_t> d_active_, d_opt_active_, d_perm_, d_pos_w_;
   DeviceArray<double> d_wperm_;
   DeviceArray<uint8_t> d_row_class_;
   int64_t P_perm_ = 0;  // patterns in weight-class order, classes padded to 256-pattern rows
@@ -290,6 +293,9 @@ class Engine {
   int opt_priority_env_ = 1;      // BITO_GP_OPT_PRIORITY=0: consumer on the engine's stream (no priority)
   cudaEvent_t ev_fork_ = nullptr, ev_ready_[2] = {nullptr, nullptr}, ev_free_[2] = {nullptr, nullptr};
   int opt_scheme_env_ = -1;       // BITO_GP_OPT_SCHEME (-1: automatic)
+  int opt_model_env_ = 1;         // BITO_GP_OPT_MODEL=0: one streamed pass per objective evaluation (round-1 scheme)
+  int opt_model_first_check_ = 4; // rounds before the host first looks at the active-edge counter
+  double local_min_weight_ = 1., min_weight_ = 1.;  // smallest positive pattern weight: this rank / all ranks
   int opt_ring_edges_env_ = 0;    // BITO_GP_OPT_RING_EDGES (0: automatic)
   DeviceArray<double> d_cluster_wperm_;
   int32_t cluster_class_row_start_[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};

@@ -679,6 +679,7 @@ __device__ void opt_init(OptState& s, const DeviceState& st, const OptParams& pr
   s.method = method;
   s.edge = op.edge;
   s.done = 0;
+  s.speculative = 0;
   s.evals = 0;
   s.iter = 0;
   s.ll_offset = (static_cast<double>(st.counts[op.parent.id]) * st.log_thr +
@@ -719,11 +720,12 @@ __device__ void opt_init(OptState& s, const DeviceState& st, const OptParams& pr
 
 __device__ void opt_finish_brent(OptState& s, const DeviceState& st) {
   // dag_branch_handler.cpp:168-176: keep the old value if the search made things worse.
+  s.done = 1;
+  if (s.speculative) return;
   const double old_bl = exp(s.cur_x);
   const double new_bl = (s.fx > s.cur_f) ? old_bl : exp(s.x);
   st.bl[s.edge] = new_bl;
   st.diff[s.edge] = fabs(old_bl - new_bl);
-  s.done = 1;
 }
 
 // Top of the do-while body of BrentMinimize up to the objective call (optimization.hpp:95-148).
@@ -1010,8 +1012,7 @@ __device__ __forceinline__ double pow_small(double t, int wi) {  // t^wi, 1 <= w
 // (A cheaper form for any two-group model - only the smaller group summed, the other taken as r.p minus it -
 // was measured and dropped: it moves rho by an ulp, which is enough to move a Brent termination decision of
 // the `hello` fixture off the reference's side; profiles/r02_sweep_ab.md.)
-__device__ __forceinline__ void ratio_coefficients(const V4& r, const V4& c, double& rho, double& c0_out) {
-  double c0, c1;
+__device__ __forceinline__ void eigen_group_coefficients(const V4& r, const V4& c, double& c0, double& c1) {
   if (c_model.is_jc69) {
     const double sr = ((r.a + r.b) + r.c) + r.d, sp = ((c.a + c.b) + c.c) + c.d;  // k = 0: V[:,0] = 1, Vinv[0,:] = 1/4
     const double ar = ((r.a - r.b) + r.c) - r.d, ap = ((c.a - c.b) + c.c) - c.d;  // k = 1: +-2, +-1/8
@@ -1032,6 +1033,10 @@ __device__ __forceinline__ void ratio_coefficients(const V4& r, const V4& c, dou
       if (c_model.group[k] == 0) c0 += term; else c1 += term;
     }
   }
+}
+__device__ __forceinline__ void ratio_coefficients(const V4& r, const V4& c, double& rho, double& c0_out) {
+  double c0, c1;
+  eigen_group_coefficients(r, c, c0, c1);
   rho = c0 != 0. ? c1 / c0 : 0.;
   c0_out = c0;
 }
@@ -1058,6 +1063,81 @@ struct LogSum {
   }
 };
 
+// The streaming loop of k_opt_prepare_ratio for the shapes every optimisation level of a GP op list has:
+// a dense parent r-PLV and a child p-PLV that is dense or a leaf (1-byte symbols). One pattern tile per
+// trip; the next tile's loads - PLVs (or the raw symbol byte) and the packed (rho position, weight code)
+// word - are issued before the current tile's arithmetic and not touched until the next trip.
+//  * rho = c1 / c0 is formed on operands scaled by 2^-exponent(c0) (exact): c0 can sit at thr^2 = 1e-80,
+//    where the IEEE division leaves its fast path; the quotient is the same bits.
+//  * K_e += w log c0 for w = 1..7 as mantissa^w (branch-free) and w * exponent: no log per pattern.
+// Not inlined, so that the two instantiations stay two tight loops.
+template <bool kSym>
+__device__ __noinline__ void prepare_span(const double* __restrict__ parent, const void* __restrict__ child,
+                                          int64_t P, int tile_begin, int tile_end,
+                                          const int32_t* __restrict__ pos_w, const double* __restrict__ weights,
+                                          double* __restrict__ rho_o, double* k_out) {
+  double prod = 1., slow = 0.;
+  int esum = 0;
+  int64_t p = static_cast<int64_t>(tile_begin) * kTile + threadIdx.x;
+  bool live = tile_begin < tile_end && p < P;
+  V4 r = {1., 1., 1., 1.}, c = r;
+  int sym = 4, code = 0;
+  if (live) {
+    r = ld256(parent + 4 * p);
+    if (kSym) sym = static_cast<const uint8_t*>(child)[p]; else c = ld256(static_cast<const double*>(child) + 4 * p);
+    code = pos_w[p];
+  }
+#pragma unroll 2
+  for (int tile = tile_begin; tile < tile_end; ++tile) {
+    const int64_t pn = p + kTile;
+    const bool live_n = tile + 1 < tile_end && pn < P;
+    V4 rn = r, cn = c;
+    int sym_n = sym, code_n = code;
+    if (live_n) {  // in flight during the arithmetic below
+      rn = ld256(parent + 4 * pn);
+      if (kSym) sym_n = static_cast<const uint8_t*>(child)[pn]; else cn = ld256(static_cast<const double*>(child) + 4 * pn);
+      code_n = pos_w[pn];
+    }
+    if (live) {
+      if (kSym) {  // InitializePLVsWithSitePatterns, gp_engine.cpp:544-562
+        const bool gap = (sym == 4);
+        c.a = (gap || sym == 0) ? 1. : 0.;
+        c.b = (gap || sym == 1) ? 1. : 0.;
+        c.c = (gap || sym == 2) ? 1. : 0.;
+        c.d = (gap || sym == 3) ? 1. : 0.;
+      }
+      double c0, c1, m, rho;
+      int e;
+      eigen_group_coefficients(r, c, c0, c1);
+      const int wi = code & 7;
+      if (split_positive(c0, m, e)) {
+        const double scale = __hiloint2double((1023 - e) << 20, 0);  // 2^-e: e in [-1021, 1024]
+        rho = (c1 * scale) / m;
+        if (wi != 0) {
+          const double m2 = m * m, m4 = m2 * m2;
+          prod *= ((wi & 1) ? m : 1.) * ((wi & 2) ? m2 : 1.) * ((wi & 4) ? m4 : 1.);  // >= 2^-7 per pattern
+          esum += e * wi;
+        } else {
+          slow += weights[p] * (log(m) + static_cast<double>(e) * 0.6931471805599453094);
+        }
+      } else {  // c0 <= 0, subnormal or not finite
+        rho = c0 != 0. ? c1 / c0 : 0.;
+        const double w = wi != 0 ? static_cast<double>(wi) : weights[p];
+        if (w != 0.) slow += w * log(c0);
+      }
+      rho_o[code >> 3] = rho;
+    }
+    r = rn;
+    c = cn;
+    sym = sym_n;
+    code = code_n;
+    p = pn;
+    live = live_n;
+  }
+  // at most 32 tiles per block: prod >= 2^-224
+  *k_out = log(prod) + static_cast<double>(esum) * 0.6931471805599453094 + slow;
+}
+
 // ---- Brent objective for two-eigenvalue models (JC69): ratio form -----------------------------
 // L_p(t) = c0_p e^{l0 t} + c1_p e^{l1 t} = c0_p e^{l0 t} (1 + rho_p x),  rho_p = c1_p / c0_p,
 // x = e^{(l1 - l0) t}. Hence  sum_p w_p log L_p = K + W l0 t + sum_p w_p log(1 + rho_p x)  with
@@ -1068,6 +1148,7 @@ __global__ void __launch_bounds__(kTile, 4)
     k_opt_prepare_ratio(DeviceState st, const OptOp* __restrict__ ops, int n_ops, int tiles,
                         int tiles_per_block, OptState* __restrict__ states, OptParams prm, int method,
                         double* __restrict__ rho, const int32_t* __restrict__ perm,
+                        const int32_t* __restrict__ pos_w,
                         int64_t rho_stride, double* __restrict__ partials,
                         int32_t* __restrict__ active, int active_capacity) {
   // tile-major: the edges of one pattern tile group are neighbours in the grid, so a parent r-PLV
@@ -1089,44 +1170,33 @@ __global__ void __launch_bounds__(kTile, 4)
     }
   }
   (void)active_capacity;
-  LogSum k_sum;  // K_e = sum_p w_p log c0_p: one log per thread, not one per pattern
   const int tile_begin = tile_group * tiles_per_block;
   const int tile_end = min(tiles, tile_begin + tiles_per_block);
   double* const rho_o = rho + static_cast<int64_t>(o) * rho_stride;
-  // two pattern tiles per trip: four 256-bit loads in flight before the first divide
-  int tile = tile_begin;
-  for (; tile + 2 <= tile_end; tile += 2) {
-    const int64_t p0 = static_cast<int64_t>(tile) * kTile + threadIdx.x, p1 = p0 + kTile;
-    const bool live0 = p0 < st.P, live1 = p1 < st.P;
-    V4 r0 = {1., 1., 1., 1.}, c0v = r0, r1 = r0, c1v = r0;
-    int32_t q0 = 0, q1 = 0;
-    double w0 = 0., w1 = 0.;
-    if (live0) { r0 = load_plv(op.parent, p0); c0v = load_plv(op.child, p0); q0 = perm[p0]; w0 = st.weights[p0]; }
-    if (live1) { r1 = load_plv(op.parent, p1); c1v = load_plv(op.child, p1); q1 = perm[p1]; w1 = st.weights[p1]; }
-    double rr, cc;
-    if (live0) {
-      ratio_coefficients(r0, c0v, rr, cc);
-      rho_o[q0] = rr;
-      k_sum.add(cc, w0);
+  double k_mine = 0.;  // this thread's share of K_e = sum_p w_p log c0_p
+  if (pos_w != nullptr && op.parent.kind == kPlvDense && op.child.kind == kPlvDense) {
+    prepare_span<false>(static_cast<const double*>(op.parent.ptr), op.child.ptr, st.P, tile_begin, tile_end, pos_w,
+                        st.weights, rho_o, &k_mine);
+  } else if (pos_w != nullptr && op.parent.kind == kPlvDense && op.child.kind == kPlvSymbols) {
+    prepare_span<true>(static_cast<const double*>(op.parent.ptr), op.child.ptr, st.P, tile_begin, tile_end, pos_w,
+                       st.weights, rho_o, &k_mine);
+  } else {  // any other pair of PLV kinds (hand-written op lists): the general loads
+    LogSum k_sum;
+#pragma unroll 1
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+      const int64_t p = static_cast<int64_t>(tile) * kTile + threadIdx.x;
+      if (p < st.P) {
+        const V4 r = load_plv(op.parent, p);
+        const V4 c = load_plv(op.child, p);
+        double rr, cc;
+        ratio_coefficients(r, c, rr, cc);
+        rho_o[perm[p]] = rr;
+        k_sum.add(cc, st.weights[p]);
+      }
     }
-    if (live1) {
-      ratio_coefficients(r1, c1v, rr, cc);
-      rho_o[q1] = rr;
-      k_sum.add(cc, w1);
-    }
+    k_mine = k_sum.value();
   }
-  for (; tile < tile_end; ++tile) {
-    const int64_t p = static_cast<int64_t>(tile) * kTile + threadIdx.x;
-    if (p < st.P) {
-      const V4 r = load_plv(op.parent, p);
-      const V4 c = load_plv(op.child, p);
-      double rr, cc;
-      ratio_coefficients(r, c, rr, cc);
-      rho_o[perm[p]] = rr;
-      k_sum.add(cc, st.weights[p]);
-    }
-  }
-  const double k_part = block_reduce(k_sum.value(), SumOp(), 0.);
+  const double k_part = block_reduce(k_mine, SumOp(), 0.);
   if (threadIdx.x == 0) partials[static_cast<int64_t>(o) * n_groups + tile_group] = k_part;
 }
 
@@ -1319,6 +1389,433 @@ __global__ void k_opt_step(DeviceState st, int n_ops, OptState* __restrict__ sta
       active[4 + (parity ^ 1) * active_capacity + atomicAdd(active + (parity ^ 1), 1)] = o;
     if (active_counter != nullptr) atomicAdd(active_counter, 1);
   }
+}
+
+
+// ---- Taylor-model Brent: the streamed scheme for plain Brent on a two-eigenvalue model ------------
+// (gp_types.h, OptPass.) Replaces "one pass over rho per objective evaluation" by "one pass per model":
+// the reference's BrentMinimize (optimization.hpp:71-188) asks for ~16 objective values per edge, the
+// first three at points that do not depend on the data (its start, a golden-section step, one of two
+// golden-section steps) and the last ones within a fraction of a percent of each other.
+
+// After k_opt_prepare_ratio: the first pass of every edge evaluates its pending request (the start)
+// together with the next requests Brent can make, found by advancing COPIES of the optimiser with
+// made-up objective values (only the order of the values matters for those steps: the parabolic fit
+// through coincident points degenerates to p = q = 0 whatever they are). Nothing depends on the
+// guesses being right: k_opt_step_model uses a cached value only if the real request equals its point.
+__global__ void k_opt_plan(DeviceState st, int n_ops, const OptState* __restrict__ states, OptParams prm,
+                           OptPass* __restrict__ pass, OptReq* __restrict__ req, int32_t* __restrict__ active) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n_ops) return;
+  if (o == 0) {
+    active[0] = n_ops;  // round 0 lists every edge (finished ones as o < 0)
+    active[1] = 0;
+  }
+  const OptState s = states[o];
+  OptPass pp;
+  for (int k = 0; k < kOptPoints; ++k) {
+    pp.px[k] = s.x_ratio;
+    pp.ps[k] = s.x_eval;
+    pp.pt[k] = s.t_eval;
+    pp.cache_s[k] = 0.;
+    pp.cache_ll[k] = 0.;
+  }
+  pp.n_pts = 1;
+  pp.centre = 0;
+  pp.n_cache = 0;
+  pp.passes = 0;
+  pp.c = 0.;
+  pp.S_c = 0.;
+  pp.radius = 0.;
+  for (int j = 0; j < kOptMoments; ++j) pp.mj[j] = 0.;
+  if (!s.done && s.method == 0 && s.phase == kPhBrentInit) {
+    auto set = [&](int k, const OptState& a) {
+      pp.px[k] = a.x_ratio;
+      pp.ps[k] = a.x_eval;
+      pp.pt[k] = a.t_eval;
+    };
+    OptState a = s;
+    a.speculative = 1;
+    opt_advance(a, st, prm, 0., 0., 0.);  // f(start) = 0
+    if (!a.done) {
+      set(1, a);
+      OptState b = a;
+      opt_advance(b, st, prm, 1., 0., 0.);  // f(u) = -1 <= f(x): accepted
+      if (!b.done) set(2, b);
+      OptState r = a;
+      opt_advance(r, st, prm, -1., 0., 0.);  // f(u) = 1 > f(x): rejected
+      if (!r.done) set(3, r);
+      pp.n_pts = kOptPoints;
+      // Where later requests will cluster is not known yet. A first optimisation starts from default
+      // lengths and mostly walks towards the accepted golden-section side; a later one
+      // (!IsFirstOptimization, dag_branch_handler.hpp:49-52) starts next to its optimum.
+      pp.centre = (prm.check_convergence || b.done) ? 0 : 2;
+    }
+  }
+  pass[o] = pp;
+  OptReq rq;
+  for (int k = 0; k < kOptPoints; ++k) rq.x[k] = pp.px[k];
+  rq.c = pp.px[pp.centre];
+  rq.o = s.done ? -1 - o : o;
+  rq.pad = 0;
+  req[o] = rq;
+}
+
+// 1 / a for a normal a > 0: hardware seed (~2^-20) and two Newton steps; within an ulp or two, which is
+// all the power sums need. a = 0 gives NaN (the model of that pass is dropped).
+__device__ __forceinline__ double rcp_newton(double a) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+  double e = fma(-a, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-a, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+
+// A[j-1] += w (a^j + b^j + c^j + d^j), j = 1..12, through the elementary symmetric polynomials of the
+// four values and Newton's identities p_j = e1 p_{j-1} - e2 p_{j-2} + e3 p_{j-3} - e4 p_{j-4}: 63 FP64
+// instructions per four values instead of 92 for explicit powers. p_1 and p_2 (the terms that carry the
+// model) are formed directly; the recurrence loses ~j^3 ulp against sum |z|^j by j = 12 (1e-12 relative),
+// on terms that are below 1e-10 of the objective inside the model's radius.
+__device__ __forceinline__ void add_moments4(double (&A)[kOptMoments], double a, double b, double c, double d,
+                                             double w) {
+  static_assert(kOptMoments == 12, "unrolled for 12 moments");
+  const double s_ab = a + b, s_cd = c + d, p_ab = a * b, p_cd = c * d;
+  const double e1 = s_ab + s_cd;
+  const double e2 = fma(s_ab, s_cd, p_ab + p_cd);
+  const double e3 = fma(p_ab, s_cd, p_cd * s_ab);
+  const double e4 = p_ab * p_cd;
+  const double p1 = e1;
+  const double p2 = fma(a, a, fma(b, b, fma(c, c, d * d)));
+  const double p3 = fma(e1, p2, fma(-e2, p1, 3. * e3));
+  const double p4 = fma(e1, p3, fma(-e2, p2, fma(e3, p1, -4. * e4)));
+  A[0] = fma(p1, w, A[0]);
+  A[1] = fma(p2, w, A[1]);
+  A[2] = fma(p3, w, A[2]);
+  A[3] = fma(p4, w, A[3]);
+  double q4 = p1, q3 = p2, q2 = p3, q1 = p4;  // p_{j-4} .. p_{j-1}
+#pragma unroll
+  for (int j = 4; j < kOptMoments; ++j) {
+    const double pj = fma(e1, q1, fma(-e2, q2, fma(e3, q3, -(e4 * q4))));
+    A[j] = fma(pj, w, A[j]);
+    q4 = q3;
+    q3 = q2;
+    q2 = q1;
+    q1 = pj;
+  }
+}
+
+// z_i = r_i / t_i for eight t_i in one reciprocal (products pairwise up, one Newton reciprocal, back down):
+// 21 multiplications + 5 instead of 8 x 6. Every t is 0 or in [2^-53, 4], so the product cannot leave the
+// normal range; a zero factor turns all eight into NaN (the model of that pass is dropped). prod8 = the
+// product of the eight t (the weight-1 log term of the centre).
+__device__ __forceinline__ void ratios8(const double (&r)[8], const double (&t)[8], double (&z)[8], double& prod8) {
+  const double t01 = t[0] * t[1], t23 = t[2] * t[3], t45 = t[4] * t[5], t67 = t[6] * t[7];
+  const double t03 = t01 * t23, t47 = t45 * t67;
+  prod8 = t03 * t47;
+  const double inv = rcp_newton(prod8);
+  const double i03 = inv * t47, i47 = inv * t03;
+  const double i01 = i03 * t23, i23 = i03 * t01, i45 = i47 * t67, i67 = i47 * t45;
+  z[0] = r[0] * (i01 * t[1]);
+  z[1] = r[1] * (i01 * t[0]);
+  z[2] = r[2] * (i23 * t[3]);
+  z[3] = r[3] * (i23 * t[2]);
+  z[4] = r[4] * (i45 * t[5]);
+  z[5] = r[5] * (i45 * t[4]);
+  z[6] = r[6] * (i67 * t[7]);
+  z[7] = r[7] * (i67 * t[6]);
+}
+
+// Sum over the warp of 16 values per lane in 16 + 15 shuffles instead of 16 x 5: each step keeps the
+// half of the values selected by one lane-id bit and hands the other half to the partner lane. Fixed
+// order, so the result is deterministic. Afterwards lanes 2k and 2k+1 hold the warp total of value k in v[0].
+__device__ __forceinline__ void warp_reduce16(double (&v)[16]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int half = 8, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+    const bool up = (lane & bit) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const double send = up ? v[i] : v[i + half];
+      const double keep = up ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+    }
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+// Running sum of w log(product of factors) for the single-weight classes: the factors of a tile group
+// multiply up raw (eight of them stay above 2^-424), the binary exponent of that product is split off and
+// the mantissas keep multiplying (at most a few hundred per segment, each >= 2^-7), so a thread pays ONE
+// log per point and segment.
+struct ProductLog {
+  double mant = 1., slow = 0.;
+  int esum = 0;
+  // *= prod8^wi, wi = 1..7 (the tile group's weight): mantissa^wi stays above 2^-7
+  __device__ __forceinline__ void mul(double prod8, int wi) {
+    double m;
+    int e;
+    if (split_positive(prod8, m, e)) {
+      mant *= wi == 1 ? m : pow_small(m, wi);
+      esum += e * wi;
+    } else {
+      slow += static_cast<double>(wi) * log(prod8);  // a zero factor: -inf, as the reference's log(0)
+    }
+  }
+  __device__ __forceinline__ double value() const {
+    return log(mant) + static_cast<double>(esum) * 0.6931471805599453094 + slow;
+  }
+};
+
+// One item = one segment (seg_len tile groups of kTile * kOptPatternsPerThread positions) of one still
+// active edge. NP = points evaluated (kOptPoints on the first pass of a search, 1 afterwards, where the
+// point is also the centre). A thread owns 8 positions of every tile group, prefetches the next tile
+// group (and the next item's request) while it works on the current one and keeps the NP log sums and the
+// 12 power sums in registers for the whole segment; one block-wide reduction per segment.
+// partials: [edge][value][segment]. The kernel is bound by FP64 issue, not by HBM (8 B per position).
+template <int NP, int MINB>
+__global__ void __launch_bounds__(kTile, MINB)
+    k_opt_eval_model(int tile_groups, int seg_len, int n_seg, const OptReq* __restrict__ req,
+                     const double* __restrict__ rho, int64_t rho_stride,
+                     const double* __restrict__ wperm, OptClassStarts classes,
+                     double* __restrict__ partials, int32_t* __restrict__ active, int parity) {
+  __shared__ double s_red[kTile / 32][kOptPassValues];
+  __shared__ double s_rq[2][sizeof(OptReq) / sizeof(double)];
+  constexpr int kReqWords = static_cast<int>(sizeof(OptReq) / sizeof(double));
+  const int n_active = active[parity];
+  if (blockIdx.x == 0 && threadIdx.x == 0) active[parity ^ 1] = 0;  // filled by this round's step
+  const int n_items = n_active * n_seg;
+  constexpr int64_t kItem = static_cast<int64_t>(kTile) * kOptPatternsPerThread;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int item = blockIdx.x;
+  if (item >= n_items) return;
+  // The request of an item is block-uniform. Its words are fetched by the first threads one item ahead
+  // (a per-thread load, so nothing waits for it) and handed over through shared memory at the barrier
+  // that ends the item.
+  if (threadIdx.x < kReqWords)
+    s_rq[0][threadIdx.x] = reinterpret_cast<const double*>(req + item / n_seg)[threadIdx.x];
+  __syncthreads();
+  int buf = 0;
+  for (; item < n_items; item += gridDim.x, buf ^= 1) {
+    const int sg = item - (item / n_seg) * n_seg;
+    const int next_item = item + static_cast<int>(gridDim.x);
+    double next_word = 0.;
+    if (threadIdx.x < kReqWords && next_item < n_items)
+      next_word = reinterpret_cast<const double*>(req + next_item / n_seg)[threadIdx.x];  // in flight below
+    OptReq cur_rq;
+#pragma unroll
+    for (int k = 0; k < kOptPoints; ++k) cur_rq.x[k] = s_rq[buf][k];
+    cur_rq.c = s_rq[buf][kOptPoints];
+    cur_rq.o = __double2loint(s_rq[buf][kOptPoints + 1]);
+    const int o = cur_rq.o;
+    const double c = NP == 1 ? cur_rq.x[0] : cur_rq.c;
+    const int tg_begin = sg * seg_len;
+    const int tg_end = o < 0 ? tg_begin : min(tile_groups, tg_begin + seg_len);  // o < 0: nothing to do
+    const double* base = rho + static_cast<int64_t>(o < 0 ? 0 : o) * rho_stride;
+    auto class_of = [&](int tg) {  // weight - 1, or 7 = general weights
+      int cls = 0;
+#pragma unroll
+      for (int k = 1; k < 8; ++k) cls += tg >= classes.start[k];
+      return cls;
+    };
+    ProductLog S[NP];
+    double A[kOptMoments];
+#pragma unroll
+    for (int j = 0; j < kOptMoments; ++j) A[j] = 0.;
+    Rho8 cur = {{0., 0., 0., 0.}, {0., 0., 0., 0.}};
+    if (tg_begin < tg_end) cur = load_rho8(base + static_cast<int64_t>(tg_begin) * kItem);
+#pragma unroll 1
+    for (int tg = tg_begin; tg < tg_end; ++tg) {
+      Rho8 nxt = cur;
+      if (tg + 1 < tg_end) nxt = load_rho8(base + static_cast<int64_t>(tg + 1) * kItem);  // in flight below
+      const int cls = class_of(tg);  // block-uniform
+      const double r[8] = {cur.lo.a, cur.lo.b, cur.lo.c, cur.lo.d, cur.hi.a, cur.hi.b, cur.hi.c, cur.hi.d};
+      double tc[8], z[8], prod_c;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) tc[i] = fma(r[i], c, 1.0);
+      ratios8(r, tc, z, prod_c);
+      if (cls < 7) {  // one weight (1..7) for the whole tile group
+        const int wi = cls + 1;
+        const double wd = static_cast<double>(wi);
+        add_moments4(A, z[0], z[1], z[2], z[3], wd);
+        add_moments4(A, z[4], z[5], z[6], z[7], wd);
+#pragma unroll
+        for (int k = 0; k < NP; ++k) {
+          double prod = prod_c;
+          if (NP > 1) {
+            const double xk = cur_rq.x[k];
+            const double t0 = fma(r[0], xk, 1.0), t1 = fma(r[1], xk, 1.0), t2 = fma(r[2], xk, 1.0),
+                         t3 = fma(r[3], xk, 1.0), t4 = fma(r[4], xk, 1.0), t5 = fma(r[5], xk, 1.0),
+                         t6 = fma(r[6], xk, 1.0), t7 = fma(r[7], xk, 1.0);
+            prod = ((t0 * t1) * (t2 * t3)) * ((t4 * t5) * (t6 * t7));
+          }
+          S[k].mul(prod, wi);
+        }
+      } else {  // general weights (padding: weight 0, rho 0): one position at a time, kept small
+        const double* wp = wperm + static_cast<int64_t>(tg) * kItem;
+        const V4 wl = ld256(wp + 4 * threadIdx.x), wh = ld256(wp + 4 * kTile + 4 * threadIdx.x);
+#pragma unroll 1
+        for (int i = 0; i < 8; ++i) {
+          const double wv = i == 0 ? wl.a : i == 1 ? wl.b : i == 2 ? wl.c : i == 3 ? wl.d
+                          : i == 4 ? wh.a : i == 5 ? wh.b : i == 6 ? wh.c : wh.d;
+          if (wv == 0.) continue;
+          double zi = z[0], ri = r[0];
+#pragma unroll
+          for (int q = 1; q < 8; ++q) {
+            zi = i == q ? z[q] : zi;
+            ri = i == q ? r[q] : ri;
+          }
+          double zp = zi;
+#pragma unroll
+          for (int j = 0; j < kOptMoments; ++j) {
+            A[j] = fma(zp, wv, A[j]);
+            zp *= zi;
+          }
+#pragma unroll
+          for (int k = 0; k < NP; ++k) S[k].slow += wv * log(fma(ri, cur_rq.x[k], 1.0));
+        }
+      }
+      cur = nxt;
+    }
+    double v[kOptPassValues];
+#pragma unroll
+    for (int k = 0; k < kOptPoints; ++k) v[k] = k < NP ? S[k < NP ? k : 0].value() : 0.;
+#pragma unroll
+    for (int j = 0; j < kOptMoments; ++j) v[kOptPoints + j] = A[j];
+    warp_reduce16(v);
+    if ((lane & 1) == 0) s_red[warp][lane >> 1] = v[0];
+    if (threadIdx.x < kReqWords) s_rq[buf ^ 1][threadIdx.x] = next_word;
+    __syncthreads();
+    if (threadIdx.x < kOptPassValues && o >= 0) {
+      double acc = s_red[0][threadIdx.x];
+#pragma unroll
+      for (int wv = 1; wv < kTile / 32; ++wv) acc += s_red[wv][threadIdx.x];
+      partials[(static_cast<int64_t>(o) * kOptPassValues + threadIdx.x) * n_seg + sg] = acc;
+    }
+    __syncthreads();  // s_red is free for the next item
+  }
+}
+
+// S(x) from the model of the last pass; false outside its radius.
+__device__ __forceinline__ bool opt_model_value(const OptPass& pp, double x, double& S) {
+  const double d = x - pp.c;  // exact: x and c are within a factor of two of each other
+  if (!(fabs(d) <= pp.radius)) return false;
+  double acc = pp.mj[kOptMoments - 2];
+#pragma unroll
+  for (int j = kOptMoments - 3; j >= 0; --j) acc = fma(acc, d, pp.mj[j]);
+  S = fma(acc, d, pp.S_c);
+  return true;
+}
+
+// Consumes one pass (the kOptPassValues sums of every still-active edge) and advances each optimiser as
+// far as it can go without another pass: requests that hit a cached point or fall inside the model's
+// radius are answered here. Single rank: partials [edge][value][segment], summed in a fixed order;
+// multi-rank: `sums` [edge][value] all-reduced. One warp per edge, lane 0 decides.
+__global__ void k_opt_step_model(DeviceState st, OptState* __restrict__ states, OptPass* __restrict__ pass,
+                                 OptReq* __restrict__ req, OptParams prm, const double* __restrict__ sums,
+                                 const double* __restrict__ partials, int n_seg,
+                                 const double* __restrict__ edge_const, double min_weight,
+                                 int32_t* __restrict__ active, int capacity, int parity) {
+  const int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (a >= active[parity]) return;
+  const int o = req[static_cast<int64_t>(parity) * capacity + a].o;
+  if (o < 0) return;
+  double mine = 0.;
+  if (lane < kOptPassValues) {
+    if (partials != nullptr) {
+      const double* row = partials + (static_cast<int64_t>(o) * kOptPassValues + lane) * n_seg;
+      for (int t = 0; t < n_seg; ++t) mine += row[t];
+    } else {
+      mine = sums[static_cast<int64_t>(o) * kOptPassValues + lane];
+    }
+  }
+  double v[kOptPassValues];
+#pragma unroll
+  for (int k = 0; k < kOptPassValues; ++k) v[k] = __shfl_sync(0xffffffffu, mine, k);
+  if (lane != 0) return;
+  OptState s = states[o];
+  OptPass pp = pass[o];
+  const double lin = st.total_weight * c_model.group_lambda[0];
+  const double base = s.ll_offset + edge_const[o];
+  pp.passes++;
+  // the points of this pass other than the request: kept until the optimiser asks for them
+  pp.n_cache = 0;
+  for (int k = 1; k < pp.n_pts; ++k) {
+    pp.cache_s[pp.n_cache] = pp.ps[k];
+    pp.cache_ll[pp.n_cache] = v[k] + base + lin * pp.pt[k];
+    pp.n_cache++;
+  }
+  const double ll0 = v[0] + base + lin * pp.pt[0];
+  // the model about px[centre]
+  {
+    const int kc = pp.n_pts > 1 ? pp.centre : 0;
+    pp.c = pp.px[kc];
+    pp.S_c = v[kc];
+    const double ll_c = v[kc] + base + lin * pp.pt[kc];
+    const double MJ = v[kOptPoints + kOptMoments - 1];
+    double sign = 1.;
+    for (int j = 1; j < kOptMoments; ++j) {
+      pp.mj[j - 1] = sign * v[kOptPoints + j - 1] / static_cast<double>(j);
+      sign = -sign;
+    }
+    pp.mj[kOptMoments - 1] = MJ;
+    pp.radius = 0.;
+    bool finite = isfinite(ll_c);
+    for (int j = 0; j < kOptMoments; ++j) finite = finite && isfinite(v[kOptPoints + j]);
+    if (finite && MJ >= 0.) {
+      if (MJ == 0.) {
+        pp.radius = 1.;  // every z is 0: S is constant
+      } else {
+        const double J = static_cast<double>(kOptMoments);
+        const double tol = 0x1p-55 * fabs(ll_c);                    // a quarter ulp of the objective
+        const double r_err = pow(tol * J / (2. * MJ), 1. / J);      // 2 M_J d^J / J <= tol
+        const double r_half = 0.5 / pow(MJ / min_weight, 1. / J);   // max |z| d <= 1/2
+        const double r = 0.99 * fmin(r_err, r_half);
+        if (r > 0. && isfinite(r)) pp.radius = r;
+      }
+    }
+  }
+  opt_advance(s, st, prm, ll0, 0., 0.);
+  while (!s.done) {
+    double ll = 0.;
+    bool have = false;
+    for (int k = 0; k < pp.n_cache; ++k) {
+      if (pp.cache_s[k] == s.x_eval) {
+        ll = pp.cache_ll[k];
+        have = true;
+      }
+    }
+    if (!have) {
+      double S;
+      if (opt_model_value(pp, s.x_ratio, S)) {
+        ll = S + base + lin * s.t_eval;
+        have = true;
+      }
+    }
+    if (!have) break;
+    opt_advance(s, st, prm, ll, 0., 0.);
+  }
+  states[o] = s;
+  if (s.done) {
+    atomicAdd(st.feval_total, static_cast<unsigned long long>(s.evals));
+    atomicAdd(st.feval_total + 1, static_cast<unsigned long long>(pp.passes));
+    pass[o].passes = pp.passes;
+    return;
+  }
+  pp.n_pts = 1;
+  pp.centre = 0;
+  pp.px[0] = s.x_ratio;
+  pp.ps[0] = s.x_eval;
+  pp.pt[0] = s.t_eval;
+  pass[o] = pp;
+  OptReq rq;
+  for (int k = 0; k < kOptPoints; ++k) rq.x[k] = s.x_ratio;
+  rq.c = s.x_ratio;
+  rq.o = o;
+  rq.pad = 0;
+  req[static_cast<int64_t>(parity ^ 1) * capacity + atomicAdd(active + (parity ^ 1), 1)] = rq;
 }
 
 // After an on-chip search: rebuild the transition matrices of the program that hold this edge from
@@ -2120,14 +2617,18 @@ int64_t OptPrepareTileGroups(int n_ops, int64_t P) {
 }
 void LaunchOptPrepareRatio(cudaStream_t s, const DeviceState& st, const OptOp* ops, int n_ops,
                            OptState* states, const OptParams& params, int method, double* rho,
-                           const int32_t* perm, int64_t rho_stride, double* partials,
+                           const int32_t* perm, const int32_t* pos_w, int64_t rho_stride, double* partials,
                            int32_t* active, int active_capacity) {
   if (n_ops == 0) return;
   const int tiles = static_cast<int>(TilesFor(st.P));
   const int tpb = TilesPerBlock(n_ops, tiles, "BITO_GP_OPT_TILES_PER_BLOCK", 32);
+  static const bool lean = [] {  // BITO_GP_PREP_LEAN=0: the general loop for every edge (A/B)
+    const char* e = getenv("BITO_GP_PREP_LEAN");
+    return e == nullptr || atoi(e) != 0;
+  }();
   k_opt_prepare_ratio<<<Grid(n_ops, (tiles + tpb - 1) / tpb), kTile, 0, s>>>(
-      st, ops, n_ops, tiles, tpb, states, params, method, rho, perm, rho_stride, partials, active,
-      active_capacity);
+      st, ops, n_ops, tiles, tpb, states, params, method, rho, perm, lean ? pos_w : nullptr, rho_stride,
+      partials, active, active_capacity);
 }
 int64_t OptRatioTileGroups(int64_t P) {
   const int64_t per_block = static_cast<int64_t>(kTile) * kOptPatternsPerThread;
@@ -2152,6 +2653,63 @@ void LaunchOptEvalRatio(cudaStream_t s, const DeviceState& st, int n_ops, const 
   }();
   k_opt_eval_ratio<<<static_cast<unsigned>(items < cap ? items : cap), kTile, 0, s>>>(
       st, groups, states, rho, rho_stride, wperm, row_class, partials, active, active_capacity, parity);
+}
+
+
+void LaunchOptPlan(cudaStream_t s, const DeviceState& st, int n_ops, const OptState* states,
+                   const OptParams& params, OptPass* pass, OptReq* req, int32_t* active) {
+  if (n_ops == 0) return;
+  k_opt_plan<<<(n_ops + 127) / 128, 128, 0, s>>>(st, n_ops, states, params, pass, req, active);
+}
+// Segments per edge of k_opt_eval_model: enough items to balance the grid, few enough that the
+// block-wide reduction at the end of a segment stays small next to its 8+ tile groups.
+void OptModelSegments(int64_t rho_stride, int* seg_len, int* n_seg) {
+  const int groups = static_cast<int>(OptRatioTileGroups(rho_stride));
+  static const int want = [] {
+    const char* e = getenv("BITO_GP_OPT_SEGMENTS");
+    return e != nullptr && atoi(e) > 0 ? atoi(e) : 8;
+  }();
+  int len = (groups + want - 1) / want;
+  if (len < 1) len = 1;
+  *seg_len = len;
+  *n_seg = (groups + len - 1) / len;
+}
+void LaunchOptEvalModel(cudaStream_t s, int n_ops, int n_points, const OptReq* req, const double* rho,
+                        int64_t rho_stride, const double* wperm, const OptClassStarts& classes, double* partials,
+                        int32_t* active, int parity) {
+  if (n_ops == 0) return;
+  const int groups = static_cast<int>(OptRatioTileGroups(rho_stride));
+  int seg_len = 1, n_seg = 1;
+  OptModelSegments(rho_stride, &seg_len, &n_seg);
+  const int64_t items = static_cast<int64_t>(n_ops) * n_seg;
+  static const int occ = [] {
+    const char* e = getenv("BITO_GP_OPT_EVAL_OCC");
+    return e != nullptr && atoi(e) == 3 ? 3 : 2;
+  }();
+  static const int64_t cap = [] {  // one resident wave
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return static_cast<int64_t>(occ) * sms;
+  }();
+  const unsigned grid = static_cast<unsigned>(items < cap ? items : cap);
+#define GP_EVAL_MODEL(NP, MINB)                                                                                 \
+  k_opt_eval_model<NP, MINB><<<grid, kTile, 0, s>>>(groups, seg_len, n_seg, req, rho, rho_stride, wperm,       \
+                                                    classes, partials, active, parity)
+  if (n_points > 1) {
+    if (occ == 3) GP_EVAL_MODEL(kOptPoints, 3); else GP_EVAL_MODEL(kOptPoints, 2);
+  } else {
+    if (occ == 3) GP_EVAL_MODEL(1, 3); else GP_EVAL_MODEL(1, 2);
+  }
+#undef GP_EVAL_MODEL
+}
+void LaunchOptStepModel(cudaStream_t s, const DeviceState& st, int n_ops, OptState* states, OptPass* pass,
+                        OptReq* req, const OptParams& params, const double* sums, const double* partials,
+                        int n_seg, const double* edge_const, double min_weight, int32_t* active, int capacity,
+                        int parity) {
+  if (n_ops == 0) return;
+  k_opt_step_model<<<(n_ops + 7) / 8, 256, 0, s>>>(st, states, pass, req, params, sums, partials, n_seg,
+                                                    edge_const, min_weight, active, capacity, parity);
 }
 
 void LaunchPeerAllReduce(cudaStream_t s, const PeerComm& pc, double* buf, int n, bool max_op) {

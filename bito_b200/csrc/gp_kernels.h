@@ -62,7 +62,9 @@ void LaunchOptStep(cudaStream_t s, const DeviceState& st, int n_ops, OptState* s
 // order, Engine::BuildWeightClasses), K_e partials per tile.
 void LaunchOptPrepareRatio(cudaStream_t s, const DeviceState& st, const OptOp* ops, int n_ops,
                            OptState* states, const OptParams& params, int method, double* rho,
-                           const int32_t* perm, int64_t rho_stride,
+                           const int32_t* perm,
+                           const int32_t* pos_w /* per pattern: rho position << 3 | weight (1..7, 0 = look it up) */,
+                           int64_t rho_stride,
                            double* partials /* n_ops x OptPrepareTileGroups(n_ops, P) */,
                            int32_t* active, int active_capacity);
 // Small alignments: one block per edge runs the whole 1-D search on chip (coefficients in
@@ -96,6 +98,22 @@ void LaunchOptEvalRatio(cudaStream_t s, const DeviceState& st, int n_ops, const 
                         const uint8_t* row_class, double* partials /* n_ops x OptRatioPartials */,
                         int32_t* active /* [4 + 2 * capacity]: counts by parity, then the two lists */,
                         int active_capacity, int parity);
+
+// Taylor-model Brent (gp_types.h, OptPass): the first requests of every search (LaunchOptPlan), one
+// streamed pass = kOptPassValues sums per still-active edge (n_points = kOptPoints on the first pass of
+// a search, 1 afterwards; partials [edge][value][segment], OptModelSegments), and the step that
+// answers every later request it can from the cache / the model before asking for another pass.
+void LaunchOptPlan(cudaStream_t s, const DeviceState& st, int n_ops, const OptState* states,
+                   const OptParams& params, OptPass* pass, OptReq* req /* [2][capacity] */,
+                   int32_t* active /* [2]: entries of req by round parity */);
+void OptModelSegments(int64_t rho_stride, int* seg_len, int* n_seg);
+void LaunchOptEvalModel(cudaStream_t s, int n_ops, int n_points, const OptReq* req /* this round's half */,
+                        const double* rho, int64_t rho_stride, const double* wperm,
+                        const OptClassStarts& classes, double* partials, int32_t* active, int parity);
+void LaunchOptStepModel(cudaStream_t s, const DeviceState& st, int n_ops, OptState* states, OptPass* pass,
+                        OptReq* req, const OptParams& params, const double* sums /* multi-rank: all-reduced */,
+                        const double* partials /* single rank */, int n_seg, const double* edge_const,
+                        double min_weight, int32_t* active, int capacity, int parity);
 
 // Quartet hybrid marginals (gp_engine.cpp:748-808): mats = 80 doubles per summand, partials =
 // n_items x TilesFor(P) weighted tile sums, out[i] = non-sequence log-probability + sums[i].

@@ -215,7 +215,51 @@ struct OptState {
   int64_t count;        // remaining iterations
   int64_t iter;
   int32_t evals;
+  int32_t speculative;  // a copy advanced with made-up objective values to learn the next request: writes nothing
+};
+
+// ---- Taylor-model Brent (plain Brent on a two-eigenvalue model, ratio form) ---------------------
+// The objective of an edge is S(x) = sum_p w_p log(1 + rho_p x), x = e^{(l1 - l0) t}. A streamed pass
+// over rho (8 B per pattern) evaluates S at up to kOptPoints points AND the power sums
+//   M_j = sum_p w_p z_p^j,  z_p = rho_p / (1 + rho_p c),  j = 1..kOptMoments,
+// about one of them (c). Since log(1 + rho x) = log(1 + rho c) + log(1 + z (x - c)),
+//   S(x) = S(c) + sum_{j < J} (-1)^{j+1} M_j (x - c)^j / j + R,   |R| <= 2 M_J |x - c|^J / J
+// whenever max_p |z_p (x - c)| <= 1/2 (J = kOptMoments is even, so M_J >= 0 bounds every |z_p|).
+// Later requests of the optimiser that fall inside the radius where that bound is below a quarter
+// ulp of the objective are answered from the model without touching HBM (OptPass, k_opt_step_model).
+constexpr int kOptPoints = 4;
+constexpr int kOptMoments = 12;
+constexpr int kOptPassValues = kOptPoints + kOptMoments;
+
+// One entry of the pass list: what k_opt_eval_model evaluates for one still-active edge. Self-contained
+// (no pointer chasing through the optimiser state), double-buffered by round parity.
+struct OptReq {
+  double x[kOptPoints];  // points ([0] only after the first pass of a search)
+  double c;              // centre of the power sums
+  int32_t o;             // edge index within the chunk; < 0: nothing to do
   int32_t pad;
+};
+
+// First tile group of each weight class of the streamed layout (Engine::BuildWeightClasses): class c
+// (weight c + 1; 7 = general weights) owns tile groups [start[c], start[c + 1]).
+struct OptClassStarts {
+  int32_t start[9];
+};
+
+struct OptPass {
+  // what the next streamed pass evaluates
+  double px[kOptPoints];  // x of each point; [0] is the optimiser's pending request
+  double ps[kOptPoints];  // the optimiser's own coordinate of each point (log t)
+  double pt[kOptPoints];  // t of each point
+  int32_t n_pts;
+  int32_t centre;         // index of the point the moments are taken about
+  // evaluated points the optimiser has not asked for (yet): speculative first requests
+  double cache_s[kOptPoints], cache_ll[kOptPoints];
+  int32_t n_cache;
+  int32_t passes;         // streamed passes this search has cost so far
+  // the model
+  double c, S_c, radius;  // radius = 0: no model
+  double mj[kOptMoments]; // (-1)^{j+1} M_j / j, j = 1..J-1 at [j-1]; [J-1] = M_J
 };
 
 struct OptParams {

@@ -270,6 +270,10 @@ typedef struct bito_gp_stats {
   int64_t peer_collective_calls;     /* of collective_calls: one-kernel all-reduces over NVLink peer memory */
   int64_t programs_evicted;          /* compiled programs freed: stale after a resize, or least recently used */
   int64_t programs_cached;           /* compiled programs alive now                                          */
+  /* Of objective_evaluations (streamed scheme, plain Brent, two-eigenvalue model): the evaluations that
+   * cost a pass over the per-pattern coefficients in HBM. The others were answered from the power-sum
+   * (Taylor) model of an earlier pass, within a quarter ulp of the objective (gp_types.h, OptPass). */
+  int64_t objective_passes;
 } bito_gp_stats;
 BITO_GP_API int bito_gp_get_stats(bito_gp_engine* e, bito_gp_stats* out);
 

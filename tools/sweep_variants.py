@@ -29,8 +29,8 @@ sweep_ops = wl.ops("branch_length_optimization" if gauss_seidel else "batched_br
 stream = torch.cuda.current_stream()
 print(f"# {name}: P={wl.pattern_count} nodes={dag.node_count} edges={dag.edge_count} "
       f"sweep={'gauss-seidel' if gauss_seidel else 'batched'} ({sweep_ops[0].shape[0]} ops)", flush=True)
-print("| variant | scheme | cluster | threads | edges in flight | sweep ms (best of 3) | evals | max abs dBL vs first | log marginal after |")
-print("|---|---|---|---|---|---|---|---|---|")
+print("| variant | scheme | cluster | threads | edges in flight | sweep ms (best of 3) | evals | passes | max abs dBL vs first | edges > 1e-9 / > 1e-6 | log marginal after |")
+print("|---|---|---|---|---|---|---|---|---|---|---|")
 first_bl = None
 for v in variants:
     for k in ("BITO_GP_OPT_CLUSTER", "BITO_GP_OPT_CLUSTER_THREADS", "BITO_GP_OPT_SCHEME", "BITO_GP_OPT_RING_EDGES"):
@@ -64,6 +64,7 @@ for v in variants:
             eng.reset_optimization_count()
             eng.process_operations(*pop)
             f0 = eng.stats()["objective_evaluations"]
+            p0 = eng.stats()["objective_passes"]
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
@@ -73,6 +74,7 @@ for v in variants:
             ms = e0.elapsed_time(e1)
             best = ms if best is None else min(best, ms)
             evals = eng.stats()["objective_evaluations"] - f0
+            passes = eng.stats()["objective_passes"] - p0
         bl = eng.get_branch_lengths()
         eng.process_operations(*pop)
         eng.process_operations(*wl.ops("marginal_likelihood"))
@@ -80,5 +82,7 @@ for v in variants:
         if first_bl is None:
             first_bl = bl
         print(f"| {label} | {st['optimizer_scheme']} | {st['optimizer_cluster_size']} | {st['optimizer_cluster_threads']} | {st['optimizer_edges_in_flight']} | "
-              f"{best:.3f} | {evals} | {np.max(np.abs(bl - first_bl)):.3e} | {eng.get_log_marginal_likelihood():.6f} |",
+              f"{best:.3f} | {evals} | {passes} | {np.max(np.abs(bl - first_bl)):.3e} | "
+              f"{int(np.sum(np.abs(bl - first_bl) > 1e-9))} / {int(np.sum(np.abs(bl - first_bl) > 1e-6))} | "
+              f"{eng.get_log_marginal_likelihood():.6f} |",
               flush=True)
