@@ -283,30 +283,49 @@ def check_jacobi_sweep(got, want, blo, cpu):
 
 
 def parity_against_cpu(wl, sub, cpu_out, local_rank):
-    """N = 1: the CUDA engine on the pattern subsample the cpu_baseline leg just ran, same op lists."""
+    """N = 1: the CUDA engine on the pattern subsample the cpu_baseline leg just ran, same op lists. The sweep is
+    checked twice: with the engine's own choice for a level of this size (one block per edge at a few thousand
+    patterns) and with the streamed Taylor-model scheme the timed full-size run uses (BITO_GP_OPT_SCHEME=0)."""
     from bito_b200.gp_engine import GPEngine
     dag = wl.dag
     pop, lik = wl.ops("populate_plvs"), wl.ops("compute_likelihoods")
     blo = wl.ops("batched_branch_length_optimization")
-    with GPEngine(sub.symbols, sub.weights, sub.site_count, dag.node_count, dag.edge_count, sbn_prior=wl.sbn_prior,
-                  unconditional_node_probabilities=wl.unconditional, inverted_sbn_prior=wl.inverted,
-                  device=local_rank) as gpu:
-        gpu.process_operations(*pop)
-        gpu.process_operations(*lik)
-        ll_err = rel_err(gpu.get_per_gpcsp_log_likelihoods(), cpu_out["per_gpcsp_ll"])
-        marg_err = rel_err(gpu.get_log_marginal_likelihood(), cpu_out["log_marginal"])
-        counts = gpu.get_rescaling_counts()
-        want_counts = cpu_out["counts"]
-        n = min(counts.size, want_counts.size)
-        counts_equal = bool(np.array_equal(counts[:n], want_counts[:n]))
-        gpu.process_operations(*blo)
-        sweep, sweep_ok = check_jacobi_sweep(gpu.get_branch_lengths(), cpu_out["branch_lengths"], blo, cpu_out["engine"])
-        scheme = gpu.stats()["optimizer_scheme"]
-    ok = ll_err <= LL_RTOL and marg_err <= LL_RTOL and counts_equal and sweep_ok
+    out = {}
+    ok = True
+    for label, scheme_env in (("engine_choice", None), ("streamed_as_timed", "0")):
+        if scheme_env is not None:
+            os.environ["BITO_GP_OPT_SCHEME"] = scheme_env
+        try:
+            with GPEngine(sub.symbols, sub.weights, sub.site_count, dag.node_count, dag.edge_count,
+                          sbn_prior=wl.sbn_prior, unconditional_node_probabilities=wl.unconditional,
+                          inverted_sbn_prior=wl.inverted, device=local_rank) as gpu:
+                gpu.process_operations(*pop)
+                gpu.process_operations(*lik)
+                if label == "engine_choice":
+                    ll_err = rel_err(gpu.get_per_gpcsp_log_likelihoods(), cpu_out["per_gpcsp_ll"])
+                    marg_err = rel_err(gpu.get_log_marginal_likelihood(), cpu_out["log_marginal"])
+                    counts = gpu.get_rescaling_counts()
+                    want_counts = cpu_out["counts"]
+                    n = min(counts.size, want_counts.size)
+                    counts_equal = bool(np.array_equal(counts[:n], want_counts[:n]))
+                s0 = gpu.stats()
+                gpu.process_operations(*blo)
+                sweep, sweep_ok = check_jacobi_sweep(gpu.get_branch_lengths(), cpu_out["branch_lengths"], blo,
+                                                     cpu_out["engine"])
+                s1 = gpu.stats()
+                sweep["optimizer_scheme"] = int(s1["optimizer_scheme"])
+                sweep["objective_evaluations"] = int(s1["objective_evaluations"] - s0["objective_evaluations"])
+                sweep["objective_passes"] = int(s1["objective_passes"] - s0["objective_passes"])
+                out[label] = sweep
+                ok = ok and sweep_ok
+        finally:
+            os.environ.pop("BITO_GP_OPT_SCHEME", None)
+    ok = ok and ll_err <= LL_RTOL and marg_err <= LL_RTOL and counts_equal
     return {"ok": bool(ok), "patterns": int(sub.pattern_count), "against": "reference CPU GPEngine, same DAG and op lists",
             "max_rel_err": max(ll_err, marg_err), "per_edge_ll_max_rel_err": ll_err, "log_marginal_rel_err": marg_err,
             "counts_equal": counts_equal, "nonzero_counts": int(np.count_nonzero(want_counts)),
-            "sweep_branch_lengths": sweep, "sweep_optimizer_scheme": int(scheme),
+            "sweep_branch_lengths": out["streamed_as_timed"], "sweep_branch_lengths_engine_choice": out["engine_choice"],
+            "sweep_optimizer_scheme": out["streamed_as_timed"]["optimizer_scheme"],
             "tolerances": {"log_likelihoods_rel": LL_RTOL, "branch_lengths_abs": BL_ATOL}}
 
 
@@ -496,6 +515,7 @@ def measure(args, name, rank, world, local_rank, extras=True):
     parity = None
     if world > 1:
         ms_alone, _ = timed(device_step, max(3, args.steps // 2), 3)
+        engine.set_branch_lengths_to_constant(0.1)  # device_step ends with optimised lengths
         pass_step()
         local_ll, local_marg = engine.get_per_gpcsp_log_likelihoods(), engine.get_log_marginal_likelihood()
         standalone = {"value_per_gpu": wl.updates_per_pass() * P_local / (ms_alone * 1e-3), "unit": UNIT,
@@ -590,7 +610,8 @@ def measure(args, name, rank, world, local_rank, extras=True):
     }
 
     # ---- the sweeps on their own -----------------------------------------------------------------
-    scheme_names = {0: "rounds: one launch per objective round over all edges of a level, rho (8 B/pattern) streamed from HBM",
+    scheme_names = {0: "streamed Taylor-model Brent: all edges of a level in lockstep; a pass over rho (8 B/pattern, HBM) yields the "
+                       "objective at up to 4 points + 12 power sums, later requests inside the model's radius cost no pass",
                     1: "on chip: one thread block per edge, coefficients in shared memory",
                     2: "on chip: one thread-block cluster per edge, rho in distributed shared memory",
                     3: "pipelined: a streaming producer turns PLVs into rho (HBM-bound) while one thread-block cluster "
@@ -605,21 +626,23 @@ def measure(args, name, rank, world, local_rank, extras=True):
             pass_step()
             barrier()
             f0 = engine.stats()["objective_evaluations"]
+            p0 = engine.stats()["objective_passes"]
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record(stream)
             engine.process_operations(*op_list)
             ev1.record(stream)
             barrier()
-            runs.append((max_over_ranks(ev0.elapsed_time(ev1)), engine.stats()["objective_evaluations"] - f0))
-        ms, fevals = min(runs)
+            runs.append((max_over_ranks(ev0.elapsed_time(ev1)), engine.stats()["objective_evaluations"] - f0,
+                         engine.stats()["objective_passes"] - p0))
+        ms, fevals, passes = min(runs)
         s = engine.stats()
         bl = engine.get_branch_lengths()
         pass_step()
         # HBM traffic as executed by the optimiser: the two PLVs of every edge once; the round scheme also
         # writes rho once and re-reads it for every objective evaluation; the pipelined scheme writes and reads it once
         executed = 64.0 * n_opt * P_local
-        if s["optimizer_scheme"] == 0:
-            executed += 8.0 * (fevals + n_opt) * P_local
+        if s["optimizer_scheme"] == 0:  # rho written once, re-read once per streamed pass
+            executed += 8.0 * ((passes if passes > 0 else fevals) + n_opt) * P_local
         elif s["optimizer_scheme"] == 3:
             executed += 16.0 * n_opt * P_local
         return {"schedule": schedule, "optimizer": scheme_names[s["optimizer_scheme"]],
@@ -627,6 +650,7 @@ def measure(args, name, rank, world, local_rank, extras=True):
                 "cluster_size": s["optimizer_cluster_size"], "cluster_threads": s["optimizer_cluster_threads"],
                 "edges_in_flight": s["optimizer_edges_in_flight"], "levels": s["levels_last"],
                 "ms": ms, "ms_first_call": runs[0][0], "edges": n_opt, "objective_evaluations": fevals,
+                "objective_passes": passes,
                 "algorithmic_bytes": 64.0 * n_opt * P_local,
                 "frac_of_hbm_peak": 64.0 * n_opt * P_local / (ms * 1e-3) / 1e9 / peak_gbs,
                 "as_executed_bytes": executed,

@@ -16,6 +16,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
+from bito_b200 import _lib  # noqa: E402
 from bito_b200.gp_engine import GPEngine  # noqa: E402
 from bito_b200.sharding import shard_bounds  # noqa: E402
 from gp_cases import BL_ATOL, LL_RTOL, Fixture, make_cuda, rel_err  # noqa: E402
@@ -57,30 +58,35 @@ for case, thresholds in (("ds1", (0, 2)), ("fluA", (0, 4)), ("five_taxon", (0, 1
         e.process_operations(*fx.ops("optimize_sbn_parameters"))
         check(f"{case} thr#{ti} sbn q", np.max(np.abs(e.sbn_parameters() - fx[f"{key}_sbn_q"])) <= 1e-6)
         e.close()
-        # Gauss-Seidel sweeps with Brent (the default method)
-        e = make_cuda(fx, ti, pattern_slice=slice(lo, hi), device=local)
-        dist.broadcast_object_list(uid := [GPEngine.make_unique_id() if rank == 0 else None], src=0)
-        e.comm_init(world, rank, uid[0])
-        skey = f"{key}_sweep_brent"
-        e.set_optimization_method("brent")
-        e.reset_optimization_count()
-        e.process_operations(*fx.ops("populate_plvs"))
-        e.process_operations(*fx.ops("marginal_likelihood"))
-        worst = 0.0
-        for s in range(int(fx["sweeps"])):
-            e.process_operations(*fx.ops("branch_length_optimization"))
+        # Gauss-Seidel sweeps with Brent (the default method): once with the engine's own choice (clusters that
+        # exchange their sums over NVLink inside the kernel), once with the streamed Taylor-model scheme
+        # (the batched sweep's path: 16 all-reduced sums per edge and pass)
+        for scheme, flags in (("cluster", 0), ("streamed", _lib.FLAG_NO_ONCHIP_OPTIMIZER)):
+            e = make_cuda(fx, ti, pattern_slice=slice(lo, hi), device=local, flags=flags)
+            dist.broadcast_object_list(uid := [GPEngine.make_unique_id() if rank == 0 else None], src=0)
+            e.comm_init(world, rank, uid[0])
+            skey = f"{key}_sweep_brent"
+            e.set_optimization_method("brent")
+            e.reset_optimization_count()
             e.process_operations(*fx.ops("populate_plvs"))
             e.process_operations(*fx.ops("marginal_likelihood"))
-            worst = max(worst, float(np.max(np.abs(e.branch_lengths() - fx[skey + "_bl"][s]))))
-            e.increment_optimization_count()
-        check(f"{case} thr#{ti} brent sweeps |dBL| {worst:.1e}", worst <= BL_ATOL)
-        want = fx[skey + "_counts"]
-        check(f"{case} thr#{ti} counts after sweeps", np.array_equal(e.rescaling_counts()[:want.size], want))
-        st = e.stats()
-        collectives[0] += st["collective_calls"]
-        collectives[1] += st["peer_collective_calls"]
-        check(f"{case} thr#{ti} no device-side assert / peer timeout", st["device_status_bits"] == 0)
-        e.close()
+            worst = 0.0
+            for s in range(int(fx["sweeps"])):
+                e.process_operations(*fx.ops("branch_length_optimization"))
+                e.process_operations(*fx.ops("populate_plvs"))
+                e.process_operations(*fx.ops("marginal_likelihood"))
+                worst = max(worst, float(np.max(np.abs(e.branch_lengths() - fx[skey + "_bl"][s]))))
+                e.increment_optimization_count()
+            check(f"{case} thr#{ti} brent sweeps ({scheme}) |dBL| {worst:.1e}", worst <= BL_ATOL)
+            want = fx[skey + "_counts"]
+            check(f"{case} thr#{ti} counts after sweeps ({scheme})", np.array_equal(e.rescaling_counts()[:want.size], want))
+            st = e.stats()
+            collectives[0] += st["collective_calls"]
+            collectives[1] += st["peer_collective_calls"]
+            check(f"{case} thr#{ti} no device-side assert / peer timeout ({scheme}, optimiser scheme "
+                  f"{st['optimizer_scheme']}, {st['objective_passes']} passes for {st['objective_evaluations']} evaluations)",
+                  st["device_status_bits"] == 0)
+            e.close()
 
 t = torch.tensor([len(failures)], device="cuda")
 dist.all_reduce(t)
