@@ -611,7 +611,8 @@ void Engine::BuildWeightClasses(const double* host_weights) {
         for (int c = 1; c <= kMaxOptCluster; ++c) {
           if (opt_cluster_env_ > 0 && c != opt_cluster_env_) continue;
           OptClusterPlan plan;
-          if (PlanOptCluster(std::max<int64_t>(cpos / row, 1), threads, c, &plan)) cluster_plans_.push_back(plan);
+          if (PlanOptCluster(std::max<int64_t>(cpos / row, 1), threads, c, &plan, opt_model_env_ != 0 && opt_scheme_env_ != 3))
+            cluster_plans_.push_back(plan);
         }
       }
     }
@@ -1774,8 +1775,11 @@ int Engine::OptScheme(int n_ops, const OptClusterPlan** plan) const {
     for (const OptClusterPlan& c : cluster_plans_) {
       if (c.active_clusters < n_ops) continue;
       const int rows_per_thread = (c.rows_per_block * kClusterThreads + c.threads - 1) / c.threads;
-      const double us = 1.0 + 2.5 * ((rows_per_thread + 1) / 2) +
-                        14.5 * (2.4 + 0.05 * rows_per_thread + (c.threads > 256 ? 0.5 : 0.));
+      const double us = opt_model_env_ != 0
+                            ? 1.0 + 2.5 * ((rows_per_thread + 1) / 2) +
+                                  5.0 * (3.0 + 0.12 * rows_per_thread + (c.threads > 512 ? 2.0 : 0.))
+                            : 1.0 + 2.5 * ((rows_per_thread + 1) / 2) +
+                                  14.5 * (2.4 + 0.05 * rows_per_thread + (c.threads > 256 ? 0.5 : 0.));
       if (best_plan == nullptr || us < best) {
         best = us;
         best_plan = &c;
@@ -1818,13 +1822,18 @@ int Engine::OptScheme(int n_ops, const OptClusterPlan** plan) const {
   //  +0.5 us with 1024-thread blocks (wider barriers); x1.4 once edges queue for SMs (co-resident
   //  clusters contend); streamed: 64 + 8 + 8 x evaluations bytes per pattern at 5.5 TB/s plus ~8 us
   //  of launches per round and the host's look at the active-edge counter.
-  const double n_evals = 14.5;
+  // With the Taylor model (k_opt_cluster_model, the default) a search is ~5 rounds of ~3 us + 0.12 us per rho
+  // row a thread walks (twelve power sums per pattern; 1024-thread blocks are held to 64 registers and
+  // spill: +2 us), and the streamed scheme re-reads rho ~3 times instead of ~15 (profiles/r02_sweep_model.md).
+  const bool model = opt_model_env_ != 0;
+  const double n_evals = model ? 5.0 : 14.5;
   double best = 0.;
   const OptClusterPlan* best_plan = nullptr;
   for (const OptClusterPlan& c : cluster_plans_) {
     const int rows_per_thread = (c.rows_per_block * kClusterThreads + c.threads - 1) / c.threads;
     const double load_us = 1.0 + 2.5 * ((rows_per_thread + 1) / 2);
-    const double eval_us = 2.4 + 0.05 * rows_per_thread + (c.threads > 256 ? 0.5 : 0.);
+    const double eval_us = model ? 3.0 + 0.12 * rows_per_thread + (c.threads > 512 ? 2.0 : 0.)
+                                 : 2.4 + 0.05 * rows_per_thread + (c.threads > 256 ? 0.5 : 0.);
     const double waves = std::ceil(static_cast<double>(n_ops) / c.active_clusters);
     const double us = waves * (load_us + n_evals * eval_us) * (waves > 1. ? 1.4 : 1.);
     if (best_plan == nullptr || us < best) {
@@ -1834,8 +1843,8 @@ int Engine::OptScheme(int n_ops, const OptClusterPlan** plan) const {
   }
   if (!forced) {
     const double streamed_bytes =
-        static_cast<double>(n_ops) * static_cast<double>(P_) * (64. + 8. + 8. * n_evals);
-    const double rounds_us = streamed_bytes / 5.5e6 + n_evals * 8. + 30.;
+        static_cast<double>(n_ops) * static_cast<double>(P_) * (64. + 8. + 8. * (model ? 3.0 : n_evals));
+    const double rounds_us = streamed_bytes / 5.5e6 + (model ? 10. : n_evals) * 8. + 30.;
     if (rounds_us < best) return 0;
   }
   if (plan != nullptr) *plan = best_plan;
@@ -1891,7 +1900,7 @@ void Engine::RunOptimizer(const OptOp* d_ops, int n_ops, int method, bool check_
     ProfScope ps(this, kProfOptCluster, 64. * n_ops * static_cast<double>(P_));
     GP_CUDA(LaunchOptCluster(stream_, st, d_ops, n_ops, d_opt_ctl_.ptr, d_cluster_inv_perm_.ptr,
                              d_cluster_wperm_.ptr, cluster_class_row_start_, *plan, opt_refresh_,
-                             PeerEdgeContext()));
+                             PeerEdgeContext(), nullptr, 0, nullptr, opt_model_env_ != 0, min_weight_));
     return;
   }
   const OptParams prm = OptimizerParams(check_convergence);

@@ -1403,16 +1403,7 @@ __global__ void k_opt_step(DeviceState st, int n_ops, OptState* __restrict__ sta
 // made-up objective values (only the order of the values matters for those steps: the parabolic fit
 // through coincident points degenerates to p = q = 0 whatever they are). Nothing depends on the
 // guesses being right: k_opt_step_model uses a cached value only if the real request equals its point.
-__global__ void k_opt_plan(DeviceState st, int n_ops, const OptState* __restrict__ states, OptParams prm,
-                           OptPass* __restrict__ pass, OptReq* __restrict__ req, int32_t* __restrict__ active) {
-  const int o = blockIdx.x * blockDim.x + threadIdx.x;
-  if (o >= n_ops) return;
-  if (o == 0) {
-    active[0] = n_ops;  // round 0 lists every edge (finished ones as o < 0)
-    active[1] = 0;
-  }
-  const OptState s = states[o];
-  OptPass pp;
+__device__ void opt_first_pass(const OptState& s, const DeviceState& st, const OptParams& prm, OptPass& pp) {
   for (int k = 0; k < kOptPoints; ++k) {
     pp.px[k] = s.x_ratio;
     pp.ps[k] = s.x_eval;
@@ -1452,6 +1443,18 @@ __global__ void k_opt_plan(DeviceState st, int n_ops, const OptState* __restrict
       pp.centre = (prm.check_convergence || b.done) ? 0 : 2;
     }
   }
+}
+__global__ void k_opt_plan(DeviceState st, int n_ops, const OptState* __restrict__ states, OptParams prm,
+                           OptPass* __restrict__ pass, OptReq* __restrict__ req, int32_t* __restrict__ active) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n_ops) return;
+  if (o == 0) {
+    active[0] = n_ops;  // round 0 lists every edge (finished ones as o < 0)
+    active[1] = 0;
+  }
+  const OptState s = states[o];
+  OptPass pp;
+  opt_first_pass(s, st, prm, pp);
   pass[o] = pp;
   OptReq rq;
   for (int k = 0; k < kOptPoints; ++k) rq.x[k] = pp.px[k];
@@ -1700,12 +1703,91 @@ __global__ void __launch_bounds__(kTile, MINB)
 // S(x) from the model of the last pass; false outside its radius.
 __device__ __forceinline__ bool opt_model_value(const OptPass& pp, double x, double& S) {
   const double d = x - pp.c;  // exact: x and c are within a factor of two of each other
-  if (!(fabs(d) <= pp.radius)) return false;
+  static_assert(kOptMoments == 12, "d^J below is written for J = 12");
+  const double d2 = d * d, d4 = d2 * d2;
+  if (!(d4 * d4 * d4 <= pp.radius)) return false;  // radius holds the J-th power
   double acc = pp.mj[kOptMoments - 2];
 #pragma unroll
   for (int j = kOptMoments - 3; j >= 0; --j) acc = fma(acc, d, pp.mj[j]);
   S = fma(acc, d, pp.S_c);
   return true;
+}
+
+// One streamed (or on-chip) pass has produced v[0 .. kOptPassValues): the objective sums at the pass's points
+// and the power sums about its centre. Builds the model, answers the pending request and then every
+// further request that hits a cached point or falls inside the model's radius. On return either s.done
+// or pp holds the next pass (one point: the optimiser's pending request, also the centre).
+__device__ void opt_consume_pass(OptState& s, OptPass& pp, const double* v, double edge_const, double min_weight,
+                                 const DeviceState& st, const OptParams& prm) {
+  const double lin = st.total_weight * c_model.group_lambda[0];
+  const double base = s.ll_offset + edge_const;
+  pp.passes++;
+  // the points of this pass other than the request: kept until the optimiser asks for them
+  pp.n_cache = 0;
+  for (int k = 1; k < pp.n_pts; ++k) {
+    pp.cache_s[pp.n_cache] = pp.ps[k];
+    pp.cache_ll[pp.n_cache] = v[k] + base + lin * pp.pt[k];
+    pp.n_cache++;
+  }
+  const double ll0 = v[0] + base + lin * pp.pt[0];
+  // the model about px[centre]
+  {
+    const int kc = pp.n_pts > 1 ? pp.centre : 0;
+    pp.c = pp.px[kc];
+    pp.S_c = v[kc];
+    const double ll_c = v[kc] + base + lin * pp.pt[kc];
+    const double MJ = v[kOptPoints + kOptMoments - 1];
+    // (-1)^{j+1} / j
+    constexpr double kInvJ[kOptMoments - 1] = {1., -1. / 2, 1. / 3, -1. / 4, 1. / 5, -1. / 6,
+                                               1. / 7, -1. / 8, 1. / 9, -1. / 10, 1. / 11};
+#pragma unroll
+    for (int j = 1; j < kOptMoments; ++j) pp.mj[j - 1] = kInvJ[j - 1] * v[kOptPoints + j - 1];
+    pp.mj[kOptMoments - 1] = MJ;
+    // The model answers x when  2 M_J d^J / J <= tol  and  max |z| d <= 1/2, d = |x - c|; both are tests
+    // on d^J (max |z|^J <= M_J / min_weight), so the radius is kept as its J-th power: no pow() here.
+    pp.radius = 0.;
+    bool finite = isfinite(ll_c);
+#pragma unroll
+    for (int j = 0; j < kOptMoments; ++j) finite = finite && isfinite(v[kOptPoints + j]);
+    if (finite && MJ >= 0.) {
+      if (MJ == 0.) {
+        pp.radius = 1.;  // every z is 0: S is constant
+      } else {
+        const double J = static_cast<double>(kOptMoments);
+        const double tol = 0x1p-55 * fabs(ll_c);  // a quarter ulp of the objective
+        const double dj_err = tol * J / (2. * MJ);
+        const double dj_half = min_weight / (MJ * static_cast<double>(1 << kOptMoments));
+        const double r = 0.88 * fmin(dj_err, dj_half);  // 0.99^12
+        if (r > 0. && isfinite(r)) pp.radius = r;
+      }
+    }
+  }
+  opt_advance(s, st, prm, ll0, 0., 0.);
+  while (!s.done) {
+    double ll = 0.;
+    bool have = false;
+    for (int k = 0; k < pp.n_cache; ++k) {
+      if (pp.cache_s[k] == s.x_eval) {
+        ll = pp.cache_ll[k];
+        have = true;
+      }
+    }
+    if (!have) {
+      double S;
+      if (opt_model_value(pp, s.x_ratio, S)) {
+        ll = S + base + lin * s.t_eval;
+        have = true;
+      }
+    }
+    if (!have) break;
+    opt_advance(s, st, prm, ll, 0., 0.);
+  }
+  if (s.done) return;
+  pp.n_pts = 1;
+  pp.centre = 0;
+  pp.px[0] = s.x_ratio;
+  pp.ps[0] = s.x_eval;
+  pp.pt[0] = s.t_eval;
 }
 
 // Consumes one pass (the kOptPassValues sums of every still-active edge) and advances each optimiser as
@@ -1737,66 +1819,7 @@ __global__ void k_opt_step_model(DeviceState st, OptState* __restrict__ states, 
   if (lane != 0) return;
   OptState s = states[o];
   OptPass pp = pass[o];
-  const double lin = st.total_weight * c_model.group_lambda[0];
-  const double base = s.ll_offset + edge_const[o];
-  pp.passes++;
-  // the points of this pass other than the request: kept until the optimiser asks for them
-  pp.n_cache = 0;
-  for (int k = 1; k < pp.n_pts; ++k) {
-    pp.cache_s[pp.n_cache] = pp.ps[k];
-    pp.cache_ll[pp.n_cache] = v[k] + base + lin * pp.pt[k];
-    pp.n_cache++;
-  }
-  const double ll0 = v[0] + base + lin * pp.pt[0];
-  // the model about px[centre]
-  {
-    const int kc = pp.n_pts > 1 ? pp.centre : 0;
-    pp.c = pp.px[kc];
-    pp.S_c = v[kc];
-    const double ll_c = v[kc] + base + lin * pp.pt[kc];
-    const double MJ = v[kOptPoints + kOptMoments - 1];
-    double sign = 1.;
-    for (int j = 1; j < kOptMoments; ++j) {
-      pp.mj[j - 1] = sign * v[kOptPoints + j - 1] / static_cast<double>(j);
-      sign = -sign;
-    }
-    pp.mj[kOptMoments - 1] = MJ;
-    pp.radius = 0.;
-    bool finite = isfinite(ll_c);
-    for (int j = 0; j < kOptMoments; ++j) finite = finite && isfinite(v[kOptPoints + j]);
-    if (finite && MJ >= 0.) {
-      if (MJ == 0.) {
-        pp.radius = 1.;  // every z is 0: S is constant
-      } else {
-        const double J = static_cast<double>(kOptMoments);
-        const double tol = 0x1p-55 * fabs(ll_c);                    // a quarter ulp of the objective
-        const double r_err = pow(tol * J / (2. * MJ), 1. / J);      // 2 M_J d^J / J <= tol
-        const double r_half = 0.5 / pow(MJ / min_weight, 1. / J);   // max |z| d <= 1/2
-        const double r = 0.99 * fmin(r_err, r_half);
-        if (r > 0. && isfinite(r)) pp.radius = r;
-      }
-    }
-  }
-  opt_advance(s, st, prm, ll0, 0., 0.);
-  while (!s.done) {
-    double ll = 0.;
-    bool have = false;
-    for (int k = 0; k < pp.n_cache; ++k) {
-      if (pp.cache_s[k] == s.x_eval) {
-        ll = pp.cache_ll[k];
-        have = true;
-      }
-    }
-    if (!have) {
-      double S;
-      if (opt_model_value(pp, s.x_ratio, S)) {
-        ll = S + base + lin * s.t_eval;
-        have = true;
-      }
-    }
-    if (!have) break;
-    opt_advance(s, st, prm, ll, 0., 0.);
-  }
+  opt_consume_pass(s, pp, v, edge_const[o], min_weight, st, prm);
   states[o] = s;
   if (s.done) {
     atomicAdd(st.feval_total, static_cast<unsigned long long>(s.evals));
@@ -1804,11 +1827,6 @@ __global__ void k_opt_step_model(DeviceState st, OptState* __restrict__ states, 
     pass[o].passes = pp.passes;
     return;
   }
-  pp.n_pts = 1;
-  pp.centre = 0;
-  pp.px[0] = s.x_ratio;
-  pp.ps[0] = s.x_eval;
-  pp.pt[0] = s.t_eval;
   pass[o] = pp;
   OptReq rq;
   for (int k = 0; k < kOptPoints; ++k) rq.x[k] = s.x_ratio;
@@ -1951,18 +1969,18 @@ __device__ __forceinline__ double peer_edge_sum(const PeerEdge& px, int slot, in
   const int R = pc->n_ranks, me = pc->rank, lane = threadIdx.x & 31;
   // bank = (search parity, round parity); tag = search number << 20 | round + 1
   const size_t bank = ((tag >> 20) & 1) * 2 + parity;
-  const size_t rec0 = PeerEdgeOffsetDoubles(R) + (static_cast<size_t>(slot) * 4 + bank) * R * 2;
+  const size_t rec0 = PeerEdgeOffsetDoubles(R) + (static_cast<size_t>(slot) * 4 + bank) * R * kPeerEdgeRecord;
   double got = 0.;
   if (lane < R) {
-    double* theirs = pc->base[lane] + rec0 + 2 * me;
+    double* theirs = pc->base[lane] + rec0 + kPeerEdgeRecord * me;
     *reinterpret_cast<volatile double*>(theirs) = v;
-    st_release_sys(reinterpret_cast<unsigned long long*>(theirs + 1), tag);
-    const double* mine = pc->base[me] + rec0 + 2 * lane;
+    st_release_sys(reinterpret_cast<unsigned long long*>(theirs + kPeerEdgeValues), tag);
+    const double* mine = pc->base[me] + rec0 + kPeerEdgeRecord * lane;
     const long long t0 = clock64();
     // ~35 s without an answer: a peer died. Fail the call instead of hanging, and once that has
     // happened never wait again (every later exchange of this engine would time out too).
     const bool dead = (*reinterpret_cast<volatile uint32_t*>(pc->status) & kErrPeerTimeout) != 0;
-    while (!dead && ld_acquire_sys(reinterpret_cast<const unsigned long long*>(mine + 1)) != tag) {
+    while (!dead && ld_acquire_sys(reinterpret_cast<const unsigned long long*>(mine + kPeerEdgeValues)) != tag) {
       if (clock64() - t0 > kPeerTimeoutCycles) {
         atomicOr(pc->status, kErrPeerTimeout);
         break;
@@ -2190,6 +2208,276 @@ __global__ void __launch_bounds__(T, T == 256 ? (kFromRho ? 4 : 3) : (T == 512 ?
     __syncthreads();
     if (s_state.done) break;  // every block of the cluster leaves in the same round
   }
+  // st.bl[edge] was written by this block's thread 0 before the barrier above
+  if (rank == 0) {
+    refresh_edge_matrices(st, op, refresh, threadIdx.x, T);
+    if (px.enabled && threadIdx.x == 0) px.seq[o] += 1;  // the next search of this slot uses fresh tags
+  }
+}
+
+// ---- the cluster-resident search with the Taylor model (gp_types.h, OptPass) ------------------------
+// Same layout and life cycle as k_opt_cluster; what changes is what one round does. A round walks the
+// cluster's shared memory once and produces kClusterVec sums - the objective at the points of the pass
+// (four on the first pass of a search: Brent's start and its data-independent next requests; one
+// afterwards), twelve power sums about one of them, and on the first pass K_e - which cross the cluster
+// (and, on several GPUs, NVLink) in ONE exchange. Every block then runs opt_consume_pass itself: all
+// requests that hit a cached point or the model cost nothing, so a search is ~3 rounds instead of ~15.
+constexpr int kClusterVec = kPeerEdgeValues;  // S[4], M[12], K_e
+
+// Sums over ranks of kClusterVec values for the edge that owns record slot `slot` (see peer_edge_sum for the
+// protocol: banked by (search parity, round parity), tagged search << 20 | round). Called by warp 0 of the
+// cluster's block 0 with v = value `lane` of this GPU (lanes >= kClusterVec: anything); returns in lane l
+// the global value l. Lane r < R ships the whole vector to rank r and waits for rank r's.
+__device__ __forceinline__ double peer_edge_sum_vec(const PeerEdge& px, int slot, int parity,
+                                                    unsigned long long tag, double v) {
+  const PeerComm* pc = px.pc;
+  const int R = pc->n_ranks, me = pc->rank, lane = threadIdx.x & 31;
+  const size_t bank = ((tag >> 20) & 1) * 2 + parity;
+  const size_t rec0 = PeerEdgeOffsetDoubles(R) + (static_cast<size_t>(slot) * 4 + bank) * R * kPeerEdgeRecord;
+  double all[kClusterVec];
+#pragma unroll
+  for (int k = 0; k < kClusterVec; ++k) all[k] = __shfl_sync(0xffffffffu, v, k);
+  if (lane < R) {
+    double* theirs = pc->base[lane] + rec0 + kPeerEdgeRecord * me;
+#pragma unroll
+    for (int k = 0; k < kClusterVec; ++k) reinterpret_cast<volatile double*>(theirs)[k] = all[k];
+    st_release_sys(reinterpret_cast<unsigned long long*>(theirs + kPeerEdgeValues), tag);
+    const double* mine = pc->base[me] + rec0 + kPeerEdgeRecord * lane;
+    const long long t0 = clock64();
+    const bool dead = (*reinterpret_cast<volatile uint32_t*>(pc->status) & kErrPeerTimeout) != 0;
+    while (!dead && ld_acquire_sys(reinterpret_cast<const unsigned long long*>(mine + kPeerEdgeValues)) != tag) {
+      if (clock64() - t0 > kPeerTimeoutCycles) {
+        atomicOr(pc->status, kErrPeerTimeout);
+        break;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kClusterVec; ++k) all[k] = reinterpret_cast<const volatile double*>(mine)[k];
+  }
+  // lane l collects value l of every rank, added in rank order (the same on every GPU)
+  double acc = 0.;
+#pragma unroll
+  for (int k = 0; k < kClusterVec; ++k) {
+    double sum = __shfl_sync(0xffffffffu, all[k], 0);
+    for (int r = 1; r < R; ++r) sum += __shfl_sync(0xffffffffu, all[k], r);
+    if (lane == k) acc = sum;
+  }
+  return acc;
+}
+
+template <int T>
+__global__ void __launch_bounds__(T, T == 256 ? 2 : 1)
+    k_opt_cluster_model(DeviceState st, const OptOp* __restrict__ ops, const OptControl* __restrict__ ctl,
+                        const int32_t* __restrict__ inv_perm, const double* __restrict__ wperm,
+                        OptClusterLayout lay, OptRefresh refresh, PeerEdge px, double min_weight) {
+  constexpr int S = T / kClusterThreads;           // rows walked per step
+  constexpr int kStep = S * kClusterThreads;       // = T positions
+  constexpr int W = T / 32;
+  extern __shared__ __align__(16) double s_rho[];  // rows_per_block x kClusterThreads
+  __shared__ OptState s_state;
+  __shared__ OptPass s_pass;
+  __shared__ double s_warp[W][kClusterVec];
+  __shared__ double s_block[kClusterVec];
+  __shared__ double s_slots[2][kClusterVec][kMaxOptCluster];
+  __shared__ double s_tot[2][kClusterVec];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = static_cast<int>(cluster.block_rank());
+  const int n_blocks = static_cast<int>(cluster.num_blocks());
+  const int o = blockIdx.x / n_blocks;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned long long tag0 = px.enabled ? (px.seq[o] << 20) : 0ull;
+  const OptOp op = ops[o];
+  const OptParams prm = ctl->prm;
+  if (threadIdx.x == 0) {
+    opt_init(s_state, st, prm, ctl->method, op);
+    opt_first_pass(s_state, st, prm, s_pass);
+  }
+  __syncthreads();
+  if (s_state.done) return;  // converged edges (dag_branch_handler.cpp:126-131): the same decision in every block
+  const int row0 = rank * lay.rows_per_block;
+  const int n_rows = max(0, min(lay.rows_per_block, lay.rows_total - row0));
+  const int64_t q0 = static_cast<int64_t>(row0) * kClusterThreads;
+  const int sub = threadIdx.x / kClusterThreads;  // this thread's rows: sub, sub + S, sub + 2 S, ...
+  const int col = threadIdx.x & (kClusterThreads - 1);
+  // the edge's PLVs, once: rho into shared memory, K_e = sum_p w_p log c0_p (as k_opt_cluster)
+  double k_part = 0.;
+  for (int r = sub; r < n_rows; r += 2 * S) {
+    const int i0 = r * kClusterThreads + col, i1 = i0 + kStep;
+    const bool two = r + S < n_rows;
+    const int32_t pa = inv_perm[q0 + i0];
+    const int32_t pb = two ? inv_perm[q0 + i1] : -1;
+    V4 ra = {1., 1., 1., 1.}, ca = ra, rb = ra, cb = ra;  // padding: any finite value, masked below
+    if (pa >= 0) ra = load_plv(op.parent, pa);
+    if (pa >= 0) ca = load_plv(op.child, pa);
+    if (pb >= 0) rb = load_plv(op.parent, pb);
+    if (pb >= 0) cb = load_plv(op.child, pb);
+    double rho, c0;
+    ratio_coefficients(ra, ca, rho, c0);
+    if (pa >= 0) k_part += wperm[q0 + i0] * log(c0);
+    s_rho[i0] = pa >= 0 ? rho : 0.;
+    if (two) {
+      ratio_coefficients(rb, cb, rho, c0);
+      if (pb >= 0) k_part += wperm[q0 + i1] * log(c0);
+      s_rho[i1] = pb >= 0 ? rho : 0.;
+    }
+  }
+  __syncthreads();  // s_rho is complete before the first pass over it
+  // this thread's rows by weight class: first row >= the class's first row that is = sub (mod S)
+  int seg_begin[8], seg_end[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int b = min(max(lay.class_row_start[c] - row0, 0), n_rows);
+    seg_begin[c] = b + ((sub - b) % S + S) % S;
+    seg_end[c] = min(max(lay.class_row_start[c + 1] - row0, 0), n_rows);
+  }
+  const double* mine = s_rho + col;
+  double edge_const = 0.;
+  for (int round = 0;; ++round) {
+    const int parity = round & 1;
+    const int np = s_pass.n_pts;
+    const double c = s_pass.px[np > 1 ? s_pass.centre : 0];
+    // ---- phase A: power sums about c, and the objective sum at c --------------------------------------
+    double A[kOptMoments];
+#pragma unroll
+    for (int j = 0; j < kOptMoments; ++j) A[j] = 0.;
+    ProductLog Sc;
+    // four rows at a time (padding rows hold rho = 0: factor 1, z = 0); one reciprocal per four
+    auto quad = [&](double r0, double r1, double r2, double r3, int wi) {
+      const double t0 = fma(r0, c, 1.0), t1 = fma(r1, c, 1.0), t2 = fma(r2, c, 1.0), t3 = fma(r3, c, 1.0);
+      const double t01 = t0 * t1, t23 = t2 * t3, prod4 = t01 * t23;
+      const double inv = rcp_newton(prod4);
+      const double i01 = inv * t23, i23 = inv * t01;
+      add_moments4(A, r0 * (i01 * t1), r1 * (i01 * t0), r2 * (i23 * t3), r3 * (i23 * t2), static_cast<double>(wi));
+      Sc.mul(prod4, wi);
+    };
+#pragma unroll 1
+    for (int cls = 0; cls < 7; ++cls) {
+      const int wi = cls + 1;
+      int r = seg_begin[cls];
+      for (; r + 3 * S < seg_end[cls]; r += 4 * S)
+        quad(mine[r * kClusterThreads], mine[(r + S) * kClusterThreads], mine[(r + 2 * S) * kClusterThreads],
+             mine[(r + 3 * S) * kClusterThreads], wi);
+      if (r < seg_end[cls]) {
+        const double r0 = mine[r * kClusterThreads];
+        const double r1 = r + S < seg_end[cls] ? mine[(r + S) * kClusterThreads] : 0.;
+        const double r2 = r + 2 * S < seg_end[cls] ? mine[(r + 2 * S) * kClusterThreads] : 0.;
+        quad(r0, r1, r2, 0., wi);
+      }
+    }
+    for (int r = seg_begin[7]; r < seg_end[7]; r += S) {  // general weights: one position at a time
+      const double w = wperm[q0 + r * kClusterThreads + col];
+      if (w == 0.) continue;
+      const double rv = mine[r * kClusterThreads];
+      const double tc = fma(rv, c, 1.0);
+      const double z = rv * rcp_newton(tc);
+      double zp = z;
+#pragma unroll
+      for (int j = 0; j < kOptMoments; ++j) {
+        A[j] = fma(zp, w, A[j]);
+        zp *= z;
+      }
+      Sc.slow += w * log(tc);
+    }
+    {
+      double v16[16];
+#pragma unroll
+      for (int k = 0; k < kOptPoints; ++k) v16[k] = 0.;
+      v16[0] = Sc.value();  // one point: the centre is the request
+#pragma unroll
+      for (int j = 0; j < kOptMoments; ++j) v16[kOptPoints + j] = A[j];
+      warp_reduce16(v16);
+      if ((lane & 1) == 0) s_warp[warp][lane >> 1] = v16[0];
+      __syncwarp();
+    }
+    // ---- phase B (first pass of a search): the objective sums at all four points --------------------------
+    if (np > 1) {
+      ProductLog Sk[kOptPoints];
+      double xk[kOptPoints];
+#pragma unroll
+      for (int k = 0; k < kOptPoints; ++k) xk[k] = s_pass.px[k];
+#pragma unroll 1
+      for (int cls = 0; cls < 7; ++cls) {
+        const int wi = cls + 1;
+        for (int r = seg_begin[cls]; r < seg_end[cls]; r += 2 * S) {
+          const double r0 = mine[r * kClusterThreads];
+          const double r1 = r + S < seg_end[cls] ? mine[(r + S) * kClusterThreads] : 0.;
+#pragma unroll
+          for (int k = 0; k < kOptPoints; ++k) Sk[k].mul(fma(r0, xk[k], 1.0) * fma(r1, xk[k], 1.0), wi);
+        }
+      }
+      for (int r = seg_begin[7]; r < seg_end[7]; r += S) {
+        const double w = wperm[q0 + r * kClusterThreads + col];
+        if (w == 0.) continue;
+        const double rv = mine[r * kClusterThreads];
+#pragma unroll
+        for (int k = 0; k < kOptPoints; ++k) Sk[k].slow += w * log(fma(rv, xk[k], 1.0));
+      }
+#pragma unroll
+      for (int k = 0; k < kOptPoints; ++k) {
+        double f = Sk[k].value();
+#pragma unroll
+        for (int sh = 16; sh > 0; sh >>= 1) f += __shfl_down_sync(0xffffffffu, f, sh);
+        if (lane == 0) s_warp[warp][k] = f;
+      }
+    }
+    {  // K_e rides on the first pass
+      double f = round == 0 ? k_part : 0.;
+#pragma unroll
+      for (int sh = 16; sh > 0; sh >>= 1) f += __shfl_down_sync(0xffffffffu, f, sh);
+      if (lane == 0) s_warp[warp][kClusterVec - 1] = f;
+    }
+    __syncthreads();
+    // ---- this block's totals -> every block of the cluster ---------------------------------------------------
+    if (warp == 0) {
+      if (lane < kClusterVec) {
+        double t = s_warp[0][lane];
+#pragma unroll
+        for (int wv = 1; wv < W; ++wv) t += s_warp[wv][lane];
+        s_block[lane] = t;
+      }
+    }
+    __syncthreads();
+    for (int b = warp; b < n_blocks; b += W)  // warp b hands this block's vector to block b
+      if (lane < kClusterVec) *cluster.map_shared_rank(&s_slots[parity][lane][rank], b) = s_block[lane];
+    cluster.sync();  // release/acquire: the remote stores above are visible to every block
+    if (warp == 0) {
+      double t = 0.;
+      if (lane < kClusterVec) {
+        // fixed pairwise tree over the (at most 16) block sums: the same order in every block
+        double v16[kMaxOptCluster];
+#pragma unroll
+        for (int k = 0; k < kMaxOptCluster; ++k) v16[k] = k < n_blocks ? s_slots[parity][lane][k] : 0.;
+#pragma unroll
+        for (int w2 = kMaxOptCluster / 2; w2 > 0; w2 >>= 1)
+#pragma unroll
+          for (int k = 0; k < w2; ++k) v16[k] += v16[k + w2];
+        t = v16[0];
+      }
+      if (!px.enabled) {
+        if (lane < kClusterVec) s_tot[parity][lane] = t;
+      } else if (rank == 0) {
+        // several GPUs: this GPU's totals go through NVLink, the global ones come back to every block
+        const double g = peer_edge_sum_vec(px, o, parity, tag0 + round + 1, t);
+        if (lane < kClusterVec)
+          for (int b = 0; b < n_blocks; ++b) *cluster.map_shared_rank(&s_tot[parity][lane], b) = g;
+      }
+    }
+    if (px.enabled) cluster.sync(); else __syncthreads();
+    if (threadIdx.x == 0) {
+      if (round == 0) s_state.ll_offset += s_tot[parity][kClusterVec - 1];  // K_e: constant for the whole search
+      double v[kOptPassValues];
+#pragma unroll
+      for (int k = 0; k < kOptPassValues; ++k) v[k] = s_tot[parity][k];
+      opt_consume_pass(s_state, s_pass, v, 0., min_weight, st, prm);
+      if (s_state.done && rank == 0) {
+        atomicAdd(st.feval_total, static_cast<unsigned long long>(s_state.evals));
+        atomicAdd(st.feval_total + 1, static_cast<unsigned long long>(s_pass.passes));
+      }
+    }
+    __syncthreads();
+    if (s_state.done) break;  // every block of the cluster leaves in the same round
+  }
+  (void)edge_const;
   // st.bl[edge] was written by this block's thread 0 before the barrier above
   if (rank == 0) {
     refresh_edge_matrices(st, op, refresh, threadIdx.x, T);
@@ -2511,7 +2799,7 @@ void LaunchOptBlock(cudaStream_t s, const DeviceState& st, const OptOp* ops, int
 // blocks per edge. Fails when the edge's rho rows do not fit the cluster's shared memory or the
 // device cannot place such a cluster; active_clusters = edges resident on the device at once.
 template <int T>
-static bool PlanOptClusterT(int64_t rows_total, int c, OptClusterPlan* plan) {
+static bool PlanOptClusterT(int64_t rows_total, int c, OptClusterPlan* plan, bool model) {
   static bool attrs_set = false;
   if (!attrs_set) {
     if (cudaFuncSetAttribute(k_opt_cluster<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -2521,6 +2809,10 @@ static bool PlanOptClusterT(int64_t rows_total, int c, OptClusterPlan* plan) {
         cudaFuncSetAttribute(k_opt_cluster<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              static_cast<int>(kOptClusterMaxSharedBytes)) != cudaSuccess ||
         cudaFuncSetAttribute(k_opt_cluster<T, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) !=
+            cudaSuccess ||
+        cudaFuncSetAttribute(k_opt_cluster_model<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(kOptClusterMaxSharedBytes)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_opt_cluster_model<T>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) !=
             cudaSuccess) {
       cudaGetLastError();
       return false;
@@ -2542,8 +2834,11 @@ static bool PlanOptClusterT(int64_t rows_total, int c, OptClusterPlan* plan) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int n = 0;
-  // the pipelined variant has the same footprint (same shared memory, fewer registers)
-  if (cudaOccupancyMaxActiveClusters(&n, k_opt_cluster<T, false>, &cfg) != cudaSuccess || n < 1) {
+  // the pipelined variant has the same footprint as k_opt_cluster<T, false> (same shared memory, fewer
+  // registers); the Taylor-model kernel has its own (more static shared memory)
+  const cudaError_t rc = model ? cudaOccupancyMaxActiveClusters(&n, k_opt_cluster_model<T>, &cfg)
+                               : cudaOccupancyMaxActiveClusters(&n, k_opt_cluster<T, false>, &cfg);
+  if (rc != cudaSuccess || n < 1) {
     cudaGetLastError();
     return false;
   }
@@ -2555,20 +2850,20 @@ static bool PlanOptClusterT(int64_t rows_total, int c, OptClusterPlan* plan) {
   plan->active_clusters = n;
   return true;
 }
-bool PlanOptCluster(int64_t rows_total, int threads, int cluster_size, OptClusterPlan* plan) {
+bool PlanOptCluster(int64_t rows_total, int threads, int cluster_size, OptClusterPlan* plan, bool model) {
   *plan = OptClusterPlan();
   if (rows_total <= 0 || rows_total > (int64_t(1) << 30)) return false;
   if (cluster_size < 1 || cluster_size > kMaxOptCluster) return false;  // any size, not only powers of two
-  if (threads == 256) return PlanOptClusterT<256>(rows_total, cluster_size, plan);
-  if (threads == 512) return PlanOptClusterT<512>(rows_total, cluster_size, plan);
-  if (threads == 1024) return PlanOptClusterT<1024>(rows_total, cluster_size, plan);
+  if (threads == 256) return PlanOptClusterT<256>(rows_total, cluster_size, plan, model);
+  if (threads == 512) return PlanOptClusterT<512>(rows_total, cluster_size, plan, model);
+  if (threads == 1024) return PlanOptClusterT<1024>(rows_total, cluster_size, plan, model);
   return false;
 }
 cudaError_t LaunchOptCluster(cudaStream_t s, const DeviceState& st, const OptOp* ops, int n_ops,
                              const OptControl* ctl, const int32_t* inv_perm, const double* wperm,
                              const int32_t class_row_start[9], const OptClusterPlan& plan,
                              const OptRefresh& refresh, const PeerEdge& peer, const double* rho_in,
-                             int64_t rho_stride, const double* edge_const_in) {
+                             int64_t rho_stride, const double* edge_const_in, bool model, double min_weight) {
   if (n_ops == 0) return cudaSuccess;
   OptClusterLayout lay;
   for (int c = 0; c < 9; ++c) lay.class_row_start[c] = class_row_start[c];
@@ -2586,6 +2881,15 @@ cudaError_t LaunchOptCluster(cudaStream_t s, const DeviceState& st, const OptOp*
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (model && rho_in == nullptr) {  // the Taylor-model search (the pipelined scheme keeps k_opt_cluster<T, true>)
+#define GP_LAUNCH_CLUSTER_MODEL(T)                                                                          \
+  return cudaLaunchKernelEx(&cfg, k_opt_cluster_model<T>, st, ops, ctl, inv_perm, wperm, lay, refresh, peer, \
+                            min_weight)
+    if (plan.threads == 1024) GP_LAUNCH_CLUSTER_MODEL(1024);
+    if (plan.threads == 512) GP_LAUNCH_CLUSTER_MODEL(512);
+    GP_LAUNCH_CLUSTER_MODEL(256);
+#undef GP_LAUNCH_CLUSTER_MODEL
+  }
 #define GP_LAUNCH_CLUSTER(T, R)                                                                          \
   return cudaLaunchKernelEx(&cfg, k_opt_cluster<T, R>, st, ops, ctl, inv_perm, wperm, lay, refresh, peer, \
                             rho_in, rho_stride, edge_const_in)

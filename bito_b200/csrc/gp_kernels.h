@@ -79,12 +79,14 @@ void LaunchOptBlock(cudaStream_t s, const DeviceState& st, const OptOp* ops, int
 // edge keeps rho in distributed shared memory and runs the whole search there (k_opt_cluster).
 // PlanOptCluster describes one cluster shape (threads per block 256 | 1024, cluster_size blocks) for
 // rows_total rho rows of kClusterThreads patterns; false if the device cannot run it.
-bool PlanOptCluster(int64_t rows_total, int threads, int cluster_size, OptClusterPlan* plan);
+bool PlanOptCluster(int64_t rows_total, int threads, int cluster_size, OptClusterPlan* plan, bool model);
 cudaError_t LaunchOptCluster(cudaStream_t s, const DeviceState& st, const OptOp* ops, int n_ops,
                              const OptControl* ctl, const int32_t* inv_perm, const double* wperm,
                              const int32_t class_row_start[9], const OptClusterPlan& plan,
                              const OptRefresh& refresh, const PeerEdge& peer, const double* rho_in = nullptr,
-                             int64_t rho_stride = 0, const double* edge_const_in = nullptr);
+                             int64_t rho_stride = 0, const double* edge_const_in = nullptr,
+                             bool model = false /* k_opt_cluster_model: the Taylor-model search */,
+                             double min_weight = 1.);
 // Pipelined cluster scheme: rho (cluster layout, position cpos[p]) and K_e tile-group partials
 // (n_ops x OptPrepareTileGroups) of a chunk of edges, written for k_opt_cluster<T, true>.
 // max_blocks > 0: a fixed grid of that many blocks walks the (edge, tile group) items.

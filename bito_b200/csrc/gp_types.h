@@ -258,7 +258,7 @@ struct OptPass {
   int32_t n_cache;
   int32_t passes;         // streamed passes this search has cost so far
   // the model
-  double c, S_c, radius;  // radius = 0: no model
+  double c, S_c, radius;  // radius = largest |x - c|^J the model answers for (0: no model)
   double mj[kOptMoments]; // (-1)^{j+1} M_j / j, j = 1..J-1 at [j-1]; [J-1] = M_J
 };
 
@@ -295,9 +295,12 @@ struct PeerComm {
   uint32_t* status;             // DeviceState::status
   int32_t n_ranks, rank;
 };
-// ... then, for the cluster-resident optimiser on several GPUs (k_opt_cluster), kPeerEdgeSlots edge
-// records [slot][parity][source rank] of {value, tag} (16 bytes): the per-evaluation sums of one edge.
+// ... then, for the cluster-resident optimiser on several GPUs (k_opt_cluster*), kPeerEdgeSlots edge
+// records [slot][bank][source rank] of {kPeerEdgeValues values, tag}: the sums of one pass of one edge
+// (k_opt_cluster uses value 0 only; k_opt_cluster_model all of them: 4 objective sums, 12 power sums, K_e).
 constexpr int kPeerEdgeSlots = 64;
+constexpr int kPeerEdgeValues = 17;
+constexpr int kPeerEdgeRecord = kPeerEdgeValues + 1;  // doubles per record (the tag last)
 #ifdef __CUDACC__
 __host__ __device__
 #endif
@@ -305,7 +308,7 @@ inline size_t PeerEdgeOffsetDoubles(int n_ranks) {
   return size_t(2) * n_ranks * kPeerCapacity + size_t(2) * n_ranks;
 }
 inline size_t PeerBufferBytes(int n_ranks) {
-  return (PeerEdgeOffsetDoubles(n_ranks) + size_t(kPeerEdgeSlots) * 4 * n_ranks * 2) * sizeof(double);
+  return (PeerEdgeOffsetDoubles(n_ranks) + size_t(kPeerEdgeSlots) * 4 * n_ranks * kPeerEdgeRecord) * sizeof(double);
 }
 // Cross-GPU part of k_opt_cluster's sums: enabled = 0 on a single rank.
 struct PeerEdge {
