@@ -658,6 +658,15 @@ void Engine::EnsureDense(int64_t id) {
            std::to_string(max_device_bytes_ >> 20) + " MiB): " +
            std::to_string(plv_pool_.SlotsInUse()) + " PLVs of " +
            std::to_string(plv_pool_.slot_bytes()) + " bytes are resident");
+    // the optimiser's coefficient scratch may hold gigabytes it only needs during a sweep: PLVs come first
+    if (d_coef_.n * sizeof(double) > (size_t(1) << 30)) {
+      size_t free_b = 0, total_b = 0;
+      if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b < 2 * plv_pool_.ChunkBytes()) {
+        GP_CUDA(cudaStreamSynchronize(stream_));
+        d_coef_.Release();
+        coef_padding_zeroed_ = false;
+      }
+    }
   }
   double* fresh = static_cast<double*>(plv_pool_.Alloc());
   if (s.kind == kPlvSymbols) {

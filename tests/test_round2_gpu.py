@@ -322,3 +322,105 @@ def test_stale_programs_are_evicted(cuda_engine_lib):
         e.process_operations(*pop)
         e.process_operations(*lik)
         assert rel_err(e.get_log_marginal_likelihood(), fx["t0_pass_log_marginal"]) <= LL_RTOL
+
+
+# ---- Taylor-model Brent (gp_types.h, OptPass): the streamed and the cluster-resident searches ---------------
+@pytest.fixture
+def opt_env(request, monkeypatch):
+    """BITO_GP_* settings read when an engine is created: "KEY=VAL,KEY=VAL"."""
+    for kv in str(request.param).split(","):
+        if kv:
+            k, _, v = kv.partition("=")
+            monkeypatch.setenv("BITO_GP_" + k, v)
+    return request.param
+
+
+def _weighted_problem(seed, taxa, patterns):
+    """Random tree problem whose weights populate every class of the optimiser's layouts: 1, 2..7, general."""
+    rng = np.random.default_rng(seed)
+    pb = _random_problem(rng, taxa, patterns)
+    w = pb["weights"].copy()
+    w[::5] = rng.integers(2, 8, size=w[::5].size)
+    w[3::7] = rng.uniform(0.25, 3.5, size=w[3::7].size)
+    w[5::31] = rng.integers(8, 400, size=w[5::31].size)
+    pb["weights"] = w
+    return pb
+
+
+@pytest.mark.parametrize("opt_env", ["OPT_SCHEME=0", "OPT_SCHEME=0,OPT_CHUNK_MB=1", "OPT_SCHEME=0,OPT_SEGMENTS=3",
+                                     "OPT_CLUSTER=4", "OPT_CLUSTER=16,OPT_CLUSTER_THREADS=512",
+                                     "OPT_CLUSTER=7,OPT_CLUSTER_THREADS=1024"], indirect=True)
+@pytest.mark.parametrize("taxa,patterns", [(6, 1), (9, 257), (14, 4099), (40, 30000)])
+def test_taylor_model_sweep_matches_oracle(cuda_engine_lib, taxa, patterns, opt_env):
+    """A batched Brent optimisation of every edge (weights of every class) under the streamed scheme (one and
+    several chunks, other segment counts) and under the cluster-resident model kernel, against the plain-C
+    oracle; most objective evaluations must have been answered without a pass."""
+    from bito_b200.gp_engine import GPEngine
+    from oracle.port_engine import PortEngine
+    pb = _weighted_problem(taxa * 7919 + patterns, taxa, patterns)
+    w = pb["weights"]
+    site_count = int(round(w.sum()))
+    cpu = PortEngine(pb["symbols"], w, site_count, pb["node_count"], pb["edge_count"])
+    with GPEngine(pb["symbols"], w, site_count, pb["node_count"], pb["edge_count"]) as gpu:
+        for e in (cpu, gpu):
+            e.set_branch_lengths(pb["branch_lengths"])
+            e.process_operations(*pb["populate"])
+            e.process_operations(*pb["likelihoods"])
+            e.process_operations(*pb["optimize"])
+        st = gpu.stats()
+        assert st["optimizer_scheme"] == (0 if "OPT_SCHEME=0" in opt_env else 2)
+        assert np.max(np.abs(gpu.get_branch_lengths() - cpu.branch_lengths())) <= BL_ATOL
+        assert 0 < st["objective_passes"] <= st["objective_evaluations"] // 2
+        assert st["device_status_bits"] == 0
+        # a second optimisation from the optimised lengths (IsFirstOptimization is false now: the first pass
+        # centres its model on the start)
+        cpu.increment_optimization_count()
+        gpu.increment_optimization_count()
+        for e in (cpu, gpu):
+            e.process_operations(*pb["populate"])
+            e.process_operations(*pb["optimize"])
+        # Second Jacobi sweeps of random trees are ill-conditioned on saturated (t ~ 3) and vanishing (t ~ 1e-6)
+        # edges - the plain-C port and the reference itself disagree there - so an edge outside 1e-6 must have
+        # the same objective value at both lengths (the CPU engine still holds the PLVs the sweep optimised against).
+        got, want = gpu.get_branch_lengths(), cpu.branch_lengths().copy()
+        off = np.nonzero(np.abs(got - want) > BL_ATOL)[0]
+        assert off.size <= max(2, want.size // 4)
+        by_edge = {int(r[3]): (int(r[1]), int(r[2])) for r in pb["optimize"][0]}
+        for g in off:
+            leafward, rootward = by_edge[int(g)]
+            values = []
+            for t in (got[g], want[g]):
+                bl = want.copy()
+                bl[g] = t
+                cpu.set_branch_lengths(bl)
+                values.append(cpu.log_likelihood_and_derivatives(int(g), rootward, leafward)[0])
+            assert abs(values[0] - values[1]) <= 1e-9 * max(1.0, abs(values[1])), (int(g), got[g], want[g], values)
+
+
+@pytest.mark.parametrize("opt_env", ["OPT_SCHEME=0"], indirect=True)
+def test_taylor_model_agrees_with_one_pass_per_evaluation(cuda_engine_lib, opt_env, monkeypatch):
+    """The same streamed sweep with the model switched off (BITO_GP_OPT_MODEL=0: every objective evaluation is
+    a pass over rho): same number of evaluations, same branch lengths up to Brent decisions that sit on a
+    boundary (an edge may differ only where the objective is flat to 1e-9)."""
+    from bito_b200.gp_engine import GPEngine
+    from bito_b200.synthetic import make_named_workload
+    wl = make_named_workload("synthetic-small", pattern_count=12000)
+    dag = wl.dag
+    pop, blo = wl.ops("populate_plvs"), wl.ops("batched_branch_length_optimization")
+    out = {}
+    for model in ("1", "0"):
+        monkeypatch.setenv("BITO_GP_OPT_MODEL", model)
+        with GPEngine(wl.symbols, wl.weights, wl.site_count, dag.node_count, dag.edge_count, sbn_prior=wl.sbn_prior,
+                      unconditional_node_probabilities=wl.unconditional, inverted_sbn_prior=wl.inverted) as e:
+            e.process_operations(*pop)
+            e.process_operations(*blo)
+            st = e.stats()
+            out[model] = (e.get_branch_lengths(), st["objective_evaluations"], st["objective_passes"])
+    bl1, ev1, passes1 = out["1"]
+    bl0, ev0, passes0 = out["0"]
+    assert passes0 == 0 and 0 < passes1 < (ev1 * 3) // 5
+    assert abs(ev1 - ev0) <= max(4, ev0 // 200)
+    off = np.abs(bl1 - bl0) > BL_ATOL
+    assert off.sum() <= max(1, bl0.size // 100)
+    tol = 2.0 ** -9
+    assert np.all(np.abs(np.log(bl1[off]) - np.log(bl0[off])) <= 4 * (tol * np.abs(np.log(bl0[off])) + tol / 4))

@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-SWEEP_VARIANTS="auto@OPT_MODEL=0,auto,16x512" timeout 900 python tools/sweep_variants.py synthetic-1000taxa-1Mpat-5000trees - gauss_seidel > gpurun_out/r02x_sweep_variants_gs.log 2>&1
-cat gpurun_out/r02x_sweep_variants_gs.log
+timeout 1200 python -m pytest tests/test_round2_gpu.py -m gpu -q -k "taylor" > gpurun_out/r02y_pytest_taylor.log 2>&1; echo "rc=$?" >> gpurun_out/r02y_pytest_taylor.log
+tail -12 gpurun_out/r02y_pytest_taylor.log | cut -c1-300
