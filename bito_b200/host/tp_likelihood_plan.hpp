@@ -24,11 +24,16 @@
 // five edges around it optionally optimised (OptimizeBranchLength ops) for a few rounds.
 #pragma once
 
+#include <algorithm>
+#include <map>
+#include <set>
 #include <vector>
 
 #include "gp_dag.hpp"
 #include "gp_operation.hpp"
+#include "nni_operation.hpp"
 #include "pv_handler.hpp"
+#include "reindexer.hpp"
 #include "tp_choice_map.hpp"
 #include "tp_evaluation_engine.hpp"
 
@@ -110,6 +115,144 @@ class TPLikelihoodPlan {
       LeafwardForEdge(ops, edge_id);
     }
     return ops;
+  }
+
+  // TPEvalEngineViaLikelihood::UpdateEngineAfterModifyingDAG (:267-460): the INCREMENTAL update after the NNI
+  // search has added node pairs to the DAG. It is not a re-evaluation - only the edges around the new NNIs
+  // are refreshed, in the reference's own order - so it is replayed step by step:
+  //   initialize: rootsplit RHat PVs, then PopulateRootwardPVForEdge over `update_edges` sorted by parent
+  //               node, PopulateLeafwardPVForEdge over them sorted by child node, descending (:306-330, 411-412);
+  //   iteration : per NNI OptimizeEdge on left child, right child, sister, focal and (below the root) parent
+  //               edge, then OptimizeEdge on every other new edge, then both local passes per NNI
+  //               (:415-447); only NEW edges are optimised (:364-367), never skipped for convergence;
+  //   score     : ComputeScores over `update_edges` (:455-457).
+  // This plan is built for the GROWN DAG and choice map (after UpdateChoiceMapAfterModifyingDAG, which also
+  // gives the new edges their starting branch lengths); the engine must have been grown with the edge
+  // reindexer (EngineNodeReindexer below) and hold those branch lengths.
+  // Run: ResetOptimizationCount; initialize; iteration x GetOptimizationMaxIteration() if IsOptimizeNewEdges(); score.
+  struct ModifiedDAGUpdate {
+    GPOperationVector initialize, iteration, score;
+    std::vector<EdgeId> update_edges;
+  };
+  ModifiedDAGUpdate UpdateAfterModifyingDAGOps(const std::map<NNIOperation, NNIOperation>& nni_to_pre_nni,
+                                               const size_t prev_edge_count, const Reindexer& edge_reindexer) const {
+    using namespace GPOperations;
+    ModifiedDAGUpdate out;
+    std::set<EdgeId> new_edges, nni_edges, extra_edges, update_edges;
+    for (size_t i = prev_edge_count; i < edge_reindexer.size(); i++) {
+      const EdgeId edge_id = EdgeId(edge_reindexer.GetNewIndexByOldIndex(i));
+      new_edges.insert(edge_id);
+      extra_edges.insert(edge_id);
+      update_edges.insert(edge_id);
+    }
+    for (const auto& [post_nni, pre_nni] : nni_to_pre_nni) {
+      std::ignore = pre_nni;
+      const auto edge_id = dag_.GetEdgeIdx(post_nni);
+      const auto& choice = choice_map_.GetEdgeChoice(edge_id);
+      nni_edges.insert(edge_id);
+      for (const EdgeId e : {choice.right_child, choice.left_child, choice.sister, edge_id, choice.parent}) {
+        extra_edges.erase(e);
+        update_edges.insert(e);
+      }
+    }
+    // the reference's (unstable) sorts on the same inputs with the same comparators
+    std::vector<EdgeId> rootward_edges(update_edges.begin(), update_edges.end());
+    std::sort(rootward_edges.begin(), rootward_edges.end(), [this](const EdgeId lhs, const EdgeId rhs) {
+      return dag_.GetDAGEdge(lhs).GetParent() < dag_.GetDAGEdge(rhs).GetParent();
+    });
+    std::vector<EdgeId> leafward_edges(update_edges.begin(), update_edges.end());
+    std::sort(leafward_edges.begin(), leafward_edges.end(), [this](const EdgeId lhs, const EdgeId rhs) {
+      return dag_.GetDAGEdge(lhs).GetChild() > dag_.GetDAGEdge(rhs).GetChild();
+    });
+    out.update_edges.assign(update_edges.begin(), update_edges.end());
+    // PopulateRootPVsWithStationaryDistribution (:901-919); the leaf P-PVs are the engine's site patterns
+    for (const auto edge_id : dag_.GetRootsplitEdgeIds())
+      out.initialize.push_back(SetToStationaryDistribution{PV(PLVType::RHat, edge_id), edge_id.value_});
+    for (const auto edge_id : rootward_edges) RootwardForEdge(out.initialize, edge_id);
+    for (const auto edge_id : leafward_edges) LeafwardForEdge(out.initialize, edge_id);
+
+    auto& it = out.iteration;
+    auto optimize_edge = [&](const EdgeId edge_id, const EdgeId parent_edge_id, const bool is_not_child_edge,
+                             const bool is_not_parent_edge) {  // OptimizeEdge, :332-383
+      const auto focal = dag_.GetFocalClade(edge_id);
+      const auto sister = dag_.GetSisterClade(edge_id);
+      if (is_not_child_edge)
+        it.push_back(Multiply{PV(PLVType::P, edge_id), PV(PLVType::PHatLeft, edge_id), PV(PLVType::PHatRight, edge_id)});
+      if (is_not_parent_edge) {
+        Assert(!dag_.IsEdgeRoot(edge_id), "TPLikelihoodPlan: OptimizeEdge on a root edge with a parent edge.");
+        it.push_back(Multiply{PV(PLVTypeEnum::RPLVType(focal), parent_edge_id), PV(PLVType::RHat, parent_edge_id),
+                              PV(PLVTypeEnum::PPLVType(sister), parent_edge_id)});
+      }
+      if (new_edges.find(edge_id) != new_edges.end()) {
+        const auto& choices = choice_map_.GetEdgeChoice(edge_id);  // GetPrimaryPVIdsOfEdge, :1042-1055
+        const size_t parent_pv = choices.parent == NoId
+                                     ? PV(PLVType::RHat, dag_.GetFirstRootsplitEdgeId())
+                                     : PV(PLVTypeEnum::RPLVType(dag_.GetFocalClade(edge_id)), choices.parent);
+        it.push_back(OptimizeBranchLength{PV(PLVType::P, edge_id), parent_pv, edge_id.value_});
+      }
+      if (is_not_parent_edge) {
+        Evolve(it, PV(PLVTypeEnum::PPLVType(focal), parent_edge_id), edge_id, PV(PLVType::P, edge_id));
+        it.push_back(Multiply{PV(PLVType::P, parent_edge_id), PV(PLVType::PHatLeft, parent_edge_id),
+                              PV(PLVType::PHatRight, parent_edge_id)});
+      }
+    };
+    for (const auto edge_id : nni_edges) {  // :417-432
+      const auto& choice = choice_map_.GetEdgeChoice(edge_id);
+      optimize_edge(choice.left_child, edge_id, false, true);
+      optimize_edge(choice.right_child, edge_id, false, true);
+      optimize_edge(choice.sister, choice.parent, false, true);
+      optimize_edge(edge_id, choice.parent, true, true);
+      if (!dag_.IsEdgeRoot(choice.parent)) {
+        const auto& choice_2 = choice_map_.GetEdgeChoice(choice.parent);
+        optimize_edge(choice.parent, choice_2.parent, true, false);
+      }
+    }
+    for (const auto edge_id : extra_edges) {  // :433-441
+      const auto& choice = choice_map_.GetEdgeChoice(edge_id);
+      if (!dag_.IsEdgeRoot(choice.parent)) optimize_edge(edge_id, choice.parent, true, true);
+    }
+    for (const auto edge_id : nni_edges) {  // NNIUpdatePVs, :384-409, 443
+      const auto& choice = choice_map_.GetEdgeChoice(edge_id);
+      const auto focal = dag_.GetFocalClade(edge_id), sister = dag_.GetSisterClade(edge_id);
+      // NNIRootwardPass: GetLocalPVIdsOfEdge (:1057-1097) names the PVs around the edge
+      Evolve(it, PV(PLVType::PHatLeft, edge_id), choice.left_child, PV(PLVType::P, choice.left_child));
+      Evolve(it, PV(PLVType::PHatRight, edge_id), choice.right_child, PV(PLVType::P, choice.right_child));
+      it.push_back(Multiply{PV(PLVType::P, edge_id), PV(PLVType::PHatLeft, edge_id), PV(PLVType::PHatRight, edge_id)});
+      Evolve(it, PV(PLVTypeEnum::PPLVType(sister), choice.parent), choice.sister, PV(PLVType::P, choice.sister));
+      Evolve(it, PV(PLVTypeEnum::PPLVType(focal), choice.parent), edge_id, PV(PLVType::P, edge_id));
+      it.push_back(Multiply{PV(PLVType::P, choice.parent), PV(PLVTypeEnum::PPLVType(focal), choice.parent),
+                            PV(PLVTypeEnum::PPLVType(sister), choice.parent)});
+      // NNILeafwardPass
+      if (!dag_.IsEdgeRoot(choice.parent)) {
+        const auto& choice_2 = choice_map_.GetEdgeChoice(choice.parent);
+        Evolve(it, PV(PLVType::RHat, choice.parent), choice.parent,
+               PV(PLVTypeEnum::RPLVType(dag_.GetFocalClade(choice.parent)), choice_2.parent));
+      }
+      it.push_back(Multiply{PV(PLVTypeEnum::RPLVType(focal), choice.parent), PV(PLVType::RHat, choice.parent),
+                            PV(PLVTypeEnum::PPLVType(sister), choice.parent)});
+      it.push_back(Multiply{PV(PLVTypeEnum::RPLVType(sister), choice.parent), PV(PLVType::RHat, choice.parent),
+                            PV(PLVTypeEnum::PPLVType(focal), choice.parent)});
+      Evolve(it, PV(PLVType::RHat, edge_id), edge_id, PV(PLVTypeEnum::RPLVType(focal), choice.parent));
+      it.push_back(Multiply{PV(PLVType::RLeft, edge_id), PV(PLVType::RHat, edge_id), PV(PLVType::PHatRight, edge_id)});
+      it.push_back(Multiply{PV(PLVType::RRight, edge_id), PV(PLVType::RHat, edge_id), PV(PLVType::PHatLeft, edge_id)});
+    }
+    for (const auto edge_id : out.update_edges) {  // ComputeScores(update_edges), :921-935
+      const auto& choices = choice_map_.GetEdgeChoice(edge_id);
+      const size_t parent_pv = choices.parent == NoId
+                                   ? PV(PLVType::RHat, dag_.GetFirstRootsplitEdgeId())
+                                   : PV(PLVTypeEnum::RPLVType(dag_.GetFocalClade(edge_id)), choices.parent);
+      out.score.push_back(Likelihood{edge_id.value_, PV(PLVType::P, edge_id), parent_pv});
+    }
+    return out;
+  }
+  // The engine's "node" slots are taxa, then edges: growing it for a DAG whose edges were reindexed by
+  // `edge_reindexer` (TPEvalEngine::GrowEdgeData, :34-49) is GrowPLVs(EngineNodeCount(), this) +
+  // GrowGPCSPs(EngineGPCSPCount(), edge_reindexer) on the plan of the grown DAG.
+  Reindexer EngineNodeReindexer(const Reindexer& edge_reindexer) const {
+    Reindexer out = Reindexer::IdentityReindexer(taxon_count_ + edge_reindexer.size());
+    for (size_t i = 0; i < edge_reindexer.size(); ++i)
+      out.SetReindex(taxon_count_ + i, taxon_count_ + edge_reindexer.GetNewIndexByOldIndex(i));
+    return out;
   }
 
   // TP PV id (PLVEdgeHandler numbering, pv_handler.hpp:487-490, 227-238: type * E + edge, spare j at

@@ -393,6 +393,109 @@ int main(int argc, char** argv) {
         }
       }
     }
+    // ---- the INCREMENTAL update the search itself performs (TPEvalEngineViaLikelihood::UpdateEngineAfterModifyingDAG,
+    // tp_evaluation_engine.cpp:267-460), replayed by TPLikelihoodPlan::UpdateAfterModifyingDAGOps on engines that
+    // PERSIST across the DAG's growth: they are grown with the search's reindexers, given the starting lengths the
+    // TP engine gave the new edges, and must then hold the scores and branch lengths the reference holds after its
+    // own partial update (which are NOT those of a re-evaluation: see `stale` above) --------------------------------
+    {
+      auto& eval = tp.GetLikelihoodEvalEngine();
+      eval.SetOptimizeNewEdges(true);
+      eval.Initialize();
+      eval.ComputeScores();
+      NNIEngine search(dag, nullptr, &tp);
+      search.SetTPLikelihoodCutoffFilteringScheme(0.0);
+      search.SetTopKScoreFilteringScheme(1);
+      size_t E0 = dag.EdgeCountWithLeafSubsplits();
+      auto plan0 = std::make_unique<TPLikelihoodPlan>(dag, tp.GetChoiceMap());
+      const size_t N0 = plan0->EngineNodeCount(), G0 = plan0->EngineGPCSPCount();
+      const EigenVectorXd ones_g0 = EigenVectorXd::Ones(G0), ones_n0 = EigenVectorXd::Ones(N0);
+      GPEngine cpu(SitePattern(alignment, trees.TagTaxonMap()), N0, G0, tag + ".gp", 1e-40, ones_g0, ones_n0, ones_g0,
+                   false);
+      std::unique_ptr<GPEngineB200> gpu;
+      if (with_gpu)
+        gpu = std::make_unique<GPEngineB200>(SitePattern(alignment, trees.TagTaxonMap()), N0, G0, tag + ".gp", 1e-40,
+                                             ones_g0, ones_n0, ones_g0, false);
+      {
+        const EigenVectorXd bl0 = eval.GetDAGBranchHandler().GetBranchLengthData().head(E0);
+        RunPlan(cpu, *plan0, bl0);
+        if (gpu) RunPlan(*gpu, *plan0, bl0);
+      }
+      double score_cpu = 0., score_gpu = 0., bl_cpu = 0., bl_gpu = 0.;
+      size_t updates = 0, updated_edges = 0, optimised_edges = 0;
+      auto replay = [&](auto& engine, const TPLikelihoodPlan& plan, const Reindexer& edge_reindexer,
+                        const TPLikelihoodPlan::ModifiedDAGUpdate& ops, const EigenVectorXd& start_lengths,
+                        const bool optimize, const size_t max_iter) {
+        engine.GrowPLVs(plan.EngineNodeCount(), plan.EngineNodeReindexer(edge_reindexer));
+        engine.GrowGPCSPs(plan.EngineGPCSPCount(), edge_reindexer);
+        engine.SetNullPrior();
+        engine.SetBranchLengths(start_lengths);
+        engine.ResetOptimizationCount();
+        engine.ProcessOperations(ops.initialize);
+        if (optimize)
+          for (size_t iter = 0; iter < max_iter; ++iter) engine.ProcessOperations(ops.iteration);
+        engine.ProcessOperations(ops.score);
+      };
+      search.SetFilterPostModificationFunction(
+          [&](NNIEngine& this_nni_engine, const SubsplitDAG::ModificationResult& mods,
+              const std::map<NNIOperation, NNIOperation>& nni_to_pre_nni) {
+            // what SetScoreViaEvalEngine's function does (nni_engine.cpp:458-468), with TPEngine::UpdateAfterModifyingDAG
+            // (tp_engine.cpp:238-260) opened up so that the evaluator's part can be replayed beside it
+            this_nni_engine.GrowEvalEngineForDAG(mods.node_reindexer, mods.edge_reindexer);
+            tp.UpdateChoiceMapAfterModifyingDAG(nni_to_pre_nni, mods.prv_node_count, mods.node_reindexer,
+                                                mods.prv_edge_count, mods.edge_reindexer);
+            const size_t E2 = dag.EdgeCountWithLeafSubsplits();
+            const EigenVectorXd start = eval.GetDAGBranchHandler().GetBranchLengthData().head(E2);
+            const TPLikelihoodPlan plan2(dag, tp.GetChoiceMap());
+            const auto ops = plan2.UpdateAfterModifyingDAGOps(nni_to_pre_nni, mods.prv_edge_count, mods.edge_reindexer);
+            replay(cpu, plan2, mods.edge_reindexer, ops, start, eval.IsOptimizeNewEdges(),
+                   eval.GetOptimizationMaxIteration());
+            if (gpu)
+              replay(*gpu, plan2, mods.edge_reindexer, ops, start, eval.IsOptimizeNewEdges(),
+                     eval.GetOptimizationMaxIteration());
+            eval.UpdateEngineAfterModifyingDAG(nni_to_pre_nni, mods.prv_node_count, mods.node_reindexer,
+                                               mods.prv_edge_count, mods.edge_reindexer);
+            const EigenVectorXd want_scores = tp.GetTopTreeLikelihoods().head(E2);
+            const EigenVectorXd want_bl = eval.GetDAGBranchHandler().GetBranchLengthData().head(E2);
+            auto compare = [&](auto& engine, double& worst_score, double& worst_bl) {
+              const EigenVectorXd got = engine.GetPerGPCSPLogLikelihoods();
+              for (const auto edge_id : ops.update_edges)
+                worst_score = std::max(worst_score, std::abs(got[edge_id.value_] - want_scores[edge_id.value_]) /
+                                                        std::max(1.0, std::abs(want_scores[edge_id.value_])));
+              const EigenVectorXd bl = engine.GetBranchLengths(0, E2);
+              worst_bl = std::max(worst_bl, (bl - want_bl).cwiseAbs().maxCoeff());
+            };
+            compare(cpu, score_cpu, bl_cpu);
+            if (gpu) compare(*gpu, score_gpu, bl_gpu);
+            ++updates;
+            updated_edges += ops.update_edges.size();
+            optimised_edges += E2 - mods.prv_edge_count;
+          });
+      search.RunInit(true);
+      for (size_t iteration = 0; iteration < 3 && search.GetAdjacentNNICount() > 0; ++iteration) {
+        search.RunMainLoop(true);
+        search.RunPostLoop(true);
+        // both sides back to the state of a fresh evaluation of the grown DAG (the next update starts from it)
+        const size_t E2 = dag.EdgeCountWithLeafSubsplits();
+        const EigenVectorXd bl2 = eval.GetDAGBranchHandler().GetBranchLengthData().head(E2);
+        eval.Initialize();
+        eval.ComputeScores();
+        const TPLikelihoodPlan plan2(dag, tp.GetChoiceMap());
+        RunPlan(cpu, plan2, bl2);
+        if (gpu) RunPlan(*gpu, plan2, bl2);
+        E0 = E2;
+      }
+      std::printf("incremental updates replayed: %zu (DAG now %zu edges; %zu edges refreshed, %zu new edges optimised)\n",
+                  updates, E0, updated_edges, optimised_edges);
+      if (updates > 0) {
+        Report("incremental update: plan on CPU GPEngine vs TPEngine, scores", score_cpu, 1e-9);
+        Report("incremental update: plan on CPU GPEngine vs TPEngine, |dBL|", bl_cpu, 1e-9);
+        if (with_gpu) {
+          Report("incremental update: plan on CUDA vs TPEngine, scores", score_gpu, 1e-7);
+          Report("incremental update: plan on CUDA vs TPEngine, |dBL|", bl_gpu, 1e-6);
+        }
+      }
+    }
     for (const char* suffix : {".tp_lik", ".tp_pars", ".gp"}) unlink((tag + suffix).c_str());
   } catch (const std::exception& e) {
     std::fprintf(stderr, "tp_parity: %s\n", e.what());

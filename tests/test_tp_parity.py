@@ -12,7 +12,10 @@ BranchLengthOptimizationOps. Finally the reference's NNI search runs three itera
 edges optimised, nni_search.py:624-642) and the plan, rebuilt for the grown DAG, must reproduce the reference's
 re-evaluation of it and the next round of proposed NNIs. BatchedProposedNNIOps scores all adjacent NNIs in one set of
 lists (disjoint temps per NNI, so the engine batches the k-th step of every NNI into one level) against the reference
-scoring them one at a time - on the CPU engine so far. 1e-9 relative (through the CPU GPEngine the plan is bit-exact; CUDA with
+scoring them one at a time (CPU engine, and `--gpu-batched`: CUDA). Last, the search's own INCREMENTAL update
+(TPEvalEngineViaLikelihood::UpdateEngineAfterModifyingDAG) is replayed by UpdateAfterModifyingDAGOps on engines that persist
+across the DAG's growth (grown with the search's reindexers): scores of the refreshed edges and all branch lengths
+must equal what the reference holds after its partial update - bit for bit through the CPU GPEngine. 1e-9 relative (through the CPU GPEngine the plan is bit-exact; CUDA with
 optimisation: scores 1e-7, lengths 1e-6); inputs are generated here (the reference's data directory does not travel)."""
 import os
 import subprocess
@@ -44,8 +47,11 @@ def test_tp_plan_matches_reference_tp_engine_on_cpu(tmp_path, taxa, sites, trees
     # the per-edge pass; proposed NNIs: scores with fixed lengths, scores and lengths after optimisation; the
     # whole-DAG branch-length optimisation; the DAG grown by three iterations of the reference's TP-mode NNI search
     # (re-evaluated from scratch + its next proposed NNIs)
-    # ... and every adjacent NNI scored in ONE batch of lists (BatchedProposedNNIOps)
-    assert sum(line.startswith("ok  ") for line in lines) == 8
+    # ... every adjacent NNI scored in ONE batch of lists (BatchedProposedNNIOps), and the search's incremental
+    # updates replayed on persistent engines (scores, branch lengths)
+    assert sum(line.startswith("ok  ") for line in lines) == 10
+    assert any("incremental update: plan on CPU GPEngine vs TPEngine, scores" in line and "err 0.000e+00" in line
+               for line in lines)  # the replay is the reference's own arithmetic in the reference's own order
 
 
 @pytest.mark.gpu
@@ -57,5 +63,16 @@ def test_tp_plan_through_the_cuda_engine_matches_reference_tp_engine(cuda_engine
     lines = _run(tmp_path, taxa, sites, trees, moves, "--gpu")
     # CPU checks as above (5) + CUDA: two per-edge passes, proposed NNIs fixed / optimised / optimised lengths,
     # whole-DAG optimisation, grown DAG + its next proposed NNIs
-    # (the batched lists are checked on the CPU engine only so far: 8 CPU + 8 CUDA checks)
-    assert sum(line.startswith("ok  ") for line in lines) == 16
+    # + the incremental updates on a persistent CUDA engine (scores, branch lengths): 10 CPU + 10 CUDA checks
+    assert sum(line.startswith("ok  ") for line in lines) == 20
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("taxa,sites,trees,moves", CASES[1:3])
+def test_tp_batched_proposed_nnis_through_the_cuda_engine(cuda_engine_lib, tmp_path, taxa, sites, trees, moves):
+    """All adjacent NNIs in one set of op lists on the CUDA engine (the level scheduler batches the k-th step of
+    every NNI into one launch) against the reference scoring them one at a time."""
+    if not os.path.exists(BINARY):
+        pytest.fail(f"{BINARY} is missing: run `make -C oracle tpparity` in the build container")
+    lines = _run(tmp_path, taxa, sites, trees, moves, "--gpu-batched")
+    assert any(line.startswith("ok  ") and "batched proposed NNIs (optimised): plan on CUDA" in line for line in lines)
