@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests/test_round2_gpu.py -m gpu -q -k "taylor" > gpurun_out/r02y_pytest_taylor.log 2>&1; echo "rc=$?" >> gpurun_out/r02y_pytest_taylor.log
-tail -12 gpurun_out/r02y_pytest_taylor.log | cut -c1-300
+timeout 1500 python -m pytest tests/test_tp_parity.py -m gpu -q > gpurun_out/r02A_pytest_tp.log 2>&1; echo "rc=$?" >> gpurun_out/r02A_pytest_tp.log
+tail -6 gpurun_out/r02A_pytest_tp.log | cut -c1-250

@@ -1,3 +1,4 @@
 mkdir -p gpurun_out
-timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/r02z_bench2.json 2> gpurun_out/r02z_bench2.err; echo "bench rc=$?" >> gpurun_out/r02z_bench2.err
-tail -3 gpurun_out/r02z_bench2.err
+N=${NG:-4}
+timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/r02B_bench$N.json 2> gpurun_out/r02B_bench$N.err; echo "bench rc=$?" >> gpurun_out/r02B_bench$N.err
+tail -2 gpurun_out/r02B_bench$N.err
