@@ -95,6 +95,21 @@ class TPLikelihoodPlan {
     return ops;
   }
 
+  // ComputeScores(opt_edge_ids): the listed edges only, in the caller's order (:921-935).
+  GPOperationVector ComputeScoresOps(const EdgeIdVector& edge_ids) const {
+    using namespace GPOperations;
+    GPOperationVector ops;
+    for (const auto edge_id : edge_ids) {
+      const auto& choices = choice_map_.GetEdgeChoice(edge_id);
+      const size_t parent_pv =
+          choices.parent == NoId
+              ? PV(PLVType::RHat, dag_.GetFirstRootsplitEdgeId())
+              : PV(PLVTypeEnum::RPLVType(dag_.GetFocalClade(edge_id)), choices.parent);
+      ops.push_back(Likelihood{edge_id.value_, PV(PLVType::P, edge_id), parent_pv});
+    }
+    return ops;
+  }
+
   // One round of TPEvalEngineViaLikelihood::BranchLengthOptimization (:988-1022) over every edge below a
   // rootsplit edge, rootward order: refresh the PVs around the edge, optimise it, push the result down.
   // The reference decides ONCE per call whether converged edges are skipped (check_branch_convergence =
