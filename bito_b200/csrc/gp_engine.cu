@@ -1785,7 +1785,7 @@ int Engine::OptScheme(int n_ops, const OptClusterPlan** plan) const {
       if (c.active_clusters < n_ops) continue;
       const int rows_per_thread = (c.rows_per_block * kClusterThreads + c.threads - 1) / c.threads;
       const double us = opt_model_env_ != 0
-                            ? 1.0 + 2.5 * ((rows_per_thread + 1) / 2) +
+                            ? 6.0 + 0.3 * ((rows_per_thread + 1) / 2) +
                                   5.0 * (3.0 + 0.12 * rows_per_thread + (c.threads > 512 ? 2.0 : 0.))
                             : 1.0 + 2.5 * ((rows_per_thread + 1) / 2) +
                                   14.5 * (2.4 + 0.05 * rows_per_thread + (c.threads > 256 ? 0.5 : 0.));
@@ -1840,7 +1840,9 @@ int Engine::OptScheme(int n_ops, const OptClusterPlan** plan) const {
   const OptClusterPlan* best_plan = nullptr;
   for (const OptClusterPlan& c : cluster_plans_) {
     const int rows_per_thread = (c.rows_per_block * kClusterThreads + c.threads - 1) / c.threads;
-    const double load_us = 1.0 + 2.5 * ((rows_per_thread + 1) / 2);
+    // (the load is a latency-bound gather of two PLVs whatever the block size: measured 16 x 512 threads 767 ms,
+    // 16 x 1024 threads 820 ms for the 11 139 single-edge levels of the 1000-taxon sweep, profiles/r02_sweep_model.md)
+    const double load_us = model ? 6.0 + 0.3 * ((rows_per_thread + 1) / 2) : 1.0 + 2.5 * ((rows_per_thread + 1) / 2);
     const double eval_us = model ? 3.0 + 0.12 * rows_per_thread + (c.threads > 512 ? 2.0 : 0.)
                                  : 2.4 + 0.05 * rows_per_thread + (c.threads > 256 ? 0.5 : 0.);
     const double waves = std::ceil(static_cast<double>(n_ops) / c.active_clusters);
