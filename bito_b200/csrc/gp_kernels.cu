@@ -2113,9 +2113,11 @@ __global__ void __launch_bounds__(T, T == 256 ? (kFromRho ? 4 : 3) : (T == 512 ?
   }
   int round = 0;
   double edge_const;
+  // every block of the cluster has started before the first store into a peer's shared memory (and s_rho is
+  // complete before the first pass over it)
+  cluster.sync();
   if (kFromRho && !px.enabled) {
     edge_const = edge_const_in[o];
-    __syncthreads();  // s_rho is complete before the first pass over it
   } else {
     // several GPUs: edge_const_in holds this rank's share of K_e; one exchange makes it global
     if (kFromRho) k_part = (rank == 0 && threadIdx.x == 0) ? edge_const_in[o] : 0.;
@@ -2321,7 +2323,9 @@ __global__ void __launch_bounds__(T, T == 256 ? 2 : 1)
       s_rho[i1] = pb >= 0 ? rho : 0.;
     }
   }
-  __syncthreads();  // s_rho is complete before the first pass over it
+  // s_rho is complete before the first pass over it - and every block of the cluster has started before the
+  // first store into a peer's shared memory (distributed shared memory may only be touched once all blocks run)
+  cluster.sync();
   // this thread's rows by weight class: first row >= the class's first row that is = sub (mod S)
   int seg_begin[8], seg_end[8];
 #pragma unroll
