@@ -592,6 +592,12 @@ def measure(args, name, rank, world, local_rank, extras=True):
         # kernel moves fewer bytes than the op list's algorithmic bytes, so `frac` can exceed 1
         "dram_achieved": (traffic / (per_launch_ms * 1e-3) / 1e9) if traffic else None,
         "dram_frac": (traffic / (per_launch_ms * 1e-3) / 1e9 / peak_gbs) if traffic else None,
+        # what bare kernels of k_node's own shape reach on this part (tools/mix_bw.cu, profiles/r02T_mix_bw.log:
+        # 1 read : 3 writes per pattern over hundreds of 4 MB PLVs = 6.1-6.2 TB/s, 2:3 = 6.4, 4:3 = 6.6): the
+        # copy peak above is a 1:1 mix over two linear streams
+        "mix_ceiling": {"GBps": 6150.0, "what": "bare 1 read : 3 writes kernel of k_node's shape, measured "
+                        "(profiles/r02_k_node_ceiling.md)",
+                        "dram_frac_of_ceiling": (traffic / (per_launch_ms * 1e-3) / 1e9 / 6150.0) if traffic else None},
         "launches_per_step": top["launches"] / prof_steps, "kernel_share_of_step": top["total_ms"] / total_prof_ms,
         "algorithmic_bytes_per_launch": per_launch_bytes, "ms_per_launch": per_launch_ms,
         # north_star's target: pass + one sweep against the HBM roofline (SURVEY 8d bytes: the sweep counts the

@@ -11,6 +11,7 @@
 // the CSV exporters. tests/test_gp_instance_parity_gpu.py compares the two outputs.
 #include <cstdio>
 #include <cstdlib>
+#include <fstream>
 #include <string>
 #include <unistd.h>
 
@@ -26,7 +27,7 @@ void PrintVector(const char* name, const EigenVectorXd& v) {
 
 int main(int argc, char** argv) {
   if (argc < 3) {
-    std::fprintf(stderr, "usage: %s fasta newick [rescaling_threshold] [max_iter]\n", argv[0]);
+    std::fprintf(stderr, "usage: %s fasta newick [rescaling_threshold] [max_iter] [other_build_branch_lengths]\n", argv[0]);
     return 2;
   }
   const double threshold = argc > 3 ? std::atof(argv[3]) : GPEngine::default_rescaling_threshold_;
@@ -62,6 +63,32 @@ int main(int argc, char** argv) {
     PrintVector("estimated_branch_lengths", engine.GetBranchLengths());
     PrintVector("estimated_per_gpcsp_llh", engine.GetPerGPCSPLogLikelihoods());
     std::printf("estimated_log_marginal %.17g\n", engine.GetLogMarginalLikelihood());
+    if (argc > 5) {
+      // Flatness check for edges on which the two builds' optimised lengths differ by more than 1e-6: the
+      // objective of edge e (Likelihood(e): parent R PLV, M(t_e), child P PLV) depends on t_e only through M, so
+      // with THIS build's PLVs in place, set those edges to the other build's lengths and score them again.
+      // Prints, per such edge: index, log-likelihood at the own length, log-likelihood at the other build's.
+      std::ifstream in(argv[5]);
+      std::vector<double> other;
+      for (double x; in >> x;) other.push_back(x);
+      const EigenVectorXd own = engine.GetBranchLengths();
+      const EigenVectorXd own_llh = engine.GetPerGPCSPLogLikelihoods();
+      EigenVectorXd mixed = own;
+      std::vector<Eigen::Index> off;
+      for (Eigen::Index i = 0; i < own.size() && size_t(i) < other.size(); ++i)
+        if (std::fabs(own[i] - other[size_t(i)]) > 1e-6) {
+          mixed[i] = other[size_t(i)];
+          off.push_back(i);
+        }
+      engine.SetBranchLengths(mixed);
+      inst.ComputeLikelihoods();
+      const EigenVectorXd other_llh = engine.GetPerGPCSPLogLikelihoods();
+      std::printf("flatness %zu", off.size());
+      for (Eigen::Index i : off) std::printf(" %ld %.17g %.17g", long(i), own_llh[i], other_llh[i]);
+      std::printf("\n");
+      engine.SetBranchLengths(own);
+      inst.ComputeLikelihoods();
+    }
 
     // configs[2]: SBN probability update, then with hybrid marginals
     inst.EstimateSBNParameters();
