@@ -47,26 +47,53 @@ constexpr double kBranchLengthDifferenceThreshold = 1e-15;
 // k_opt_block keeps G doubles per pattern in shared memory: up to 10240 patterns under JC69 (G = 2)
 constexpr size_t kOptBlockMaxSharedBytes = 160 * 1024;
 
-// Two independent 64-bit hashes of an op list: `seed` 0 keys the program cache, `seed` 1 is kept in
-// the Program and compared on every hit, so a collision of the key alone cannot run another list.
-uint64_t HashOps(const bito_gp_op* ops, int64_t n, const int64_t* vec, int64_t vec_len, int seed = 0) {
-  uint64_t h = seed == 0 ? 1469598103934665603ull : 0x9e3779b97f4a7c15ull;
-  const uint64_t mul = seed == 0 ? 1099511628211ull : 0xff51afd7ed558ccdull;
-  const int shift = seed == 0 ? 29 : 33;
-  auto mix = [&h, mul, shift](const void* data, size_t bytes) {
+// Two independent 64-bit hashes of an op list in ONE pass over it: `key` keys the program cache, `check` is
+// kept in the Program and compared on every hit, so a collision of the key alone cannot run another
+// list. Multiply-xorshift over 8-byte words (the inputs are int64 tables) in four interleaved lanes per
+// hash: a single dependent chain costs ~1 ms per hash on the bench's 84 000-op list (4 MB) - host time
+// during which the GPU sits idle at the head of every call - eight independent chains stream it.
+struct OpsHash {
+  uint64_t key, check;
+};
+OpsHash HashOps(const bito_gp_op* ops, int64_t n, const int64_t* vec, int64_t vec_len) {
+  constexpr uint64_t kMulA = 1099511628211ull, kMulB = 0xff51afd7ed558ccdull;
+  uint64_t a[4] = {1469598103934665603ull, 0x9ae16a3b2f90404full, 0xc3a5c85c97cb3127ull, 0xb492b66fbe98f273ull};
+  uint64_t b[4] = {0x9e3779b97f4a7c15ull, 0xbf58476d1ce4e5b9ull, 0x94d049bb133111ebull, 0x2545f4914f6cdd1dull};
+  auto word = [&](int lane, uint64_t w) {
+    a[lane] = (a[lane] ^ w) * kMulA;
+    a[lane] ^= a[lane] >> 29;
+    b[lane] = (b[lane] ^ w) * kMulB;
+    b[lane] ^= b[lane] >> 33;
+  };
+  auto mix = [&](const void* data, size_t bytes) {
     const unsigned char* p = static_cast<const unsigned char*>(data);
-    // FNV-1a over 8-byte words (inputs are int64 tables).
-    for (size_t i = 0; i + 8 <= bytes; i += 8) {
+    const size_t words = bytes / 8;
+    size_t i = 0;
+    for (; i + 4 <= words; i += 4) {
+      uint64_t w[4];
+      std::memcpy(w, p + 8 * i, 32);
+      word(0, w[0]);
+      word(1, w[1]);
+      word(2, w[2]);
+      word(3, w[3]);
+    }
+    for (; i < words; ++i) {  // the tail goes through lane (i mod 4): position still matters
       uint64_t w;
-      std::memcpy(&w, p + i, 8);
-      h = (h ^ w) * mul;
-      h ^= h >> shift;
+      std::memcpy(&w, p + 8 * i, 8);
+      word(static_cast<int>(i & 3), w);
     }
   };
-  mix(&n, sizeof n);
+  const int64_t head[2] = {n, vec_len};
+  mix(head, sizeof head);
   mix(ops, static_cast<size_t>(n) * sizeof(bito_gp_op));
-  mix(&vec_len, sizeof vec_len);
   if (vec_len > 0) mix(vec, static_cast<size_t>(vec_len) * sizeof(int64_t));
+  OpsHash h = {a[0], b[0]};
+  for (int lane = 1; lane < 4; ++lane) {
+    h.key = (h.key ^ a[lane]) * kMulA;
+    h.key ^= h.key >> 29;
+    h.check = (h.check ^ b[lane]) * kMulB;
+    h.check ^= h.check >> 33;
+  }
   return h;
 }
 
@@ -1619,8 +1646,9 @@ Program* Engine::Compile(const bito_gp_op* ops, int64_t n, const int64_t* vec, i
 
   stats_.programs_compiled++;
   Program* raw = prog.get();
-  const uint64_t key = HashOps(ops, n, vec, vec_len);
-  prog->check_hash = HashOps(ops, n, vec, vec_len, 1);
+  const OpsHash hash = HashOps(ops, n, vec, vec_len);
+  const uint64_t key = hash.key;
+  prog->check_hash = hash.check;
   prog->n_ops = n;
   prog->vec_len = vec_len;
   prog->last_used = ++program_clock_;
@@ -2257,11 +2285,11 @@ void Engine::ProcessOperations(const bito_gp_op* ops, int64_t n, const int64_t* 
   BindModel();
   stats_.process_calls++;
   if (n == 0) return;
-  const uint64_t key = HashOps(ops, n, vec, vec_len);
+  const OpsHash hash = HashOps(ops, n, vec, vec_len);
   Program* prog = nullptr;
-  auto it = programs_.find(key);
+  auto it = programs_.find(hash.key);
   if (it != programs_.end() && it->second->alloc_version == alloc_version_ && it->second->n_ops == n &&
-      it->second->vec_len == vec_len && it->second->check_hash == HashOps(ops, n, vec, vec_len, 1)) {
+      it->second->vec_len == vec_len && it->second->check_hash == hash.check) {
     prog = it->second.get();
     prog->last_used = ++program_clock_;
   } else {
