@@ -796,6 +796,8 @@ void Engine::CommInit(int n_ranks, int rank, const uint8_t id[128]) {
 // clusters its device keeps resident for its shard; the minimum over ranks bounds the edges of a
 // level that may take the cluster path. Collective: called by every rank at the same points.
 void Engine::AgreeOnClusterScheme() {
+  const int old_ops = multi_rank_cluster_ops_;
+  const double old_min_weight = min_weight_;
   multi_rank_cluster_ops_ = 0;
   if (n_ranks_ <= 1) return;
   int local = 0;
@@ -811,7 +813,10 @@ void Engine::AgreeOnClusterScheme() {
   GP_CUDA(cudaStreamSynchronize(stream_));
   multi_rank_cluster_ops_ = std::min<int>(static_cast<int>(-out[0]), kPeerEdgeSlots);
   min_weight_ = (-out[1] > 0. && -out[1] < 1e300) ? -out[1] : 1.;
-  DropGraphs();
+  // Captured levels bake both in (which optimiser kernel a level launches, the model's radius bound). A
+  // re-upload of the same alignment - every step of a caller that streams its data in - changes neither:
+  // keep the graphs (dropping them here cost a re-capture + re-instantiation of every program per upload).
+  if (multi_rank_cluster_ops_ != old_ops || min_weight_ != old_min_weight) DropGraphs();
 }
 
 // Exchange buffers for k_peer_allreduce: one cudaMalloc per rank, its IPC handle all-gathered over
