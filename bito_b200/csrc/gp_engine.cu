@@ -470,9 +470,13 @@ void Engine::SetSitePatterns(const uint8_t* symbols, const double* weights, bool
   // An empty shard (P_ == 0: a rank of a multi-GPU run that owns no pattern) uploads nothing but
   // runs every collective below with a zero contribution, so that all ranks issue the same sequence.
   if (P_ > 0) {
-    GP_CUDA(cudaMemcpy2DAsync(d_symbols_.ptr, static_cast<size_t>(P_stride_), symbols,
-                              static_cast<size_t>(P_), static_cast<size_t>(P_),
-                              static_cast<size_t>(taxon_count_), kind, stream_));
+    if (P_ == P_stride_)  // rows are back to back on both sides: one linear copy instead of taxon_count_ rows
+      GP_CUDA(cudaMemcpyAsync(d_symbols_.ptr, symbols, static_cast<size_t>(P_) * static_cast<size_t>(taxon_count_),
+                              kind, stream_));
+    else
+      GP_CUDA(cudaMemcpy2DAsync(d_symbols_.ptr, static_cast<size_t>(P_stride_), symbols,
+                                static_cast<size_t>(P_), static_cast<size_t>(P_),
+                                static_cast<size_t>(taxon_count_), kind, stream_));
     GP_CUDA(cudaMemcpyAsync(d_weights_.ptr, weights, static_cast<size_t>(P_) * sizeof(double), kind,
                             stream_));
   }
@@ -2221,13 +2225,18 @@ void Engine::Execute(Program& prog) {
     grow(d_mtab_lik_, 16 * static_cast<int64_t>(prog.n_lik_total));
     if (grew) DropGraphs();  // captured graphs hold the old scratch addresses
   }
-  const bool opt_on_chip = prog.n_opt_total > 0 && ProgramOptimizesOnChip(prog);
+  // A program that holds a captured graph was captured under the current settings (everything the
+  // per-level choice of optimiser kernel depends on drops the graphs when it changes), so a replay
+  // does not walk its levels again: the reference's Gauss-Seidel list has 11 139 optimiser levels, and
+  // two cost-model evaluations per level were milliseconds of host time in front of every launch.
+  const bool replay = prog.graph != nullptr && !(cfg_.flags & BITO_GP_FLAG_NO_CUDA_GRAPHS) && !profiling_;
+  const bool opt_on_chip = replay ? prog.n_opt_total > 0 : (prog.n_opt_total > 0 && ProgramOptimizesOnChip(prog));
   const bool want_graph = !(cfg_.flags & BITO_GP_FLAG_NO_CUDA_GRAPHS) &&
                           (prog.n_opt_total == 0 || opt_on_chip) && !profiling_;
   // optimiser launches are counted where they are issued (RunOptimizer), except inside a graph
   // replay, where every OptimizeBranchLength level is exactly one on-chip launch
   const int64_t launches = prog.launches;
-  if (opt_on_chip) {  // the pipelined scheme's buffers cannot be (re)allocated inside a capture
+  if (opt_on_chip && !replay) {  // the pipelined scheme's buffers cannot be (re)allocated inside a capture
     for (const Level& L : prog.levels) {
       const OptClusterPlan* plan = nullptr;
       if (L.n_opt > 0 && OptScheme(L.n_opt, &plan) == 3) EnsurePipelineBuffers(L.n_opt, *plan);
