@@ -441,7 +441,10 @@ void Engine::InstallModel(const double* v, const double* vinv, const double* lam
 
 void Engine::BindModel() {
   if (device_ < 64 && g_bound_model[device_] == model_id_) return;
-  GP_CUDA(cudaStreamSynchronize(stream_));  // nothing of this engine is in flight while the symbol changes
+  // The eigensystem is one __constant__ symbol per device, shared by every engine of the process: nothing
+  // of ANY engine may be in flight while it changes (a ProcessOperations call can return before its
+  // graph has finished, so the engine that bound the previous model may still be running).
+  GP_CUDA(cudaDeviceSynchronize());
   GP_CUDA(UploadModel(model_));
   if (device_ < 64) g_bound_model[device_] = model_id_;
 }
@@ -744,6 +747,8 @@ void Engine::EnsureScratch(int64_t partial_doubles, int64_t packed_doubles) {
 }
 
 void Engine::DropGraphs() {
+  // a single-GPU ProcessOperations no longer waits for the device: do not destroy a graph that may be running
+  if (stream_ != nullptr) cudaStreamSynchronize(stream_);
   for (auto& kv : programs_) {
     if (kv.second->graph != nullptr) {
       cudaGraphExecDestroy(kv.second->graph);
@@ -931,6 +936,7 @@ void Engine::Synchronize() {
 // Surface device-side asserts with the reference's messages (gp_engine.cpp:237-238, 256-257,
 // 283, 325, 585-586).
 void Engine::CheckStatus() {
+  status_pending_ = false;
   uint32_t* h = static_cast<uint32_t*>(pinned_);
   GP_CUDA(cudaMemcpyAsync(h, d_status_.ptr, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream_));
   GP_CUDA(cudaStreamSynchronize(stream_));
@@ -1696,6 +1702,7 @@ void Engine::EvictPrograms(const Program* keep) {
 }
 
 void Engine::FreeProgram(Program& p) {
+  if ((p.graph != nullptr || p.arena != nullptr) && stream_ != nullptr) cudaStreamSynchronize(stream_);  // may be running
   if (p.graph != nullptr) cudaGraphExecDestroy(p.graph);
   p.graph = nullptr;
   if (p.arena != nullptr) cudaFree(p.arena);
@@ -2319,7 +2326,15 @@ void Engine::ProcessOperations(const bito_gp_op* ops, int64_t n, const int64_t* 
   Execute(*prog);
   GP_CUDA(cudaEventRecord(ev_end_, stream_));
   timing_pending_ = true;
-  CheckStatus();
+  // The device status word mirrors the reference's Asserts. On one GPU without STRICT_ASSERTS they are
+  // Release-build no-ops that only accumulate in the statistics, so the call does not wait for the device:
+  // the host hashes and launches the caller's next list while this one runs (every getter is ordered on
+  // stream_ and synchronises it; Synchronize / GetStats collect the word). With peers a timed-out exchange
+  // must fail THIS call, and STRICT_ASSERTS promises the reference's exception here: both wait.
+  if (n_ranks_ > 1 || (cfg_.flags & BITO_GP_FLAG_STRICT_ASSERTS))
+    CheckStatus();
+  else
+    status_pending_ = true;
 }
 
 // ---- branch lengths / optimiser settings ---------------------------------------------------------
@@ -2905,6 +2920,7 @@ void Engine::ResetKernelProfile() {
 void Engine::GetStats(bito_gp_stats* out) {
   Activate();
   GP_CUDA(cudaStreamSynchronize(stream_));
+  if (status_pending_) CheckStatus();
   if (timing_pending_) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, ev_begin_, ev_end_) == cudaSuccess) stats_.last_process_ms = ms;

@@ -253,6 +253,7 @@ class Engine {
   int64_t optimization_count_ = 0;
   bool have_patterns_ = false;
   bool timing_pending_ = false;
+  bool status_pending_ = false;  // a ProcessOperations call returned without reading the device status word
   int n_eigen_groups_ = 2;
   double group_lambda_[kMaxEigenGroups] = {0., 0., 0., 0.};
   int64_t opt_chunk_bytes_ = 0;  // coefficient scratch per optimiser batch (0: 1 GiB)

@@ -131,6 +131,11 @@ BITO_GP_API int bito_gp_initialize_priors(bito_gp_engine* e, const double* sbn_p
 BITO_GP_API int bito_gp_set_null_prior(bito_gp_engine* e);
 
 /* ---- the hot call: GPEngine::ProcessOperations (gp_engine.cpp:335-339) -------------- */
+/* The list is compiled (or found in the program cache) and enqueued on the engine's stream; `ops` / `vec`
+ * are not retained. On one GPU without BITO_GP_FLAG_STRICT_ASSERTS the call may return before the device
+ * has finished (the caller's next list is hashed and launched meanwhile): every getter and setter is
+ * ordered on the same stream and waits as needed, bito_gp_synchronize / bito_gp_get_stats collect the
+ * device status word. With a communicator, or with STRICT_ASSERTS, the call waits and fails here. */
 BITO_GP_API int bito_gp_process_operations(bito_gp_engine* e, const bito_gp_op* ops, int64_t n_ops,
                                const int64_t* vec, int64_t vec_len);
 
