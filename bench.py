@@ -336,7 +336,9 @@ def small_configs(local_rank):
     import torch
     from bito_b200.gp_engine import GPEngine
     out = {}
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()  # a real stream: the handle of torch's default stream is NULL, which bito_gp_set_stream reads as
+    # "the engine's own stream", and events recorded on the default stream do not see work on that one
+    torch.cuda.set_stream(stream)
 
     def load(name):
         # NpzFile re-reads (and unzips) an array on EVERY z[...]: read everything once, so that the timed loops
@@ -470,7 +472,9 @@ def measure(args, name, rank, world, local_rank, extras=True):
     engine = GPEngine(sym_pinned.numpy(), w_pinned.numpy(), wl.site_count * world, dag.node_count, dag.edge_count,
                       sbn_prior=wl.sbn_prior, unconditional_node_probabilities=wl.unconditional,
                       inverted_sbn_prior=wl.inverted, device=local_rank, flags=flags)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()  # a real stream: the handle of torch's default stream is NULL, which bito_gp_set_stream reads as
+    # "the engine's own stream", and events recorded on the default stream do not see work on that one
+    torch.cuda.set_stream(stream)
     engine.set_stream(stream.cuda_stream)
 
     barrier, max_over_ranks = D.barrier, D.max_over_ranks

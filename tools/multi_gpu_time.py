@@ -24,7 +24,8 @@ total = int(sys.argv[2]) if len(sys.argv) > 2 else 40000
 wl = make_named_workload(name, pattern_count=total)
 dag = wl.dag
 lo, hi = shard_bounds(wl.pattern_count, world, rank)
-stream = torch.cuda.current_stream()
+stream = torch.cuda.Stream()  # not torch's default stream: its handle is NULL = "the engine's own stream" to set_stream
+torch.cuda.set_stream(stream)
 eng = GPEngine(np.ascontiguousarray(wl.symbols[:, lo:hi]), np.ascontiguousarray(wl.weights[lo:hi]), wl.site_count,
                dag.node_count, dag.edge_count, sbn_prior=wl.sbn_prior, unconditional_node_probabilities=wl.unconditional,
                inverted_sbn_prior=wl.inverted, flags=_lib.FLAG_NO_LOGLIK_MATRIX, device=local)

@@ -26,7 +26,8 @@ dag = wl.dag
 flags = _lib.FLAG_NO_LOGLIK_MATRIX if dag.edge_count * wl.pattern_count * 8 > 16e9 else 0
 pop = wl.ops("populate_plvs")
 sweep_ops = wl.ops("branch_length_optimization" if gauss_seidel else "batched_branch_length_optimization")
-stream = torch.cuda.current_stream()
+stream = torch.cuda.Stream()  # not torch's default stream: its handle is NULL = "the engine's own stream" to set_stream
+torch.cuda.set_stream(stream)
 print(f"# {name}: P={wl.pattern_count} nodes={dag.node_count} edges={dag.edge_count} "
       f"sweep={'gauss-seidel' if gauss_seidel else 'batched'} ({sweep_ops[0].shape[0]} ops)", flush=True)
 print("| variant | scheme | cluster | threads | edges in flight | sweep ms (best of 3) | evals | passes | max abs dBL vs first | edges > 1e-9 / > 1e-6 | log marginal after |")

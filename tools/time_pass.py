@@ -20,7 +20,8 @@ dag = wl.dag
 flags = _lib.FLAG_NO_LOGLIK_MATRIX if dag.edge_count * wl.pattern_count * 8 > 16e9 else 0
 eng = GPEngine(wl.symbols, wl.weights, wl.site_count, dag.node_count, dag.edge_count, sbn_prior=wl.sbn_prior,
                unconditional_node_probabilities=wl.unconditional, inverted_sbn_prior=wl.inverted, flags=flags)
-stream = torch.cuda.current_stream()
+stream = torch.cuda.Stream()  # not torch's default stream: its handle is NULL = "the engine's own stream" to set_stream
+torch.cuda.set_stream(stream)
 eng.set_stream(stream.cuda_stream)
 pop, lik = wl.ops("populate_plvs"), wl.ops("compute_likelihoods")
 
