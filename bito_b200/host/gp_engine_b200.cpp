@@ -21,6 +21,7 @@ int64_t I(size_t v) { return static_cast<int64_t>(v); }
 struct Flatten {
   std::vector<bito_gp_op>& ops;
   std::vector<int64_t>& vec;
+  bool changes_branch_lengths = false;  // the list holds an OptimizeBranchLength: the only op that writes them
   void Push(int64_t kind, int64_t a = 0, int64_t b = 0, int64_t c = 0, int64_t off = 0,
             int64_t len = 0) {
     ops.push_back(bito_gp_op{kind, a, b, c, off, len});
@@ -47,6 +48,7 @@ struct Flatten {
   }
   void operator()(const GPOperations::OptimizeBranchLength& o) {
     Push(BITO_GP_OPTIMIZE_BRANCH_LENGTH, I(o.leafward_), I(o.rootward_), I(o.gpcsp_));
+    changes_branch_lengths = true;
   }
   void operator()(const GPOperations::UpdateSBNProbabilities& o) {
     Push(BITO_GP_UPDATE_SBN_PROBABILITIES, I(o.start_), I(o.stop_));
@@ -155,7 +157,9 @@ void Self::ProcessOperations(GPOperationVector operations) {
   Flatten flatten{ops, vec};
   for (const auto& op : operations) std::visit(flatten, op);
   Check(bito_gp_process_operations(H(), ops.data(), I(ops.size()), vec.data(), I(vec.size())));
-  AfterBranchLengthChange();
+  // the DAGBranchHandler mirror is read back (a device -> host copy that waits for the list) only after a
+  // list that can have changed branch lengths or differences; a likelihood pass returns as soon as it is queued
+  if (flatten.changes_branch_lengths) AfterBranchLengthChange();
 }
 
 // ---- optimiser settings -----------------------------------------------------------------------
